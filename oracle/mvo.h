@@ -1,0 +1,100 @@
+/* mvo.h — ORACLE C API (test infrastructure, NOT product code).
+ *
+ * CPU restatement (scalar C++17 + OpenMP) of the reference's cube-map-space volume rendering path:
+ * CSVolumeCull, CSRayMarchL, CSRayMarchV, RayCast, CubeCast, depth-peel / PSResolveOIT, CSTemporalAA,
+ * PSToneMap, SH evaluation / projection and CSInitGridData (reference: MultiVolumes/Content/Shaders).
+ * It mirrors the product C-ABI (include/mv.h) call for call so the parity tests drive both the same
+ * way. Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load this library; the product (libmv_b200.so) never does.
+ *
+ * Parity pinning status: the reference ships no golden vectors, tests or CPU path and its shaders
+ * cannot run here (HLSL/DXIL, D3D12-only) — see DESIGN.md. The oracle is pinned by the analytic
+ * known-answer tests in tests/test_oracle_kat.py (closed-form transmittance, symmetry, empty volume,
+ * SH of constant radiance ...); the SH *projection* kernels exist only as DXIL in the reference and
+ * are "parity unpinned".
+ */
+#ifndef MVO_H
+#define MVO_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mvo_caster mvo_caster;
+
+typedef struct mvo_desc {
+    uint32_t grid_size;         /* G: volume and cube-map edge (reference default 128) */
+    uint32_t light_grid_size;   /* L: light-map edge (default 96) */
+    uint32_t num_volumes;       /* N instances */
+    uint32_t num_volume_srcs;   /* distinct density textures; VolTexId = i % srcs */
+    uint32_t width, height;     /* viewport */
+    uint32_t max_ray_samples;   /* default 256 */
+    uint32_t max_light_samples; /* default 96 */
+    uint32_t tex_filter_model;  /* 0 = exact fp32 trilinear weights, 1 = sm_100a texture-unit model */
+    uint32_t num_threads;       /* 0 = OpenMP default */
+} mvo_desc;
+
+typedef struct mvo_stats {
+    uint64_t view_rays, view_samples, view_light_fetches;
+    uint64_t light_voxels, light_dense_voxels, light_samples;
+    uint64_t direct_rays, direct_samples, direct_light_fetches;
+    uint64_t oit_fragments;
+    uint32_t visible_count, cubemap_count;
+    uint32_t light_volume;      /* volume whose light map the last render filled */
+    uint32_t threads;
+} mvo_stats;
+
+int  mvo_create(const mvo_desc* desc, mvo_caster** out);
+void mvo_destroy(mvo_caster* c);
+
+/* MultiRayCaster::InitVolumeData / LoadVolumeData */
+int mvo_volume_init_procedural(mvo_caster* c, uint32_t src, uint32_t mode, uint32_t seed);
+int mvo_volume_upload_rgba16f(mvo_caster* c, uint32_t src, const uint16_t* texels);
+int mvo_volume_upload_r32f(mvo_caster* c, uint32_t src, const float* density);
+int mvo_volume_read(mvo_caster* c, uint32_t src, uint16_t* texels_out);
+
+/* MultiRayCaster::SetRenderTargets / SetViewport: borrowed scene depth, shadow map, colour RT */
+int mvo_set_targets(mvo_caster* c, const float* depth, const uint16_t* shadow_d16, uint32_t shadow_size,
+                    const uint16_t* color_rgba16f, const uint16_t* velocity_rg16f);
+int mvo_set_sh(mvo_caster* c, const float* coeffs27);
+int mvo_set_max_samples(mvo_caster* c, uint32_t ray, uint32_t light);
+int mvo_set_volumes_world(mvo_caster* c, float size, const float center[3]);
+int mvo_set_volume_world(mvo_caster* c, uint32_t i, float size, const float pos[3]);
+int mvo_set_volume_world_matrix(mvo_caster* c, uint32_t i, const float world43[12]);
+int mvo_set_light(mvo_caster* c, const float pos[3], const float color[3], float intensity);
+int mvo_set_ambient(mvo_caster* c, const float color[3], float intensity);
+int mvo_update_frame(mvo_caster* c, const float view_proj[16], const float shadow_vp[16], const float eye[3]);
+
+/* passes; mvo_render = cull -> light march (one volume, round-robin) -> view march -> OIT, frame++ */
+int mvo_render(mvo_caster* c, uint32_t oit_method);
+int mvo_cull(mvo_caster* c);
+int mvo_ray_march_light(mvo_caster* c, int32_t volume_override);   /* -1: reference round-robin */
+int mvo_ray_march_view(mvo_caster* c);
+int mvo_resolve_oit(mvo_caster* c);
+int mvo_postprocess(mvo_caster* c, uint32_t taa_on);
+int mvo_sh_project(mvo_caster* c, const float* cube_rgb_f32, uint32_t size, float* coeffs27_out);
+
+/* read-backs */
+int mvo_read_per_object(mvo_caster* c, float* out56xN);
+int mvo_read_visible(mvo_caster* c, uint32_t* ids, uint32_t* count);
+int mvo_read_cube_volumes(mvo_caster* c, uint32_t* ids, uint32_t* count);
+int mvo_read_attribs(mvo_caster* c, uint16_t* out4xN);
+int mvo_read_cubemap(mvo_caster* c, uint32_t volume, uint32_t mip, uint16_t* rgba16f, float* depth);
+int mvo_read_lightmap(mvo_caster* c, uint32_t volume, uint16_t* rgba16f);
+int mvo_read_frame(mvo_caster* c, uint16_t* rgba16f);
+int mvo_read_post(mvo_caster* c, uint16_t* taa_rgba16f, uint8_t* rgba8);
+int mvo_get_stats(mvo_caster* c, mvo_stats* out);
+int mvo_set_frame_index(mvo_caster* c, uint32_t frame_idx);
+
+/* stand-alone helpers used by the known-answer tests */
+void  mvo_sample_volume(mvo_caster* c, uint32_t src, const float uvw[3], float rgba_out[4]);
+float mvo_quantize_r11(float v);
+float mvo_quantize_b10(float v);
+uint16_t mvo_f32_to_f16(float v);
+float mvo_f16_to_f32(uint16_t h);
+void  mvo_eval_sh_irradiance(const float* coeffs27, const float normal[3], float out4[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

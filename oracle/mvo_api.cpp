@@ -1,0 +1,305 @@
+// mvo_api.cpp — ORACLE (test infrastructure, not product code): C API over the restated passes.
+// Host-side scene maths follows MultiRayCaster.cpp:266-353 (SetVolumesWorld / SetVolumeWorld /
+// UpdateFrame) of the reference.
+#include "mvo_core.h"
+#include <omp.h>
+#include <new>
+
+using namespace mvo;
+
+struct mvo_caster { Caster c; };
+
+static int ok_src(Caster& c, uint32_t s) { return s < c.d.num_volume_srcs; }
+static int ok_vol(Caster& c, uint32_t v) { return v < c.d.num_volumes; }
+
+static void set_volume_world(Caster& c, uint32_t i, float size, const float pos[3])   // MultiRayCaster.cpp:297-303
+{
+    size *= 0.5f;
+    m43& w = c.volumeWorlds[i];
+    w = {{{size, 0, 0}, {0, size, 0}, {0, 0, size}, {pos[0], pos[1], pos[2]}}};
+}
+
+static void set_volumes_world(Caster& c, float size, const float center[3])   // MultiRayCaster.cpp:277-295
+{
+    const uint32_t numVolumes = c.d.num_volumes;
+    const uint32_t rowLength = (uint32_t)ceilf(sqrtf((float)numVolumes));
+    const uint32_t colLength = (uint32_t)ceilf((float)(numVolumes / rowLength));   // integer division first, as in the reference
+    float pos[3] = {center[0], center[1], center[2]};
+    pos[2] -= ((float)colLength / 2.0f - 0.5f) * size * 1.5f;
+    for (uint32_t m = 0; m < colLength; ++m) {
+        pos[0] = center[0] - ((float)rowLength / 2.0f - 0.5f) * size * 1.5f;
+        for (uint32_t n = 0; n < rowLength; ++n) {
+            set_volume_world(c, rowLength * m + n, size, pos);
+            pos[0] += size * 1.5f;
+        }
+        pos[2] += size * 1.5f;
+    }
+}
+
+extern "C" {
+
+int mvo_create(const mvo_desc* d, mvo_caster** out)
+{
+    if (!d || !out || d->grid_size == 0 || d->num_volumes == 0 || d->num_volume_srcs == 0 || d->width == 0 || d->height == 0) return -1;
+    if (d->grid_size >= (1u << 14) || d->num_volume_srcs >= (1u << 14) || (d->grid_size >> (kNumCubeMip - 1)) == 0) return -1;
+    mvo_caster* h = new (std::nothrow) mvo_caster();
+    if (!h) return -2;
+    Caster& c = h->c;
+    c.d = *d;
+    if (c.d.light_grid_size == 0) c.d.light_grid_size = 96;
+    if (c.d.max_ray_samples == 0) c.d.max_ray_samples = 256;
+    if (c.d.max_light_samples == 0) c.d.max_light_samples = 96;
+    c.filterModel = d->tex_filter_model ? MODEL_SM100 : MODEL_EXACT;
+    if (d->num_threads) omp_set_num_threads((int)d->num_threads);
+    const uint32_t G = c.d.grid_size, L = c.d.light_grid_size, N = c.d.num_volumes;
+    c.volumes.resize(c.d.num_volume_srcs);
+    for (auto& t : c.volumes) { t.n = G; t.texels.assign((size_t)G * G * G * 4, 0); }
+    c.lightMaps.resize(N);
+    for (auto& t : c.lightMaps) { t.n = L; t.texels.assign((size_t)L * L * L * 4, 0); }
+    c.cubeMaps.resize(N);
+    for (auto& cm : c.cubeMaps)
+        for (uint32_t m = 0; m < kNumCubeMip; ++m) {
+            const size_t s = G >> m;
+            cm.color[m].assign(6 * s * s * 4, 0);
+            cm.depth[m].assign(6 * s * s, 0.0f);
+        }
+    c.volumeWorlds.assign(N, m43{{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}}});
+    c.perObject.resize(N);
+    c.volumeDescs.resize(N);
+    for (uint32_t i = 0; i < N; ++i)   // MultiRayCaster.cpp:470-479
+        c.volumeDescs[i] = (i % c.d.num_volume_srcs) | (kNumCubeMip << 14) | (G << 18);
+    c.attribs.assign((size_t)N * 4, 0);
+    const size_t px = (size_t)c.d.width * c.d.height;
+    c.depth.assign(px, 1.0f);
+    c.shadowSize = 0;
+    c.color.assign(px * 4, 0);
+    c.velocity.assign(px * 2, 0);
+    c.taaHistory[0].assign(px * 4, 0); c.taaHistory[1].assign(px * 4, 0);
+    c.backBuffer.assign(px * 4, 0);
+    // MultiRayCaster.cpp:62-64 defaults
+    c.lightPt = {75.0f, 75.0f, -75.0f};
+    c.lightColor = {1.0f, 0.7f, 0.3f, 1.0f};
+    c.ambient = {0.0f, 0.3f, 1.0f, 0.4f};
+    c.stats = mvo_stats();
+    c.stats.threads = (uint32_t)omp_get_max_threads();
+    const float center[3] = {0, 0, 0};
+    set_volumes_world(c, 20.0f, center);
+    *out = h;
+    return 0;
+}
+
+void mvo_destroy(mvo_caster* h) { delete h; }
+
+int mvo_volume_init_procedural(mvo_caster* h, uint32_t src, uint32_t mode, uint32_t seed)
+{
+    if (!h || !ok_src(h->c, src)) return -1;
+    init_grid_data(h->c, src, mode, seed);
+    return 0;
+}
+int mvo_volume_upload_rgba16f(mvo_caster* h, uint32_t src, const uint16_t* texels)
+{
+    if (!h || !texels || !ok_src(h->c, src)) return -1;
+    auto& t = h->c.volumes[src];
+    std::copy(texels, texels + t.texels.size(), t.texels.begin());
+    return 0;
+}
+int mvo_volume_upload_r32f(mvo_caster* h, uint32_t src, const float* density)   // CSR32FToRGBA16F.hlsl:16-26
+{
+    if (!h || !density || !ok_src(h->c, src)) return -1;
+    auto& t = h->c.volumes[src];
+    const size_t n = (size_t)t.n * t.n * t.n;
+    const uint16_t one = f32_to_f16(1.0f);
+    for (size_t i = 0; i < n; ++i) {
+        t.texels[i * 4 + 0] = one; t.texels[i * 4 + 1] = one; t.texels[i * 4 + 2] = one;
+        t.texels[i * 4 + 3] = f32_to_f16(density[i] * 0.25f);
+    }
+    return 0;
+}
+int mvo_volume_read(mvo_caster* h, uint32_t src, uint16_t* out)
+{
+    if (!h || !out || !ok_src(h->c, src)) return -1;
+    auto& t = h->c.volumes[src];
+    std::copy(t.texels.begin(), t.texels.end(), out);
+    return 0;
+}
+
+int mvo_set_targets(mvo_caster* h, const float* depth, const uint16_t* shadow, uint32_t shadowSize, const uint16_t* color, const uint16_t* velocity)
+{
+    if (!h) return -1;
+    Caster& c = h->c;
+    const size_t px = (size_t)c.d.width * c.d.height;
+    if (depth) std::copy(depth, depth + px, c.depth.begin()); else c.depth.assign(px, 1.0f);
+    if (shadow && shadowSize) { c.shadowSize = shadowSize; c.shadow.assign(shadow, shadow + (size_t)shadowSize * shadowSize); }
+    else { c.shadowSize = 0; c.shadow.clear(); }
+    if (color) std::copy(color, color + px * 4, c.color.begin()); else c.color.assign(px * 4, 0);
+    if (velocity) std::copy(velocity, velocity + px * 2, c.velocity.begin()); else c.velocity.assign(px * 2, 0);
+    return 0;
+}
+int mvo_set_sh(mvo_caster* h, const float* k)
+{
+    if (!h) return -1;
+    h->c.hasSH = k != nullptr;
+    if (k) for (int i = 0; i < 9; ++i) h->c.sh[i] = {k[i * 3], k[i * 3 + 1], k[i * 3 + 2]};
+    return 0;
+}
+int mvo_set_max_samples(mvo_caster* h, uint32_t ray, uint32_t light)
+{
+    if (!h || !ray || !light) return -1;
+    h->c.d.max_ray_samples = ray; h->c.d.max_light_samples = light;
+    return 0;
+}
+int mvo_set_volumes_world(mvo_caster* h, float size, const float center[3]) { if (!h) return -1; set_volumes_world(h->c, size, center); return 0; }
+int mvo_set_volume_world(mvo_caster* h, uint32_t i, float size, const float pos[3])
+{
+    if (!h || !ok_vol(h->c, i)) return -1;
+    set_volume_world(h->c, i, size, pos);
+    return 0;
+}
+int mvo_set_volume_world_matrix(mvo_caster* h, uint32_t i, const float w[12])
+{
+    if (!h || !ok_vol(h->c, i)) return -1;
+    for (int r = 0; r < 4; ++r) for (int k = 0; k < 3; ++k) h->c.volumeWorlds[i].m[r][k] = w[r * 3 + k];
+    return 0;
+}
+int mvo_set_light(mvo_caster* h, const float p[3], const float col[3], float intensity)
+{
+    if (!h) return -1;
+    h->c.lightPt = {p[0], p[1], p[2]}; h->c.lightColor = {col[0], col[1], col[2], intensity};
+    return 0;
+}
+int mvo_set_ambient(mvo_caster* h, const float col[3], float intensity)
+{
+    if (!h) return -1;
+    h->c.ambient = {col[0], col[1], col[2], intensity};
+    return 0;
+}
+
+int mvo_update_frame(mvo_caster* h, const float viewProj[16], const float shadowVP[16], const float eye[3])   // MultiRayCaster.cpp:316-353
+{
+    if (!h || !viewProj || !eye) return -1;
+    Caster& c = h->c;
+    m44 vp, svp;
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) { vp.m[i][j] = viewProj[i * 4 + j]; svp.m[i][j] = shadowVP ? shadowVP[i * 4 + j] : (i == j ? 1.0f : 0.0f); }
+    c.cb.eyePt = {eye[0], eye[1], eye[2]};
+    c.cb.viewport = {(float)c.d.width, (float)c.d.height};
+    c.cb.screenToWorld = inverse44(vp);
+    c.cb.shadowViewProj = svp;
+    c.cb.lightPos = {c.lightPt.x, c.lightPt.y, c.lightPt.z, 1.0f};
+    c.cb.lightColor = c.lightColor;
+    c.cb.ambient = c.ambient;
+    c.cb.frameIdx = c.frameIdx;
+    for (uint32_t i = 0; i < c.d.num_volumes; ++i) {
+        const m44 world = from43(c.volumeWorlds[i]);
+        const m44 worldI = inverse44(world);
+        const m44 wvp = mul44(world, vp);
+        PerObject& po = c.perObject[i];
+        po.WorldViewProj = wvp;
+        po.WorldViewProjI = inverse44(wvp);
+        po.WorldI = to43(worldI);
+        po.World = to43(world);
+    }
+    return 0;
+}
+
+int mvo_cull(mvo_caster* h) { if (!h) return -1; cull_volumes(h->c); return 0; }
+int mvo_ray_march_light(mvo_caster* h, int32_t v)
+{
+    if (!h || v >= (int32_t)h->c.d.num_volumes) return -1;
+    ray_march_light(h->c, v);
+    return 0;
+}
+int mvo_ray_march_view(mvo_caster* h) { if (!h) return -1; ray_march_view(h->c); return 0; }
+int mvo_resolve_oit(mvo_caster* h) { if (!h) return -1; resolve_oit(h->c); return 0; }
+
+int mvo_render(mvo_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
+{
+    if (!h) return -1;
+    (void)oit;   // only the K-buffer semantics (default branch, :377-381) are restated
+    Caster& c = h->c;
+    cull_volumes(c);
+    ray_march_light(c, -1);
+    ray_march_view(c);
+    resolve_oit(c);
+    if (c.frameIdx != 0xffffffffu) ++c.frameIdx;
+    return 0;
+}
+int mvo_postprocess(mvo_caster* h, uint32_t taa) { if (!h) return -1; temporal_aa(h->c, taa != 0); tone_map(h->c); return 0; }
+int mvo_sh_project(mvo_caster* h, const float* cube, uint32_t size, float* out27)
+{
+    (void)h;
+    if (!cube || !out27 || !size) return -1;
+    sh_project(cube, size, out27);
+    return 0;
+}
+
+int mvo_read_per_object(mvo_caster* h, float* out)
+{
+    if (!h || !out) return -1;
+    for (const PerObject& po : h->c.perObject) {
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) *out++ = po.WorldViewProj.m[i][j];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) *out++ = po.WorldViewProjI.m[i][j];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 3; ++j) *out++ = po.WorldI.m[i][j];
+        for (int i = 0; i < 4; ++i) for (int j = 0; j < 3; ++j) *out++ = po.World.m[i][j];
+    }
+    return 0;
+}
+int mvo_read_visible(mvo_caster* h, uint32_t* ids, uint32_t* count)
+{
+    if (!h || !count) return -1;
+    *count = (uint32_t)h->c.visible.size();
+    if (ids) std::copy(h->c.visible.begin(), h->c.visible.end(), ids);
+    return 0;
+}
+int mvo_read_cube_volumes(mvo_caster* h, uint32_t* ids, uint32_t* count)
+{
+    if (!h || !count) return -1;
+    *count = (uint32_t)h->c.cubeVolumes.size();
+    if (ids) std::copy(h->c.cubeVolumes.begin(), h->c.cubeVolumes.end(), ids);
+    return 0;
+}
+int mvo_read_attribs(mvo_caster* h, uint16_t* out) { if (!h || !out) return -1; std::copy(h->c.attribs.begin(), h->c.attribs.end(), out); return 0; }
+int mvo_read_cubemap(mvo_caster* h, uint32_t v, uint32_t mip, uint16_t* rgba, float* depth)
+{
+    if (!h || !ok_vol(h->c, v) || mip >= kNumCubeMip) return -1;
+    const CubeMap& cm = h->c.cubeMaps[v];
+    if (rgba) std::copy(cm.color[mip].begin(), cm.color[mip].end(), rgba);
+    if (depth) std::copy(cm.depth[mip].begin(), cm.depth[mip].end(), depth);
+    return 0;
+}
+int mvo_read_lightmap(mvo_caster* h, uint32_t v, uint16_t* out)
+{
+    if (!h || !out || !ok_vol(h->c, v)) return -1;
+    const auto& t = h->c.lightMaps[v].texels;
+    std::copy(t.begin(), t.end(), out);
+    return 0;
+}
+int mvo_read_frame(mvo_caster* h, uint16_t* out) { if (!h || !out) return -1; std::copy(h->c.color.begin(), h->c.color.end(), out); return 0; }
+int mvo_read_post(mvo_caster* h, uint16_t* taa, uint8_t* rgba8)
+{
+    if (!h) return -1;
+    const auto& t = h->c.taaHistory[h->c.frameParity];
+    if (taa) std::copy(t.begin(), t.end(), taa);
+    if (rgba8) std::copy(h->c.backBuffer.begin(), h->c.backBuffer.end(), rgba8);
+    return 0;
+}
+int mvo_get_stats(mvo_caster* h, mvo_stats* out) { if (!h || !out) return -1; *out = h->c.stats; return 0; }
+int mvo_set_frame_index(mvo_caster* h, uint32_t f) { if (!h) return -1; h->c.frameIdx = f; h->c.cb.frameIdx = f; return 0; }
+
+void mvo_sample_volume(mvo_caster* h, uint32_t src, const float uvw[3], float out[4])
+{
+    const f4 r = sample3d(h->c.volumes[src], {uvw[0], uvw[1], uvw[2]}, h->c.filterModel);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+float mvo_quantize_r11(float v) { return quantize_ufloat(v, 6); }
+float mvo_quantize_b10(float v) { return quantize_ufloat(v, 5); }
+uint16_t mvo_f32_to_f16(float v) { return f32_to_f16(v); }
+float mvo_f16_to_f32(uint16_t hbits) { return f16_to_f32(hbits); }
+void mvo_eval_sh_irradiance(const float* k, const float n[3], float out4[4])
+{
+    f3 sh[9];
+    for (int i = 0; i < 9; ++i) sh[i] = {k[i * 3], k[i * 3 + 1], k[i * 3 + 2]};
+    const f4 r = evaluate_sh_irradiance(sh, {n[0], n[1], n[2]});
+    out4[0] = r.x; out4[1] = r.y; out4[2] = r.z; out4[3] = r.w;
+}
+
+} // extern "C"

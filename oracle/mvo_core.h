@@ -1,0 +1,84 @@
+// mvo_core.h — ORACLE (test infrastructure, not product code): scene state shared by the passes.
+#pragma once
+#include "mvo.h"
+#include "mvo_math.h"
+#include "mvo_sampler.h"
+#include <vector>
+#include <atomic>
+
+namespace mvo {
+
+// SharedConsts.h:5-10
+constexpr uint32_t kGroupVolumeCount = 4;
+constexpr uint32_t kNumCubeMip = 5;
+constexpr uint32_t kNumOitLayers = 8;
+constexpr float kZNear = 1.0f, kZFar = 1000.0f;
+// Common.hlsli:12, RayMarch.hlsli:11-12,17
+constexpr uint32_t kCubeMapRayMarchBit = 1u << 15;
+constexpr float kAbsorption = 0.8f;
+constexpr float kZeroThreshold = 0.01f;
+constexpr float kFltMax = 3.402823466e+38f;
+constexpr float kPi = 3.1415926535897f;           // SHIrradiance.hlsli:6
+
+// Common.hlsli:28-34 / MultiRayCaster.cpp:35-41. Stored un-transposed, row-vector convention.
+struct PerObject {
+    m44 WorldViewProj;
+    m44 WorldViewProjI;
+    m43 WorldI;
+    m43 World;
+};
+
+// Common.hlsli:39-49
+struct PerFrame {
+    f3 eyePt;
+    f2 viewport;
+    m44 screenToWorld;
+    m44 shadowViewProj;
+    f4 lightPos, lightColor, ambient;
+    uint32_t frameIdx;
+};
+
+struct CubeMap {               // RGBA16F colour + R32F depth, 6 faces x kNumCubeMip mips
+    std::vector<uint16_t> color[kNumCubeMip];
+    std::vector<float> depth[kNumCubeMip];
+};
+
+struct Caster {
+    mvo_desc d;
+    std::vector<Tex3D> volumes;           // per source
+    std::vector<Tex3D> lightMaps;         // per instance; RGBA16F holding R11G11B10F-quantised rgb
+    std::vector<CubeMap> cubeMaps;        // per instance
+    std::vector<m43> volumeWorlds;        // m_volumeWorlds
+    std::vector<PerObject> perObject;
+    std::vector<uint32_t> volumeDescs;    // VolTexId:14 | NumMips:4 | CubeMapSize:14
+    std::vector<uint16_t> attribs;        // N x {MipLevel, SmpCount, MaskBits, VolTexId}
+    std::vector<uint32_t> visible, cubeVolumes;
+    PerFrame cb;
+    f3 lightPt; f4 lightColor, ambient;
+    bool hasSH = false; f3 sh[9];
+    // borrowed targets (copied in)
+    std::vector<float> depth;             // W*H, D32
+    std::vector<uint16_t> shadow;         // S*S, D16 unorm
+    uint32_t shadowSize = 0;
+    std::vector<uint16_t> color;          // W*H RGBA16F: in = background, out = composited frame
+    std::vector<uint16_t> velocity;       // W*H RG16F
+    std::vector<uint16_t> taaHistory[2];  // RGBA16F ping-pong
+    std::vector<uint8_t> backBuffer;      // RGBA8
+    uint32_t frameParity = 0;
+    uint32_t frameIdx = 0;
+    mvo_stats stats;
+    int filterModel = MODEL_SM100;
+};
+
+// passes (mvo_passes.cpp)
+void cull_volumes(Caster& c);
+void ray_march_light(Caster& c, int volumeOverride);
+void ray_march_view(Caster& c);
+void resolve_oit(Caster& c);
+void temporal_aa(Caster& c, bool taaOn);
+void tone_map(Caster& c);
+void init_grid_data(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
+void sh_project(const float* cubeRGB, uint32_t size, float out27[27]);
+f4 evaluate_sh_irradiance(const f3 sh[9], f3 norm);
+
+} // namespace mvo

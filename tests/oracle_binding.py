@@ -1,0 +1,42 @@
+"""Test-side binding of the CPU oracle (oracle/_build/libmv_oracle.so). Never imported by the product."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from multivolumes_b200._abi import Binding, CasterBase, P, f32, u32, _vp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libmv_oracle.so")
+
+_EXTRA = {
+    "sample_volume": (None, [_vp, u32, P(f32), P(f32)]),
+    "quantize_r11": (f32, [f32]),
+    "quantize_b10": (f32, [f32]),
+    "f32_to_f16": (C.c_uint16, [f32]),
+    "f16_to_f32": (f32, [C.c_uint16]),
+    "eval_sh_irradiance": (None, [_vp, P(f32), P(f32)]),
+}
+_binding = None
+
+
+def oracle_binding():
+    global _binding
+    if _binding is None:
+        _binding = Binding(ORACLE_SO, "mvo_", _EXTRA)
+        assert not _binding.missing, _binding.missing
+    return _binding
+
+
+class OracleCaster(CasterBase):
+    """CPU oracle behind the MultiRayCaster surface. filter_model: 1 = sm_100a texture-unit model, 0 = exact fp32."""
+
+    def __init__(self, filter_model=1, threads=0, **kw):
+        super().__init__(oracle_binding(), opt0=filter_model, opt1=threads, **kw)
+
+    def SampleVolume(self, src, uvw):
+        uvw = np.ascontiguousarray(uvw, np.float32).reshape(-1, 3)
+        out = np.empty((len(uvw), 4), np.float32)
+        for i in range(len(uvw)):
+            self.b.sample_volume(self.h, src, uvw[i].ctypes.data_as(P(f32)), out[i].ctypes.data_as(P(f32)))
+        return out
