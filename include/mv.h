@@ -1,0 +1,182 @@
+/* mv.h — C-ABI of the B200-native cube-map-space multi-volume renderer (libmv_b200.so).
+ *
+ * This is the drop-in boundary for the ONE hot path of StarsX/MultiVolumes: the public section of
+ * `class MultiRayCaster` (reference: MultiVolumes/Content/MultiRayCaster.h:28-50) and the post-process
+ * entry of ObjectRenderer (MultiVolumes/Content/ObjectRenderer.h:46-48). Each export below cites the
+ * reference interface it replaces. The XUSG/D3D12 plumbing (command lists, descriptor tables,
+ * barriers, ExecuteIndirect) collapses into one CUDA stream owned by the handle.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative mv_status otherwise; mv_last_error() gives text;
+ *   - one handle = one owner thread = one CUDA device + stream; calls are asynchronous on that
+ *     stream until a mv_read_* or mv_sync;
+ *   - matrices are row-major float arrays in the reference's row-vector convention
+ *     (v' = v * M, DirectXMath layout before the reference's XMMatrixTranspose for upload);
+ *   - images are tightly packed, row-major, top row first; RGBA16F = 4 x IEEE binary16;
+ *   - volumes are RGBA16F, x fastest then y then z; cube maps are [face][y][x] with the D3D face
+ *     order +X,-X,+Y,-Y,+Z,-Z;
+ *   - there is NO CPU fallback: mv_create fails with MV_ERR_NO_DEVICE when no sm_100 device exists.
+ */
+#ifndef MV_H
+#define MV_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mv_caster mv_caster;
+
+enum mv_status {
+    MV_OK = 0,
+    MV_ERR_INVALID = -1,     /* bad argument */
+    MV_ERR_NOMEM = -2,       /* host or device allocation failed */
+    MV_ERR_CUDA = -3,        /* a CUDA call failed; see mv_last_error */
+    MV_ERR_NO_DEVICE = -4    /* no usable CUDA device (the product has no CPU path) */
+};
+
+/* mv_desc.flags */
+#define MV_FLAG_COUNT_SAMPLES   1u   /* keep exact ray/sample counters (mv_get_stats); small cost */
+#define MV_FLAG_TIME_PASSES     2u   /* bracket every pass with CUDA events (mv_get_timings) */
+
+/* MultiRayCaster::Init arguments (MultiRayCaster.h:31-34) + viewport (SetViewport, :38) +
+ * SetMaxSamples defaults (MultiVolumes.cpp:27-68). */
+typedef struct mv_desc {
+    uint32_t grid_size;         /* G: volume and cube-map edge (reference default 128) */
+    uint32_t light_grid_size;   /* L: light-map edge (default 96) */
+    uint32_t num_volumes;       /* N instances */
+    uint32_t num_volume_srcs;   /* distinct density textures; VolTexId = i % srcs (MultiRayCaster.cpp:476) */
+    uint32_t width, height;     /* viewport */
+    uint32_t max_ray_samples;   /* default 256 */
+    uint32_t max_light_samples; /* default 96 */
+    uint32_t device;            /* CUDA device ordinal */
+    uint32_t flags;             /* MV_FLAG_* */
+} mv_desc;
+
+typedef struct mv_stats {
+    uint64_t view_rays, view_samples, view_light_fetches;        /* CSRayMarchV */
+    uint64_t light_voxels, light_dense_voxels, light_samples;    /* CSRayMarchL */
+    uint64_t direct_rays, direct_samples, direct_light_fetches;  /* RayCast inside the OIT pass */
+    uint64_t oit_fragments;
+    uint32_t visible_count, cubemap_count;
+    uint32_t light_volume;      /* volume whose light map the last render filled */
+    uint32_t threads;           /* CUDA: SM count of the device */
+} mv_stats;
+
+/* per-pass device time of the last frame, milliseconds (CUDA events on the caster's stream) */
+typedef struct mv_timings {
+    float cull, ray_march_light, ray_march_view, resolve_oit, postprocess, total;
+} mv_timings;
+
+const char* mv_last_error(void);
+uint32_t mv_abi_version(void);
+
+/* Init (MultiRayCaster.h:31-34, MultiRayCaster.cpp:79-166) / destructor */
+int  mv_create(const mv_desc* desc, mv_caster** out);
+void mv_destroy(mv_caster* c);
+
+/* InitVolumeData (MultiRayCaster.h:40, CSInitGridData.hlsl:10-27); mode 1 adds seeded value noise.
+ * LoadVolumeData (MultiRayCaster.h:35-36): RGBA16F texels, or R32F density through the
+ * CSR32FToRGBA16F conversion (rgb = 1, a = 0.25 * src). Host pointers. */
+int mv_volume_init_procedural(mv_caster* c, uint32_t src, uint32_t mode, uint32_t seed);
+int mv_volume_upload_rgba16f(mv_caster* c, uint32_t src, const uint16_t* texels);
+int mv_volume_upload_r32f(mv_caster* c, uint32_t src, const float* density);
+int mv_volume_read(mv_caster* c, uint32_t src, uint16_t* texels_out);
+
+/* SetRenderTargets / SetViewport (MultiRayCaster.h:37-38): scene depth D32 WxH (NULL = 1.0),
+ * shadow map D16 SxS (NULL = none -> unshadowed), colour RT RGBA16F WxH that the volumes are
+ * composited over (NULL = zeros), velocity RG16F for the TAA (NULL = zeros). HOST pointers, copied. */
+int mv_set_targets(mv_caster* c, const float* depth, const uint16_t* shadow_d16, uint32_t shadow_size,
+                   const uint16_t* color_rgba16f, const uint16_t* velocity_rg16f);
+/* same, DEVICE pointers on the caster's device; copied device-to-device on the caster's stream */
+int mv_set_targets_device(mv_caster* c, const float* depth, const uint16_t* shadow_d16, uint32_t shadow_size,
+                          const uint16_t* color_rgba16f, const uint16_t* velocity_rg16f);
+/* restores the colour RT to the background given to the last mv_set_targets* (what the mesh and
+ * environment passes do every frame in the reference, MultiVolumes.cpp:645-673) */
+int mv_reset_color(mv_caster* c);
+
+int mv_set_sh(mv_caster* c, const float* coeffs27);                          /* SetSH, :41 (NULL = no probe) */
+int mv_set_max_samples(mv_caster* c, uint32_t ray, uint32_t light);          /* SetMaxSamples, :42 */
+int mv_set_volumes_world(mv_caster* c, float size, const float center[3]);   /* SetVolumesWorld, :43 */
+int mv_set_volume_world(mv_caster* c, uint32_t i, float size, const float pos[3]); /* SetVolumeWorld, :44 */
+int mv_set_volume_world_matrix(mv_caster* c, uint32_t i, const float world43[12]); /* animated transforms */
+int mv_set_light(mv_caster* c, const float pos[3], const float color[3], float intensity);   /* SetLight, :45 */
+int mv_set_ambient(mv_caster* c, const float color[3], float intensity);                     /* SetAmbient, :46 */
+/* UpdateFrame (:47-48, MultiRayCaster.cpp:316-353): builds CBPerFrame and the N PerObject records */
+int mv_update_frame(mv_caster* c, const float view_proj[16], const float shadow_vp[16], const float eye[3]);
+
+/* Render (:49-50, MultiRayCaster.cpp:355-385) = cull -> light march (one volume, round-robin) ->
+ * view march -> OIT resolve into the colour RT; frame index++. The individual passes are exported
+ * for the parity tests. */
+int mv_render(mv_caster* c, uint32_t oit_method);
+int mv_cull(mv_caster* c);                                   /* cullVolumes, MultiRayCaster.cpp:1249-1285 */
+int mv_ray_march_light(mv_caster* c, int32_t volume_override); /* rayMarchL, :1299-1327; -1 = round-robin */
+int mv_ray_march_view(mv_caster* c);                         /* rayMarchV, :1329-1368 */
+int mv_resolve_oit(mv_caster* c);                            /* cubeDepthPeel+renderCube+resolveOIT, :1440-1633 */
+/* ObjectRenderer::Postprocess (ObjectRenderer.h:46-48): CSTemporalAA (or copy when taa_on = 0) + PSToneMap */
+int mv_postprocess(mv_caster* c, uint32_t taa_on);
+/* SphericalHarmonics::Transform (XUSGSphericalHarmonics.h:25-26), order 3; cube = 6 x size x size x RGB f32 (host) */
+int mv_sh_project(mv_caster* c, const float* cube_rgb_f32, uint32_t size, float* coeffs27_out);
+
+/* read-backs (host pointers; each synchronises the stream). The reference has no read-back API. */
+int mv_read_per_object(mv_caster* c, float* out56xN);
+int mv_read_visible(mv_caster* c, uint32_t* ids, uint32_t* count);
+int mv_read_cube_volumes(mv_caster* c, uint32_t* ids, uint32_t* count);
+int mv_read_attribs(mv_caster* c, uint16_t* out4xN);
+int mv_read_cubemap(mv_caster* c, uint32_t volume, uint32_t mip, uint16_t* rgba16f, float* depth);
+int mv_read_lightmap(mv_caster* c, uint32_t volume, uint16_t* rgba16f);
+int mv_read_frame(mv_caster* c, uint16_t* rgba16f);
+int mv_read_post(mv_caster* c, uint16_t* taa_rgba16f, uint8_t* rgba8);
+int mv_get_stats(mv_caster* c, mv_stats* out);
+int mv_get_timings(mv_caster* c, mv_timings* out);
+int mv_set_frame_index(mv_caster* c, uint32_t frame_idx);
+int mv_sync(mv_caster* c);
+
+/* pinned host memory for the read-backs / uploads of a frame loop */
+void* mv_host_alloc(size_t bytes);
+void  mv_host_free(void* p);
+
+/* ---- multi-GPU (one process per GPU; no counterpart in the single-adapter reference) ----
+ * Partition (BASELINE.json north_star): the cull is replicated; volume v's cube map is marched by
+ * rank v % world; the light map of the frame's light volume is filled in z-slabs, slab r by rank r;
+ * the OIT resolve + post-process run on a band of rows per rank. Every buffer that crosses GPUs lives
+ * in ONE device allocation per caster, the exchange block:
+ *     [cube-map arena | light-map staging | back buffer RGBA8 | barrier flags]
+ * with identical layout on every rank. Two ways to move the data:
+ *   (a) fused: map every peer's block with mv_ipc_export / mv_ipc_import; the march, light and
+ *       post-process kernels then store their results straight into all peers' blocks over NVLink and
+ *       mv_peer_barrier orders the phases with device-side flags — no collective call at all;
+ *   (b) collective: leave the peers unmapped and run NCCL (all-gather / broadcast / gather) on
+ *       regions of the block between the passes (mv_exchange_block gives the pointer, mv_cube_region
+ *       and mv_exchange_layout the offsets). */
+typedef struct mv_exchange_layout {
+    uint64_t block_bytes;
+    uint64_t arena_offset, arena_bytes;                 /* cube maps of all volumes, all mips */
+    uint64_t light_staging_offset, light_staging_bytes; /* world x slab: [z][y][x] RGBA16F, slabs padded to ceil(L / world) */
+    uint64_t back_buffer_offset, back_buffer_bytes;     /* H x W RGBA8 */
+    uint64_t flags_offset, flags_bytes;
+    uint32_t light_slab_depth;                          /* ceil(L / world) */
+    uint32_t reserved;
+} mv_exchange_layout;
+
+int mv_set_shard(mv_caster* c, uint32_t rank, uint32_t world);
+int mv_set_row_band(mv_caster* c, uint32_t row0, uint32_t row1);     /* rows this rank resolves and post-processes */
+int mv_exchange_block(mv_caster* c, void** dev_ptr, uint64_t* bytes);
+int mv_exchange_layout_get(mv_caster* c, mv_exchange_layout* out);
+/* byte offsets (from the block base) of volume `volume`'s cube map at `mip`: [face][y][x] colour, then depth */
+int mv_cube_region(mv_caster* c, uint32_t volume, uint32_t mip, uint64_t* color_offset, uint64_t* color_bytes,
+                   uint64_t* depth_offset, uint64_t* depth_bytes);
+int mv_ipc_export(mv_caster* c, void* handle64);                     /* 64-byte cudaIpcMemHandle_t of the block */
+int mv_ipc_import(mv_caster* c, uint32_t peer_rank, const void* handle64);
+int mv_peer_barrier(mv_caster* c);                                   /* device-side all-ranks barrier on the stream (fused mode) */
+int mv_light_commit(mv_caster* c);                                   /* light-map staging -> the light volume's 3-D array */
+/* enqueue the caster's work on an external stream (e.g. the one NCCL collectives are ordered on); NULL = own stream */
+int mv_set_stream(mv_caster* c, void* cuda_stream);
+int mv_get_stream(mv_caster* c, void** cuda_stream);
+/* device pointers of the frame images: colour RT RGBA16F, TAA output RGBA16F (current), back buffer RGBA8 */
+int mv_frame_buffers(mv_caster* c, void** color_rgba16f, void** post_rgba16f, void** back_rgba8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

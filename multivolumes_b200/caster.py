@@ -1,0 +1,170 @@
+"""Product binding: the MultiRayCaster operator surface over libmv_b200.so (CUDA, sm_100a).
+
+There is no CPU path. Importing this module without the built library, or creating a caster without a
+B200-class device, raises — it never falls back to anything else.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from ._abi import Binding, CasterBase, P, f32, u32, _vp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libmv_b200.so")
+
+FLAG_COUNT_SAMPLES = 1
+FLAG_TIME_PASSES = 2
+
+
+class Timings(C.Structure):
+    _fields_ = [(k, f32) for k in ("cull", "ray_march_light", "ray_march_view", "resolve_oit", "postprocess", "total")]
+
+    def as_dict(self):
+        return {k: float(getattr(self, k)) for k, _ in self._fields_}
+
+
+class ExchangeLayout(C.Structure):
+    _fields_ = [(k, C.c_uint64) for k in ("block_bytes", "arena_offset", "arena_bytes", "light_staging_offset", "light_staging_bytes",
+                                          "back_buffer_offset", "back_buffer_bytes", "flags_offset", "flags_bytes")] + \
+               [("light_slab_depth", u32), ("reserved", u32)]
+
+
+u64p = P(C.c_uint64)
+_EXTRA = {
+    "last_error": (C.c_char_p, []),
+    "abi_version": (u32, []),
+    "set_targets_device": (C.c_int, [_vp, _vp, _vp, u32, _vp, _vp]),
+    "reset_color": (C.c_int, [_vp]),
+    "get_timings": (C.c_int, [_vp, P(Timings)]),
+    "sync": (C.c_int, [_vp]),
+    "host_alloc": (_vp, [C.c_size_t]),
+    "host_free": (None, [_vp]),
+    "set_shard": (C.c_int, [_vp, u32, u32]),
+    "set_row_band": (C.c_int, [_vp, u32, u32]),
+    "exchange_block": (C.c_int, [_vp, P(_vp), u64p]),
+    "exchange_layout_get": (C.c_int, [_vp, P(ExchangeLayout)]),
+    "cube_region": (C.c_int, [_vp, u32, u32, u64p, u64p, u64p, u64p]),
+    "ipc_export": (C.c_int, [_vp, _vp]),
+    "ipc_import": (C.c_int, [_vp, u32, _vp]),
+    "peer_barrier": (C.c_int, [_vp]),
+    "light_commit": (C.c_int, [_vp]),
+    "set_stream": (C.c_int, [_vp, _vp]),
+    "get_stream": (C.c_int, [_vp, P(_vp)]),
+    "frame_buffers": (C.c_int, [_vp, P(_vp), P(_vp), P(_vp)]),
+}
+
+_binding = None
+
+
+def binding():
+    """Loads libmv_b200.so (built by `make -C multivolumes_b200/csrc` or __graft_entry__.build())."""
+    global _binding
+    if _binding is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} is missing: build it with `make -C multivolumes_b200/csrc` "
+                               "(the product has no CPU fallback)")
+        b = Binding(LIB_PATH, "mv_", _EXTRA)
+        if b.missing:
+            raise RuntimeError(f"libmv_b200.so does not export: {b.missing}")
+        _binding = b
+    return _binding
+
+
+class PinnedBuffer:
+    """Page-locked host memory from mv_host_alloc, exposed as a numpy array."""
+
+    def __init__(self, shape, dtype):
+        self.b = binding()
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = self.b.host_alloc(n)
+        if not self.ptr:
+            raise MemoryError(self.b.last_error().decode())
+        buf = (C.c_char * n).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.b.host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class MultiRayCaster(CasterBase):
+    """MultiVolumes/Content/MultiRayCaster.h:28-50 on one B200. Method names follow the reference class."""
+
+    def __init__(self, device=0, count_samples=True, time_passes=False, **kw):
+        flags = (FLAG_COUNT_SAMPLES if count_samples else 0) | (FLAG_TIME_PASSES if time_passes else 0)
+        super().__init__(binding(), opt0=device, opt1=flags, **kw)
+        self.device = device
+
+    # --- product-only calls ---
+    def SetRenderTargetsDevice(self, depth=0, shadow=0, shadow_size=0, color=0, velocity=0):
+        self._ck(self.b.set_targets_device(self.h, depth or None, shadow or None, shadow_size, color or None, velocity or None),
+                 "set_targets_device")
+
+    def ResetColor(self):
+        self._ck(self.b.reset_color(self.h), "reset_color")
+
+    def Sync(self):
+        self._ck(self.b.sync(self.h), "sync")
+
+    def GetTimings(self):
+        t = Timings()
+        self._ck(self.b.get_timings(self.h, C.byref(t)), "get_timings")
+        return t.as_dict()
+
+    def ReadPostInto(self, rgba8_ptr=None, taa_ptr=None):
+        """Read-back into caller-owned (pinned) memory; pointers are integers."""
+        self._ck(self.b.read_post(self.h, taa_ptr, rgba8_ptr), "read_post")
+
+    # --- multi-GPU ---
+    def SetShard(self, rank, world):
+        self._ck(self.b.set_shard(self.h, rank, world), "set_shard")
+
+    def SetRowBand(self, row0, row1):
+        self._ck(self.b.set_row_band(self.h, row0, row1), "set_row_band")
+
+    def ExchangeBlock(self):
+        p, n = _vp(), C.c_uint64()
+        self._ck(self.b.exchange_block(self.h, C.byref(p), C.byref(n)), "exchange_block")
+        return p.value, n.value
+
+    def ExchangeLayout(self):
+        lay = ExchangeLayout()
+        self._ck(self.b.exchange_layout_get(self.h, C.byref(lay)), "exchange_layout_get")
+        return lay
+
+    def CubeRegion(self, volume, mip):
+        a, b_, c_, d = (C.c_uint64() for _ in range(4))
+        self._ck(self.b.cube_region(self.h, volume, mip, C.byref(a), C.byref(b_), C.byref(c_), C.byref(d)), "cube_region")
+        return a.value, b_.value, c_.value, d.value
+
+    def IpcExport(self):
+        buf = C.create_string_buffer(64)
+        self._ck(self.b.ipc_export(self.h, buf), "ipc_export")
+        return bytes(buf.raw)
+
+    def IpcImport(self, peer, handle):
+        buf = C.create_string_buffer(bytes(handle), 64)
+        self._ck(self.b.ipc_import(self.h, peer, buf), "ipc_import")
+
+    def PeerBarrier(self):
+        self._ck(self.b.peer_barrier(self.h), "peer_barrier")
+
+    def LightCommit(self):
+        self._ck(self.b.light_commit(self.h), "light_commit")
+
+    def SetStream(self, stream_ptr):
+        self._ck(self.b.set_stream(self.h, stream_ptr or None), "set_stream")
+
+    def FrameBuffers(self):
+        a, b_, c_ = _vp(), _vp(), _vp()
+        self._ck(self.b.frame_buffers(self.h, C.byref(a), C.byref(b_), C.byref(c_)), "frame_buffers")
+        return a.value, b_.value, c_.value

@@ -1,0 +1,199 @@
+// k_cull.cu — per-volume viewport cull, face-visibility mask, cube-map LOD / sample-count estimate,
+// cube-map-vs-direct decision and visible-list compaction.
+//
+// Replaces CSVolumeCull (MultiVolumes/Content/Shaders/CSVolumeCull.hlsl:13-78 with
+// VolumeCull.hlsli:27-334) and CSCopyVolumeDrawArg. Same lane mapping as the reference — 8 lanes per
+// volume (one cube corner each), 4 volumes per warp — on __ballot_sync / __shfl_sync, but the two
+// atomic AppendStructuredBuffer appends become a ballot + block prefix sum, so both lists come out in
+// ascending volume order on every run. The kernel also produces what the reference needs extra
+// dispatches or ExecuteIndirect arguments for: the tile prefix of the view march (exact
+// (G >> mip)^2 texels per visible face, as the work-graph variant LibRayMarch.hlsl:120-121 launches),
+// the work-stealing cursors, and the light-march volume of this frame (CSRayMarchL.hlsl:29-33).
+// One CTA of 32 warps (128 volumes per sweep); N <= a few thousand, so this is latency-bound.
+#include "mv_internal.h"
+
+namespace mv {
+
+namespace {
+
+constexpr int kCullThreads = 1024;
+constexpr int kCullWarps = kCullThreads / 32;
+constexpr uint32_t kFull = 0xffffffffu;
+
+// VolumeCull.hlsli:119-138 — unique edge id -> (corner, corner)
+__constant__ unsigned char c_edgeLanes[12][2] = {{0, 1}, {3, 2}, {1, 3}, {2, 0}, {6, 7}, {5, 4},
+                                                 {4, 6}, {7, 5}, {4, 0}, {2, 6}, {7, 3}, {1, 5}};
+// VolumeCull.hlsli:213-223 — face (by mask bit) -> 4 unique edge ids
+__constant__ unsigned char c_faceEdges[6][4] = {{8, 3, 9, 6}, {10, 2, 11, 7}, {0, 8, 5, 11},
+                                                {1, 10, 4, 9}, {0, 2, 1, 3}, {4, 6, 5, 7}};
+
+MV_D V3 project_to_viewport(uint32_t i, const float* wvp, float vw, float vh)   // VolumeCull.hlsli:27-41
+{
+    const V3 p3 = {(i & 1) ? 1.0f : -1.0f, ((i >> 1) & 1) ? 1.0f : -1.0f, (i >> 2) ? 1.0f : -1.0f};
+    V4 p = mul_p44(p3, wvp);
+    p.x /= p.w; p.y /= p.w; p.z /= p.w;
+    p.x = p.x * 0.5f + 0.5f; p.y = p.y * 0.5f + 0.5f;
+    p.y = 1.0f - p.y;
+    return {p.x * vw, p.y * vh, p.z};
+}
+
+__global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB cb)
+{
+    __shared__ uint32_t s_warpVis[kCullWarps], s_warpCube[kCullWarps];
+    __shared__ uint32_t s_baseVis, s_baseCube;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t grp = lane >> 3, corner = lane & 7, baseLane = grp * 8;
+    const uint32_t N = cb.numVolumes;
+    if (threadIdx.x == 0) { s_baseVis = 0; s_baseCube = 0; }
+    __syncthreads();
+
+    for (uint32_t chunk = 0; chunk < N; chunk += kCullWarps * kGroupVolumeCount) {
+        const uint32_t volumeId = chunk + warp * kGroupVolumeCount + grp;
+        const bool valid = volumeId < N;
+        const PerObject* po = s.perObject + (valid ? volumeId : 0);
+
+        // CSVolumeCull.hlsl:29-38 — one corner per lane
+        V3 v = {0.0f, 0.0f, 0.0f};
+        bool isInView = false;
+        if (valid) {
+            v = project_to_viewport(corner, po->wvp, cb.viewport[0], cb.viewport[1]);
+            isInView = (v.x <= cb.viewport[0] && v.y <= cb.viewport[1] && v.x >= 0.0f && v.y >= 0.0f) && v.z > 0.0f && v.z < 1.0f;
+        }
+        const uint32_t volumeVis = (__ballot_sync(kFull, isInView) >> baseLane) & 0xffu;
+        const bool visible = valid && volumeVis != 0;
+
+        // GenVisibilityMask, VolumeCull.hlsli:46-66 — one face per lane
+        bool faceVis = false;
+        if (visible && corner < 6) {
+            const V3 eye = {cb.eye[0], cb.eye[1], cb.eye[2]};
+            const V3 localEye = mul_p43(eye, po->worldI);
+            const float viewComp = comp(localEye, (int)(corner >> 1));
+            faceVis = (corner & 1) ? viewComp > -1.0f : viewComp < 1.0f;
+        }
+        const uint32_t faceMask = (__ballot_sync(kFull, faceVis) >> baseLane) & 0xffu;
+
+        // GetCubeEdgePairPerLane, :156-181 — lanes 0..5 hold unique edges 2c and 2c + 1
+        const uint32_t ec = corner < 6 ? corner : 0;
+        float ex[2], ey[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t a = baseLane + c_edgeLanes[2 * ec + k][0], b = baseLane + c_edgeLanes[2 * ec + k][1];
+            const float ax = __shfl_sync(kFull, v.x, a), ay = __shfl_sync(kFull, v.y, a);
+            const float bx = __shfl_sync(kFull, v.x, b), by = __shfl_sync(kFull, v.y, b);
+            ex[k] = bx - ax; ey[k] = by - ay;
+        }
+        // EstimateCubeMaxEdgeLength, :248-262
+        const float ms = corner < 6 ? fmaxf(length(V2{ex[0], ey[0]}), length(V2{ex[1], ey[1]})) : 0.0f;
+        float maxEdge = __shfl_sync(kFull, ms, baseLane);
+#pragma unroll
+        for (int k = 1; k < 6; ++k) maxEdge = fmaxf(maxEdge, __shfl_sync(kFull, ms, baseLane + k));
+
+        // EstimateProjCoverage, :299-322 — one face per lane, area of the quad spanned by its 4 edges
+        float fe[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint32_t id = c_faceEdges[ec][k];
+            const uint32_t src = baseLane + (id >> 1);
+            const float x0 = __shfl_sync(kFull, ex[0], src), y0 = __shfl_sync(kFull, ey[0], src);
+            const float x1 = __shfl_sync(kFull, ex[1], src), y1 = __shfl_sync(kFull, ey[1], src);
+            fe[k][0] = (id & 1) ? x1 : x0; fe[k][1] = (id & 1) ? y1 : y0;
+        }
+        float faceArea = 0.0f;
+        if (corner < 6 && (faceMask & (1u << corner))) {
+            const float t0 = 0.5f * fabsf(fe[0][0] * fe[1][1] - fe[0][1] * fe[1][0]);   // CalcTriangleArea :71-74
+            const float t1 = 0.5f * fabsf(fe[2][0] * fe[3][1] - fe[2][1] * fe[3][0]);
+            faceArea = t0 + t1;
+        }
+        // WaveActiveSum pinned to a lane-ascending sequential sum
+        float projCov = __shfl_sync(kFull, faceArea, baseLane);
+#pragma unroll
+        for (int k = 1; k < 6; ++k) projCov = projCov + __shfl_sync(kFull, faceArea, baseLane + k);
+
+        bool useCubeMap = false;
+        if (visible && corner == 0) {
+            const uint32_t volumeIn = s.volumeDescs[volumeId];
+            const uint32_t cubeMapSize = volumeIn >> 18, numMips = (volumeIn >> 14) & 0xfu;
+            // EstimateCubeMapLOD, :267-294 (upscale 2, raySampleCountScale 2)
+            const float sqrt3 = sqrtf(3.0f);
+            float sz = maxEdge / 2.0f;
+            float raySampleAmt = 2.0f * sz / sqrt3;
+            const uint32_t raySampleCnt = float_to_uint_sat(ceilf(raySampleAmt));
+            const uint32_t raySampleCount = min(raySampleCnt, cb.maxRaySamples);
+            raySampleAmt = fminf(raySampleAmt, (float)raySampleCount);
+            sz = raySampleAmt / 2.0f * sqrt3;
+            const uint32_t level = floor_log2_clamped((float)cubeMapSize / sz);
+            const uint32_t mipLevel = min(level, numMips - 1);
+            // EstimateCubeMapVisiblePixels, :327-334; CSVolumeCull.hlsl:66-67
+            const uint32_t edgeLength = cubeMapSize >> mipLevel;
+            const float cubeMapPix = (float)(edgeLength * edgeLength) * (float)__popc(faceMask);
+            useCubeMap = cubeMapPix <= projCov;
+            const uint32_t maskBits = useCubeMap ? (faceMask | kCubeMapRayMarchBit) : faceMask;
+            s.attribs[volumeId] = make_ushort4((unsigned short)mipLevel, (unsigned short)raySampleCount,
+                                               (unsigned short)maskBits, (unsigned short)(volumeIn & 0x3fffu));
+        }
+
+        // ordered compaction: ballot inside the warp, prefix over the 32 warps through shared memory
+        const uint32_t visBits = __ballot_sync(kFull, visible && corner == 0);
+        const uint32_t cubeBits = __ballot_sync(kFull, useCubeMap);
+        if (lane == 0) { s_warpVis[warp] = __popc(visBits); s_warpCube[warp] = __popc(cubeBits); }
+        __syncthreads();
+        uint32_t offVis = s_baseVis, offCube = s_baseCube;
+        for (uint32_t w = 0; w < warp; ++w) { offVis += s_warpVis[w]; offCube += s_warpCube[w]; }
+        const uint32_t below = (1u << lane) - 1u;
+        if (visible && corner == 0) s.visible[offVis + __popc(visBits & below)] = volumeId;
+        if (useCubeMap) s.cubeVolumes[offCube + __popc(cubeBits & below)] = volumeId;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tv = 0, tc = 0;
+            for (int w = 0; w < kCullWarps; ++w) { tv += s_warpVis[w]; tc += s_warpCube[w]; }
+            s_baseVis += tv; s_baseCube += tc;
+        }
+        __syncthreads();
+    }
+
+    // tile prefix of the view march over the cube-map volumes this rank owns (warp 0, shuffle scan)
+    const uint32_t visibleCount = s_baseVis, cubeCount = s_baseCube;
+    if (warp == 0) {
+        uint32_t running = 0;
+        for (uint32_t base = 0; base < cubeCount; base += 32) {
+            const uint32_t k = base + lane;
+            uint32_t tiles = 0;
+            if (k < cubeCount) {
+                const uint32_t vol = s.cubeVolumes[k];
+                if (vol % s.shardWorld == s.shardRank) {
+                    const ushort4 a = s.attribs[vol];
+                    const uint32_t size = cb.gridSize >> a.x;
+                    tiles = ((size + 7) / 8) * ((size + 3) / 4) * __popc(a.z & 0x3fu);
+                }
+            }
+            uint32_t incl = tiles;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t t = __shfl_up_sync(kFull, incl, d);
+                if (lane >= (uint32_t)d) incl += t;
+            }
+            if (k < cubeCount) s.cubeTilePrefix[k] = running + incl - tiles;
+            running += __shfl_sync(kFull, incl, 31);
+        }
+        if (lane == 0) {
+            s.cubeTilePrefix[cubeCount] = running;
+            FrameLists* L = s.lists;
+            L->visibleCount = visibleCount;
+            L->cubeCount = cubeCount;
+            L->marchTileTotal = running;
+            L->marchTileCursor = 0;
+            L->oitTileCursor = 0;
+            // CSRayMarchL.hlsl:29-33 (visible[] was written by other threads of this CTA before the last barrier)
+            L->lightVolume = visibleCount ? s.visible[cb.frameIdx % visibleCount] : cb.frameIdx % N;
+        }
+    }
+}
+
+} // namespace
+
+void launch_cull(Caster& c)
+{
+    k_cull<<<1, kCullThreads, 0, c.stream>>>(c.scene(), c.cb);
+}
+
+} // namespace mv

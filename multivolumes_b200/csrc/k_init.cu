@@ -1,0 +1,92 @@
+// k_init.cu — volume ingest kernels.
+//
+// k_init_grid replaces CSInitGridData (MultiVolumes/Content/Shaders/CSInitGridData.hlsl:10-27; host
+// MultiRayCaster.cpp:243-264): procedural RGBA16F density, a = saturate(2 (1 - r^2)^4), colour lerped
+// by height. Mode 1 multiplies the same envelope by three octaves of seeded value noise so that the
+// sources of a synthetic scene differ. k_r32f_to_rgba16f replaces CSR32FToRGBA16F
+// (CSR32FToRGBA16F.hlsl:16-26; host MultiRayCaster.cpp:168-209): rgb = 1, a = 0.25 * density.
+// Both write the 3-D CUDA array through a surface object, 8 B per voxel, x fastest.
+#include "mv_internal.h"
+
+namespace mv {
+
+namespace {
+
+MV_D uint32_t hash3(uint32_t x, uint32_t y, uint32_t z, uint32_t seed)
+{
+    uint32_t h = seed ^ (x * 0x8da6b343u) ^ (y * 0xd8163841u) ^ (z * 0xcb1ab31fu);
+    h ^= h >> 13; h *= 0x5bd1e995u; h ^= h >> 15; h *= 0x27d4eb2fu; h ^= h >> 16;
+    return h;
+}
+MV_D float lattice(uint32_t x, uint32_t y, uint32_t z, uint32_t seed)
+{
+    return (float)(hash3(x, y, z, seed) >> 8) * (1.0f / 16777216.0f);
+}
+MV_D float value_noise(V3 p, uint32_t seed)   // p in lattice units, p >= 0; smoothstep-faded trilinear
+{
+    const float fx = floorf(p.x), fy = floorf(p.y), fz = floorf(p.z);
+    const uint32_t ix = (uint32_t)fx, iy = (uint32_t)fy, iz = (uint32_t)fz;
+    float tx = p.x - fx, ty = p.y - fy, tz = p.z - fz;
+    tx = tx * tx * (3.0f - 2.0f * tx); ty = ty * ty * (3.0f - 2.0f * ty); tz = tz * tz * (3.0f - 2.0f * tz);
+    const float c000 = lattice(ix, iy, iz, seed), c001 = lattice(ix + 1, iy, iz, seed);
+    const float c010 = lattice(ix, iy + 1, iz, seed), c011 = lattice(ix + 1, iy + 1, iz, seed);
+    const float c100 = lattice(ix, iy, iz + 1, seed), c101 = lattice(ix + 1, iy, iz + 1, seed);
+    const float c110 = lattice(ix, iy + 1, iz + 1, seed), c111 = lattice(ix + 1, iy + 1, iz + 1, seed);
+    const float x00 = lerp(c000, c001, tx), x10 = lerp(c010, c011, tx);
+    const float x01 = lerp(c100, c101, tx), x11 = lerp(c110, c111, tx);
+    return lerp(lerp(x00, x10, ty), lerp(x01, x11, ty), tz);
+}
+
+__global__ void __launch_bounds__(256) k_init_grid(cudaSurfaceObject_t surf, uint32_t n, uint32_t mode, uint32_t seed)
+{
+    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const uint32_t z = blockIdx.z;
+    if (x >= n || y >= n) return;
+    const float gridSize = (float)n;
+    const V3 pos = {((float)x + 0.5f) / gridSize * 2.0f - 1.0f, ((float)y + 0.5f) / gridSize * 2.0f - 1.0f,
+                    ((float)z + 0.5f) / gridSize * 2.0f - 1.0f};        // :17
+    const float r_sq = dot(pos, pos);                                   // :18
+    float a = 1.0f - r_sq;                                              // :19
+    a *= a;                                                             // :20
+    a = saturate(a * a * 2.0f);                                         // :21
+    if (mode == 1) {
+        const V3 q = {(pos.x + 1.0f) * 2.0f, (pos.y + 1.0f) * 2.0f, (pos.z + 1.0f) * 2.0f};
+        float nz = 0.5f * value_noise(q, seed);
+        nz += 0.3f * value_noise(q * 2.0f, seed ^ 0x68bc21ebu);
+        nz += 0.2f * value_noise(q * 4.0f, seed ^ 0x02e5be93u);
+        a = saturate(a * (0.25f + 1.5f * nz));
+    }
+    const V3 colorU = {1.0f, 0.6f, 0.0f}, colorD = {0.5f, 0.8f, 1.0f};  // :23-24
+    const float t = saturate(pos.y * 0.5f + 0.2f);                      // :25
+    const V4 out = {lerp(colorD.x, colorU.x, t), lerp(colorD.y, colorU.y, t), lerp(colorD.z, colorU.z, t), a};
+    surf3Dwrite(pack_half4(out), surf, (int)(x * 8), (int)y, (int)z);
+}
+
+__global__ void __launch_bounds__(256) k_r32f_to_rgba16f(cudaSurfaceObject_t surf, const float* __restrict__ density, uint32_t n)
+{
+    const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const uint32_t z = blockIdx.z;
+    if (x >= n || y >= n) return;
+    const float d = density[((size_t)z * n + y) * n + x];
+    surf3Dwrite(pack_half4(V4{1.0f, 1.0f, 1.0f, d * 0.25f}), surf, (int)(x * 8), (int)y, (int)z);
+}
+
+} // namespace
+
+void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed)
+{
+    const uint32_t n = c.d.grid_size;
+    dim3 grid((n + 31) / 32, (n + 7) / 8, n);
+    k_init_grid<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, n, mode, seed);
+}
+
+void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity)
+{
+    const uint32_t n = c.d.grid_size;
+    dim3 grid((n + 31) / 32, (n + 7) / 8, n);
+    k_r32f_to_rgba16f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, devDensity, n);
+}
+
+} // namespace mv

@@ -1,0 +1,154 @@
+// k_march.cuh — device functions shared by the light march, the view march and the direct
+// screen-space ray cast: RayMarch.hlsli of the reference restated for sm_100a.
+//
+// Volumes and light maps are CUDA 3-D arrays of RGBA16F sampled through texture objects with
+// normalised coordinates, clamp addressing and hardware trilinear filtering — the LINEAR_CLAMP
+// sampler of the reference (MultiRayCaster.cpp:556-560).
+#pragma once
+#include "mv_internal.h"
+
+namespace mv {
+
+MV_D V4 sample_volume(cudaTextureObject_t tex, V3 uvw)   // GetSample, RayMarch.hlsli:44-50
+{
+    const float4 c = tex3D<float4>(tex, uvw.x, uvw.y, uvw.z);
+    return {c.x, c.y, c.z, c.w};
+}
+
+MV_D V3 local_to_tex3d(V3 pos)   // LocalToTex3DSpace, RayMarch.hlsli:170-177
+{
+    return {pos.x * 0.5f + 0.5f, pos.y * 0.5f + 0.5f, pos.z * 0.5f + 0.5f};
+}
+
+MV_D bool inside_unit_box(V3 p) { return fabsf(p.x) <= 1.0f && fabsf(p.y) <= 1.0f && fabsf(p.z) <= 1.0f; }
+MV_D bool outside_unit_box(V3 p) { return fabsf(p.x) > 1.0f || fabsf(p.y) > 1.0f || fabsf(p.z) > 1.0f; }
+
+// ComputeRayOrigin, RayMarch.hlsli:128-155: an eye outside the box is moved to the entry point
+// (slab test per axis, nearest non-negative hit), then clamped to the box; false on a miss.
+MV_D bool compute_ray_origin(V3& rayOrigin, V3 rayDir)
+{
+    if (inside_unit_box(rayOrigin)) return true;
+    float U = kFltMax;
+    bool isHit = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const int j = (i + 1) % 3, k = (i + 2) % 3;
+        const float d = comp(rayDir, i), o = comp(rayOrigin, i);
+        const float u = (-sign(d) - o) / d;
+        if (u < 0.0f) continue;
+        if (fabsf(comp(rayDir, j) * u + comp(rayOrigin, j)) > 1.0f) continue;
+        if (fabsf(comp(rayDir, k) * u + comp(rayOrigin, k)) > 1.0f) continue;
+        if (u < U) { U = u; isHit = true; }
+    }
+    rayOrigin = {clamp1(rayDir.x * U + rayOrigin.x), clamp1(rayDir.y * U + rayOrigin.y), clamp1(rayDir.z * U + rayOrigin.z)};
+    return isHit;
+}
+
+// GetStep, RayMarch.hlsli:182-192
+MV_D float get_step(float dDensity, float transm, float density, float step)
+{
+    const float factorEv = fminf(1.0f / 256.0f / fabsf(dDensity), 2.0f);
+    const float factorUi = fminf(1.0f - density, 1.0f);
+    const float factorTh = 1.0f - transm;
+    return step * fmaxf(1.5f * factorEv * factorUi * factorTh, 1.0f);
+}
+
+// GetTMax, RayMarch.hlsli:82-92: ray parameter at which the scene depth occludes the ray
+MV_D float get_tmax(V3 clipPos, V3 rayOrigin, V3 rayDir, const float* wvpi)
+{
+    if (clipPos.z >= 1.0f) return kFltMax;
+    const V4 h = mul_p44(clipPos, wvpi);
+    const V3 p = {h.x / h.w, h.y / h.w, h.z / h.w};
+    const V3 t = (p - rayOrigin) / rayDir;
+    return max3(t.x, t.y, t.z);
+}
+
+struct MarchCount { uint32_t samples, lightFetches; };
+
+// The per-ray loop of CSRayMarch.hlsl:112-155 and RayCast.hlsli:57-105 (identical bodies).
+// One trilinear density fetch per step, one trilinear light-map fetch when the sample is non-empty,
+// adaptive step from the density change, front-to-back accumulation, early out at transmittance < 0.01.
+MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t smpCount, V3 rayOrigin, V3 rayDir,
+                  float tMax, MarchCount& mc)
+{
+    const float maxDist = 2.0f * sqrtf(3.0f);            // g_maxDist, RayMarch.hlsli:17
+    const float stepScale = maxDist / (float)smpCount;
+    V4 scatter = {0.0f, 0.0f, 0.0f, 0.0f};
+    float t = 0.0f;
+    float prevDensity = 0.0f;
+    for (uint32_t i = 0; i < smpCount; ++i) {
+        const V3 pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
+        if (outside_unit_box(pos)) break;
+        const V3 uvw = local_to_tex3d(pos);
+        V4 color = sample_volume(grid, uvw);
+        ++mc.samples;
+        float newStep = stepScale;
+        if (color.w > kZeroThreshold) {                  // skip empty space
+            const float4 l = tex3D<float4>(light, uvw.x, uvw.y, uvw.z);   // GetLight, RayMarch.hlsli:235-240
+            ++mc.lightFetches;
+            const float transm = 1.0f - scatter.w;
+            const float dDensity = color.w - prevDensity;
+            newStep = get_step(dDensity, transm, color.w, stepScale);
+            prevDensity = color.w;
+            color.x *= color.w; color.y *= color.w; color.z *= color.w;   // colours are not pre-multiplied
+            color.x *= l.x; color.y *= l.y; color.z *= l.z;
+            scatter.x += color.x * kAbsorption * transm;
+            scatter.y += color.y * kAbsorption * transm;
+            scatter.z += color.z * kAbsorption * transm;
+            scatter.w += color.w * kAbsorption * transm;
+            if (transm < kZeroThreshold) break;
+        }
+        t += newStep;
+        if (t > tMax) break;
+    }
+    const float twoPi = 2.0f * kPi;
+    scatter.x /= twoPi; scatter.y /= twoPi; scatter.z /= twoPi;
+    return scatter;
+}
+
+// CastLightRay, RayMarch.hlsli:197-230 (mip 0): transmittance toward the light / along the AO direction
+MV_D void cast_light_ray(float& transm, cudaTextureObject_t grid, V3 rayOrigin, V3 rayDir, float stepScale,
+                         uint32_t numSamples, uint32_t& samples)
+{
+    float t = stepScale;
+    float step = stepScale;
+    float prevDensity = 0.0f;
+    for (uint32_t i = 0; i < numSamples; ++i) {
+        const V3 pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
+        if (outside_unit_box(pos)) break;
+        const V3 uvw = local_to_tex3d(pos);
+        const float density = tex3D<float4>(grid, uvw.x, uvw.y, uvw.z).w;
+        ++samples;
+        const float dDensity = density - prevDensity;
+        const float opacity = saturate(density * step);
+        const float newStep = get_step(dDensity, transm, opacity, stepScale);
+        prevDensity = density;
+        transm *= 1.0f - density * kAbsorption;
+        if (transm < kZeroThreshold) break;
+        step = newStep;
+        t += step;
+    }
+}
+
+// EvaluateSHIrradiance, XUSG/Shaders/SHIrradianceTypeless.hlsli:16-37 (x and y negated)
+MV_D V3 evaluate_sh_irradiance(const float* sh, V3 norm)
+{
+    const float c1 = 0.42904276540489171563379376569857f;
+    const float c2 = 0.51166335397324424423977581244463f;
+    const float c3 = 0.24770795610037568833406429782001f;
+    const float c4 = 0.88622692545275801364908374167057f;
+    const float x = -norm.x, y = -norm.y, z = norm.z;
+    float irr[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float t1 = (c1 * (x * x - y * y)) * sh[8 * 3 + k];
+        const float t2 = (c3 * (3.0f * z * z - 1.0f)) * sh[6 * 3 + k];
+        const float t3 = c4 * sh[k];
+        const float t4 = 2.0f * c1 * ((sh[4 * 3 + k] * x * y + sh[7 * 3 + k] * x * z) + sh[5 * 3 + k] * y * z);
+        const float t5 = 2.0f * c2 * ((sh[3 * 3 + k] * x + sh[1 * 3 + k] * y) + sh[2 * 3 + k] * z);
+        irr[k] = fmaxf(0.0f, (((t1 + t2) + t3) + t4) + t5);
+    }
+    return {irr[0], irr[1], irr[2]};
+}
+
+} // namespace mv

@@ -1,0 +1,277 @@
+// k_oit.cu — order-independent-transparency resolve of the visible volumes, one thread per pixel.
+//
+// Replaces the reference's K-buffer path — VSCubeDP + PSDepthPeel (PSDepthPeel.hlsl:12-24), VSCube +
+// PSCube (PSCube.hlsl:30-60, VSCube.hlsl:51-76), CubeCast (PSCube.hlsli:51-108), RayCast
+// (RayCast.hlsli:42-107) and PSResolveOIT (PSResolveOIT.hlsl:12-26), host side
+// MultiRayCaster.cpp:1440-1633 — with one fused kernel. The hardware rasteriser of the back faces is
+// replaced by the analytic exit point of the pixel-centre ray on every visible volume's box (the
+// formulation of the reference's own ray-traced variants, RTCube.hlsl:72-98 / PSCubeRT.hlsl:63-142);
+// the 8 nearest exits are kept sorted in registers, so the 96 B/pixel K-buffers (8 x R32_UINT +
+// 8 x RGBA16F, MultiRayCaster.cpp:230-236) and their atomics never touch memory.
+// Per layer the colour comes from the volume's cube map through the depth-aware 4-tap reconstruction
+// (CubeCast) or, for volumes the cull put on the direct scheme, from a screen-space march (RayCast).
+#include "k_march.cuh"
+
+namespace mv {
+
+namespace {
+
+MV_D float unproject_z(float depth)   // UnprojectZ, PSCube.hlsli:21-26
+{
+    return (kZNear * kZFar) / (depth * (kZNear - kZFar) + kZFar);
+}
+
+// D3D cube-map convention: (u, v) in [0, 1] of point p on face `face` of the unit cube
+MV_D void cube_face_uv(V3 p, int face, float& u, float& v)
+{
+    switch (face) {
+    case 0: u = -p.z * 0.5f + 0.5f; v = -p.y * 0.5f + 0.5f; break;
+    case 1: u = p.z * 0.5f + 0.5f; v = -p.y * 0.5f + 0.5f; break;
+    case 2: u = p.x * 0.5f + 0.5f; v = p.z * 0.5f + 0.5f; break;
+    case 3: u = p.x * 0.5f + 0.5f; v = -p.z * 0.5f + 0.5f; break;
+    case 4: u = p.x * 0.5f + 0.5f; v = -p.y * 0.5f + 0.5f; break;
+    default: u = -p.x * 0.5f + 0.5f; v = -p.y * 0.5f + 0.5f; break;
+    }
+}
+
+// Seamless cube addressing for the Gather* taps of CubeCast: texel (i, j) of `face`, where an index
+// may be -1 or S, resolved to the edge-adjacent texel of the neighbouring face (a corner is pinned to
+// the edge texel). Integer arithmetic on odd coordinates in units of 1 / S.
+MV_D void cube_resolve_texel(int S, int face, int i, int j, int& oface, int& oi, int& oj)
+{
+    const bool iOut = i < 0 || i >= S;
+    if (iOut && (j < 0 || j >= S)) j = j < 0 ? 0 : S - 1;
+    const bool jOut = j < 0 || j >= S;
+    if (!iOut && !jOut) { oface = face; oi = i; oj = j; return; }
+    const int a = 2 * i + 1 - S, b = 2 * j + 1 - S;
+    int P[3];
+    switch (face) {
+    case 0: P[0] = S; P[1] = -b; P[2] = -a; break;
+    case 1: P[0] = -S; P[1] = -b; P[2] = a; break;
+    case 2: P[0] = a; P[1] = S; P[2] = b; break;
+    case 3: P[0] = a; P[1] = -S; P[2] = -b; break;
+    case 4: P[0] = a; P[1] = -b; P[2] = S; break;
+    default: P[0] = -a; P[1] = -b; P[2] = -S; break;
+    }
+    const int major = face >> 1;
+    int over = -1;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) if (k != major && (P[k] > S || P[k] < -S)) over = k;
+    // exactly one in-plane coordinate is outside by one half-texel step: fold it onto the neighbour
+    const int pm = major == 0 ? P[0] : (major == 1 ? P[1] : P[2]);
+    const int po = over == 0 ? P[0] : (over == 1 ? P[1] : P[2]);
+    const int e = (po > 0 ? po : -po) - S;
+    const int newMajor = (pm > 0 ? 1 : -1) * (S - e);
+    const int newOver = po > 0 ? S : -S;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { if (k == major) P[k] = newMajor; if (k == over) P[k] = newOver; }
+    oface = over * 2 + (newOver > 0 ? 0 : 1);
+    int ua, vb;
+    switch (oface) {
+    case 0: ua = -P[2]; vb = -P[1]; break;
+    case 1: ua = P[2]; vb = -P[1]; break;
+    case 2: ua = P[0]; vb = P[2]; break;
+    case 3: ua = P[0]; vb = -P[2]; break;
+    case 4: ua = P[0]; vb = -P[1]; break;
+    default: ua = -P[0]; vb = -P[1]; break;
+    }
+    oi = (ua + S - 1) / 2; oj = (vb + S - 1) / 2;
+}
+
+// CubeCast, PSCube.hlsli:51-108
+MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, uint32_t mip, float sceneDepth, int face, V3 pos, V3 rayDir)
+{
+    const int S = (int)(cb.gridSize >> mip);
+    const float gridSize = (float)S;
+    const uint2* colors = reinterpret_cast<const uint2*>(s.arena.base + arena_color_offset(s.arena, volumeId, mip));
+    const float* depths = reinterpret_cast<const float*>(s.arena.base + arena_depth_offset(s.arena, volumeId, mip));
+    float u, v;
+    cube_face_uv(pos, face, u, v);
+    const float fx = u * gridSize - 0.5f, fy = v * gridSize - 0.5f;
+    const float flx = floorf(fx), fly = floorf(fy);
+    const int i0 = (int)flx, j0 = (int)fly;
+    V4 smp[4]; float zs[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {    // Gather order (-,+), (+,+), (+,-), (-,-)
+        const int ti = (k == 1 || k == 2) ? i0 + 1 : i0, tj = (k < 2) ? j0 + 1 : j0;
+        int f, i, j;
+        cube_resolve_texel(S, face, ti, tj, f, i, j);
+        const size_t idx = ((size_t)f * S + j) * S + i;
+        smp[k] = unpack_half4(__ldg(colors + idx));
+        zs[k] = __ldg(depths + idx);
+    }
+    // GetDomain, :31-46
+    float uvx = u * gridSize, uvy = v * gridSize;
+    float domx = frac(uvx + 0.5f), domy = frac(uvy + 0.5f);
+    const float bound = gridSize - 1.0f;
+    const V3 axes = pos * gridSize;
+    const bool edge = (fabsf(axes.x) > bound && axes.x * rayDir.x < 0.0f) || (fabsf(axes.y) > bound && axes.y * rayDir.y < 0.0f) ||
+                      (fabsf(axes.z) > bound && axes.z * rayDir.z < 0.0f);
+    if (edge) {   // clamp the exterior edge
+        uvx = fminf(uvx, gridSize - 0.5f); uvy = fminf(uvy, gridSize - 0.5f);
+        domx = uvx < 0.5f ? 1.0f : 0.0f; domy = uvy < 0.5f ? 1.0f : 0.0f;
+    }
+    const float dix = 1.0f - domx, diy = 1.0f - domy;
+    const float wb[4] = {dix * domy, domx * domy, domx * diy, dix * diy};
+    const float depth = unproject_z(sceneDepth);
+    V4 result = {0.0f, 0.0f, 0.0f, 0.0f};
+    float ws = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float zi = unproject_z(zs[k]);
+        float w = fmaxf(1.0f - 0.5f * fabsf(depth - zi), 0.0f);
+        w *= wb[k];
+        result.x += smp[k].x * w; result.y += smp[k].y * w; result.z += smp[k].z * w; result.w += smp[k].w * w;
+        ws += w;
+    }
+    if (ws > 0.0f) return {result.x / ws, result.y / ws, result.z / ws, result.w / ws};
+    // all taps rejected by depth: plain bilinear SampleLevel of the same footprint (:57, :105)
+    const float bx = fx - flx, by = fy - fly;
+    const float bw[4] = {(1.0f - bx) * by, bx * by, bx * (1.0f - by), (1.0f - bx) * (1.0f - by)};
+    V4 col = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { col.x += smp[k].x * bw[k]; col.y += smp[k].y * bw[k]; col.z += smp[k].z * bw[k]; col.w += smp[k].w * bw[k]; }
+    return col;
+}
+
+__global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
+{
+    const int W = (int)cb.width;
+    // 16x16-pixel CTA made of 8 warps of 8x4 pixels
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = (int)(blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7));
+    const int py = (int)(s.row0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3));
+    const bool valid = px < W && py < (int)s.row1;
+
+    const uint32_t nvis = valid ? s.lists->visibleCount : 0u;
+    // pixel-centre ray: unproject z = 0 through screenToWorld (RTCube.hlsl:54-70; PSCube.hlsl:38-40)
+    float sx = ((float)px + 0.5f) / cb.viewport[0], sy = ((float)py + 0.5f) / cb.viewport[1];
+    sx = sx * 2.0f - 1.0f; sy = sy * 2.0f - 1.0f;
+    sy = -sy;
+    const V4 wh = mul_p44(V3{sx, sy, 0.0f}, cb.screenToWorld);
+    const V3 wpos = {wh.x / wh.w, wh.y / wh.w, wh.z / wh.w};
+    const V3 eye = {cb.eye[0], cb.eye[1], cb.eye[2]};
+    const V3 dirW = wpos - eye;
+
+    // depth peel: the kNumOitLayers nearest back-face exits (PSDepthPeel.hlsl:12-24), sorted, stable
+    uint32_t keys[kNumOitLayers], ids[kNumOitLayers];
+#pragma unroll
+    for (int l = 0; l < (int)kNumOitLayers; ++l) { keys[l] = 0xffffffffu; ids[l] = 0xffffffffu; }
+    uint32_t frags = 0;
+    for (uint32_t k = 0; k < nvis; ++k) {
+        const uint32_t volumeId = __ldg(s.visible + k);
+        const PerObject* po = s.perObject + volumeId;
+        const V3 o = mul_p43(eye, po->worldI);
+        const V3 d = mul_v33(dirW, po->worldI);
+        float tmin = -kFltMax, tmax = kFltMax; int exitAxis = -1; bool miss = false;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float da = comp(d, a), oa = comp(o, a);
+            if (da == 0.0f) { if (fabsf(oa) > 1.0f) miss = true; continue; }
+            const float t1 = (-1.0f - oa) / da, t2 = (1.0f - oa) / da;
+            const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
+            if (tn > tmin) tmin = tn;
+            if (tf < tmax) { tmax = tf; exitAxis = a; }
+        }
+        if (miss || exitAxis < 0 || !(tmax > 0.0f) || !(tmin < tmax)) continue;
+        V3 lpt = {clamp1(o.x + d.x * tmax), clamp1(o.y + d.y * tmax), clamp1(o.z + d.z * tmax)};
+        const float sgn = comp(d, exitAxis) > 0.0f ? 1.0f : -1.0f;
+        if (exitAxis == 0) lpt.x = sgn; else if (exitAxis == 1) lpt.y = sgn; else lpt.z = sgn;
+        const V4 clip = mul_p44(lpt, po->wvp);
+        if (!(clip.w > 0.0f)) continue;
+        const float z = clip.z / clip.w;
+        if (!(z >= 0.0f && z <= 1.0f)) continue;       // rasteriser depth clip
+        ++frags;
+        // insert (key, k) keeping ascending keys; equal keys keep list order
+        uint32_t key = as_uint(z), id = k | ((uint32_t)(exitAxis * 2 + (sgn > 0.0f ? 0 : 1)) << 24);
+#pragma unroll
+        for (int l = 0; l < (int)kNumOitLayers; ++l) {
+            if (key < keys[l]) {
+                const uint32_t tk = keys[l], ti = ids[l];
+                keys[l] = key; ids[l] = id; key = tk; id = ti;
+            }
+        }
+    }
+
+    // shade + resolve front to back (PSCube.hlsl:30-60, PSResolveOIT.hlsl:12-26)
+    const float sceneDepth = valid ? __ldg(s.depth + (size_t)py * W + px) : 1.0f;
+    V4 result = {0.0f, 0.0f, 0.0f, 0.0f};
+    uint32_t dRays = 0, dSamples = 0, dLight = 0;
+#pragma unroll 1
+    for (int l = 0; l < (int)kNumOitLayers; ++l) {
+        // (register arrays are indexed by a runtime l here; the loop is kept rolled because the body is large)
+        uint32_t id = 0xffffffffu;
+#pragma unroll
+        for (int m = 0; m < (int)kNumOitLayers; ++m) if (m == l) id = ids[m];
+        if (id == 0xffffffffu) break;
+        const uint32_t volumeId = __ldg(s.visible + (id & 0xffffffu));
+        const int face = (int)(id >> 24);
+        const PerObject* po = s.perObject + volumeId;
+        const ushort4 a = s.attribs[volumeId];
+        const V3 localEye = mul_p43(eye, po->worldI);
+        // the fragment's local-space position: exit point of the pixel ray on the back face
+        const V3 d = mul_v33(dirW, po->worldI);
+        const int axis = face >> 1;
+        const float sgn = (face & 1) ? -1.0f : 1.0f;
+        const float tmax = (sgn - comp(localEye, axis)) / comp(d, axis);
+        V3 lpt = {clamp1(localEye.x + d.x * tmax), clamp1(localEye.y + d.y * tmax), clamp1(localEye.z + d.z * tmax)};
+        if (axis == 0) lpt.x = sgn; else if (axis == 1) lpt.y = sgn; else lpt.z = sgn;
+        const V3 rayDir = lpt - localEye;                                        // PSCube.hlsl:34
+        const uint32_t smpCnt = (a.z & kCubeMapRayMarchBit) ? 0u : (uint32_t)a.y;   // VSCube.hlsl:73
+        V4 color;
+        if (smpCnt > 0) {
+            // RayCast.hlsli:42-107
+            V3 ro = localEye; const V3 rd = normalize(rayDir);
+            if (!compute_ray_origin(ro, rd)) color = {0.0f, 0.0f, 0.0f, 0.0f};
+            else {
+                const float tMax = get_tmax(V3{sx, sy, sceneDepth}, ro, rd, po->wvpi);
+                MarchCount mc = {0, 0};
+                color = march_ray(s.volumeTex[a.w], s.lightTex[volumeId], smpCnt, ro, rd, tMax, mc);
+                ++dRays; dSamples += mc.samples; dLight += mc.lightFetches;
+            }
+        } else color = cube_cast(s, cb, volumeId, a.x, sceneDepth, face, lpt, rayDir);
+        // K-colour layers are RGBA16F; a layer is written only if 0 < alpha <= 1 (PSCube.hlsl:57)
+        V4 src = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
+        const float k1 = 1.0f - result.w;
+        result = {result.x + src.x * k1, result.y + src.y * k1, result.z + src.z * k1, result.w + src.w * k1};
+    }
+    result.w = fminf(result.w, 0.9997f);                                         // PSResolveOIT.hlsl:22
+    if (valid) {
+        // premultiplied-alpha blend onto the colour RT (Graphics::PREMULTIPLITED, MultiRayCaster.cpp:931)
+        uint2* dst = s.color + (size_t)py * W + px;
+        const V4 d4 = unpack_half4(*dst);
+        const float ia = 1.0f - result.w;
+        *dst = pack_half4(V4{result.x + d4.x * ia, result.y + d4.y * ia, result.z + d4.z * ia, result.w + d4.w * ia});
+    }
+
+    if (s.stats) {
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) {
+            frags += __shfl_xor_sync(0xffffffffu, frags, dd);
+            dRays += __shfl_xor_sync(0xffffffffu, dRays, dd);
+            dSamples += __shfl_xor_sync(0xffffffffu, dSamples, dd);
+            dLight += __shfl_xor_sync(0xffffffffu, dLight, dd);
+        }
+        if (lane == 0 && frags) {
+            atomicAdd(&s.stats->oit_fragments, (unsigned long long)frags);
+            if (dRays) {
+                atomicAdd(&s.stats->direct_rays, (unsigned long long)dRays);
+                atomicAdd(&s.stats->direct_samples, (unsigned long long)dSamples);
+                atomicAdd(&s.stats->direct_light_fetches, (unsigned long long)dLight);
+            }
+        }
+    }
+}
+
+} // namespace
+
+void launch_resolve_oit(Caster& c)
+{
+    const uint32_t rows = c.row1 - c.row0;
+    if (rows == 0) return;
+    dim3 grid((c.d.width + 15) / 16, (rows + 15) / 16);
+    k_resolve_oit<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb);
+}
+
+} // namespace mv

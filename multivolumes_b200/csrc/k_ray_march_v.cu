@@ -1,0 +1,169 @@
+// k_ray_march_v.cu — cube-map-space view march on the interior faces of every cube-map volume.
+//
+// Replaces CSRayMarchV (MultiVolumes/Content/Shaders/CSRayMarch.hlsl:77-158) and the ExecuteIndirect
+// that launches it (MultiRayCaster.cpp:1329-1368). Differences in *shape*, not in arithmetic:
+//   * exactly (G >> mip)^2 texels per visible face are marched (the reference's indirect dispatch
+//     covers the mip-0 size and drops the surplus threads' writes; its work-graph variant
+//     LibRayMarch.hlsl:120-121 launches the exact grid, as here);
+//   * one persistent launch: warps pull 8x4-texel tiles from a device-side cursor that the cull kernel
+//     reset (no host round trip for the indirect arguments), tiles of one face are consecutive work
+//     items so that co-resident warps walk neighbouring rays through the same texture-cache lines;
+//   * the per-volume constants (PerObject record, attributes, output addresses) are staged once per
+//     tile in shared memory;
+//   * with peers mapped (multi-GPU), each texel is stored straight into every peer's cube-map arena
+//     over NVLink from this kernel — the all-gather of the per-volume cube maps is fused into the march.
+#include "k_march.cuh"
+
+namespace mv {
+
+namespace {
+
+constexpr int kMarchThreads = 256;
+constexpr int kMarchWarps = kMarchThreads / 32;
+constexpr uint32_t kFull = 0xffffffffu;
+
+struct TileConst {                 // per-warp shared-memory staging
+    float po[56];                  // PerObject: wvp, wvpi, worldI, world
+    float eyeL[3];
+    uint32_t pad;
+};
+
+// GetLocalPos, CSRayMarch.hlsl:28-53
+MV_D V3 get_local_pos(float px, float py, uint32_t slice, float gridSize)
+{
+    const float x = (px + 0.5f) / gridSize * 2.0f - 1.0f;
+    float y = (py + 0.5f) / gridSize * 2.0f - 1.0f;
+    y = -y;
+    switch (slice) {
+    case 0: return {1.0f, y, -x};
+    case 1: return {-1.0f, y, x};
+    case 2: return {x, 1.0f, -y};
+    case 3: return {x, -1.0f, y};
+    case 4: return {x, y, 1.0f};
+    default: return {-x, y, -1.0f};
+    }
+}
+
+MV_D uint32_t nth_set_bit(uint32_t mask, uint32_t n)
+{
+    for (uint32_t i = 0; i < n; ++i) mask &= mask - 1;
+    return __ffs(mask) - 1;
+}
+
+__global__ void __launch_bounds__(kMarchThreads) k_ray_march_v(DeviceScene s, FrameCB cb)
+{
+    __shared__ TileConst s_tc[kMarchWarps];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TileConst& tc = s_tc[warp];
+    const uint32_t total = s.lists->marchTileTotal;
+    const uint32_t cubeCount = s.lists->cubeCount;
+    uint32_t nRays = 0, nSamples = 0, nLight = 0;
+    uint32_t stagedVolume = 0xffffffffu;
+
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&s.lists->marchTileCursor, 1u);
+        w = __shfl_sync(kFull, w, 0);
+        if (w >= total) break;
+
+        // work item -> (cube-map volume, face, tile): upper bound in the tile prefix
+        uint32_t lo = 0, hi = cubeCount;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(s.cubeTilePrefix + mid) <= w) lo = mid; else hi = mid;
+        }
+        const uint32_t volumeId = __ldg(s.cubeVolumes + lo);
+        const uint32_t local = w - __ldg(s.cubeTilePrefix + lo);
+        const ushort4 a = s.attribs[volumeId];
+        const uint32_t mip = a.x, smpCount = a.y, maskBits = a.z, volTexId = a.w;
+        const uint32_t size = cb.gridSize >> mip;
+        const uint32_t tilesX = (size + 7) >> 3, tilesY = (size + 3) >> 2;
+        const uint32_t tilesPerFace = tilesX * tilesY;
+        const uint32_t faceOrd = local / tilesPerFace, tile = local - faceOrd * tilesPerFace;
+        const uint32_t face = nth_set_bit(maskBits & 0x3fu, faceOrd);
+        const uint32_t ty = tile / tilesX, tx = tile - ty * tilesX;
+        const uint32_t x = tx * 8 + (lane & 7), y = ty * 4 + (lane >> 3);
+
+        // stage the volume's constants (once per run of tiles of the same volume)
+        if (stagedVolume != volumeId) {
+            __syncwarp();
+            const float* src = reinterpret_cast<const float*>(s.perObject + volumeId);
+            tc.po[lane] = __ldg(src + lane);
+            if (lane < 24) tc.po[32 + lane] = __ldg(src + 32 + lane);
+            __syncwarp();
+            if (lane == 0) {
+                const V3 eye = {cb.eye[0], cb.eye[1], cb.eye[2]};
+                const V3 e = mul_p43(eye, tc.po + 32);               // CSRayMarch.hlsl:88
+                tc.eyeL[0] = e.x; tc.eyeL[1] = e.y; tc.eyeL[2] = e.z;
+            }
+            __syncwarp();
+            stagedVolume = volumeId;
+        }
+
+        if (x < size && y < size) {
+            V3 rayOrigin = {tc.eyeL[0], tc.eyeL[1], tc.eyeL[2]};
+            const V3 target = get_local_pos((float)x, (float)y, face, (float)size);   // :93
+            const V3 rayDir = normalize(target - rayOrigin);                           // :94
+            if (compute_ray_origin(rayOrigin, rayDir)) {                               // :95
+                const V3 u = (target - rayOrigin) / rayDir;                            // ComputeTargetHit
+                float tMax = max3(u.x, u.y, u.z);
+                // GetClipPos, :59-71 (scene depth point-sampled at the projection of origin + 0.01 dir)
+                const V3 p01 = {rayOrigin.x + 0.01f * rayDir.x, rayOrigin.y + 0.01f * rayDir.y, rayOrigin.z + 0.01f * rayDir.z};
+                const V4 hPos = mul_p44(p01, tc.po);
+                const float cx = hPos.x / hPos.w, cy = hPos.y / hPos.w;
+                const float uvx = cx * 0.5f + 0.5f;
+                const float uvy = 1.0f - (cy * 0.5f + 0.5f);
+                int ix = (int)floorf(uvx * (float)cb.width), iy = (int)floorf(uvy * (float)cb.height);
+                if (!(uvx == uvx)) ix = 0;
+                if (!(uvy == uvy)) iy = 0;
+                ix = min(max(ix, 0), (int)cb.width - 1); iy = min(max(iy, 0), (int)cb.height - 1);
+                const float z = __ldg(s.depth + (size_t)iy * cb.width + ix);
+                tMax = fminf(get_tmax(V3{cx, cy, z}, rayOrigin, rayDir, tc.po + 16), tMax);   // :106
+
+                MarchCount mc = {0, 0};
+                const V4 scatter = march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCount, rayOrigin, rayDir, tMax, mc);
+
+                const size_t idx = ((size_t)face * size + y) * size + x;
+                const unsigned long long cOfs = arena_color_offset(s.arena, volumeId, mip) + idx * 8ull;
+                const unsigned long long dOfs = arena_depth_offset(s.arena, volumeId, mip) + idx * 4ull;
+                const uint2 packed = pack_half4(scatter);
+                *reinterpret_cast<uint2*>(s.arena.base + cOfs) = packed;        // g_rwCubeMaps[uavIdx][index], :157
+                *reinterpret_cast<float*>(s.arena.base + dOfs) = z;             // g_rwCubeDepths[uavIdx][index], :105
+                for (uint32_t p = 0; p < s.arena.numPeers; ++p) {
+                    unsigned char* pb = s.arena.peer[p];
+                    if (pb) {
+                        *reinterpret_cast<uint2*>(pb + cOfs) = packed;
+                        *reinterpret_cast<float*>(pb + dOfs) = z;
+                    }
+                }
+                ++nRays; nSamples += mc.samples; nLight += mc.lightFetches;
+            }
+        }
+    }
+
+    if (s.stats) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            nRays += __shfl_xor_sync(kFull, nRays, d);
+            nSamples += __shfl_xor_sync(kFull, nSamples, d);
+            nLight += __shfl_xor_sync(kFull, nLight, d);
+        }
+        if (lane == 0 && nRays) {
+            atomicAdd(&s.stats->view_rays, (unsigned long long)nRays);
+            atomicAdd(&s.stats->view_samples, (unsigned long long)nSamples);
+            atomicAdd(&s.stats->view_light_fetches, (unsigned long long)nLight);
+        }
+    }
+}
+
+} // namespace
+
+void launch_ray_march_view(Caster& c)
+{
+    int perSM = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_v, kMarchThreads, 0);
+    if (perSM < 1) perSM = 1;
+    k_ray_march_v<<<c.smCount * perSM, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
+}
+
+} // namespace mv

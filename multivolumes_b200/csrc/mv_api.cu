@@ -1,0 +1,790 @@
+// mv_api.cu — C-ABI of libmv_b200.so (include/mv.h): resource ownership, host-side scene maths and
+// pass ordering of the reference's MultiRayCaster (MultiVolumes/Content/MultiRayCaster.cpp) over one
+// CUDA stream. No CPU path: every entry point that computes launches sm_100a kernels.
+#include "mv_internal.h"
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+using namespace mv;
+
+struct mv_caster { Caster c; };
+
+namespace mv {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof g_error, fmt, ap);
+    va_end(ap);
+}
+
+#define MV_CUDA(expr)                                                                                     \
+    do {                                                                                                  \
+        const cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                          \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);        \
+            return MV_ERR_CUDA;                                                                           \
+        }                                                                                                 \
+    } while (0)
+
+#define MV_REQUIRE(cond)                                                          \
+    do {                                                                          \
+        if (!(cond)) { set_error("invalid argument: %s", #cond); return MV_ERR_INVALID; } \
+    } while (0)
+
+DeviceScene Caster::scene() const
+{
+    DeviceScene s{};
+    s.perObject = dPerObject;
+    s.volumeDescs = dVolumeDescs;
+    s.attribs = dAttribs;
+    s.lists = reinterpret_cast<FrameLists*>(dLists);
+    const uint32_t N = d.num_volumes;
+    uint32_t* tail = reinterpret_cast<uint32_t*>(dLists + sizeof(FrameLists));
+    s.visible = tail;
+    s.cubeVolumes = tail + N;
+    s.cubeTilePrefix = tail + 2 * N;
+    s.volumeTex = dVolumeTex;
+    s.lightTex = dLightTex;
+    s.lightSurf = dLightSurf;
+    s.depth = dDepth;
+    s.shadow = dShadow;
+    s.color = dColor;
+    s.stats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dStats : nullptr;
+    s.arena = arena;
+    s.shardRank = shardRank; s.shardWorld = shardWorld;
+    s.row0 = row0; s.row1 = row1;
+    return s;
+}
+
+// ---- host matrix algebra (DirectXMath call sites: MultiRayCaster.cpp:325-350) ----
+// Products and inverses are evaluated in double and rounded once to fp32.
+static void mul44(const float* A, const float* B, float* R)
+{
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += (double)A[i * 4 + k] * (double)B[k * 4 + j];
+            R[i * 4 + j] = (float)s;
+        }
+}
+
+static void inverse44(const float* A, float* R)   // adjugate / determinant
+{
+    double a[4][4];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) a[i][j] = A[i * 4 + j];
+    auto minor3 = [&](const int r[3], const int c[3]) {
+        return a[r[0]][c[0]] * (a[r[1]][c[1]] * a[r[2]][c[2]] - a[r[1]][c[2]] * a[r[2]][c[1]])
+             - a[r[0]][c[1]] * (a[r[1]][c[0]] * a[r[2]][c[2]] - a[r[1]][c[2]] * a[r[2]][c[0]])
+             + a[r[0]][c[2]] * (a[r[1]][c[0]] * a[r[2]][c[1]] - a[r[1]][c[1]] * a[r[2]][c[0]]);
+    };
+    double cof[4][4];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            int r[3], c[3], ri = 0, ci = 0;
+            for (int k = 0; k < 4; ++k) { if (k != i) r[ri++] = k; if (k != j) c[ci++] = k; }
+            const double m = minor3(r, c);
+            cof[i][j] = ((i + j) & 1) ? -m : m;
+        }
+    const double det = a[0][0] * cof[0][0] + a[0][1] * cof[0][1] + a[0][2] * cof[0][2] + a[0][3] * cof[0][3];
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 4; ++j) R[i * 4 + j] = (float)(cof[j][i] / det);
+}
+
+static void world_from43(const float* W, float* M)
+{
+    for (int i = 0; i < 4; ++i) { for (int j = 0; j < 3; ++j) M[i * 4 + j] = W[i * 3 + j]; M[i * 4 + 3] = (i == 3) ? 1.0f : 0.0f; }
+}
+static void to43(const float* M, float* W)
+{
+    for (int i = 0; i < 4; ++i) for (int j = 0; j < 3; ++j) W[i * 3 + j] = M[i * 4 + j];
+}
+
+static void set_volume_world(Caster& c, uint32_t i, float size, const float pos[3])   // MultiRayCaster.cpp:297-303
+{
+    size *= 0.5f;
+    float* w = &c.volumeWorlds[(size_t)i * 12];
+    const float m[12] = {size, 0, 0, 0, size, 0, 0, 0, size, pos[0], pos[1], pos[2]};
+    memcpy(w, m, sizeof m);
+}
+
+static void set_volumes_world(Caster& c, float size, const float center[3])   // MultiRayCaster.cpp:277-295
+{
+    const uint32_t numVolumes = c.d.num_volumes;
+    const uint32_t rowLength = (uint32_t)ceilf(sqrtf((float)numVolumes));
+    const uint32_t colLength = (uint32_t)ceilf((float)(numVolumes / rowLength));   // integer division first, as in the reference
+    float pos[3] = {center[0], center[1], center[2]};
+    pos[2] -= ((float)colLength / 2.0f - 0.5f) * size * 1.5f;
+    for (uint32_t m = 0; m < colLength; ++m) {
+        pos[0] = center[0] - ((float)rowLength / 2.0f - 0.5f) * size * 1.5f;
+        for (uint32_t n = 0; n < rowLength; ++n) {
+            set_volume_world(c, rowLength * m + n, size, pos);
+            pos[0] += size * 1.5f;
+        }
+        pos[2] += size * 1.5f;
+    }
+}
+
+static int make_volume3d(Volume3D& v, uint32_t n)
+{
+    const cudaChannelFormatDesc cd = cudaCreateChannelDescHalf4();
+    MV_CUDA(cudaMalloc3DArray(&v.array, &cd, make_cudaExtent(n, n, n), cudaArraySurfaceLoadStore));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = v.array;
+    cudaTextureDesc td{};
+    td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;   // LINEAR_CLAMP
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeElementType;
+    td.normalizedCoords = 1;
+    MV_CUDA(cudaCreateTextureObject(&v.tex, &rd, &td, nullptr));
+    MV_CUDA(cudaCreateSurfaceObject(&v.surf, &rd));
+    return MV_OK;
+}
+
+static int clear_volume3d(Caster& c, Volume3D& v, uint32_t n)
+{
+    // zero-fill through a device staging row-block (cudaMemset3D does not take arrays)
+    const size_t bytes = (size_t)n * n * n * 8;
+    void* z = nullptr;
+    MV_CUDA(cudaMalloc(&z, bytes));
+    MV_CUDA(cudaMemsetAsync(z, 0, bytes, c.stream));
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr(z, (size_t)n * 8, n, n);
+    p.dstArray = v.array;
+    p.extent = make_cudaExtent(n, n, n);
+    p.kind = cudaMemcpyDeviceToDevice;
+    MV_CUDA(cudaMemcpy3DAsync(&p, c.stream));
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    MV_CUDA(cudaFree(z));
+    return MV_OK;
+}
+
+static void record(Caster& c, int i)
+{
+    if (c.d.flags & MV_FLAG_TIME_PASSES) { cudaEventRecord(c.ev[i], c.stream); c.evValid[i] = true; }
+}
+
+static int check_launch(const char* what)
+{
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { set_error("%s launch failed: %s", what, cudaGetErrorString(e)); return MV_ERR_CUDA; }
+    return MV_OK;
+}
+
+static void destroy_caster(Caster& c)
+{
+    cudaSetDevice(c.device);
+    if (c.stream) cudaStreamSynchronize(c.stream);
+    for (void* p : c.openedIpc) cudaIpcCloseMemHandle(p);
+    auto kill = [](Volume3D& v) {
+        if (v.tex) cudaDestroyTextureObject(v.tex);
+        if (v.surf) cudaDestroySurfaceObject(v.surf);
+        if (v.array) cudaFreeArray(v.array);
+    };
+    for (auto& v : c.volumes) kill(v);
+    for (auto& v : c.lightMaps) kill(v);
+    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dBlock,
+                     c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
+    for (void* p : frees) if (p) cudaFree(p);
+    if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
+    for (auto& e : c.ev) if (e) cudaEventDestroy(e);
+    if (c.uploadDone) cudaEventDestroy(c.uploadDone);
+    if (c.ownStream) cudaStreamDestroy(c.ownStream);
+}
+
+} // namespace mv
+
+extern "C" {
+
+const char* mv_last_error(void) { return g_error; }
+uint32_t mv_abi_version(void) { return 1; }
+
+int mv_create(const mv_desc* d, mv_caster** out)
+{
+    if (out) *out = nullptr;
+    MV_REQUIRE(d && out);
+    MV_REQUIRE(d->grid_size != 0 && d->num_volumes != 0 && d->num_volume_srcs != 0 && d->width != 0 && d->height != 0);
+    MV_REQUIRE(d->grid_size < (1u << 14) && d->num_volume_srcs < (1u << 14) && (d->grid_size >> (kNumCubeMip - 1)) != 0);
+    MV_REQUIRE(d->num_volumes < (1u << 24));
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device: libmv_b200 has no CPU path");
+        return MV_ERR_NO_DEVICE;
+    }
+    MV_REQUIRE((int)d->device < ndev);
+    cudaDeviceProp prop{};
+    MV_CUDA(cudaGetDeviceProperties(&prop, (int)d->device));
+    if (prop.major != 10) {
+        set_error("device %u is sm_%d%d; libmv_b200 is built for sm_100a only", d->device, prop.major, prop.minor);
+        return MV_ERR_NO_DEVICE;
+    }
+    mv_caster* h = new (std::nothrow) mv_caster();
+    if (!h) { set_error("out of host memory"); return MV_ERR_NOMEM; }
+    Caster& c = h->c;
+    c.d = *d;
+    if (c.d.light_grid_size == 0) c.d.light_grid_size = 96;
+    if (c.d.max_ray_samples == 0) c.d.max_ray_samples = 256;
+    if (c.d.max_light_samples == 0) c.d.max_light_samples = 96;
+    c.device = (int)d->device;
+    c.smCount = prop.multiProcessorCount;
+    const uint32_t G = c.d.grid_size, L = c.d.light_grid_size, N = c.d.num_volumes, S = c.d.num_volume_srcs;
+    const size_t px = (size_t)c.d.width * c.d.height;
+    c.row0 = 0; c.row1 = c.d.height;
+
+    auto fail = [&](int rc) { destroy_caster(c); delete h; return rc; };
+#define MV_TRY(expr) do { const int rc_ = (expr); if (rc_ != MV_OK) return fail(rc_); } while (0)
+#define MV_CUDA_C(expr)                                                                                   \
+    do {                                                                                                  \
+        const cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                          \
+            set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);        \
+            return fail(e_ == cudaErrorMemoryAllocation ? MV_ERR_NOMEM : MV_ERR_CUDA);                    \
+        }                                                                                                 \
+    } while (0)
+
+    MV_CUDA_C(cudaSetDevice(c.device));
+    MV_CUDA_C(cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking));
+    c.stream = c.ownStream;
+    for (auto& e : c.ev) MV_CUDA_C(cudaEventCreate(&e));
+
+    // MultiRayCaster.cpp:99-126 — per-source volumes, per-instance light maps and cube maps
+    c.volumes.resize(S);
+    for (auto& v : c.volumes) { MV_TRY(make_volume3d(v, G)); MV_TRY(clear_volume3d(c, v, G)); }
+    c.lightMaps.resize(N);
+    for (auto& v : c.lightMaps) { MV_TRY(make_volume3d(v, L)); MV_TRY(clear_volume3d(c, v, L)); }
+    std::vector<cudaTextureObject_t> vt(S), lt(N);
+    std::vector<cudaSurfaceObject_t> ls(N);
+    for (uint32_t i = 0; i < S; ++i) vt[i] = c.volumes[i].tex;
+    for (uint32_t i = 0; i < N; ++i) { lt[i] = c.lightMaps[i].tex; ls[i] = c.lightMaps[i].surf; }
+    MV_CUDA_C(cudaMalloc(&c.dVolumeTex, S * sizeof(cudaTextureObject_t)));
+    MV_CUDA_C(cudaMalloc(&c.dLightTex, N * sizeof(cudaTextureObject_t)));
+    MV_CUDA_C(cudaMalloc(&c.dLightSurf, N * sizeof(cudaSurfaceObject_t)));
+    MV_CUDA_C(cudaMemcpy(c.dVolumeTex, vt.data(), S * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice));
+    MV_CUDA_C(cudaMemcpy(c.dLightTex, lt.data(), N * sizeof(cudaTextureObject_t), cudaMemcpyHostToDevice));
+    MV_CUDA_C(cudaMemcpy(c.dLightSurf, ls.data(), N * sizeof(cudaSurfaceObject_t), cudaMemcpyHostToDevice));
+
+    // cube-map arena: colour region then depth region, volume-major, [mip][face][y][x] inside a slot
+    uint32_t texels = 0;
+    for (uint32_t m = 0; m < kNumCubeMip; ++m) { c.arena.mipTexelOffset[m] = texels; texels += 6u * (G >> m) * (G >> m); }
+    c.arena.mipTexelOffset[kNumCubeMip] = texels;
+    c.arena.colorStride = (unsigned long long)texels * 8ull;
+    c.arena.depthStride = (unsigned long long)texels * 4ull;
+    c.arena.depthBase = c.arena.colorStride * N;
+    c.arenaBytes = (size_t)(c.arena.depthBase + c.arena.depthStride * N);
+    // exchange block (include/mv.h): arena | light staging | back buffer | flags, 256-B aligned parts
+    auto align256 = [](uint64_t v) { return (v + 255ull) & ~255ull; };
+    mv_exchange_layout& lay = c.layout;
+    lay.arena_offset = 0; lay.arena_bytes = c.arenaBytes;
+    lay.light_staging_offset = align256(lay.arena_offset + lay.arena_bytes);
+    lay.light_staging_bytes = (uint64_t)(L + kMaxPeers) * L * L * 8ull;
+    lay.back_buffer_offset = align256(lay.light_staging_offset + lay.light_staging_bytes);
+    lay.back_buffer_bytes = (uint64_t)px * 4ull;
+    lay.flags_offset = align256(lay.back_buffer_offset + lay.back_buffer_bytes);
+    lay.flags_bytes = 256;
+    lay.block_bytes = lay.flags_offset + lay.flags_bytes;
+    lay.light_slab_depth = L;
+    MV_CUDA_C(cudaMalloc(&c.dBlock, lay.block_bytes));
+    MV_CUDA_C(cudaMemsetAsync(c.dBlock, 0, lay.block_bytes, c.stream));
+    c.dArena = c.dBlock + lay.arena_offset;
+    c.dLightStaging = reinterpret_cast<uint2*>(c.dBlock + lay.light_staging_offset);
+    c.dBackBuffer = reinterpret_cast<uchar4*>(c.dBlock + lay.back_buffer_offset);
+    c.dFlags = reinterpret_cast<uint32_t*>(c.dBlock + lay.flags_offset);
+    c.arena.base = c.dArena;
+    c.arena.numPeers = 0;
+
+    // createVolumeInfoBuffers, MultiRayCaster.cpp:455-549
+    MV_CUDA_C(cudaMalloc(&c.dPerObject, N * sizeof(PerObject)));
+    MV_CUDA_C(cudaMemsetAsync(c.dPerObject, 0, N * sizeof(PerObject), c.stream));
+    MV_CUDA_C(cudaMallocHost(&c.hPerObjectPinned, N * sizeof(PerObject)));
+    c.perObjectHost.resize(N);
+    memset(c.perObjectHost.data(), 0, N * sizeof(PerObject));
+    std::vector<uint32_t> descs(N);
+    for (uint32_t i = 0; i < N; ++i) descs[i] = (i % S) | (kNumCubeMip << 14) | (G << 18);   // :470-479
+    MV_CUDA_C(cudaMalloc(&c.dVolumeDescs, N * sizeof(uint32_t)));
+    MV_CUDA_C(cudaMemcpy(c.dVolumeDescs, descs.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    MV_CUDA_C(cudaMalloc(&c.dAttribs, N * sizeof(ushort4)));
+    MV_CUDA_C(cudaMemsetAsync(c.dAttribs, 0, N * sizeof(ushort4), c.stream));
+    const size_t listBytes = sizeof(FrameLists) + (3 * (size_t)N + 1) * sizeof(uint32_t);
+    MV_CUDA_C(cudaMalloc(&c.dLists, listBytes));
+    MV_CUDA_C(cudaMemsetAsync(c.dLists, 0, listBytes, c.stream));
+    MV_CUDA_C(cudaMalloc(&c.dStats, sizeof(StatsDev)));
+    MV_CUDA_C(cudaMemsetAsync(c.dStats, 0, sizeof(StatsDev), c.stream));
+
+    // borrowed targets are copied in (SetRenderTargets), plus the post-process images
+    MV_CUDA_C(cudaMalloc(&c.dDepth, px * sizeof(float)));
+    MV_CUDA_C(cudaMalloc(&c.dColor, px * 8));
+    MV_CUDA_C(cudaMalloc(&c.dBackground, px * 8));
+    MV_CUDA_C(cudaMalloc(&c.dVelocity, px * 4));
+    MV_CUDA_C(cudaMalloc(&c.dHistory[0], px * 8));
+    MV_CUDA_C(cudaMalloc(&c.dHistory[1], px * 8));
+    {
+        std::vector<float> ones(px, 1.0f);
+        MV_CUDA_C(cudaMemcpy(c.dDepth, ones.data(), px * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    MV_CUDA_C(cudaMemsetAsync(c.dColor, 0, px * 8, c.stream));
+    MV_CUDA_C(cudaMemsetAsync(c.dBackground, 0, px * 8, c.stream));
+    MV_CUDA_C(cudaMemsetAsync(c.dVelocity, 0, px * 4, c.stream));
+    MV_CUDA_C(cudaMemsetAsync(c.dHistory[0], 0, px * 8, c.stream));
+    MV_CUDA_C(cudaMemsetAsync(c.dHistory[1], 0, px * 8, c.stream));
+    c.scratchBytes = (size_t)c.smCount * 4 * 8 * 28 * sizeof(float);
+    MV_CUDA_C(cudaMalloc(&c.dScratch, c.scratchBytes));
+
+    c.volumeWorlds.assign((size_t)N * 12, 0.0f);
+    for (uint32_t i = 0; i < N; ++i) { float* w = &c.volumeWorlds[(size_t)i * 12]; w[0] = w[4] = w[8] = 1.0f; }
+    const float center[3] = {0, 0, 0};
+    set_volumes_world(c, 20.0f, center);                    // MultiRayCaster.cpp:143-144
+
+    memset(&c.cb, 0, sizeof c.cb);
+    c.cb.numVolumes = N; c.cb.gridSize = G; c.cb.lightGridSize = L;
+    c.cb.width = c.d.width; c.cb.height = c.d.height;
+    c.cb.maxRaySamples = c.d.max_ray_samples; c.cb.maxLightSamples = c.d.max_light_samples;
+    c.cb.viewport[0] = (float)c.d.width; c.cb.viewport[1] = (float)c.d.height;
+    MV_CUDA_C(cudaStreamSynchronize(c.stream));
+#undef MV_TRY
+#undef MV_CUDA_C
+    *out = h;
+    return MV_OK;
+}
+
+void mv_destroy(mv_caster* h)
+{
+    if (!h) return;
+    destroy_caster(h->c);
+    delete h;
+}
+
+#define MV_ENTER(h)                                  \
+    MV_REQUIRE(h != nullptr);                        \
+    Caster& c = h->c;                                \
+    MV_CUDA(cudaSetDevice(c.device))
+
+int mv_volume_init_procedural(mv_caster* h, uint32_t src, uint32_t mode, uint32_t seed)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(src < c.d.num_volume_srcs && mode <= 1);
+    launch_init_grid(c, src, mode, seed);
+    return check_launch("k_init_grid");
+}
+
+int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(texels && src < c.d.num_volume_srcs);
+    const uint32_t n = c.d.grid_size;
+    cudaMemcpy3DParms p{};
+    p.srcPtr = make_cudaPitchedPtr((void*)texels, (size_t)n * 8, n, n);
+    p.dstArray = c.volumes[src].array;
+    p.extent = make_cudaExtent(n, n, n);
+    p.kind = cudaMemcpyHostToDevice;
+    MV_CUDA(cudaMemcpy3DAsync(&p, c.stream));
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    return MV_OK;
+}
+
+int mv_volume_upload_r32f(mv_caster* h, uint32_t src, const float* density)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(density && src < c.d.num_volume_srcs);
+    const uint32_t n = c.d.grid_size;
+    const size_t bytes = (size_t)n * n * n * sizeof(float);
+    float* dtmp = nullptr;
+    MV_CUDA(cudaMalloc(&dtmp, bytes));
+    cudaError_t e = cudaMemcpyAsync(dtmp, density, bytes, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) { launch_r32f_to_rgba16f(c, src, dtmp); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    cudaFree(dtmp);
+    if (e != cudaSuccess) { set_error("volume_upload_r32f: %s", cudaGetErrorString(e)); return MV_ERR_CUDA; }
+    return MV_OK;
+}
+
+int mv_volume_read(mv_caster* h, uint32_t src, uint16_t* out)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(out && src < c.d.num_volume_srcs);
+    const uint32_t n = c.d.grid_size;
+    cudaMemcpy3DParms p{};
+    p.srcArray = c.volumes[src].array;
+    p.dstPtr = make_cudaPitchedPtr(out, (size_t)n * 8, n, n);
+    p.extent = make_cudaExtent(n, n, n);
+    p.kind = cudaMemcpyDeviceToHost;
+    MV_CUDA(cudaMemcpy3DAsync(&p, c.stream));
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    return MV_OK;
+}
+
+static int set_targets_impl(Caster& c, const float* depth, const uint16_t* shadow, uint32_t shadowSize, const uint16_t* color,
+                            const uint16_t* velocity, cudaMemcpyKind kind)
+{
+    const size_t px = (size_t)c.d.width * c.d.height;
+    if (depth) MV_CUDA(cudaMemcpyAsync(c.dDepth, depth, px * sizeof(float), kind, c.stream));
+    else {
+        std::vector<float> ones(px, 1.0f);
+        MV_CUDA(cudaMemcpyAsync(c.dDepth, ones.data(), px * sizeof(float), cudaMemcpyHostToDevice, c.stream));
+        MV_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    if (shadow && shadowSize) {
+        if (shadowSize != c.shadowSize) {
+            if (c.dShadow) { MV_CUDA(cudaStreamSynchronize(c.stream)); MV_CUDA(cudaFree(c.dShadow)); c.dShadow = nullptr; }
+            MV_CUDA(cudaMalloc(&c.dShadow, (size_t)shadowSize * shadowSize * sizeof(uint16_t)));
+            c.shadowSize = shadowSize;
+        }
+        MV_CUDA(cudaMemcpyAsync(c.dShadow, shadow, (size_t)shadowSize * shadowSize * sizeof(uint16_t), kind, c.stream));
+    } else c.shadowSize = 0;
+    c.cb.shadowSize = c.shadowSize;
+    if (color) MV_CUDA(cudaMemcpyAsync(c.dBackground, color, px * 8, kind, c.stream));
+    else MV_CUDA(cudaMemsetAsync(c.dBackground, 0, px * 8, c.stream));
+    MV_CUDA(cudaMemcpyAsync(c.dColor, c.dBackground, px * 8, cudaMemcpyDeviceToDevice, c.stream));
+    if (velocity) MV_CUDA(cudaMemcpyAsync(c.dVelocity, velocity, px * 4, kind, c.stream));
+    else MV_CUDA(cudaMemsetAsync(c.dVelocity, 0, px * 4, c.stream));
+    if (kind == cudaMemcpyHostToDevice) MV_CUDA(cudaStreamSynchronize(c.stream));   // host buffers may be pageable / freed by the caller
+    return MV_OK;
+}
+
+int mv_set_targets(mv_caster* h, const float* depth, const uint16_t* shadow, uint32_t shadowSize, const uint16_t* color, const uint16_t* velocity)
+{
+    MV_ENTER(h);
+    return set_targets_impl(c, depth, shadow, shadowSize, color, velocity, cudaMemcpyHostToDevice);
+}
+
+int mv_set_targets_device(mv_caster* h, const float* depth, const uint16_t* shadow, uint32_t shadowSize, const uint16_t* color, const uint16_t* velocity)
+{
+    MV_ENTER(h);
+    return set_targets_impl(c, depth, shadow, shadowSize, color, velocity, cudaMemcpyDeviceToDevice);
+}
+
+int mv_reset_color(mv_caster* h)
+{
+    MV_ENTER(h);
+    const size_t px = (size_t)c.d.width * c.d.height;
+    MV_CUDA(cudaMemcpyAsync(c.dColor, c.dBackground, px * 8, cudaMemcpyDeviceToDevice, c.stream));
+    return MV_OK;
+}
+
+int mv_set_sh(mv_caster* h, const float* k)
+{
+    MV_ENTER(h);
+    c.cb.hasSH = k ? 1u : 0u;
+    if (k) memcpy(c.cb.sh, k, 27 * sizeof(float));
+    return MV_OK;
+}
+
+int mv_set_max_samples(mv_caster* h, uint32_t ray, uint32_t light)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(ray != 0 && light != 0 && ray < 65536 && light < 65536);
+    c.d.max_ray_samples = ray; c.d.max_light_samples = light;
+    c.cb.maxRaySamples = ray; c.cb.maxLightSamples = light;
+    return MV_OK;
+}
+
+int mv_set_volumes_world(mv_caster* h, float size, const float center[3])
+{
+    MV_ENTER(h);
+    MV_REQUIRE(center);
+    set_volumes_world(c, size, center);
+    return MV_OK;
+}
+
+int mv_set_volume_world(mv_caster* h, uint32_t i, float size, const float pos[3])
+{
+    MV_ENTER(h);
+    MV_REQUIRE(pos && i < c.d.num_volumes);
+    set_volume_world(c, i, size, pos);
+    return MV_OK;
+}
+
+int mv_set_volume_world_matrix(mv_caster* h, uint32_t i, const float w[12])
+{
+    MV_ENTER(h);
+    MV_REQUIRE(w && i < c.d.num_volumes);
+    memcpy(&c.volumeWorlds[(size_t)i * 12], w, 12 * sizeof(float));
+    return MV_OK;
+}
+
+int mv_set_light(mv_caster* h, const float p[3], const float col[3], float intensity)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(p && col);
+    memcpy(c.lightPt, p, 3 * sizeof(float));
+    c.lightColor[0] = col[0]; c.lightColor[1] = col[1]; c.lightColor[2] = col[2]; c.lightColor[3] = intensity;
+    return MV_OK;
+}
+
+int mv_set_ambient(mv_caster* h, const float col[3], float intensity)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(col);
+    c.ambient[0] = col[0]; c.ambient[1] = col[1]; c.ambient[2] = col[2]; c.ambient[3] = intensity;
+    return MV_OK;
+}
+
+int mv_update_frame(mv_caster* h, const float viewProj[16], const float shadowVP[16], const float eye[3])   // MultiRayCaster.cpp:316-353
+{
+    MV_ENTER(h);
+    MV_REQUIRE(viewProj && eye);
+    FrameCB& cb = c.cb;
+    memcpy(cb.eye, eye, 3 * sizeof(float));
+    cb.viewport[0] = (float)c.d.width; cb.viewport[1] = (float)c.d.height;
+    inverse44(viewProj, cb.screenToWorld);
+    if (shadowVP) memcpy(cb.shadowViewProj, shadowVP, 16 * sizeof(float));
+    else for (int i = 0; i < 16; ++i) cb.shadowViewProj[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+    cb.lightPos[0] = c.lightPt[0]; cb.lightPos[1] = c.lightPt[1]; cb.lightPos[2] = c.lightPt[2]; cb.lightPos[3] = 1.0f;
+    memcpy(cb.lightColor, c.lightColor, sizeof cb.lightColor);
+    memcpy(cb.ambient, c.ambient, sizeof cb.ambient);
+    cb.frameIdx = c.frameIdx;
+    const uint32_t N = c.d.num_volumes;
+    // the previous frame's upload must have left the pinned staging buffer before it is rewritten
+    if (c.uploadPending) { MV_CUDA(cudaEventSynchronize(c.uploadDone)); c.uploadPending = false; }
+    for (uint32_t i = 0; i < N; ++i) {
+        float world[16], worldI[16], wvp[16];
+        world_from43(&c.volumeWorlds[(size_t)i * 12], world);
+        inverse44(world, worldI);
+        mul44(world, viewProj, wvp);
+        PerObject& po = c.hPerObjectPinned[i];
+        memcpy(po.wvp, wvp, sizeof wvp);
+        inverse44(wvp, po.wvpi);
+        to43(worldI, po.worldI);
+        to43(world, po.world);
+    }
+    memcpy(c.perObjectHost.data(), c.hPerObjectPinned, N * sizeof(PerObject));
+    MV_CUDA(cudaMemcpyAsync(c.dPerObject, c.hPerObjectPinned, N * sizeof(PerObject), cudaMemcpyHostToDevice, c.stream));
+    if (!c.uploadDone) MV_CUDA(cudaEventCreateWithFlags(&c.uploadDone, cudaEventDisableTiming));
+    MV_CUDA(cudaEventRecord(c.uploadDone, c.stream));
+    c.uploadPending = true;
+    return MV_OK;
+}
+
+int mv_cull(mv_caster* h)
+{
+    MV_ENTER(h);
+    launch_cull(c);
+    return check_launch("k_cull");
+}
+
+int mv_ray_march_light(mv_caster* h, int32_t v)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(v < (int32_t)c.d.num_volumes);
+    launch_ray_march_light(c, v);
+    return check_launch("k_ray_march_l");
+}
+
+int mv_ray_march_view(mv_caster* h)
+{
+    MV_ENTER(h);
+    if (c.d.flags & MV_FLAG_COUNT_SAMPLES)
+        MV_CUDA(cudaMemsetAsync(&c.dStats->view_rays, 0, 3 * sizeof(unsigned long long), c.stream));
+    launch_ray_march_view(c);
+    return check_launch("k_ray_march_v");
+}
+
+int mv_resolve_oit(mv_caster* h)
+{
+    MV_ENTER(h);
+    if (c.d.flags & MV_FLAG_COUNT_SAMPLES)
+        MV_CUDA(cudaMemsetAsync(&c.dStats->direct_rays, 0, 4 * sizeof(unsigned long long), c.stream));
+    launch_resolve_oit(c);
+    return check_launch("k_resolve_oit");
+}
+
+int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
+{
+    MV_ENTER(h);
+    (void)oit;   // one OIT implementation: the K-buffer semantics of the default branch (:377-381)
+    if (c.d.flags & MV_FLAG_COUNT_SAMPLES) MV_CUDA(cudaMemsetAsync(c.dStats, 0, sizeof(StatsDev), c.stream));
+    record(c, 0);
+    launch_cull(c);
+    record(c, 1);
+    launch_ray_march_light(c, -1);
+    record(c, 2);
+    launch_ray_march_view(c);
+    record(c, 3);
+    launch_resolve_oit(c);
+    record(c, 4);
+    c.evValid[5] = false;
+    if (c.frameIdx != 0xffffffffu) ++c.frameIdx;
+    return check_launch("render");
+}
+
+int mv_postprocess(mv_caster* h, uint32_t taa)
+{
+    MV_ENTER(h);
+    if (!c.evValid[4]) record(c, 4);
+    launch_postprocess(c, taa != 0);
+    record(c, 5);
+    return check_launch("k_postprocess");
+}
+
+int mv_sh_project(mv_caster* h, const float* cube, uint32_t size, float* out27)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(cube && out27 && size != 0 && size <= 8192);
+    const size_t bytes = (size_t)6 * size * size * 3 * sizeof(float);
+    float* dcube = nullptr; float* dout = nullptr;
+    MV_CUDA(cudaMalloc(&dcube, bytes));
+    cudaError_t e = cudaMalloc(&dout, 27 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dcube, cube, bytes, cudaMemcpyHostToDevice, c.stream);
+    if (e == cudaSuccess) { launch_sh_project(c, dcube, size, dout); e = cudaGetLastError(); }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out27, dout, 27 * sizeof(float), cudaMemcpyDeviceToHost, c.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
+    cudaFree(dcube); if (dout) cudaFree(dout);
+    if (e != cudaSuccess) { set_error("sh_project: %s", cudaGetErrorString(e)); return MV_ERR_CUDA; }
+    return MV_OK;
+}
+
+// ---- read-backs ----
+static int d2h(Caster& c, void* dst, const void* src, size_t bytes)
+{
+    MV_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.stream));
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    return MV_OK;
+}
+
+int mv_read_per_object(mv_caster* h, float* out)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(out);
+    return d2h(c, out, c.dPerObject, c.d.num_volumes * sizeof(PerObject));
+}
+
+static int read_list(Caster& c, uint32_t* ids, uint32_t* count, bool cube)
+{
+    FrameLists fl;
+    int rc = d2h(c, &fl, c.dLists, sizeof fl);
+    if (rc != MV_OK) return rc;
+    const uint32_t n = cube ? fl.cubeCount : fl.visibleCount;
+    *count = n;
+    if (ids && n) {
+        const DeviceScene s = c.scene();
+        return d2h(c, ids, cube ? s.cubeVolumes : s.visible, n * sizeof(uint32_t));
+    }
+    return MV_OK;
+}
+
+int mv_read_visible(mv_caster* h, uint32_t* ids, uint32_t* count)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(count);
+    return read_list(c, ids, count, false);
+}
+
+int mv_read_cube_volumes(mv_caster* h, uint32_t* ids, uint32_t* count)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(count);
+    return read_list(c, ids, count, true);
+}
+
+int mv_read_attribs(mv_caster* h, uint16_t* out)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(out);
+    return d2h(c, out, c.dAttribs, c.d.num_volumes * sizeof(ushort4));
+}
+
+int mv_read_cubemap(mv_caster* h, uint32_t v, uint32_t mip, uint16_t* rgba, float* depth)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(v < c.d.num_volumes && mip < kNumCubeMip);
+    const size_t s = c.d.grid_size >> mip, texels = 6 * s * s;
+    if (rgba) { const int rc = d2h(c, rgba, c.dArena + arena_color_offset(c.arena, v, mip), texels * 8); if (rc) return rc; }
+    if (depth) { const int rc = d2h(c, depth, c.dArena + arena_depth_offset(c.arena, v, mip), texels * 4); if (rc) return rc; }
+    return MV_OK;
+}
+
+int mv_read_lightmap(mv_caster* h, uint32_t v, uint16_t* out)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(out && v < c.d.num_volumes);
+    const uint32_t n = c.d.light_grid_size;
+    cudaMemcpy3DParms p{};
+    p.srcArray = c.lightMaps[v].array;
+    p.dstPtr = make_cudaPitchedPtr(out, (size_t)n * 8, n, n);
+    p.extent = make_cudaExtent(n, n, n);
+    p.kind = cudaMemcpyDeviceToHost;
+    MV_CUDA(cudaMemcpy3DAsync(&p, c.stream));
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    return MV_OK;
+}
+
+int mv_read_frame(mv_caster* h, uint16_t* out)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(out);
+    return d2h(c, out, c.dColor, (size_t)c.d.width * c.d.height * 8);
+}
+
+int mv_read_post(mv_caster* h, uint16_t* taa, uint8_t* rgba8)
+{
+    MV_ENTER(h);
+    const size_t px = (size_t)c.d.width * c.d.height;
+    if (taa) MV_CUDA(cudaMemcpyAsync(taa, c.dHistory[c.frameParity], px * 8, cudaMemcpyDeviceToHost, c.stream));
+    if (rgba8) MV_CUDA(cudaMemcpyAsync(rgba8, c.dBackBuffer, px * 4, cudaMemcpyDeviceToHost, c.stream));
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    return MV_OK;
+}
+
+int mv_get_stats(mv_caster* h, mv_stats* out)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(out);
+    StatsDev sd; FrameLists fl;
+    int rc = d2h(c, &sd, c.dStats, sizeof sd);
+    if (rc) return rc;
+    rc = d2h(c, &fl, c.dLists, sizeof fl);
+    if (rc) return rc;
+    memset(out, 0, sizeof *out);
+    out->view_rays = sd.view_rays; out->view_samples = sd.view_samples; out->view_light_fetches = sd.view_light_fetches;
+    const uint64_t L = c.d.light_grid_size;
+    out->light_voxels = L * L * L; out->light_dense_voxels = sd.light_dense_voxels; out->light_samples = sd.light_samples;
+    out->direct_rays = sd.direct_rays; out->direct_samples = sd.direct_samples; out->direct_light_fetches = sd.direct_light_fetches;
+    out->oit_fragments = sd.oit_fragments;
+    out->visible_count = fl.visibleCount; out->cubemap_count = fl.cubeCount; out->light_volume = fl.lightVolume;
+    out->threads = (uint32_t)c.smCount;
+    return MV_OK;
+}
+
+int mv_get_timings(mv_caster* h, mv_timings* out)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(out);
+    MV_REQUIRE(c.d.flags & MV_FLAG_TIME_PASSES);
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    memset(out, 0, sizeof *out);
+    float* slots[5] = {&out->cull, &out->ray_march_light, &out->ray_march_view, &out->resolve_oit, &out->postprocess};
+    int last = 0;
+    for (int i = 0; i < 5; ++i)
+        if (c.evValid[i] && c.evValid[i + 1]) { MV_CUDA(cudaEventElapsedTime(slots[i], c.ev[i], c.ev[i + 1])); last = i + 1; }
+    if (c.evValid[0] && last) MV_CUDA(cudaEventElapsedTime(&out->total, c.ev[0], c.ev[last]));
+    return MV_OK;
+}
+
+int mv_set_frame_index(mv_caster* h, uint32_t f)
+{
+    MV_ENTER(h);
+    c.frameIdx = f; c.cb.frameIdx = f;
+    return MV_OK;
+}
+
+int mv_sync(mv_caster* h)
+{
+    MV_ENTER(h);
+    MV_CUDA(cudaStreamSynchronize(c.stream));
+    return MV_OK;
+}
+
+void* mv_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); set_error("cudaMallocHost(%zu) failed", bytes); return nullptr; }
+    return p;
+}
+void mv_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+} // extern "C"

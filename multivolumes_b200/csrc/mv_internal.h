@@ -1,0 +1,187 @@
+// mv_internal.h — device-visible records and the host-side caster state of libmv_b200.so.
+#pragma once
+#include "mv_math.cuh"
+#include "../../include/mv.h"
+#include <vector>
+#include <string>
+
+namespace mv {
+
+constexpr int kMaxPeers = 8;
+
+// Common.hlsli:28-34 / MultiRayCaster.cpp:35-41 — 56 floats, matrices NOT transposed (row-vector use).
+struct PerObject {
+    float wvp[16];
+    float wvpi[16];
+    float worldI[12];
+    float world[12];
+};
+
+// Common.hlsli:39-56 (cbPerFrame + cbSampleRes) plus the SH coefficients (g_roSHCoeffs, 9 x float3).
+// Passed to every kernel by value (constant bank).
+struct FrameCB {
+    float eye[3];
+    float viewport[2];
+    float screenToWorld[16];
+    float shadowViewProj[16];
+    float lightPos[4];
+    float lightColor[4];
+    float ambient[4];
+    uint32_t frameIdx;
+    uint32_t hasSH;
+    float sh[27];
+    uint32_t numVolumes;
+    uint32_t gridSize;          // G
+    uint32_t lightGridSize;     // L
+    uint32_t width, height;
+    uint32_t maxRaySamples, maxLightSamples;
+    uint32_t shadowSize;        // 0 = no shadow map bound
+};
+
+// Per-frame lists produced by the cull kernel (device memory, one allocation).
+struct FrameLists {
+    uint32_t visibleCount;
+    uint32_t cubeCount;
+    uint32_t marchTileTotal;    // total 8x4 texel tiles of the view march
+    uint32_t marchTileCursor;   // work-stealing cursor of the persistent view-march kernel
+    uint32_t lightVolume;       // CSRayMarchL.hlsl:29-33
+    uint32_t oitTileCursor;
+    uint32_t pad[2];
+    // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1]
+};
+
+struct StatsDev {
+    unsigned long long view_rays, view_samples, view_light_fetches;
+    unsigned long long light_voxels, light_dense_voxels, light_samples;
+    unsigned long long direct_rays, direct_samples, direct_light_fetches;
+    unsigned long long oit_fragments;
+};
+
+// Cube-map arena: one device allocation holding, for every volume, the RGBA16F colour and R32F depth
+// of all kNumCubeMip mips ([mip][face][y][x]). The same layout on every rank of a multi-GPU run, so
+// a peer's texel lives at the same byte offset in the peer's arena.
+struct CubeArena {
+    unsigned char* base;                 // this device
+    unsigned char* peer[kMaxPeers];      // peer-mapped arenas (nullptr = not mapped); peer[rank] = nullptr
+    uint32_t numPeers;                   // world size when peers are mapped, else 0
+    unsigned long long colorStride;      // bytes per volume, colour
+    unsigned long long depthBase;        // byte offset of the depth region
+    unsigned long long depthStride;      // bytes per volume, depth
+    uint32_t mipTexelOffset[kNumCubeMip + 1];   // texel offset of each mip inside a volume slot
+};
+
+MV_HD unsigned long long arena_color_offset(const CubeArena& a, uint32_t volume, uint32_t mip)
+{
+    return (unsigned long long)volume * a.colorStride + (unsigned long long)a.mipTexelOffset[mip] * 8ull;
+}
+MV_HD unsigned long long arena_depth_offset(const CubeArena& a, uint32_t volume, uint32_t mip)
+{
+    return a.depthBase + (unsigned long long)volume * a.depthStride + (unsigned long long)a.mipTexelOffset[mip] * 4ull;
+}
+
+// Everything the kernels need, passed by value.
+struct DeviceScene {
+    const PerObject* perObject;          // [N]
+    const uint32_t* volumeDescs;         // [N] VolTexId:14 | NumMips:4 | CubeMapSize:14
+    ushort4* attribs;                    // [N] {MipLevel, SmpCount, MaskBits, VolTexId}
+    FrameLists* lists;
+    uint32_t* visible;                   // [N]
+    uint32_t* cubeVolumes;               // [N]
+    uint32_t* cubeTilePrefix;            // [N + 1]
+    const cudaTextureObject_t* volumeTex;   // [srcs]
+    const cudaTextureObject_t* lightTex;    // [N]
+    const cudaSurfaceObject_t* lightSurf;   // [N]
+    const float* depth;                  // W*H D32
+    const uint16_t* shadow;              // S*S D16
+    uint2* color;                        // W*H RGBA16F (half4 as uint2)
+    StatsDev* stats;                     // nullptr when counters are off
+    CubeArena arena;
+    uint32_t shardRank, shardWorld;      // volume v is marched by rank v % world
+    uint32_t row0, row1;                 // rows of the frame this rank resolves
+};
+
+struct Caster;
+
+// kernel launchers (one translation unit per pass)
+void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
+void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity);
+void launch_cull(Caster& c);
+void launch_ray_march_light(Caster& c, int volumeOverride);
+void launch_ray_march_view(Caster& c);
+void launch_resolve_oit(Caster& c);
+void launch_postprocess(Caster& c, bool taaOn);
+void launch_sh_project(Caster& c, const float* devCube, uint32_t size, float* devOut27);
+void launch_light_commit(Caster& c);
+void launch_peer_barrier(Caster& c);
+
+struct Volume3D {
+    cudaArray_t array = nullptr;
+    cudaTextureObject_t tex = 0;
+    cudaSurfaceObject_t surf = 0;
+};
+
+struct Caster {
+    mv_desc d{};
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    // host scene state (MultiRayCaster.h:189-215)
+    std::vector<float> volumeWorlds;     // N x 12 (float4x3)
+    std::vector<PerObject> perObjectHost;
+    float lightPt[3] = {75.0f, 75.0f, -75.0f};
+    float lightColor[4] = {1.0f, 0.7f, 0.3f, 1.0f};
+    float ambient[4] = {0.0f, 0.3f, 1.0f, 0.4f};
+    FrameCB cb{};
+    uint32_t frameIdx = 0;
+    uint32_t frameParity = 0;
+    // device resources
+    std::vector<Volume3D> volumes;       // per source, RGBA16F G^3
+    std::vector<Volume3D> lightMaps;     // per instance, RGBA16F L^3 holding R11G11B10F-quantised rgb
+    cudaTextureObject_t* dVolumeTex = nullptr;
+    cudaTextureObject_t* dLightTex = nullptr;
+    cudaSurfaceObject_t* dLightSurf = nullptr;
+    PerObject* dPerObject = nullptr;
+    PerObject* hPerObjectPinned = nullptr;
+    uint32_t* dVolumeDescs = nullptr;
+    ushort4* dAttribs = nullptr;
+    unsigned char* dLists = nullptr;     // FrameLists + visible + cubeVolumes + cubeTilePrefix
+    StatsDev* dStats = nullptr;
+    unsigned char* dBlock = nullptr;     // exchange block: arena | light staging | back buffer | flags
+    mv_exchange_layout layout{};
+    unsigned char* dArena = nullptr;     // = dBlock + layout.arena_offset
+    size_t arenaBytes = 0;
+    CubeArena arena{};
+    uint2* dLightStaging = nullptr;      // inside the block
+    uint32_t* dFlags = nullptr;          // inside the block: [kMaxPeers] arrival counters
+    unsigned char* peerBlock[kMaxPeers] = {};
+    uint32_t barrierSeq = 0;
+    uint32_t** dPeerFlagPtrs = nullptr;  // [kMaxPeers] flag arrays of every rank (peer-mapped)
+    bool peersMapped = false;
+    cudaStream_t ownStream = nullptr;
+    cudaEvent_t uploadDone = nullptr;
+    bool uploadPending = false;
+    float* dDepth = nullptr;
+    uint16_t* dShadow = nullptr;
+    uint32_t shadowSize = 0;
+    uint2* dColor = nullptr;             // colour RT
+    uint2* dBackground = nullptr;        // copy of the colour RT given to set_targets
+    uint32_t* dVelocity = nullptr;       // RG16F
+    uint2* dHistory[2] = {nullptr, nullptr};
+    uchar4* dBackBuffer = nullptr;
+    uchar4* dPeerBackBuffer = nullptr;   // rank 0's back buffer (peer-mapped) in a multi-GPU run
+    float* dScratch = nullptr;           // SH projection partial sums
+    size_t scratchBytes = 0;
+    // sharding
+    uint32_t shardRank = 0, shardWorld = 1;
+    uint32_t row0 = 0, row1 = 0;
+    std::vector<void*> openedIpc;
+    // timing
+    cudaEvent_t ev[8] = {};
+    bool evValid[8] = {};
+    mv_timings lastTimings{};
+    DeviceScene scene() const;
+};
+
+void set_error(const char* fmt, ...);
+
+} // namespace mv

@@ -21,3 +21,12 @@ def oracle_lib():
     if not os.path.exists(out) or any(os.path.getmtime(s) > os.path.getmtime(out) for s in srcs):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
     return out
+
+
+@pytest.fixture(scope="session")
+def product_lib():
+    """Path of the built product library; building it is __graft_entry__.build()'s job."""
+    from multivolumes_b200 import LIB_PATH
+    if not os.path.exists(LIB_PATH):
+        subprocess.check_call(["make", "-C", os.path.join(ROOT, "multivolumes_b200", "csrc"), "-j8"], stdout=subprocess.DEVNULL)
+    return LIB_PATH

@@ -1,0 +1,97 @@
+"""Shared scene set-up for the parity tests: drives the CPU oracle and the CUDA product through the
+same MultiRayCaster calls with the same seeded inputs (the oracle is the checker, never the product)."""
+import numpy as np
+
+from multivolumes_b200 import scene
+
+TOL_MAX_ABS = 2e-3      # BASELINE.json north_star: max-abs 2e-3 on RGBA16F
+TOL_PSNR_DB = 50.0      # and PSNR >= 50 dB
+
+
+def psnr(a, b, peak=None):
+    a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
+    mse = np.mean((a - b) ** 2)
+    if mse == 0:
+        return np.inf
+    if peak is None:
+        peak = max(float(np.abs(b).max()), 1.0)
+    return 10.0 * np.log10(peak * peak / mse)
+
+
+def assert_image_close(got_h, want_h, what=""):
+    """got/want: float16 arrays. Bar: max-abs <= 2e-3 (relative to max(1, |want|)) and PSNR >= 50 dB."""
+    g = got_h.astype(np.float32); w = want_h.astype(np.float32)
+    assert np.isfinite(g).all() == np.isfinite(w).all(), what
+    fin = np.isfinite(w)
+    err = np.abs(g[fin] - w[fin]) / np.maximum(1.0, np.abs(w[fin]))
+    assert err.size == 0 or err.max() <= TOL_MAX_ABS, f"{what}: max-abs {err.max():.3e}"
+    assert psnr(g[fin], w[fin]) >= TOL_PSNR_DB, f"{what}: PSNR {psnr(g[fin], w[fin]):.1f} dB"
+
+
+def rotation_y(angle):
+    c, s = np.cos(angle), np.sin(angle)
+    return np.array([[c, 0, -s], [0, 1, 0], [s, 0, c]], np.float64)
+
+
+def rotation_xyz(rs):
+    a, b, c = rs.uniform(0, 2 * np.pi, 3)
+    rx = np.array([[1, 0, 0], [0, np.cos(a), np.sin(a)], [0, -np.sin(a), np.cos(a)]])
+    rz = np.array([[np.cos(c), np.sin(c), 0], [-np.sin(c), np.cos(c), 0], [0, 0, 1]])
+    return rx @ rotation_y(b) @ rz
+
+
+def world43(scale, rot3, pos):
+    m = np.zeros((4, 3), np.float32)
+    m[:3, :3] = (np.eye(3) * scale) @ rot3
+    m[3] = pos
+    return m
+
+
+def configure(c, *, mode=1, sh=False, depth=None, shadow=None, background=None, eye=(4.0, 16.0, -80.0), focus=(0.0, 0.0, 0.0),
+              random_transforms=0, light_intensity=scene.LIGHT_INTENSITY, velocity=None):
+    """Same calls on either backend. Returns (view_proj, eye)."""
+    for i in range(c.srcs):
+        c.InitVolumeData(i, mode, (0x9E3779B9 * (i + 1)) & 0xffffffff)
+    c.SetLight(scene.LIGHT_PT, scene.LIGHT_COLOR, light_intensity)
+    c.SetAmbient(scene.AMBIENT_COLOR, scene.AMBIENT_INTENSITY)
+    c.SetVolumesWorld(20.0, (0, 0, 0))
+    if random_transforms:
+        rs = np.random.RandomState(random_transforms)
+        for i in range(c.N):
+            pos = rs.uniform(-60, 60, 3) * np.array([1, 0.3, 1])
+            c.SetVolumeWorldMatrix(i, world43(rs.uniform(4, 14), rotation_xyz(rs), pos))
+    vp, eye = scene.default_camera(c.W, c.H, eye=eye, focus=focus)
+    if sh:
+        # coefficients are an INPUT here (fixed numbers), so both backends light with identical SH
+        c.SetSH(sh_coeffs())
+    else:
+        c.SetSH(None)
+    c.SetRenderTargets(depth=depth, shadow=shadow, color=background, velocity=velocity)
+    svp = scene.shadow_view_proj() if shadow is not None else None
+    c.UpdateFrame(vp, svp, eye)
+    return vp, eye
+
+
+def sh_coeffs():
+    rs = np.random.RandomState(7)
+    k = rs.uniform(-0.3, 0.3, (9, 3)).astype(np.float32)
+    k[0] = [2.9, 3.1, 3.6]
+    return k
+
+
+def checker_background(W, H):
+    y, x = np.mgrid[0:H, 0:W]
+    bg = np.zeros((H, W, 4), np.float16)
+    bg[..., 0] = 0.2 + 0.3 * ((x // 8 + y // 8) & 1)
+    bg[..., 1] = 0.35
+    bg[..., 2] = 0.1 + 0.5 * (y / H)
+    bg[..., 3] = 1.0
+    return bg
+
+
+def blob_shadow(size=64):
+    """D16 shadow map: a disc of near depth (an occluder) in a far field."""
+    y, x = np.mgrid[0:size, 0:size]
+    d = np.full((size, size), 65535, np.uint16)
+    d[(x - size * 0.45) ** 2 + (y - size * 0.5) ** 2 < (size * 0.2) ** 2] = 9000
+    return d

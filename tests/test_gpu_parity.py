@@ -1,0 +1,318 @@
+"""Parity of the CUDA path (libmv_b200.so, through the C-ABI) against the CPU oracle on the same
+seeded inputs. Integer outputs (visible lists, attributes, OIT layer order) must be bit-exact;
+RGBA16F outputs must be within max-abs 2e-3 and PSNR >= 50 dB (BASELINE.json north_star) — the
+implementation pins the evaluation order, so they are in fact compared bit for bit first and the
+tolerance is only the fallback bar. Run on the B200 box: pytest -m gpu."""
+import numpy as np
+import pytest
+
+from harness import (assert_image_close, blob_shadow, checker_background, configure, psnr, sh_coeffs)
+from oracle_binding import OracleCaster
+from multivolumes_b200 import scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(oracle_lib):
+    return oracle_lib
+
+
+def _product(**kw):
+    from multivolumes_b200 import MultiRayCaster
+    return MultiRayCaster(**kw)
+
+
+def _pair(**kw):
+    return OracleCaster(filter_model=1, **kw), _product(**kw)
+
+
+SMALL = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=160, height=90)
+
+
+def _same_bits(a, b):
+    return np.array_equal(np.asarray(a).view(np.uint16), np.asarray(b).view(np.uint16))
+
+
+# ---------------------------------------------------------------- inputs
+@pytest.mark.parametrize("mode", [0, 1])
+def test_procedural_volume_bit_exact(mode):
+    o, p = _pair(**SMALL)
+    for c in (o, p):
+        c.InitVolumeData(1, mode, 1234567)
+    assert _same_bits(o.ReadVolume(1), p.ReadVolume(1))
+
+
+def test_r32f_ingest_bit_exact():
+    o, p = _pair(**SMALL)
+    d = np.random.RandomState(3).uniform(0, 4, (32, 32, 32)).astype(np.float32)
+    for c in (o, p):
+        c.LoadVolumeData(0, d)
+    assert _same_bits(o.ReadVolume(0), p.ReadVolume(0))
+
+
+def test_rgba16f_upload_roundtrip():
+    p = _product(**SMALL)
+    t = np.random.RandomState(4).uniform(0, 1, (32, 32, 32, 4)).astype(np.float16)
+    p.LoadVolumeData(2, t)
+    assert _same_bits(p.ReadVolume(2), t)
+
+
+def test_per_object_records_bit_exact():
+    o, p = _pair(**SMALL)
+    for c in (o, p):
+        configure(c, random_transforms=11)
+    assert np.array_equal(o.ReadPerObject().view(np.uint32), p.ReadPerObject().view(np.uint32))
+
+
+# ---------------------------------------------------------------- cull
+def _cull_equal(o, p):
+    vo, vp_ = o.ReadVisible(), p.ReadVisible()
+    assert np.array_equal(vo, vp_), (vo, vp_)
+    assert np.array_equal(o.ReadCubeVolumes(), p.ReadCubeVolumes())
+    ao, ap = o.ReadAttribs(), p.ReadAttribs()
+    assert np.array_equal(ao[vo], ap[vo])      # culled volumes keep stale attributes in the reference
+    return vo
+
+
+@pytest.mark.parametrize("n,g,w,h", [(4, 128, 1280, 720), (16, 128, 1920, 1080), (64, 256, 1920, 1080), (64, 256, 3840, 2160),
+                                     (529, 512, 3840, 2160), (1, 32, 64, 36), (130, 32, 320, 180)])
+def test_cull_named_configs_bit_exact(n, g, w, h):
+    """The five BASELINE.json configs (cfg5 as 23 x 23 so the reference's grid rule places every volume)
+    plus ragged sizes; only the cull runs, so the big shapes cost nothing (volumes are never touched)."""
+    kw = dict(grid_size=g if n <= 16 else 32, light_grid_size=8, num_volumes=n, num_volume_srcs=1, width=w, height=h)
+    o, p = _pair(**kw)
+    for c in (o, p):
+        c.SetVolumesWorld(20.0, (0, 0, 0))
+        vp, eye = scene.default_camera(w, h)
+        c.UpdateFrame(vp, None, eye)
+        c.Cull()
+    vis = _cull_equal(o, p)
+    assert len(vis) > 0
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5])
+def test_cull_random_transforms_and_cameras_bit_exact(seed):
+    rs = np.random.RandomState(100 + seed)
+    kw = dict(grid_size=64, light_grid_size=8, num_volumes=97, num_volume_srcs=3, width=1920, height=1080)
+    o, p = _pair(**kw)
+    eye = tuple(rs.uniform(-70, 70, 3))
+    for c in (o, p):
+        configure(c, mode=0, random_transforms=seed, eye=eye) if False else None
+        c.SetVolumesWorld(20.0, (0, 0, 0))
+        r2 = np.random.RandomState(seed)
+        from harness import world43, rotation_xyz
+        for i in range(c.N):
+            pos = r2.uniform(-60, 60, 3) * np.array([1, 0.3, 1])
+            c.SetVolumeWorldMatrix(i, world43(r2.uniform(2, 16), rotation_xyz(r2), pos))
+        vp, e = scene.default_camera(1920, 1080, eye=eye)
+        c.SetMaxSamples(int(r2.randint(16, 300)), 32)
+        c.UpdateFrame(vp, None, e)
+        c.Cull()
+    _cull_equal(o, p)
+
+
+def test_cull_nothing_visible():
+    o, p = _pair(**SMALL)
+    for c in (o, p):
+        vp, eye = scene.default_camera(c.W, c.H, eye=(0, 0, -80), focus=(0, 0, -200))   # looking away
+        c.UpdateFrame(vp, None, eye)
+        c.Cull()
+    assert len(o.ReadVisible()) == 0 and len(p.ReadVisible()) == 0
+    assert len(p.ReadCubeVolumes()) == 0
+
+
+# ---------------------------------------------------------------- light march
+@pytest.mark.parametrize("sh,shadow", [(False, False), (True, False), (True, True)])
+def test_light_map_parity(sh, shadow):
+    o, p = _pair(**SMALL)
+    for c in (o, p):
+        configure(c, sh=sh, shadow=blob_shadow() if shadow else None)
+        c.Cull()
+        for v in range(c.N):
+            c.RayMarchL(v)
+    for v in range(4):
+        lo, lp = o.ReadLightMap(v), p.ReadLightMap(v)
+        if not _same_bits(lo, lp):
+            assert_image_close(lp, lo, f"light map {v}")
+    so, sp = o.GetStats(), p.GetStats()
+    assert sp["light_voxels"] == so["light_voxels"]
+
+
+def test_light_round_robin_volume_choice():
+    o, p = _pair(**SMALL)
+    for c in (o, p):
+        configure(c)
+        c.SetFrameIndex(6)
+        vp, eye = scene.default_camera(c.W, c.H)
+        c.UpdateFrame(vp, None, eye)
+        c.Cull()
+        c.RayMarchL(-1)
+    assert o.GetStats()["light_volume"] == p.GetStats()["light_volume"]
+
+
+# ---------------------------------------------------------------- view march
+def _march_both(o, p, **cfg):
+    for c in (o, p):
+        configure(c, **cfg)
+        c.Cull()
+        for v in range(c.N):
+            c.RayMarchL(v)
+        c.RayMarchV()
+
+
+def _compare_cubemaps(o, p):
+    att = o.ReadAttribs()
+    n_exact = n_total = 0
+    for v in o.ReadCubeVolumes():
+        mip = int(att[v][0])
+        co, do = o.ReadCubeMap(int(v), mip)
+        cp, dp = p.ReadCubeMap(int(v), mip)
+        assert np.array_equal(do, dp), f"cube depth volume {v}"
+        n_total += 1
+        if _same_bits(co, cp):
+            n_exact += 1
+        else:
+            assert_image_close(cp, co, f"cube map volume {v} mip {mip}")
+    return n_exact, n_total
+
+
+@pytest.mark.parametrize("cfg", [dict(), dict(sh=True), dict(eye=(10.0, 5.0, -30.0)), dict(random_transforms=5, eye=(0, 30, -70))])
+def test_view_march_cube_maps_parity(cfg):
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=640, height=360)
+    o, p = _pair(**kw)
+    _march_both(o, p, **cfg)
+    assert len(o.ReadCubeVolumes()) > 0
+    _compare_cubemaps(o, p)
+    so, sp = o.GetStats(), p.GetStats()
+    for k in ("view_rays", "view_samples", "view_light_fetches"):
+        assert so[k] == sp[k], (k, so[k], sp[k])
+
+
+def test_view_march_with_scene_depth():
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=640, height=360)
+    o, p = _pair(**kw)
+    vp, _ = scene.default_camera(640, 360)
+    depth = scene.sphere_depth(640, 360, vp, center=(0, 0, 0), radius=14.0)
+    assert (depth < 1).any()
+    _march_both(o, p, depth=depth)
+    _compare_cubemaps(o, p)
+
+
+def test_view_march_eye_inside_volume():
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=1, width=320, height=180)
+    o, p = _pair(**kw)
+    for c in (o, p):
+        c.InitVolumeData(0, 1, 77)
+        c.SetVolumeWorld(0, 20.0, (0, 0, 0))
+        c.SetRenderTargets()
+        vp, eye = scene.default_camera(c.W, c.H, eye=(2.0, 1.0, -3.0), focus=(0, 0, 30))
+        c.UpdateFrame(vp, None, eye)
+        c.Cull(); c.RayMarchL(0); c.RayMarchV()
+    _compare_cubemaps(o, p)
+
+
+# ---------------------------------------------------------------- OIT + frame
+@pytest.mark.parametrize("cfg", [dict(), dict(sh=True, random_transforms=9, eye=(0, 40, -90)), dict(eye=(30.0, 10.0, -45.0))])
+def test_frame_parity(cfg):
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=9, num_volume_srcs=3, width=320, height=180)
+    o, p = _pair(**kw)
+    bg = checker_background(320, 180)
+    for c in (o, p):
+        configure(c, background=bg, **cfg)
+        for _ in range(3):
+            c.Render()
+    fo, fp = o.ReadFrame(), p.ReadFrame()
+    if not _same_bits(fo, fp):
+        assert_image_close(fp, fo, "frame")
+    so, sp = o.GetStats(), p.GetStats()
+    assert so["oit_fragments"] == sp["oit_fragments"]
+    assert so["direct_rays"] == sp["direct_rays"] and so["direct_samples"] == sp["direct_samples"]
+
+
+def test_frame_parity_with_mesh_depth_and_shadow():
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=16, num_volume_srcs=4, width=320, height=180)
+    o, p = _pair(**kw)
+    vp, _ = scene.default_camera(320, 180)
+    depth = scene.sphere_depth(320, 180, vp, center=(0, 0, 0), radius=18.0)
+    for c in (o, p):
+        configure(c, sh=True, depth=depth, shadow=blob_shadow(), background=checker_background(320, 180))
+        for _ in range(2):
+            c.Render()
+    fo, fp = o.ReadFrame(), p.ReadFrame()
+    if not _same_bits(fo, fp):
+        assert_image_close(fp, fo, "frame")
+
+
+# ---------------------------------------------------------------- TAA + tone map
+def test_postprocess_parity_taa_off_and_on():
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=320, height=180)
+    o, p = _pair(**kw)
+    rs = np.random.RandomState(5)
+    vel = (rs.uniform(-1, 1, (180, 320, 2)) * 0.004).astype(np.float16)
+    for c in (o, p):
+        configure(c, background=checker_background(320, 180), velocity=vel)
+        c.Render(); c.Postprocess(taa=False)
+    (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
+    assert _same_bits(to, tp) and np.array_equal(bo, bp)
+    for c in (o, p):
+        for _ in range(3):
+            c.Render(); c.Postprocess(taa=True)
+    (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
+    if not _same_bits(to, tp):
+        assert_image_close(tp, to, "taa")
+    assert np.abs(bo.astype(int) - bp.astype(int)).max() <= 1
+
+
+# ---------------------------------------------------------------- SH
+def test_sh_projection_matches_oracle_and_closed_form():
+    o, p = _pair(**SMALL)
+    sky = scene.procedural_sky(64)
+    so, sp = o.TransformSH(sky), p.TransformSH(sky)
+    assert np.allclose(so, sp, rtol=2e-4, atol=2e-4)
+    const = np.full((6, 32, 32, 3), 0.75, np.float32)
+    k = p.TransformSH(const)
+    assert np.allclose(k[0], 2 * np.sqrt(np.pi) * 0.75, rtol=2e-3) and np.abs(k[1:]).max() < 5e-3
+    odd = p.TransformSH(np.random.RandomState(1).uniform(0, 2, (6, 7, 7, 3)).astype(np.float32))   # ragged size
+    assert np.allclose(odd, o.TransformSH(np.random.RandomState(1).uniform(0, 2, (6, 7, 7, 3)).astype(np.float32)), rtol=2e-4, atol=2e-4)
+
+
+# ---------------------------------------------------------------- properties at full size (no oracle)
+def test_full_size_empty_volumes_leave_frame_untouched():
+    p = _product(grid_size=128, light_grid_size=96, num_volumes=16, num_volume_srcs=1, width=1920, height=1080)
+    bg = checker_background(1920, 1080)
+    p.SetRenderTargets(color=bg)
+    vp, eye = scene.default_camera(1920, 1080)
+    p.UpdateFrame(vp, None, eye)
+    p.Render()
+    assert _same_bits(p.ReadFrame(), bg)
+    st = p.GetStats()
+    assert st["view_light_fetches"] == 0 and st["visible_count"] > 0
+
+
+def test_full_size_sharded_march_equals_unsharded():
+    """k virtual shards on one device: the union of the shards' cube maps and row bands is bit-identical
+    to the single-GPU frame (sharding by volume does not change any per-volume arithmetic)."""
+    kw = dict(grid_size=128, light_grid_size=32, num_volumes=16, num_volume_srcs=2, width=960, height=540)
+    ref = _product(**kw)
+    configure(ref, sh=True, background=checker_background(960, 540))
+    ref.Render()
+    att = ref.ReadAttribs(); cubes = ref.ReadCubeVolumes()
+    want = ref.ReadFrame()
+    world = 3
+    bands = [(r * 540 // world, (r + 1) * 540 // world) for r in range(world)]
+    got = np.zeros_like(want)
+    shards = []
+    for r in range(world):
+        s = _product(**kw)
+        configure(s, sh=True, background=checker_background(960, 540))
+        s.SetShard(r, world)
+        s.Cull(); s.RayMarchL(-1); s.RayMarchV()
+        shards.append(s)
+    for v in cubes:
+        mip = int(att[v][0])
+        cw, dw = ref.ReadCubeMap(int(v), mip)
+        cg, dg = shards[int(v) % world].ReadCubeMap(int(v), mip)
+        assert _same_bits(cw, cg) and np.array_equal(dw, dg)
+        other = shards[(int(v) + 1) % world].ReadCubeMap(int(v), mip)[0]
+        assert not other.view(np.uint16).any()          # not marched by a non-owner
