@@ -3,6 +3,8 @@ seeded inputs. Integer outputs (visible lists, attributes, OIT layer order) must
 RGBA16F outputs must be within max-abs 2e-3 and PSNR >= 50 dB (BASELINE.json north_star) — the
 implementation pins the evaluation order, so they are in fact compared bit for bit first and the
 tolerance is only the fallback bar. Run on the B200 box: pytest -m gpu."""
+import os
+
 import numpy as np
 import pytest
 
@@ -30,8 +32,16 @@ def _pair(**kw):
 SMALL = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=160, height=90)
 
 
+STRICT = os.environ.get("MV_PARITY_STRICT", "1") != "0"   # bit-exact RGBA16F; 0 = the north_star tolerance only
+
+
 def _same_bits(a, b):
-    return np.array_equal(np.asarray(a).view(np.uint16), np.asarray(b).view(np.uint16))
+    same = np.array_equal(np.asarray(a).view(np.uint16), np.asarray(b).view(np.uint16))
+    if STRICT and not same:
+        d = np.asarray(a).view(np.uint16) != np.asarray(b).view(np.uint16)
+        raise AssertionError(f"not bit-exact: {int(d.sum())} of {d.size} halves differ "
+                             f"(max abs {np.abs(np.asarray(a, np.float32) - np.asarray(b, np.float32)).max():.3e})")
+    return same
 
 
 # ---------------------------------------------------------------- inputs
@@ -98,7 +108,6 @@ def test_cull_random_transforms_and_cameras_bit_exact(seed):
     o, p = _pair(**kw)
     eye = tuple(rs.uniform(-70, 70, 3))
     for c in (o, p):
-        configure(c, mode=0, random_transforms=seed, eye=eye) if False else None
         c.SetVolumesWorld(20.0, (0, 0, 0))
         r2 = np.random.RandomState(seed)
         from harness import world43, rotation_xyz
@@ -261,7 +270,7 @@ def test_postprocess_parity_taa_off_and_on():
     (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
     if not _same_bits(to, tp):
         assert_image_close(tp, to, "taa")
-    assert np.abs(bo.astype(int) - bp.astype(int)).max() <= 1
+    assert np.abs(bo.astype(int) - bp.astype(int)).max() <= (0 if STRICT else 1)
 
 
 # ---------------------------------------------------------------- SH
