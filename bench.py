@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py — frames/s and ray-march samples/s of the cube-map-space volume rendering path.
+
+  python bench.py --gpus 1 --steps K --warmup W                 (one process; N = 1)
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+  python bench.py --impl reference ...                          (the CPU oracle on the host cores)
+
+A step is one frame: UpdateFrame (camera on the reference's orbit, MultiVolumes.cpp:328-337) ->
+colour-RT reset -> Render (cull, light march of one volume, view march, OIT resolve) -> Postprocess
+(TAA + tone map). Workload at every N: BASELINE.json configs[1] — 16 volumes of 128^3, 1920x1080, SH
+environment lighting — unless --workload says otherwise. Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: N, srcs, G, L, W, H, sh, taa
+    "cfg1": dict(n=4, g=128, l=96, w=1280, h=720, sh=False, taa=False, note="BASELINE.json configs[0]"),
+    "cfg2": dict(n=16, g=128, l=96, w=1920, h=1080, sh=True, taa=True, note="BASELINE.json configs[1]"),
+    "cfg3": dict(n=64, g=256, l=96, w=1920, h=1080, sh=True, taa=True, note="BASELINE.json configs[2] (analytic sphere occluder)"),
+    "cfg4": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, note="BASELINE.json configs[3]"),
+    "tiny": dict(n=4, g=32, l=16, w=320, h=180, sh=True, taa=True, note="CI-sized"),
+}
+TEX_PEAK_GFETCH = 575.9   # measured on this pool's B200: profiles/r01_tex_probe.json (trilinear RGBA16F fetches/s, L1-resident)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_scene(c, wl, scene, sky_coeffs):
+    for i in range(c.srcs):
+        c.InitVolumeData(i, 1, (0x9E3779B9 * (i + 1)) & 0xffffffff)
+    c.SetLight(scene.LIGHT_PT, scene.LIGHT_COLOR, scene.LIGHT_INTENSITY)
+    c.SetAmbient(scene.AMBIENT_COLOR, scene.AMBIENT_INTENSITY)
+    c.SetVolumesWorld(20.0, (0, 0, 0))
+    c.SetSH(sky_coeffs if wl["sh"] else None)
+    depth = None
+    if wl is WORKLOADS["cfg3"]:
+        vp, _ = scene.default_camera(wl["w"], wl["h"])
+        depth = scene.sphere_depth(wl["w"], wl["h"], vp, center=(0, 0, 0), radius=9.0)
+    c.SetRenderTargets(depth=depth)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        self.t0, self.t1 = t0, t1
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if self.t0 - 0.05 <= t <= self.t1 + 0.15] or [r for _, r in self.rows[-3:]]
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def camera(scene, wl, frame):
+    return scene.orbit_camera(wl["w"], wl["h"], frame)
+
+
+# --------------------------------------------------------------------------------------------
+def run_reference(args, wl, rank, world):
+    """--impl reference: the reference publishes no CPU implementation (HLSL on D3D12 only), so the arm
+    times the scalar C++/OpenMP transliteration (the oracle) on the host cores, all threads."""
+    if rank != 0:
+        return None
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleCaster
+    from multivolumes_b200 import scene
+    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], width=wl["w"], height=wl["h"])
+    sky = o.TransformSH(scene.procedural_sky(64))
+    build_scene(o, wl, scene, sky)
+    cores = o.GetStats()["threads"]
+
+    def frame(i, shard=None):
+        vp, eye = camera(scene, wl, i)
+        if shard:
+            o.SetShard(*shard)
+            o.SetRowBand(*shard_band(wl["h"], *shard))
+        o.UpdateFrame(vp, None, eye); o.ResetColor(); o.Render(); o.Postprocess(wl["taa"])
+        st = o.GetStats()
+        return st["view_samples"] + st["direct_samples"] + st["light_samples"]
+
+    def shard_band(H, r, w):
+        return (H * r) // w, (H * (r + 1)) // w
+
+    # calibrate with one full frame, then size the per-step sample so the whole run stays bounded
+    t = time.perf_counter(); frame(0); t_full = time.perf_counter() - t
+    budget = float(args.ref_budget)
+    S = int(min(wl["n"], max(1, np.ceil((args.steps + args.warmup) * t_full / budget))))
+    for i in range(args.warmup):
+        frame(1 + i, (i % S, S))
+    t0 = time.perf_counter(); samples = 0
+    for i in range(args.steps):
+        samples += frame(1 + args.warmup + i, (i % S, S))
+    dt = time.perf_counter() - t0
+    fps = args.steps / (dt * S)            # S sample-steps make one frame's worth of work
+    line = {"impl": "reference", "metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, wl, world), "samples_per_s": samples / dt,
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                             "sample": f"each step = 1/{S} of a frame (volumes v % {S} == step % {S}, light-map slab, row band {S}-th); "
+                                       f"frames/s = steps / (time x {S}); calibration full frame {t_full:.2f} s"},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    return line
+
+
+def workload_config(args, wl, world):
+    return {"workload": f"{args.workload}: {wl['n']} volumes x {wl['g']}^3 RGBA16F (procedural density x seeded value noise), "
+                        f"{wl['w']}x{wl['h']}, light map {wl['l']}^3, SH {'on' if wl['sh'] else 'off'}, TAA {'on' if wl['taa'] else 'off'}, "
+                        f"orbit camera; {wl['note']}",
+            "l2_policy": f"inputs larger than L2 ({wl['n'] * wl['g'] ** 3 * 8 / 1e6:.0f} MB of volume textures vs 126 MB)",
+            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: volumes v % {world}, light-map z-slabs, {world} row bands; exchange = {args.exchange}",
+            "e2e_inputs": "per-frame matrices (PerObject records) from pinned host memory; result = tone-mapped RGBA8 frame read back to pinned host memory"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--exchange", default="fused", choices=["fused", "collective"])
+    ap.add_argument("--cpu-baseline-frames", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU time the reference arm may use")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.warmup < 3:
+        args.warmup = 3
+
+    if args.impl == "reference":
+        line = run_reference(args, wl, rank, world)
+        if line:
+            print(json.dumps(line), flush=True)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from multivolumes_b200 import MultiRayCaster, PinnedBuffer, scene
+    from multivolumes_b200.dist import CudaExchange, ShardedRenderer
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the product has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    hbm_peak, peak_src = peaks()
+
+    c = MultiRayCaster(device=local_rank, count_samples=True, time_passes=True, grid_size=wl["g"], light_grid_size=wl["l"],
+                       num_volumes=wl["n"], width=wl["w"], height=wl["h"])
+    stream = torch.cuda.Stream()
+    c.SetStream(stream.cuda_stream)      # order the caster's kernels with torch's events / NCCL on one stream
+    sky = c.TransformSH(scene.procedural_sky(64))
+    build_scene(c, wl, scene, sky)
+    with torch.cuda.stream(stream):
+        x = CudaExchange(c, rank, world) if world > 1 and args.exchange == "collective" else None
+        r = ShardedRenderer(c, rank, world, mode=args.exchange, exchange=x)
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        def frame(i):
+            vp, eye = camera(scene, wl, i)
+            r.render(vp, None, eye, taa=wl["taa"])
+
+        # ---- device-resident throughput ----
+        for i in range(args.warmup):
+            frame(i)
+        barrier()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        acc = {k: 0.0 for k in ("cull", "ray_march_light", "ray_march_view", "resolve_oit", "postprocess")}
+        stats_acc = {}
+        t_wall0 = time.time()
+        e0.record(stream)
+        for i in range(args.steps):
+            frame(args.warmup + i)
+        e1.record(stream)
+        barrier()
+        t_wall1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        ms_total = float(ms.item())
+        clocks = None
+        if sampler:
+            sampler.window(t_wall0, t_wall1)
+            clocks = sampler.stop()
+
+        # ---- per-pass device time and sample counts: a second, instrumented pass over the same frames ----
+        n_prof = min(args.steps, 50)
+        for i in range(n_prof):
+            frame(args.warmup + i)
+            t = c.GetTimings()            # CUDA events recorded on the caster's stream around every pass
+            for k in acc:
+                acc[k] += t[k]
+            st = c.GetStats()
+            for k, v in st.items():
+                stats_acc[k] = stats_acc.get(k, 0) + v
+        barrier()
+        per_pass = {k: v / n_prof for k, v in acc.items()}
+        samples_frame = (stats_acc["view_samples"] + stats_acc["direct_samples"] + stats_acc["light_samples"]) / n_prof
+        if world > 1:   # whole-job samples: sum over ranks
+            tsum = torch.tensor([samples_frame], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tsum)
+            samples_frame = float(tsum.item())
+
+        # ---- end to end: host matrices in, RGBA8 frame out, every step ----
+        out = PinnedBuffer((wl["h"], wl["w"], 4), np.uint8)
+        n_e2e = min(args.steps, 100)
+        for i in range(3):
+            frame(i)
+            if rank == 0:
+                c.ReadPostInto(rgba8_ptr=out.ptr)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            frame(args.warmup + i)
+            if rank == 0:
+                c.ReadPostInto(rgba8_ptr=out.ptr)     # D2H into pinned memory + stream sync
+            else:
+                c.Sync()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e_fps = n_e2e / float(dt.item())
+        checksum = int(out.array[::16, ::16].astype(np.uint64).sum()) if rank == 0 else 0
+
+    if rank == 0:
+        fps = args.steps / (ms_total / 1000.0)
+        view_ms = per_pass["ray_march_view"]
+        vs, vl, vr = (stats_acc[k] / n_prof for k in ("view_samples", "view_light_fetches", "view_rays"))
+        # 8 B density texel per sample (+ 8 B RGBA16F light texel when alpha > 0.01); per ray 4 B depth read,
+        # 8 B colour + 4 B cube-depth write
+        alg_bytes = vs * 8 + vl * 8 + vr * 16
+        achieved = alg_bytes / (view_ms / 1000.0) / 1e9 if view_ms > 0 else 0.0
+        fetches = (vs + vl) / (view_ms / 1000.0) / 1e9 if view_ms > 0 else 0.0
+        line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl, world),
+                "samples_per_s": samples_frame * fps, "samples_per_frame": samples_frame,
+                "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": wl["n"] * 224, "d2h_bytes_per_step": wl["w"] * wl["h"] * 4,
+                        "steps": n_e2e, "checksum": checksum},
+                "gpu_launches": args.steps * (5 if world == 1 else (10 if args.exchange == "fused" else 6)),
+                "clocks": clocks,
+                "per_pass_ms": per_pass,
+                "roofline": {"kernel": "k_ray_march_v", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": view_ms,
+                             "tex": {"achieved": fetches, "peak": TEX_PEAK_GFETCH, "unit": "Gfetch/s", "frac": fetches / TEX_PEAK_GFETCH,
+                                     "peak_source": "profiles/r01_tex_probe.json"}}}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, wl)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(args, wl):
+    """The oracle on this box's host cores, a bounded sample of the same workload (whole frames)."""
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleCaster
+    from multivolumes_b200 import scene
+    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], width=wl["w"], height=wl["h"])
+    build_scene(o, wl, scene, o.TransformSH(scene.procedural_sky(64)))
+    n, t0, samples = 0, time.perf_counter(), 0
+    while n < args.cpu_baseline_frames and (n == 0 or time.perf_counter() - t0 < 25.0):
+        vp, eye = camera(scene, wl, args.warmup + n)
+        o.UpdateFrame(vp, None, eye); o.ResetColor(); o.Render(); o.Postprocess(wl["taa"])
+        st = o.GetStats(); samples += st["view_samples"] + st["direct_samples"] + st["light_samples"]
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n / dt, "unit": "frames/s", "cores": o.GetStats()["threads"], "kind": "port",
+            "sample": f"{n} whole frames of the same workload (frames {args.warmup}..{args.warmup + n - 1} of the orbit)",
+            "samples_per_s": samples / dt}
+
+
+if __name__ == "__main__":
+    main()

@@ -39,6 +39,7 @@ _COMMON = {
     "volume_upload_r32f": (C.c_int, [_vp, u32, _vp]),
     "volume_read": (C.c_int, [_vp, u32, _vp]),
     "set_targets": (C.c_int, [_vp, _vp, _vp, u32, _vp, _vp]),
+    "reset_color": (C.c_int, [_vp]),
     "set_sh": (C.c_int, [_vp, _vp]),
     "set_max_samples": (C.c_int, [_vp, u32, u32]),
     "set_volumes_world": (C.c_int, [_vp, f32, P(f32)]),
@@ -64,6 +65,8 @@ _COMMON = {
     "read_post": (C.c_int, [_vp, _vp, _vp]),
     "get_stats": (C.c_int, [_vp, P(Stats)]),
     "set_frame_index": (C.c_int, [_vp, u32]),
+    "set_shard": (C.c_int, [_vp, u32, u32]),
+    "set_row_band": (C.c_int, [_vp, u32, u32]),
 }
 
 
@@ -166,6 +169,9 @@ class CasterBase:
         self._ck(self.b.set_targets(self.h, ptr(depth, np.float32, self.W * self.H), ptr(shadow, np.uint16, ssize * ssize), ssize,
                                     ptr(color, np.uint16, self.W * self.H * 4), ptr(velocity, np.uint16, self.W * self.H * 2)), "set_targets")
 
+    def ResetColor(self):
+        self._ck(self.b.reset_color(self.h), "reset_color")
+
     def SetSH(self, coeffs):
         if coeffs is None:
             self._ck(self.b.set_sh(self.h, None), "set_sh")
@@ -231,8 +237,19 @@ class CasterBase:
         self._ck(self.b.sh_project(self.h, cube.ctypes.data, size, out.ctypes.data), "sh_project")
         return out.reshape(9, 3)
 
+    def SetShard(self, rank, world):
+        self._ck(self.b.set_shard(self.h, rank, world), "set_shard")
+
+    def SetRowBand(self, row0, row1):
+        self._ck(self.b.set_row_band(self.h, row0, row1), "set_row_band")
+
     def SetFrameIndex(self, f):
+        self._frame = f
         self._ck(self.b.set_frame_index(self.h, f), "set_frame_index")
+
+    def AdvanceFrame(self):
+        """What Render() does to m_frameIdx (MultiRayCaster.cpp:384), for callers that run the passes one by one."""
+        self.SetFrameIndex(getattr(self, "_frame", 0) + 1)
 
     # --- read-backs ---
     def ReadPerObject(self):

@@ -35,13 +35,10 @@ _EXTRA = {
     "last_error": (C.c_char_p, []),
     "abi_version": (u32, []),
     "set_targets_device": (C.c_int, [_vp, _vp, _vp, u32, _vp, _vp]),
-    "reset_color": (C.c_int, [_vp]),
     "get_timings": (C.c_int, [_vp, P(Timings)]),
     "sync": (C.c_int, [_vp]),
     "host_alloc": (_vp, [C.c_size_t]),
     "host_free": (None, [_vp]),
-    "set_shard": (C.c_int, [_vp, u32, u32]),
-    "set_row_band": (C.c_int, [_vp, u32, u32]),
     "exchange_block": (C.c_int, [_vp, P(_vp), u64p]),
     "exchange_layout_get": (C.c_int, [_vp, P(ExchangeLayout)]),
     "cube_region": (C.c_int, [_vp, u32, u32, u64p, u64p, u64p, u64p]),
@@ -109,9 +106,6 @@ class MultiRayCaster(CasterBase):
         self._ck(self.b.set_targets_device(self.h, depth or None, shadow or None, shadow_size, color or None, velocity or None),
                  "set_targets_device")
 
-    def ResetColor(self):
-        self._ck(self.b.reset_color(self.h), "reset_color")
-
     def Sync(self):
         self._ck(self.b.sync(self.h), "sync")
 
@@ -125,12 +119,6 @@ class MultiRayCaster(CasterBase):
         self._ck(self.b.read_post(self.h, taa_ptr, rgba8_ptr), "read_post")
 
     # --- multi-GPU ---
-    def SetShard(self, rank, world):
-        self._ck(self.b.set_shard(self.h, rank, world), "set_shard")
-
-    def SetRowBand(self, row0, row1):
-        self._ck(self.b.set_row_band(self.h, row0, row1), "set_row_band")
-
     def ExchangeBlock(self):
         p, n = _vp(), C.c_uint64()
         self._ck(self.b.exchange_block(self.h, C.byref(p), C.byref(n)), "exchange_block")

@@ -140,8 +140,11 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
     // 16x16-pixel CTA made of 8 warps of 8x4 pixels
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int px = (int)(blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7));
-    const int py = (int)(s.row0 + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3));
-    const bool valid = px < W && py < (int)s.row1;
+    // rows [row0, row1) plus a one-row halo on each side (clipped): the TAA's 3x3 neighbourhood of the
+    // band's border rows reads them
+    const int rowBegin = max((int)s.row0 - 1, 0), rowEnd = min((int)s.row1 + 1, (int)cb.height);
+    const int py = (int)(rowBegin + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3));
+    const bool valid = px < W && py < rowEnd;
 
     const uint32_t nvis = valid ? s.lists->visibleCount : 0u;
     // pixel-centre ray: unproject z = 0 through screenToWorld (RTCube.hlsl:54-70; PSCube.hlsl:38-40)
@@ -268,8 +271,9 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
 
 void launch_resolve_oit(Caster& c)
 {
-    const uint32_t rows = c.row1 - c.row0;
-    if (rows == 0) return;
+    if (c.row1 <= c.row0) return;
+    const uint32_t rowBegin = c.row0 > 0 ? c.row0 - 1 : 0, rowEnd = min(c.row1 + 1, c.d.height);
+    const uint32_t rows = rowEnd - rowBegin;
     dim3 grid((c.d.width + 15) / 16, (rows + 15) / 16);
     k_resolve_oit<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb);
 }

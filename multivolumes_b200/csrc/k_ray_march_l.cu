@@ -54,10 +54,20 @@ MV_D V3 density_gradient(cudaTextureObject_t grid, V3 uvw, float invGrid)
     return {q1 - q0, q3 - q2, q5 - q4};
 }
 
-// z0/z1: slab of the light map this launch fills (whole map on one GPU).
-__global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, FrameCB cb, int volumeOverride, uint32_t z0, uint32_t z1,
-                                                              uint2* staging)
+// Where the voxels of this launch go. One GPU: straight into the light volume's 3-D array (surface
+// store). Sharded: the rank fills the z-slab [z0, z1) into the linear staging buffer of its own
+// exchange block and, when peers are mapped, into every peer's (NVLink stores); mv_light_commit then
+// moves the assembled staging buffer into the array on every rank.
+struct LightTarget {
+    uint32_t z0, z1;
+    uint2* staging;                 // nullptr = surface store
+    uint2* peerStaging[kMaxPeers];
+    uint32_t numPeers;
+};
+
+__global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
 {
+    const uint32_t z0 = tgt.z0, z1 = tgt.z1;
     const uint32_t L = cb.lightGridSize, N = cb.numVolumes;
     // 8x4x4 voxel bricks: a warp is an 8x4 slice, neighbouring rays stay coherent in the texture cache
     const uint32_t bricksX = (L + 7) / 8, bricksY = (L + 3) / 4;
@@ -122,8 +132,11 @@ __global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, Fr
         const V4 out = {quantize_ufloat(shadow * lightColor.x + ambient.x, 6), quantize_ufloat(shadow * lightColor.y + ambient.y, 6),
                         quantize_ufloat(shadow * lightColor.z + ambient.z, 5), 0.0f};
         const uint2 packed = pack_half4(out);
-        if (staging) staging[((size_t)z * L + y) * L + x] = packed;
-        else surf3Dwrite(packed, s.lightSurf[volumeId], (int)(x * 8), (int)y, (int)z);             // :120
+        if (tgt.staging) {
+            const size_t idx = ((size_t)z * L + y) * L + x;
+            tgt.staging[idx] = packed;
+            for (uint32_t p = 0; p < tgt.numPeers; ++p) if (tgt.peerStaging[p]) tgt.peerStaging[p][idx] = packed;
+        } else surf3Dwrite(packed, s.lightSurf[volumeId], (int)(x * 8), (int)y, (int)z);           // :120
     }
     if (s.stats) {
 #pragma unroll
@@ -143,8 +156,19 @@ __global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, Fr
 void launch_ray_march_light(Caster& c, int volumeOverride)
 {
     const uint32_t L = c.d.light_grid_size;
-    const uint32_t bricks = ((L + 7) / 8) * ((L + 3) / 4) * ((L + 3) / 4);
-    k_ray_march_l<<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, 0u, L, nullptr);
+    LightTarget tgt{};
+    tgt.z0 = 0; tgt.z1 = L;
+    if (c.shardWorld > 1) {
+        const uint32_t slab = (L + c.shardWorld - 1) / c.shardWorld;
+        tgt.z0 = min(L, c.shardRank * slab); tgt.z1 = min(L, tgt.z0 + slab);
+        tgt.staging = c.dLightStaging;
+        tgt.numPeers = c.peersMapped ? c.shardWorld : 0;
+        for (uint32_t p = 0; p < tgt.numPeers; ++p)
+            tgt.peerStaging[p] = (p == c.shardRank) ? nullptr : reinterpret_cast<uint2*>(c.peerBlock[p] + c.layout.light_staging_offset);
+    }
+    if (tgt.z1 <= tgt.z0) return;
+    const uint32_t bricks = ((L + 7) / 8) * ((L + 3) / 4) * ((tgt.z1 - tgt.z0 + 3) / 4);
+    k_ray_march_l<<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
 }
 
 } // namespace mv

@@ -193,7 +193,7 @@ static void destroy_caster(Caster& c)
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
     for (auto& e : c.ev) if (e) cudaEventDestroy(e);
-    if (c.uploadDone) cudaEventDestroy(c.uploadDone);
+    for (auto& e : c.uploadDone) if (e) cudaEventDestroy(e);
     if (c.ownStream) cudaStreamDestroy(c.ownStream);
 }
 
@@ -301,9 +301,8 @@ int mv_create(const mv_desc* d, mv_caster** out)
     // createVolumeInfoBuffers, MultiRayCaster.cpp:455-549
     MV_CUDA_C(cudaMalloc(&c.dPerObject, N * sizeof(PerObject)));
     MV_CUDA_C(cudaMemsetAsync(c.dPerObject, 0, N * sizeof(PerObject), c.stream));
-    MV_CUDA_C(cudaMallocHost(&c.hPerObjectPinned, N * sizeof(PerObject)));
-    c.perObjectHost.resize(N);
-    memset(c.perObjectHost.data(), 0, N * sizeof(PerObject));
+    MV_CUDA_C(cudaMallocHost(&c.hPerObjectPinned, (size_t)kUploadRing * N * sizeof(PerObject)));
+    for (auto& e : c.uploadDone) MV_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     std::vector<uint32_t> descs(N);
     for (uint32_t i = 0; i < N; ++i) descs[i] = (i % S) | (kNumCubeMip << 14) | (G << 18);   // :470-479
     MV_CUDA_C(cudaMalloc(&c.dVolumeDescs, N * sizeof(uint32_t)));
@@ -539,24 +538,25 @@ int mv_update_frame(mv_caster* h, const float viewProj[16], const float shadowVP
     memcpy(cb.ambient, c.ambient, sizeof cb.ambient);
     cb.frameIdx = c.frameIdx;
     const uint32_t N = c.d.num_volumes;
-    // the previous frame's upload must have left the pinned staging buffer before it is rewritten
-    if (c.uploadPending) { MV_CUDA(cudaEventSynchronize(c.uploadDone)); c.uploadPending = false; }
+    // upload ring: a slot is rewritten only after the copy that last read it has completed
+    const uint32_t slot = c.uploadSlot;
+    c.uploadSlot = (slot + 1) % kUploadRing;
+    if (c.uploadPending[slot]) { MV_CUDA(cudaEventSynchronize(c.uploadDone[slot])); c.uploadPending[slot] = false; }
+    PerObject* staging = c.hPerObjectPinned + (size_t)slot * N;
     for (uint32_t i = 0; i < N; ++i) {
         float world[16], worldI[16], wvp[16];
         world_from43(&c.volumeWorlds[(size_t)i * 12], world);
         inverse44(world, worldI);
         mul44(world, viewProj, wvp);
-        PerObject& po = c.hPerObjectPinned[i];
+        PerObject& po = staging[i];
         memcpy(po.wvp, wvp, sizeof wvp);
         inverse44(wvp, po.wvpi);
         to43(worldI, po.worldI);
         to43(world, po.world);
     }
-    memcpy(c.perObjectHost.data(), c.hPerObjectPinned, N * sizeof(PerObject));
-    MV_CUDA(cudaMemcpyAsync(c.dPerObject, c.hPerObjectPinned, N * sizeof(PerObject), cudaMemcpyHostToDevice, c.stream));
-    if (!c.uploadDone) MV_CUDA(cudaEventCreateWithFlags(&c.uploadDone, cudaEventDisableTiming));
-    MV_CUDA(cudaEventRecord(c.uploadDone, c.stream));
-    c.uploadPending = true;
+    MV_CUDA(cudaMemcpyAsync(c.dPerObject, staging, N * sizeof(PerObject), cudaMemcpyHostToDevice, c.stream));
+    MV_CUDA(cudaEventRecord(c.uploadDone[slot], c.stream));
+    c.uploadPending[slot] = true;
     return MV_OK;
 }
 
@@ -601,9 +601,15 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
     record(c, 0);
     launch_cull(c);
     record(c, 1);
+    if (c.shardWorld > 1 && !c.peersMapped) {
+        set_error("sharded caster without mapped peers: run the passes and the collectives one by one (mv_cull, mv_ray_march_light, ...)");
+        return MV_ERR_INVALID;
+    }
     launch_ray_march_light(c, -1);
+    if (c.shardWorld > 1) { launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
     record(c, 2);
     launch_ray_march_view(c);
+    if (c.shardWorld > 1) launch_peer_barrier(c);                                // every owner's cube maps have landed
     record(c, 3);
     launch_resolve_oit(c);
     record(c, 4);

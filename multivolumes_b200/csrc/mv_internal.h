@@ -8,6 +8,7 @@
 namespace mv {
 
 constexpr int kMaxPeers = 8;
+constexpr int kUploadRing = 3;   // MultiRayCaster.h:52 FrameCount
 
 // Common.hlsli:28-34 / MultiRayCaster.cpp:35-41 — 56 floats, matrices NOT transposed (row-vector use).
 struct PerObject {
@@ -127,7 +128,6 @@ struct Caster {
     cudaStream_t stream = nullptr;
     // host scene state (MultiRayCaster.h:189-215)
     std::vector<float> volumeWorlds;     // N x 12 (float4x3)
-    std::vector<PerObject> perObjectHost;
     float lightPt[3] = {75.0f, 75.0f, -75.0f};
     float lightColor[4] = {1.0f, 0.7f, 0.3f, 1.0f};
     float ambient[4] = {0.0f, 0.3f, 1.0f, 0.4f};
@@ -141,7 +141,8 @@ struct Caster {
     cudaTextureObject_t* dLightTex = nullptr;
     cudaSurfaceObject_t* dLightSurf = nullptr;
     PerObject* dPerObject = nullptr;
-    PerObject* hPerObjectPinned = nullptr;
+    PerObject* hPerObjectPinned = nullptr;  // ring of kUploadRing x N records (the reference keeps FrameCount = 3 upload slots)
+    uint32_t uploadSlot = 0;
     uint32_t* dVolumeDescs = nullptr;
     ushort4* dAttribs = nullptr;
     unsigned char* dLists = nullptr;     // FrameLists + visible + cubeVolumes + cubeTilePrefix
@@ -158,8 +159,8 @@ struct Caster {
     uint32_t** dPeerFlagPtrs = nullptr;  // [kMaxPeers] flag arrays of every rank (peer-mapped)
     bool peersMapped = false;
     cudaStream_t ownStream = nullptr;
-    cudaEvent_t uploadDone = nullptr;
-    bool uploadPending = false;
+    cudaEvent_t uploadDone[3] = {};
+    bool uploadPending[3] = {};
     float* dDepth = nullptr;
     uint16_t* dShadow = nullptr;
     uint32_t shadowSize = 0;

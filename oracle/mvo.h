@@ -56,6 +56,7 @@ int mvo_volume_read(mvo_caster* c, uint32_t src, uint16_t* texels_out);
 /* MultiRayCaster::SetRenderTargets / SetViewport: borrowed scene depth, shadow map, colour RT */
 int mvo_set_targets(mvo_caster* c, const float* depth, const uint16_t* shadow_d16, uint32_t shadow_size,
                     const uint16_t* color_rgba16f, const uint16_t* velocity_rg16f);
+int mvo_reset_color(mvo_caster* c);
 int mvo_set_sh(mvo_caster* c, const float* coeffs27);
 int mvo_set_max_samples(mvo_caster* c, uint32_t ray, uint32_t light);
 int mvo_set_volumes_world(mvo_caster* c, float size, const float center[3]);
@@ -85,6 +86,13 @@ int mvo_read_frame(mvo_caster* c, uint16_t* rgba16f);
 int mvo_read_post(mvo_caster* c, uint16_t* taa_rgba16f, uint8_t* rgba8);
 int mvo_get_stats(mvo_caster* c, mvo_stats* out);
 int mvo_set_frame_index(mvo_caster* c, uint32_t frame_idx);
+/* sharding, same semantics as mv_set_shard / mv_set_row_band */
+int mvo_set_shard(mvo_caster* c, uint32_t rank, uint32_t world);
+int mvo_set_row_band(mvo_caster* c, uint32_t row0, uint32_t row1);
+/* raw access for the exchange steps of the multi-rank host logic (tests): cube map / light map of a volume */
+int mvo_write_cubemap(mvo_caster* c, uint32_t volume, uint32_t mip, const uint16_t* rgba16f, const float* depth);
+int mvo_write_lightmap_slab(mvo_caster* c, uint32_t volume, uint32_t z0, uint32_t z1, const uint16_t* rgba16f_slab);
+int mvo_write_rows(mvo_caster* c, uint32_t what, uint32_t row0, uint32_t row1, const void* rows);
 
 /* stand-alone helpers used by the known-answer tests */
 void  mvo_sample_volume(mvo_caster* c, uint32_t src, const float uvw[3], float rgba_out[4]);

@@ -82,6 +82,7 @@ int mvo_create(const mvo_desc* d, mvo_caster** out)
     c.ambient = {0.0f, 0.3f, 1.0f, 0.4f};
     c.stats = mvo_stats();
     c.stats.threads = (uint32_t)omp_get_max_threads();
+    c.row0 = 0; c.row1 = c.d.height;
     const float center[3] = {0, 0, 0};
     set_volumes_world(c, 20.0f, center);
     *out = h;
@@ -132,7 +133,14 @@ int mvo_set_targets(mvo_caster* h, const float* depth, const uint16_t* shadow, u
     if (shadow && shadowSize) { c.shadowSize = shadowSize; c.shadow.assign(shadow, shadow + (size_t)shadowSize * shadowSize); }
     else { c.shadowSize = 0; c.shadow.clear(); }
     if (color) std::copy(color, color + px * 4, c.color.begin()); else c.color.assign(px * 4, 0);
+    c.background = c.color;
     if (velocity) std::copy(velocity, velocity + px * 2, c.velocity.begin()); else c.velocity.assign(px * 2, 0);
+    return 0;
+}
+int mvo_reset_color(mvo_caster* h)
+{
+    if (!h) return -1;
+    if (h->c.background.size() == h->c.color.size()) h->c.color = h->c.background; else std::fill(h->c.color.begin(), h->c.color.end(), 0);
     return 0;
 }
 int mvo_set_sh(mvo_caster* h, const float* k)
@@ -284,6 +292,45 @@ int mvo_read_post(mvo_caster* h, uint16_t* taa, uint8_t* rgba8)
 }
 int mvo_get_stats(mvo_caster* h, mvo_stats* out) { if (!h || !out) return -1; *out = h->c.stats; return 0; }
 int mvo_set_frame_index(mvo_caster* h, uint32_t f) { if (!h) return -1; h->c.frameIdx = f; h->c.cb.frameIdx = f; return 0; }
+
+int mvo_set_shard(mvo_caster* h, uint32_t rank, uint32_t world)
+{
+    if (!h || world == 0 || rank >= world) return -1;
+    h->c.shardRank = rank; h->c.shardWorld = world;
+    return 0;
+}
+int mvo_set_row_band(mvo_caster* h, uint32_t row0, uint32_t row1)
+{
+    if (!h || row0 > row1 || row1 > h->c.d.height) return -1;
+    h->c.row0 = row0; h->c.row1 = row1;
+    return 0;
+}
+int mvo_write_cubemap(mvo_caster* h, uint32_t v, uint32_t mip, const uint16_t* rgba, const float* depth)
+{
+    if (!h || !ok_vol(h->c, v) || mip >= kNumCubeMip) return -1;
+    CubeMap& cm = h->c.cubeMaps[v];
+    if (rgba) std::copy(rgba, rgba + cm.color[mip].size(), cm.color[mip].begin());
+    if (depth) std::copy(depth, depth + cm.depth[mip].size(), cm.depth[mip].begin());
+    return 0;
+}
+int mvo_write_lightmap_slab(mvo_caster* h, uint32_t v, uint32_t z0, uint32_t z1, const uint16_t* slab)
+{
+    if (!h || !slab || !ok_vol(h->c, v) || z0 > z1 || z1 > h->c.d.light_grid_size) return -1;
+    const size_t L = h->c.d.light_grid_size;
+    std::copy(slab, slab + (size_t)(z1 - z0) * L * L * 4, h->c.lightMaps[v].texels.begin() + (size_t)z0 * L * L * 4);
+    return 0;
+}
+int mvo_write_rows(mvo_caster* h, uint32_t what, uint32_t row0, uint32_t row1, const void* rows)
+{
+    if (!h || !rows || row0 > row1 || row1 > h->c.d.height) return -1;
+    Caster& c = h->c;
+    const size_t W = c.d.width, n = (size_t)(row1 - row0) * W;
+    if (what == 0) std::copy((const uint16_t*)rows, (const uint16_t*)rows + n * 4, c.color.begin() + (size_t)row0 * W * 4);
+    else if (what == 1) std::copy((const uint16_t*)rows, (const uint16_t*)rows + n * 4, c.taaHistory[c.frameParity].begin() + (size_t)row0 * W * 4);
+    else if (what == 2) std::copy((const uint8_t*)rows, (const uint8_t*)rows + n * 4, c.backBuffer.begin() + (size_t)row0 * W * 4);
+    else return -1;
+    return 0;
+}
 
 void mvo_sample_volume(mvo_caster* h, uint32_t src, const float uvw[3], float out[4])
 {

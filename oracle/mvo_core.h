@@ -61,6 +61,7 @@ struct Caster {
     std::vector<uint16_t> shadow;         // S*S, D16 unorm
     uint32_t shadowSize = 0;
     std::vector<uint16_t> color;          // W*H RGBA16F: in = background, out = composited frame
+    std::vector<uint16_t> background;     // the colour RT as given to set_targets (mvo_reset_color)
     std::vector<uint16_t> velocity;       // W*H RG16F
     std::vector<uint16_t> taaHistory[2];  // RGBA16F ping-pong
     std::vector<uint8_t> backBuffer;      // RGBA8
@@ -68,6 +69,10 @@ struct Caster {
     uint32_t frameIdx = 0;
     mvo_stats stats;
     int filterModel = MODEL_SM100;
+    // sharding (mirrors mv_set_shard / mv_set_row_band of the product): volume v is marched by rank v % world,
+    // the light map is filled in z-slabs of ceil(L / world), OIT and post-process cover rows [row0, row1)
+    uint32_t shardRank = 0, shardWorld = 1;
+    uint32_t row0 = 0, row1 = 0;
 };
 
 // passes (mvo_passes.cpp)

@@ -301,6 +301,7 @@ void ray_march_view(Caster& c)
 {
     uint64_t rays = 0, samples = 0, lightFetches = 0;
     for (uint32_t volumeId : c.cubeVolumes) {
+        if (volumeId % c.shardWorld != c.shardRank) continue;   // marched by its owner rank
         const uint16_t* a = &c.attribs[volumeId * 4];
         const uint32_t mip = a[0], smpCount = a[1], maskBits = a[2], volTexId = a[3];
         const PerObject& po = c.perObject[volumeId];
@@ -441,8 +442,10 @@ void ray_march_light(Caster& c, int volumeOverride)
     const float gStep = maxDist / (float)numSamples;     // RayMarch.hlsli:18
     Tex3D& lm = c.lightMaps[volumeId];
     uint64_t dense = 0, samples = 0;
+    const int slab = (L + (int)c.shardWorld - 1) / (int)c.shardWorld;
+    const int zBegin = std::min(L, (int)c.shardRank * slab), zEnd = std::min(L, zBegin + slab);
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : dense, samples)
-    for (int z = 0; z < L; ++z)
+    for (int z = zBegin; z < zEnd; ++z)
         for (int y = 0; y < L; ++y)
             for (int x = 0; x < L; ++x) {
                 f3 rayOrigin = {((float)x + 0.5f) / gridSize * 2.0f - 1.0f, ((float)y + 0.5f) / gridSize * 2.0f - 1.0f,
@@ -625,8 +628,10 @@ void resolve_oit(Caster& c)
     const size_t nvis = c.visible.size();
     std::vector<f3> eyeL(nvis);
     for (size_t k = 0; k < nvis; ++k) eyeL[k] = mul_p43(c.cb.eyePt, c.perObject[c.visible[k]].WorldI);
+    // rows [row0, row1) plus a one-row halo (clipped), read by the TAA of the band's border rows
+    const int rowBegin = c.row1 > c.row0 ? std::max((int)c.row0 - 1, 0) : 0, rowEnd = c.row1 > c.row0 ? std::min((int)c.row1 + 1, H) : 0;
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : frags, dRays, dSamples, dLight)
-    for (int py = 0; py < H; ++py)
+    for (int py = rowBegin; py < rowEnd; ++py)
         for (int px = 0; px < W; ++px) {
             // pixel-centre ray (RTCube.hlsl GenerateCameraRay: unproject z = 0 through screenToWorld)
             f2 xy = {((float)px + 0.5f) / c.cb.viewport.x, ((float)py + 0.5f) / c.cb.viewport.y};   // PSCube.hlsl:38-40
@@ -736,7 +741,7 @@ void temporal_aa(Caster& c, bool taaOn)
     c.frameParity ^= 1u;                                   // ObjectRenderer.cpp:217
     std::vector<uint16_t>& out = c.taaHistory[c.frameParity];
     const std::vector<uint16_t>& hist = c.taaHistory[c.frameParity ^ 1u];
-    if (!taaOn) { out = c.color; return; }
+    if (!taaOn) { std::copy(c.color.begin() + (size_t)c.row0 * W * 4, c.color.begin() + (size_t)c.row1 * W * 4, out.begin() + (size_t)c.row0 * W * 4); return; }
     auto loadC = [&](const std::vector<uint16_t>& img, int x, int y) -> f4 {   // Texture2D[] load: out of bounds -> 0
         if (x < 0 || y < 0 || x >= W || y >= H) return {0, 0, 0, 0};
         const uint16_t* p = &img[((size_t)y * W + x) * 4];
@@ -750,7 +755,7 @@ void temporal_aa(Caster& c, bool taaOn)
     static const int offs[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};   // :46-50
     const float historyMax = 15.0f;                                                                         // :41-43
 #pragma omp parallel for schedule(static)
-    for (int y = 0; y < H; ++y)
+    for (int y = (int)c.row0; y < (int)c.row1; ++y)
         for (int x = 0; x < W; ++x) {
             const f2 texSize = {(float)W, (float)H};
             const f2 uv = {((float)x + 0.5f) / texSize.x, ((float)y + 0.5f) / texSize.y};
@@ -845,8 +850,9 @@ void tone_map(Caster& c)
 {
     const int W = (int)c.d.width, H = (int)c.d.height;
     const std::vector<uint16_t>& src = c.taaHistory[c.frameParity];
+    (void)H;
 #pragma omp parallel for schedule(static)
-    for (int i = 0; i < W * H; ++i) {
+    for (int i = (int)c.row0 * W; i < (int)c.row1 * W; ++i) {
         float r[3];
         for (int k = 0; k < 3; ++k) {
             float v = f16_to_f32(src[(size_t)i * 4 + k]);

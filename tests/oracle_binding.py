@@ -16,6 +16,9 @@ _EXTRA = {
     "f32_to_f16": (C.c_uint16, [f32]),
     "f16_to_f32": (f32, [C.c_uint16]),
     "eval_sh_irradiance": (None, [_vp, P(f32), P(f32)]),
+    "write_cubemap": (C.c_int, [_vp, u32, u32, _vp, _vp]),
+    "write_lightmap_slab": (C.c_int, [_vp, u32, u32, u32, _vp]),
+    "write_rows": (C.c_int, [_vp, u32, u32, u32, _vp]),
 }
 _binding = None
 
