@@ -11,7 +11,8 @@ import numpy as np
 from ._abi import Binding, CasterBase, P, f32, u32, _vp
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libmv_b200.so")
+# MV_B200_LIB lets the tuning scripts under tools/ load an experimental build of the same library
+LIB_PATH = os.environ.get("MV_B200_LIB") or os.path.join(HERE, "libmv_b200.so")
 
 FLAG_COUNT_SAMPLES = 1
 FLAG_TIME_PASSES = 2

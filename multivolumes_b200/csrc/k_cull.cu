@@ -27,10 +27,11 @@ __constant__ unsigned char c_edgeLanes[12][2] = {{0, 1}, {3, 2}, {1, 3}, {2, 0},
 __constant__ unsigned char c_faceEdges[6][4] = {{8, 3, 9, 6}, {10, 2, 11, 7}, {0, 8, 5, 11},
                                                 {1, 10, 4, 9}, {0, 2, 1, 3}, {4, 6, 5, 7}};
 
-MV_D V3 project_to_viewport(uint32_t i, const float* wvp, float vw, float vh)   // VolumeCull.hlsli:27-41
+MV_D V3 project_to_viewport(uint32_t i, const float* wvp, float vw, float vh, float& w)   // VolumeCull.hlsli:27-41
 {
     const V3 p3 = {(i & 1) ? 1.0f : -1.0f, ((i >> 1) & 1) ? 1.0f : -1.0f, (i >> 2) ? 1.0f : -1.0f};
     V4 p = mul_p44(p3, wvp);
+    w = p.w;
     p.x /= p.w; p.y /= p.w; p.z /= p.w;
     p.x = p.x * 0.5f + 0.5f; p.y = p.y * 0.5f + 0.5f;
     p.y = 1.0f - p.y;
@@ -54,9 +55,10 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
 
         // CSVolumeCull.hlsl:29-38 — one corner per lane
         V3 v = {0.0f, 0.0f, 0.0f};
+        float clipW = 1.0f;
         bool isInView = false;
         if (valid) {
-            v = project_to_viewport(corner, po->wvp, cb.viewport[0], cb.viewport[1]);
+            v = project_to_viewport(corner, po->wvp, cb.viewport[0], cb.viewport[1], clipW);
             isInView = (v.x <= cb.viewport[0] && v.y <= cb.viewport[1] && v.x >= 0.0f && v.y >= 0.0f) && v.z > 0.0f && v.z < 1.0f;
         }
         const uint32_t volumeVis = (__ballot_sync(kFull, isInView) >> baseLane) & 0xffu;
@@ -132,6 +134,18 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
                                                (unsigned short)maskBits, (unsigned short)(volumeIn & 0x3fffu));
         }
 
+        // conservative screen rectangle of the projected box for the OIT resolve (not a reference output):
+        // min / max of the eight corners, two pixels of slack; any corner on or behind the eye plane
+        // (or a non-finite projection) makes it the whole screen
+        const bool badCorner = !(clipW > 0.0f) || !(fabsf(v.x) <= 3.0e8f) || !(fabsf(v.y) <= 3.0e8f);
+        const uint32_t badBits = (__ballot_sync(kFull, badCorner) >> baseLane) & 0xffu;
+        float bx0 = v.x, bx1 = v.x, by0 = v.y, by1 = v.y;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            bx0 = fminf(bx0, __shfl_xor_sync(kFull, bx0, d)); bx1 = fmaxf(bx1, __shfl_xor_sync(kFull, bx1, d));
+            by0 = fminf(by0, __shfl_xor_sync(kFull, by0, d)); by1 = fmaxf(by1, __shfl_xor_sync(kFull, by1, d));
+        }
+
         // ordered compaction: ballot inside the warp, prefix over the 32 warps through shared memory
         const uint32_t visBits = __ballot_sync(kFull, visible && corner == 0);
         const uint32_t cubeBits = __ballot_sync(kFull, useCubeMap);
@@ -140,7 +154,22 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
         uint32_t offVis = s_baseVis, offCube = s_baseCube;
         for (uint32_t w = 0; w < warp; ++w) { offVis += s_warpVis[w]; offCube += s_warpCube[w]; }
         const uint32_t below = (1u << lane) - 1u;
-        if (visible && corner == 0) s.visible[offVis + __popc(visBits & below)] = volumeId;
+        if (visible && corner == 0) {
+            const uint32_t slot = offVis + __popc(visBits & below);
+            s.visible[slot] = volumeId;
+            VisInfo vi;
+            const V3 eye = {cb.eye[0], cb.eye[1], cb.eye[2]};
+            const V3 e = mul_p43(eye, po->worldI);
+            vi.eyeL[0] = e.x; vi.eyeL[1] = e.y; vi.eyeL[2] = e.z;
+            vi.volumeId = volumeId;
+            const int W = (int)cb.width, H = (int)cb.height;
+            if (badBits) { vi.x0 = 0; vi.y0 = 0; vi.x1 = W - 1; vi.y1 = H - 1; }
+            else {
+                vi.x0 = max((int)floorf(bx0) - 2, 0); vi.y0 = max((int)floorf(by0) - 2, 0);
+                vi.x1 = min((int)ceilf(bx1) + 2, W - 1); vi.y1 = min((int)ceilf(by1) + 2, H - 1);
+            }
+            s.visInfo[slot] = vi;
+        }
         if (useCubeMap) s.cubeVolumes[offCube + __popc(cubeBits & below)] = volumeId;
         __syncthreads();
         if (threadIdx.x == 0) {

@@ -134,19 +134,25 @@ MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, ui
     return col;
 }
 
+constexpr int kOitChunk = 256;   // visible volumes binned per pass over the CTA's 16x16-pixel tile
+
 __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
 {
+    __shared__ VisInfo s_cand[kOitChunk];       // volumes whose screen rectangle overlaps this tile, list order kept
+    __shared__ uint32_t s_candSlot[kOitChunk];  // their index in the visible list
+    __shared__ uint32_t s_warpCount[8];
     const int W = (int)cb.width;
     // 16x16-pixel CTA made of 8 warps of 8x4 pixels
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int px = (int)(blockIdx.x * 16 + (warp & 1) * 8 + (lane & 7));
     // rows [row0, row1) plus a one-row halo on each side (clipped): the TAA's 3x3 neighbourhood of the
     // band's border rows reads them
     const int rowBegin = max((int)s.row0 - 1, 0), rowEnd = min((int)s.row1 + 1, (int)cb.height);
-    const int py = (int)(rowBegin + blockIdx.y * 16 + (warp >> 1) * 4 + (lane >> 3));
+    const int tileX0 = (int)blockIdx.x * 16, tileY0 = rowBegin + (int)blockIdx.y * 16;
+    const int px = tileX0 + (int)((warp & 1) * 8 + (lane & 7));
+    const int py = tileY0 + (int)((warp >> 1) * 4 + (lane >> 3));
     const bool valid = px < W && py < rowEnd;
 
-    const uint32_t nvis = valid ? s.lists->visibleCount : 0u;
+    const uint32_t nvis = s.lists->visibleCount;
     // pixel-centre ray: unproject z = 0 through screenToWorld (RTCube.hlsl:54-70; PSCube.hlsl:38-40)
     float sx = ((float)px + 0.5f) / cb.viewport[0], sy = ((float)py + 0.5f) / cb.viewport[1];
     sx = sx * 2.0f - 1.0f; sy = sy * 2.0f - 1.0f;
@@ -161,39 +167,60 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
 #pragma unroll
     for (int l = 0; l < (int)kNumOitLayers; ++l) { keys[l] = 0xffffffffu; ids[l] = 0xffffffffu; }
     uint32_t frags = 0;
-    for (uint32_t k = 0; k < nvis; ++k) {
-        const uint32_t volumeId = __ldg(s.visible + k);
-        const PerObject* po = s.perObject + volumeId;
-        const V3 o = mul_p43(eye, po->worldI);
-        const V3 d = mul_v33(dirW, po->worldI);
-        float tmin = -kFltMax, tmax = kFltMax; int exitAxis = -1; bool miss = false;
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const float da = comp(d, a), oa = comp(o, a);
-            if (da == 0.0f) { if (fabsf(oa) > 1.0f) miss = true; continue; }
-            const float t1 = (-1.0f - oa) / da, t2 = (1.0f - oa) / da;
-            const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
-            if (tn > tmin) tmin = tn;
-            if (tf < tmax) { tmax = tf; exitAxis = a; }
+    for (uint32_t base = 0; base < nvis; base += kOitChunk) {
+        // bin: which of the next kOitChunk visible volumes can touch this tile (ordered compaction)
+        const uint32_t k = base + threadIdx.x;
+        bool overlap = false;
+        VisInfo vi;
+        if (k < nvis) {
+            vi = s.visInfo[k];
+            overlap = vi.x0 <= tileX0 + 15 && vi.x1 >= tileX0 && vi.y0 <= tileY0 + 15 && vi.y1 >= tileY0;
         }
-        if (miss || exitAxis < 0 || !(tmax > 0.0f) || !(tmin < tmax)) continue;
-        V3 lpt = {clamp1(o.x + d.x * tmax), clamp1(o.y + d.y * tmax), clamp1(o.z + d.z * tmax)};
-        const float sgn = comp(d, exitAxis) > 0.0f ? 1.0f : -1.0f;
-        if (exitAxis == 0) lpt.x = sgn; else if (exitAxis == 1) lpt.y = sgn; else lpt.z = sgn;
-        const V4 clip = mul_p44(lpt, po->wvp);
-        if (!(clip.w > 0.0f)) continue;
-        const float z = clip.z / clip.w;
-        if (!(z >= 0.0f && z <= 1.0f)) continue;       // rasteriser depth clip
-        ++frags;
-        // insert (key, k) keeping ascending keys; equal keys keep list order
-        uint32_t key = as_uint(z), id = k | ((uint32_t)(exitAxis * 2 + (sgn > 0.0f ? 0 : 1)) << 24);
+        const uint32_t bits = __ballot_sync(0xffffffffu, overlap);
+        if (lane == 0) s_warpCount[warp] = __popc(bits);
+        __syncthreads();
+        uint32_t off = 0, total = 0;
 #pragma unroll
-        for (int l = 0; l < (int)kNumOitLayers; ++l) {
-            if (key < keys[l]) {
-                const uint32_t tk = keys[l], ti = ids[l];
-                keys[l] = key; ids[l] = id; key = tk; id = ti;
+        for (uint32_t w = 0; w < 8; ++w) { const uint32_t c = s_warpCount[w]; if (w < warp) off += c; total += c; }
+        if (overlap) { const uint32_t slot = off + __popc(bits & ((1u << lane) - 1u)); s_cand[slot] = vi; s_candSlot[slot] = k; }
+        __syncthreads();
+        if (valid) {
+            for (uint32_t ci = 0; ci < total; ++ci) {
+                const uint32_t volumeId = s_cand[ci].volumeId;
+                const PerObject* po = s.perObject + volumeId;
+                const V3 o = {s_cand[ci].eyeL[0], s_cand[ci].eyeL[1], s_cand[ci].eyeL[2]};   // mul(float4(g_eyePt, 1), WorldI)
+                const V3 d = mul_v33(dirW, po->worldI);
+                float tmin = -kFltMax, tmax = kFltMax; int exitAxis = -1; bool miss = false;
+#pragma unroll
+                for (int a = 0; a < 3; ++a) {
+                    const float da = comp(d, a), oa = comp(o, a);
+                    if (da == 0.0f) { if (fabsf(oa) > 1.0f) miss = true; continue; }
+                    const float t1 = (-1.0f - oa) / da, t2 = (1.0f - oa) / da;
+                    const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
+                    if (tn > tmin) tmin = tn;
+                    if (tf < tmax) { tmax = tf; exitAxis = a; }
+                }
+                if (miss || exitAxis < 0 || !(tmax > 0.0f) || !(tmin < tmax)) continue;
+                V3 lpt = {clamp1(o.x + d.x * tmax), clamp1(o.y + d.y * tmax), clamp1(o.z + d.z * tmax)};
+                const float sgn = comp(d, exitAxis) > 0.0f ? 1.0f : -1.0f;
+                if (exitAxis == 0) lpt.x = sgn; else if (exitAxis == 1) lpt.y = sgn; else lpt.z = sgn;
+                const V4 clip = mul_p44(lpt, po->wvp);
+                if (!(clip.w > 0.0f)) continue;
+                const float z = clip.z / clip.w;
+                if (!(z >= 0.0f && z <= 1.0f)) continue;       // rasteriser depth clip
+                ++frags;
+                // insert (key, visible-list index) keeping ascending keys; equal keys keep list order
+                uint32_t key = as_uint(z), id = s_candSlot[ci] | ((uint32_t)(exitAxis * 2 + (sgn > 0.0f ? 0 : 1)) << 24);
+#pragma unroll
+                for (int l = 0; l < (int)kNumOitLayers; ++l) {
+                    if (key < keys[l]) {
+                        const uint32_t tk = keys[l], ti = ids[l];
+                        keys[l] = key; ids[l] = id; key = tk; id = ti;
+                    }
+                }
             }
         }
+        __syncthreads();
     }
 
     // shade + resolve front to back (PSCube.hlsl:30-60, PSResolveOIT.hlsl:12-26)
@@ -211,7 +238,7 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
         const int face = (int)(id >> 24);
         const PerObject* po = s.perObject + volumeId;
         const ushort4 a = s.attribs[volumeId];
-        const V3 localEye = mul_p43(eye, po->worldI);
+        const V3 localEye = {__ldg(&s.visInfo[id & 0xffffffu].eyeL[0]), __ldg(&s.visInfo[id & 0xffffffu].eyeL[1]), __ldg(&s.visInfo[id & 0xffffffu].eyeL[2])};
         // the fragment's local-space position: exit point of the pixel ray on the back face
         const V3 d = mul_v33(dirW, po->worldI);
         const int axis = face >> 1;

@@ -67,110 +67,132 @@ MV_D V2 load_v(const uint32_t* img, int x, int y, int W, int H)
     return {f16_to_f32((uint16_t)(p & 0xffffu)), f16_to_f32((uint16_t)(p >> 16))};
 }
 
-__global__ void __launch_bounds__(256) k_postprocess(PostArgs a)
+constexpr int kPostW = 32, kPostH = 8;                    // pixels per CTA: a warp is 32 pixels of one row
+constexpr int kTileW = kPostW + 2, kTileH = kPostH + 2;   // + one-pixel halo for the 3x3 neighbourhood
+
+// The tone-mapped YCoCg colour TM(c) of every pixel is needed by its eight neighbours as well
+// (NeighborMinMax); it is computed once per pixel into a shared-memory tile (3 IEEE divides each)
+// instead of nine times, with the same expressions, so the result is unchanged.
+__global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
 {
+    __shared__ float4 s_tm[kTileH][kTileW];   // xyz = TM(colour), w = colour alpha
     const int W = a.W, H = a.H;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // a warp covers 32 consecutive pixels of one row (coalesced 256-B rows of RGBA16F); 8 rows per CTA
-    const int x = (int)(blockIdx.x * 32 + lane);
-    const int y = a.row0 + (int)(blockIdx.y * 8 + warp);
-    if (x >= W || y >= a.row1) return;
+    const int tx = (int)threadIdx.x & 31, ty = (int)threadIdx.x >> 5;
+    const int x0 = (int)blockIdx.x * kPostW, y0 = a.row0 + (int)blockIdx.y * kPostH;
+    const int x = x0 + tx, y = y0 + ty;
+    const bool valid = x < W && y < a.row1;
+
+    if (!a.taaOn) {
+        if (valid) {
+            const size_t pix = (size_t)y * W + x;
+            const uint2 t = __ldg(a.color + pix);
+            a.out[pix] = t;
+            const uchar4 bb = tone_map(t);
+            a.backBuffer[pix] = bb;
+            if (a.peerBackBuffer) a.peerBackBuffer[pix] = bb;
+        }
+        return;
+    }
+
+    for (int i = (int)threadIdx.x; i < kTileW * kTileH; i += kPostW * kPostH) {
+        const int lx = i % kTileW, ly = i / kTileW;
+        const V4 c = load_c(a.color, x0 + lx - 1, y0 + ly - 1, W, H);
+        const V3 t = TM(V3{c.x, c.y, c.z});
+        s_tm[ly][lx] = make_float4(t.x, t.y, t.z, c.w);
+    }
+    __syncthreads();
+    if (!valid) return;
     const size_t pix = (size_t)y * W + x;
 
-    uint2 outTexel;
-    if (!a.taaOn) outTexel = __ldg(a.color + pix);
-    else {
-        const int offs[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};   // :46-50
-        const float historyMax = 15.0f;                                                                   // :41-43
-        const V2 texSize = {(float)W, (float)H};
-        const V2 uv = {((float)x + 0.5f) / texSize.x, ((float)y + 0.5f) / texSize.y};
-        const V4 current = load_c(a.color, x, y, W, H);
-        // VelocityMax :133-161
-        V2 vmax = load_v(a.velocity, x, y, W, H);
-        float speedSq = dot(vmax, vmax);
+    const int offs[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};   // :46-50
+    const float historyMax = 15.0f;                                                                   // :41-43
+    const V2 texSize = {(float)W, (float)H};
+    const V2 uv = {((float)x + 0.5f) / texSize.x, ((float)y + 0.5f) / texSize.y};
+    const float4 own = s_tm[ty + 1][tx + 1];
+    // VelocityMax :133-161
+    V2 vmax = load_v(a.velocity, x, y, W, H);
+    float speedSq = dot(vmax, vmax);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const V2 nb = load_v(a.velocity, x + offs[i + 4][0], y + offs[i + 4][1], W, H);
-            const float sq = dot(nb, nb);
-            if (sq > speedSq) { vmax = nb; speedSq = sq; }
-        }
-        const V2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
-        // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp, fp32 weights
-        V4 history;
-        {
-            const float fx = uvBack.x * texSize.x - 0.5f, fy = uvBack.y * texSize.y - 0.5f;
-            const float flx = floorf(fx), fly = floorf(fy);
-            const float wx = fx - flx, wy = fy - fly;
-            const int ix = (int)flx, iy = (int)fly;
-            const int x0 = min(max(ix, 0), W - 1), x1 = min(max(ix + 1, 0), W - 1);
-            const int y0 = min(max(iy, 0), H - 1), y1 = min(max(iy + 1, 0), H - 1);
-            const V4 t00 = load_c(a.history, x0, y0, W, H), t10 = load_c(a.history, x1, y0, W, H);
-            const V4 t01 = load_c(a.history, x0, y1, W, H), t11 = load_c(a.history, x1, y1, W, H);
-            history = {lerp(lerp(t00.x, t10.x, wx), lerp(t01.x, t11.x, wx), wy), lerp(lerp(t00.y, t10.y, wx), lerp(t01.y, t11.y, wx), wy),
-                       lerp(lerp(t00.z, t10.z, wx), lerp(t01.z, t11.z, wx), wy), lerp(lerp(t00.w, t10.w, wx), lerp(t01.w, t11.w, wx), wy)};
-        }
-        // :267-275
-        const V2 historyBlurAmp = {4.0f * texSize.x, 4.0f * texSize.y};
-        const V2 historyBlurs = {fabsf(vmax.x) * historyBlurAmp.x, fabsf(vmax.y) * historyBlurAmp.y};
-        float curHistoryBlur = historyBlurs.x + historyBlurs.y;
-        float historyBlur = 1.0f - history.w;
-        historyBlur = fmaxf(historyBlur, curHistoryBlur);
-        history.w = history.w * historyMax + 1.0f;
-        // :278-287 (ALPHA_BOUND = 1.0)
-        const V3 ctm = TM(V3{current.x, current.y, current.z});
-        const V4 currentTM = {ctm.x, ctm.y, ctm.z, current.w};
-        const float gamma = (historyBlur > 0.0f || current.w < 1.0f) ? 1.0f : 16.0f;
-        // NeighborMinMax :166-236
-        V4 cur = currentTM;
-        V3 mu = {cur.x, cur.y, cur.z};
-        cur.w = cur.w < 1.0f ? 0.0f : 1.0f;
-        V3 m2 = mu * mu;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float wgt = i < 4 ? 0.5f : 0.25f;
-            const V4 nbr = load_c(a.color, x + offs[i][0], y + offs[i][1], W, H);
-            const V3 ntm = TM(V3{nbr.x, nbr.y, nbr.z});
-            const V4 neighbor = {ntm.x, ntm.y, ntm.z, nbr.w < 1.0f ? 0.0f : 1.0f};
-            cur = cur + neighbor * wgt;
-            mu = mu + ntm;
-            m2 = m2 + ntm * ntm;
-        }
-        cur = {cur.x / 4.0f, cur.y / 4.0f, cur.z / 4.0f, cur.w / 4.0f};
-        mu = mu / 9.0f;
-        const V3 m2n = m2 / 9.0f;
-        const V3 sigma = {sqrtf(fabsf(m2n.x - mu.x * mu.x)), sqrtf(fabsf(m2n.y - mu.y * mu.y)), sqrtf(fabsf(m2n.z - mu.z * mu.z))};
-        const V3 gsigma = sigma * gamma;
-        V4 nmin, nmax;
-        nmin.x = fminf(mu.x - gsigma.x, cur.x); nmin.y = fminf(mu.y - gsigma.y, cur.y); nmin.z = fminf(mu.z - gsigma.z, cur.z);
-        nmax.x = fmaxf(mu.x + gsigma.x, cur.x); nmax.y = fmaxf(mu.y + gsigma.y, cur.y); nmax.z = fmaxf(mu.z + gsigma.z, cur.z);
-        nmin.w = mu.x - sigma.x;   // GET_LUMA4 = .x in YCoCg
-        nmax.w = mu.x + sigma.x;
-        V4 filtered = cur;
-        // :290-301
-        curHistoryBlur = saturate(curHistoryBlur);
-        historyBlur = saturate(historyBlur);
-        V3 historyTM = TM(V3{history.x, history.y, history.z});
-        historyTM = {fminf(fmaxf(historyTM.x, nmin.x), nmax.x), fminf(fmaxf(historyTM.y, nmin.y), nmax.y), fminf(fmaxf(historyTM.z, nmin.z), nmax.z)};
-        const float contrast = nmax.w - nmin.w;
-        // :304-311
-        const float lumContrastFactor = 32.0f * 4.0f;
-        float addAlias = historyBlur * 0.5f + 0.25f;
-        addAlias = saturate(addAlias + 1.0f / (1.0f + contrast * lumContrastFactor));
-        filtered.x = lerp(filtered.x, currentTM.x, addAlias); filtered.y = lerp(filtered.y, currentTM.y, addAlias);
-        filtered.z = lerp(filtered.z, currentTM.z, addAlias);
-        // :314-326
-        const float lumHist = historyTM.x;
-        const float distToClamp = fminf(fabsf(nmin.w - lumHist), fabsf(nmax.w - lumHist));
-        const float historyAmt = fminf(1.0f / history.w + historyBlur / 8.0f, 1.0f);
-        float blend = 0.25f / lerp(8.0f, distToClamp + contrast, historyAmt);
-        blend = fminf(blend, 0.25f);
-        blend = filtered.w > 0.0f ? blend : 1.0f;
-        // :328-330
-        V3 result = ITM(V3{lerp(historyTM.x, filtered.x, blend), lerp(historyTM.y, filtered.y, blend), lerp(historyTM.z, filtered.z, blend)});
-        if (result.x != result.x || result.y != result.y || result.z != result.z) result = ITM(V3{filtered.x, filtered.y, filtered.z});
-        history.w = fminf(history.w / historyMax, 1.0f - curHistoryBlur);
-        outTexel = pack_half4(V4{result.x, result.y, result.z, history.w});
+    for (int i = 0; i < 4; ++i) {
+        const V2 nb = load_v(a.velocity, x + offs[i + 4][0], y + offs[i + 4][1], W, H);
+        const float sq = dot(nb, nb);
+        if (sq > speedSq) { vmax = nb; speedSq = sq; }
     }
+    const V2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
+    // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp, fp32 weights
+    V4 history;
+    {
+        const float fx = uvBack.x * texSize.x - 0.5f, fy = uvBack.y * texSize.y - 0.5f;
+        const float flx = floorf(fx), fly = floorf(fy);
+        const float wx = fx - flx, wy = fy - fly;
+        const int ix = (int)flx, iy = (int)fly;
+        const int xa = min(max(ix, 0), W - 1), xb = min(max(ix + 1, 0), W - 1);
+        const int ya = min(max(iy, 0), H - 1), yb = min(max(iy + 1, 0), H - 1);
+        const V4 t00 = load_c(a.history, xa, ya, W, H), t10 = load_c(a.history, xb, ya, W, H);
+        const V4 t01 = load_c(a.history, xa, yb, W, H), t11 = load_c(a.history, xb, yb, W, H);
+        history = {lerp(lerp(t00.x, t10.x, wx), lerp(t01.x, t11.x, wx), wy), lerp(lerp(t00.y, t10.y, wx), lerp(t01.y, t11.y, wx), wy),
+                   lerp(lerp(t00.z, t10.z, wx), lerp(t01.z, t11.z, wx), wy), lerp(lerp(t00.w, t10.w, wx), lerp(t01.w, t11.w, wx), wy)};
+    }
+    // :267-275
+    const V2 historyBlurAmp = {4.0f * texSize.x, 4.0f * texSize.y};
+    const V2 historyBlurs = {fabsf(vmax.x) * historyBlurAmp.x, fabsf(vmax.y) * historyBlurAmp.y};
+    float curHistoryBlur = historyBlurs.x + historyBlurs.y;
+    float historyBlur = 1.0f - history.w;
+    historyBlur = fmaxf(historyBlur, curHistoryBlur);
+    history.w = history.w * historyMax + 1.0f;
+    // :278-287 (ALPHA_BOUND = 1.0)
+    const V4 currentTM = {own.x, own.y, own.z, own.w};
+    const float gamma = (historyBlur > 0.0f || own.w < 1.0f) ? 1.0f : 16.0f;
+    // NeighborMinMax :166-236
+    V4 cur = currentTM;
+    V3 mu = {cur.x, cur.y, cur.z};
+    cur.w = cur.w < 1.0f ? 0.0f : 1.0f;
+    V3 m2 = mu * mu;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float wgt = i < 4 ? 0.5f : 0.25f;
+        const float4 nb = s_tm[ty + 1 + offs[i][1]][tx + 1 + offs[i][0]];
+        const V3 ntm = {nb.x, nb.y, nb.z};
+        const V4 neighbor = {ntm.x, ntm.y, ntm.z, nb.w < 1.0f ? 0.0f : 1.0f};
+        cur = cur + neighbor * wgt;
+        mu = mu + ntm;
+        m2 = m2 + ntm * ntm;
+    }
+    cur = {cur.x / 4.0f, cur.y / 4.0f, cur.z / 4.0f, cur.w / 4.0f};
+    mu = mu / 9.0f;
+    const V3 m2n = m2 / 9.0f;
+    const V3 sigma = {sqrtf(fabsf(m2n.x - mu.x * mu.x)), sqrtf(fabsf(m2n.y - mu.y * mu.y)), sqrtf(fabsf(m2n.z - mu.z * mu.z))};
+    const V3 gsigma = sigma * gamma;
+    V4 nmin, nmax;
+    nmin.x = fminf(mu.x - gsigma.x, cur.x); nmin.y = fminf(mu.y - gsigma.y, cur.y); nmin.z = fminf(mu.z - gsigma.z, cur.z);
+    nmax.x = fmaxf(mu.x + gsigma.x, cur.x); nmax.y = fmaxf(mu.y + gsigma.y, cur.y); nmax.z = fmaxf(mu.z + gsigma.z, cur.z);
+    nmin.w = mu.x - sigma.x;   // GET_LUMA4 = .x in YCoCg
+    nmax.w = mu.x + sigma.x;
+    V4 filtered = cur;
+    // :290-301
+    curHistoryBlur = saturate(curHistoryBlur);
+    historyBlur = saturate(historyBlur);
+    V3 historyTM = TM(V3{history.x, history.y, history.z});
+    historyTM = {fminf(fmaxf(historyTM.x, nmin.x), nmax.x), fminf(fmaxf(historyTM.y, nmin.y), nmax.y), fminf(fmaxf(historyTM.z, nmin.z), nmax.z)};
+    const float contrast = nmax.w - nmin.w;
+    // :304-311
+    const float lumContrastFactor = 32.0f * 4.0f;
+    float addAlias = historyBlur * 0.5f + 0.25f;
+    addAlias = saturate(addAlias + 1.0f / (1.0f + contrast * lumContrastFactor));
+    filtered.x = lerp(filtered.x, currentTM.x, addAlias); filtered.y = lerp(filtered.y, currentTM.y, addAlias);
+    filtered.z = lerp(filtered.z, currentTM.z, addAlias);
+    // :314-326
+    const float lumHist = historyTM.x;
+    const float distToClamp = fminf(fabsf(nmin.w - lumHist), fabsf(nmax.w - lumHist));
+    const float historyAmt = fminf(1.0f / history.w + historyBlur / 8.0f, 1.0f);
+    float blend = 0.25f / lerp(8.0f, distToClamp + contrast, historyAmt);
+    blend = fminf(blend, 0.25f);
+    blend = filtered.w > 0.0f ? blend : 1.0f;
+    // :328-330
+    V3 result = ITM(V3{lerp(historyTM.x, filtered.x, blend), lerp(historyTM.y, filtered.y, blend), lerp(historyTM.z, filtered.z, blend)});
+    if (result.x != result.x || result.y != result.y || result.z != result.z) result = ITM(V3{filtered.x, filtered.y, filtered.z});
+    history.w = fminf(history.w / historyMax, 1.0f - curHistoryBlur);
+    const uint2 outTexel = pack_half4(V4{result.x, result.y, result.z, history.w});
     a.out[pix] = outTexel;
     const uchar4 bb = tone_map(outTexel);
     a.backBuffer[pix] = bb;
@@ -194,8 +216,8 @@ void launch_postprocess(Caster& c, bool taaOn)
     a.taaOn = taaOn ? 1 : 0;
     const uint32_t rows = c.row1 - c.row0;
     if (rows == 0) return;
-    dim3 grid((c.d.width + 31) / 32, (rows + 7) / 8);
-    k_postprocess<<<grid, 256, 0, c.stream>>>(a);
+    dim3 grid((c.d.width + kPostW - 1) / kPostW, (rows + kPostH - 1) / kPostH);
+    k_postprocess<<<grid, kPostW * kPostH, 0, c.stream>>>(a);
 }
 
 } // namespace mv

@@ -18,6 +18,9 @@ namespace mv {
 
 namespace {
 
+#ifndef MV_MARCH_MIN_BLOCKS
+#define MV_MARCH_MIN_BLOCKS 4
+#endif
 constexpr int kMarchThreads = 256;
 constexpr int kMarchWarps = kMarchThreads / 32;
 constexpr uint32_t kFull = 0xffffffffu;
@@ -50,7 +53,7 @@ MV_D uint32_t nth_set_bit(uint32_t mask, uint32_t n)
     return __ffs(mask) - 1;
 }
 
-__global__ void __launch_bounds__(kMarchThreads) k_ray_march_v(DeviceScene s, FrameCB cb)
+__global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_march_v(DeviceScene s, FrameCB cb)
 {
     __shared__ TileConst s_tc[kMarchWarps];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;

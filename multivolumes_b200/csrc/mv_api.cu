@@ -49,6 +49,7 @@ DeviceScene Caster::scene() const
     s.visible = tail;
     s.cubeVolumes = tail + N;
     s.cubeTilePrefix = tail + 2 * N;
+    s.visInfo = reinterpret_cast<VisInfo*>(dLists + ((sizeof(FrameLists) + (3 * (size_t)N + 1) * sizeof(uint32_t) + 31) & ~(size_t)31));
     s.volumeTex = dVolumeTex;
     s.lightTex = dLightTex;
     s.lightSurf = dLightSurf;
@@ -309,7 +310,7 @@ int mv_create(const mv_desc* d, mv_caster** out)
     MV_CUDA_C(cudaMemcpy(c.dVolumeDescs, descs.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
     MV_CUDA_C(cudaMalloc(&c.dAttribs, N * sizeof(ushort4)));
     MV_CUDA_C(cudaMemsetAsync(c.dAttribs, 0, N * sizeof(ushort4), c.stream));
-    const size_t listBytes = sizeof(FrameLists) + (3 * (size_t)N + 1) * sizeof(uint32_t);
+    const size_t listBytes = ((sizeof(FrameLists) + (3 * (size_t)N + 1) * sizeof(uint32_t) + 31) & ~(size_t)31) + (size_t)N * sizeof(VisInfo);
     MV_CUDA_C(cudaMalloc(&c.dLists, listBytes));
     MV_CUDA_C(cudaMemsetAsync(c.dLists, 0, listBytes, c.stream));
     MV_CUDA_C(cudaMalloc(&c.dStats, sizeof(StatsDev)));

@@ -51,6 +51,14 @@ struct FrameLists {
     // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1]
 };
 
+// Per visible volume (same order as the visible list), written by the cull for the OIT resolve: the
+// eye in the volume's local space and a conservative screen rectangle of its projected box.
+struct VisInfo {
+    float eyeL[3];
+    uint32_t volumeId;
+    int x0, y0, x1, y1;   // inclusive pixel bounds; full screen when a corner is behind the eye plane
+};
+
 struct StatsDev {
     unsigned long long view_rays, view_samples, view_light_fetches;
     unsigned long long light_voxels, light_dense_voxels, light_samples;
@@ -89,6 +97,7 @@ struct DeviceScene {
     uint32_t* visible;                   // [N]
     uint32_t* cubeVolumes;               // [N]
     uint32_t* cubeTilePrefix;            // [N + 1]
+    VisInfo* visInfo;                    // [N]
     const cudaTextureObject_t* volumeTex;   // [srcs]
     const cudaTextureObject_t* lightTex;    // [N]
     const cudaSurfaceObject_t* lightSurf;   // [N]

@@ -315,8 +315,9 @@ def test_full_size_sharded_march_equals_unsharded():
     for r in range(world):
         s = _product(**kw)
         configure(s, sh=True, background=checker_background(960, 540))
+        s.Cull(); s.RayMarchL(-1)         # whole light map (the slab exchange is covered by the multi-rank tests)
         s.SetShard(r, world)
-        s.Cull(); s.RayMarchL(-1); s.RayMarchV()
+        s.Cull(); s.RayMarchV()
         shards.append(s)
     for v in cubes:
         mip = int(att[v][0])
