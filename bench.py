@@ -31,6 +31,9 @@ WORKLOADS = {
     "cfg4": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, note="BASELINE.json configs[3]"),
     "tiny": dict(n=4, g=32, l=16, w=320, h=180, sh=True, taa=True, note="CI-sized"),
 }
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_ray_march_v from the committed ncu --set full capture
+# (profiles/r01_march_v_ncu_raw.csv); only known for the workload that was profiled
+NCU_TRAFFIC_BYTES = {"cfg2": 177.6e6 + 11.5e6}
 TEX_PEAK_GFETCH = 575.9   # measured on this pool's B200: profiles/r01_tex_probe.json (trilinear RGBA16F fetches/s, L1-resident)
 
 
@@ -198,7 +201,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = peaks()
 
-    c = MultiRayCaster(device=local_rank, count_samples=True, time_passes=True, grid_size=wl["g"], light_grid_size=wl["l"],
+    c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, grid_size=wl["g"], light_grid_size=wl["l"],
                        num_volumes=wl["n"], width=wl["w"], height=wl["h"])
     stream = torch.cuda.Stream()
     c.SetStream(stream.cuda_stream)      # order the caster's kernels with torch's events / NCCL on one stream
@@ -243,6 +246,7 @@ def main():
 
         # ---- per-pass device time and sample counts: a second, instrumented pass over the same frames ----
         n_prof = min(args.steps, 50)
+        c.SetInstrumentation(True, True)
         for i in range(n_prof):
             frame(args.warmup + i)
             t = c.GetTimings()            # CUDA events recorded on the caster's stream around every pass
@@ -252,6 +256,7 @@ def main():
             for k, v in st.items():
                 stats_acc[k] = stats_acc.get(k, 0) + v
         barrier()
+        c.SetInstrumentation(False, False)
         per_pass = {k: v / n_prof for k, v in acc.items()}
         samples_frame = (stats_acc["view_samples"] + stats_acc["direct_samples"] + stats_acc["light_samples"]) / n_prof
         if world > 1:   # whole-job samples: sum over ranks
@@ -300,7 +305,7 @@ def main():
                 "clocks": clocks,
                 "per_pass_ms": per_pass,
                 "roofline": {"kernel": "k_ray_march_v", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                             "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": view_ms,
                              "tex": {"achieved": fetches, "peak": TEX_PEAK_GFETCH, "unit": "Gfetch/s", "frac": fetches / TEX_PEAK_GFETCH,
                                      "peak_source": "profiles/r01_tex_probe.json"}}}

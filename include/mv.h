@@ -130,6 +130,7 @@ int mv_read_post(mv_caster* c, uint16_t* taa_rgba16f, uint8_t* rgba8);
 int mv_get_stats(mv_caster* c, mv_stats* out);
 int mv_get_timings(mv_caster* c, mv_timings* out);
 int mv_set_frame_index(mv_caster* c, uint32_t frame_idx);
+int mv_set_flags(mv_caster* c, uint32_t flags);            /* MV_FLAG_*: switch the instrumentation on or off between frames */
 int mv_sync(mv_caster* c);
 
 /* pinned host memory for the read-backs / uploads of a frame loop */

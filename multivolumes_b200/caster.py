@@ -38,6 +38,7 @@ _EXTRA = {
     "set_targets_device": (C.c_int, [_vp, _vp, _vp, u32, _vp, _vp]),
     "get_timings": (C.c_int, [_vp, P(Timings)]),
     "sync": (C.c_int, [_vp]),
+    "set_flags": (C.c_int, [_vp, u32]),
     "host_alloc": (_vp, [C.c_size_t]),
     "host_free": (None, [_vp]),
     "exchange_block": (C.c_int, [_vp, P(_vp), u64p]),
@@ -106,6 +107,9 @@ class MultiRayCaster(CasterBase):
     def SetRenderTargetsDevice(self, depth=0, shadow=0, shadow_size=0, color=0, velocity=0):
         self._ck(self.b.set_targets_device(self.h, depth or None, shadow or None, shadow_size, color or None, velocity or None),
                  "set_targets_device")
+
+    def SetInstrumentation(self, count_samples, time_passes):
+        self._ck(self.b.set_flags(self.h, (FLAG_COUNT_SAMPLES if count_samples else 0) | (FLAG_TIME_PASSES if time_passes else 0)), "set_flags")
 
     def Sync(self):
         self._ck(self.b.sync(self.h), "sync")

@@ -18,8 +18,11 @@ namespace mv {
 
 namespace {
 
+// 5 CTAs x 256 threads / SM = 40 resident warps (<= 51 registers): the loop is latency-bound on a
+// dependent texture round trip per step, measured T = 0.088 ms + 5.55 ms / warps-per-SM on cfg 2 up to
+// 32 warps, flattening beyond 40; 6 CTAs (40 registers) spills and is no faster (profiles/r01_notes.md)
 #ifndef MV_MARCH_MIN_BLOCKS
-#define MV_MARCH_MIN_BLOCKS 4
+#define MV_MARCH_MIN_BLOCKS 5
 #endif
 constexpr int kMarchThreads = 256;
 constexpr int kMarchWarps = kMarchThreads / 32;
@@ -53,6 +56,7 @@ MV_D uint32_t nth_set_bit(uint32_t mask, uint32_t n)
     return __ffs(mask) - 1;
 }
 
+template <bool kStats>
 __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_march_v(DeviceScene s, FrameCB cb)
 {
     __shared__ TileConst s_tc[kMarchWarps];
@@ -139,12 +143,12 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
                         *reinterpret_cast<float*>(pb + dOfs) = z;
                     }
                 }
-                ++nRays; nSamples += mc.samples; nLight += mc.lightFetches;
+                if (kStats) { ++nRays; nSamples += mc.samples; nLight += mc.lightFetches; }
             }
         }
     }
 
-    if (s.stats) {
+    if (kStats) {
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
             nRays += __shfl_xor_sync(kFull, nRays, d);
@@ -163,10 +167,13 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
 
 void launch_ray_march_view(Caster& c)
 {
+    const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0;
     int perSM = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_v, kMarchThreads, 0);
+    if (stats) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_v<true>, kMarchThreads, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_v<false>, kMarchThreads, 0);
     if (perSM < 1) perSM = 1;
-    k_ray_march_v<<<c.smCount * perSM, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
+    if (stats) k_ray_march_v<true><<<c.smCount * perSM, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
+    else k_ray_march_v<false><<<c.smCount * perSM, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
 }
 
 } // namespace mv

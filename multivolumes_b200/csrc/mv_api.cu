@@ -779,6 +779,15 @@ int mv_set_frame_index(mv_caster* h, uint32_t f)
     return MV_OK;
 }
 
+int mv_set_flags(mv_caster* h, uint32_t flags)
+{
+    MV_ENTER(h);
+    MV_REQUIRE((flags & ~(MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES)) == 0);
+    c.d.flags = flags;
+    for (auto& v : c.evValid) v = false;
+    return MV_OK;
+}
+
 int mv_sync(mv_caster* h)
 {
     MV_ENTER(h);
