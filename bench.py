@@ -303,7 +303,7 @@ def main():
                         "steps": n_e2e, "checksum": checksum},
                 "gpu_launches": args.steps * (5 if world == 1 else (10 if args.exchange == "fused" else 6)),
                 "clocks": clocks,
-                "per_pass_ms": per_pass,
+                "per_pass_ms": per_pass, "per_pass_note": "rank 0, instrumented pass (CUDA events around each pass; at N > 1 the light and view marches include their peer barriers)",
                 "roofline": {"kernel": "k_ray_march_v", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": view_ms,

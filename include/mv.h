@@ -162,6 +162,9 @@ typedef struct mv_exchange_layout {
 
 int mv_set_shard(mv_caster* c, uint32_t rank, uint32_t world);
 int mv_set_row_band(mv_caster* c, uint32_t row0, uint32_t row1);     /* rows this rank resolves and post-processes */
+/* interleaved alternative to a contiguous band (better balance when the expensive pixels cluster): with
+ * stripe_height > 0 and world > 1 the rank owns the rows r with (r / stripe_height) % world == rank; 0 = band */
+int mv_set_row_stripes(mv_caster* c, uint32_t stripe_height);
 int mv_exchange_block(mv_caster* c, void** dev_ptr, uint64_t* bytes);
 int mv_exchange_layout_get(mv_caster* c, mv_exchange_layout* out);
 /* byte offsets (from the block base) of volume `volume`'s cube map at `mip`: [face][y][x] colour, then depth */

@@ -41,6 +41,7 @@ _EXTRA = {
     "set_flags": (C.c_int, [_vp, u32]),
     "host_alloc": (_vp, [C.c_size_t]),
     "host_free": (None, [_vp]),
+    "set_row_stripes": (C.c_int, [_vp, u32]),
     "exchange_block": (C.c_int, [_vp, P(_vp), u64p]),
     "exchange_layout_get": (C.c_int, [_vp, P(ExchangeLayout)]),
     "cube_region": (C.c_int, [_vp, u32, u32, u64p, u64p, u64p, u64p]),
@@ -124,6 +125,9 @@ class MultiRayCaster(CasterBase):
         self._ck(self.b.read_post(self.h, taa_ptr, rgba8_ptr), "read_post")
 
     # --- multi-GPU ---
+    def SetRowStripes(self, stripe_height):
+        self._ck(self.b.set_row_stripes(self.h, stripe_height), "set_row_stripes")
+
     def ExchangeBlock(self):
         p, n = _vp(), C.c_uint64()
         self._ck(self.b.exchange_block(self.h, C.byref(p), C.byref(n)), "exchange_block")

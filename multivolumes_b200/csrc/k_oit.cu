@@ -146,8 +146,15 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // rows [row0, row1) plus a one-row halo on each side (clipped): the TAA's 3x3 neighbourhood of the
     // band's border rows reads them
-    const int rowBegin = max((int)s.row0 - 1, 0), rowEnd = min((int)s.row1 + 1, (int)cb.height);
-    const int tileX0 = (int)blockIdx.x * 16, tileY0 = rowBegin + (int)blockIdx.y * 16;
+    int rowBegin, rowEnd, tileRow = (int)blockIdx.y;
+    if (s.stripeH) {   // this rank's k-th stripe, + halo
+        const int tilesPerStripe = ((int)s.stripeH + 2 + 15) / 16;
+        const int k = tileRow / tilesPerStripe;
+        tileRow -= k * tilesPerStripe;
+        const int r0 = (k * (int)s.shardWorld + (int)s.shardRank) * (int)s.stripeH;
+        rowBegin = max(r0 - 1, 0); rowEnd = min(r0 + (int)s.stripeH + 1, (int)cb.height);
+    } else { rowBegin = max((int)s.row0 - 1, 0); rowEnd = min((int)s.row1 + 1, (int)cb.height); }
+    const int tileX0 = (int)blockIdx.x * 16, tileY0 = rowBegin + tileRow * 16;
     const int px = tileX0 + (int)((warp & 1) * 8 + (lane & 7));
     const int py = tileY0 + (int)((warp >> 1) * 4 + (lane >> 3));
     const bool valid = px < W && py < rowEnd;
@@ -298,10 +305,15 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
 
 void launch_resolve_oit(Caster& c)
 {
-    if (c.row1 <= c.row0) return;
-    const uint32_t rowBegin = c.row0 > 0 ? c.row0 - 1 : 0, rowEnd = min(c.row1 + 1, c.d.height);
-    const uint32_t rows = rowEnd - rowBegin;
-    dim3 grid((c.d.width + 15) / 16, (rows + 15) / 16);
+    uint32_t tileRows;
+    if (c.shardWorld > 1 && c.stripeH) tileRows = num_own_stripes(c.d.height, c.stripeH, c.shardRank, c.shardWorld) * ((c.stripeH + 2 + 15) / 16);
+    else {
+        if (c.row1 <= c.row0) return;
+        const uint32_t rowBegin = c.row0 > 0 ? c.row0 - 1 : 0, rowEnd = min(c.row1 + 1, c.d.height);
+        tileRows = (rowEnd - rowBegin + 15) / 16;
+    }
+    if (tileRows == 0) return;
+    dim3 grid((c.d.width + 15) / 16, tileRows);
     k_resolve_oit<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb);
 }
 

@@ -52,6 +52,7 @@ struct PostArgs {
     uchar4* backBuffer;       // RGBA8
     uchar4* peerBackBuffer;   // rank 0's back buffer when this rank resolves a band of a multi-GPU frame
     int W, H, row0, row1;
+    int stripeH, rank, world;   // stripeH > 0: interleaved stripes instead of the band
     int taaOn;
 };
 
@@ -78,9 +79,16 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
     __shared__ float4 s_tm[kTileH][kTileW];   // xyz = TM(colour), w = colour alpha
     const int W = a.W, H = a.H;
     const int tx = (int)threadIdx.x & 31, ty = (int)threadIdx.x >> 5;
-    const int x0 = (int)blockIdx.x * kPostW, y0 = a.row0 + (int)blockIdx.y * kPostH;
+    int rowBegin = a.row0, rowEnd = a.row1, blockRow = (int)blockIdx.y;
+    if (a.stripeH) {
+        const int blocksPerStripe = (a.stripeH + kPostH - 1) / kPostH;
+        const int k = blockRow / blocksPerStripe;
+        blockRow -= k * blocksPerStripe;
+        rowBegin = (k * a.world + a.rank) * a.stripeH; rowEnd = min(rowBegin + a.stripeH, H);
+    }
+    const int x0 = (int)blockIdx.x * kPostW, y0 = rowBegin + blockRow * kPostH;
     const int x = x0 + tx, y = y0 + ty;
-    const bool valid = x < W && y < a.row1;
+    const bool valid = x < W && y < rowEnd;
 
     if (!a.taaOn) {
         if (valid) {
@@ -214,9 +222,12 @@ void launch_postprocess(Caster& c, bool taaOn)
     a.W = (int)c.d.width; a.H = (int)c.d.height;
     a.row0 = (int)c.row0; a.row1 = (int)c.row1;
     a.taaOn = taaOn ? 1 : 0;
-    const uint32_t rows = c.row1 - c.row0;
-    if (rows == 0) return;
-    dim3 grid((c.d.width + kPostW - 1) / kPostW, (rows + kPostH - 1) / kPostH);
+    const bool stripes = c.shardWorld > 1 && c.stripeH;
+    a.stripeH = stripes ? (int)c.stripeH : 0; a.rank = (int)c.shardRank; a.world = (int)c.shardWorld;
+    const uint32_t blockRows = stripes ? num_own_stripes(c.d.height, c.stripeH, c.shardRank, c.shardWorld) * ((c.stripeH + kPostH - 1) / kPostH)
+                                       : (c.row1 - c.row0 + kPostH - 1) / kPostH;
+    if (blockRows == 0) return;
+    dim3 grid((c.d.width + kPostW - 1) / kPostW, blockRows);
     k_postprocess<<<grid, kPostW * kPostH, 0, c.stream>>>(a);
 }
 

@@ -60,6 +60,7 @@ DeviceScene Caster::scene() const
     s.arena = arena;
     s.shardRank = shardRank; s.shardWorld = shardWorld;
     s.row0 = row0; s.row1 = row1;
+    s.stripeH = (shardWorld > 1) ? stripeH : 0;
     return s;
 }
 

@@ -108,7 +108,16 @@ struct DeviceScene {
     CubeArena arena;
     uint32_t shardRank, shardWorld;      // volume v is marched by rank v % world
     uint32_t row0, row1;                 // rows of the frame this rank resolves
+    uint32_t stripeH;                    // > 0: interleaved stripes (r / stripeH) % shardWorld == shardRank instead of the band
 };
+
+// Row ownership. Band: rows [row0, row1). Stripes (multi-GPU, better balanced): stripe g = rows
+// [g stripeH, (g + 1) stripeH) belongs to rank g % world; the rank's k-th stripe is g = k world + rank.
+MV_HD uint32_t num_own_stripes(uint32_t height, uint32_t stripeH, uint32_t rank, uint32_t world)
+{
+    const uint32_t total = (height + stripeH - 1) / stripeH;
+    return total > rank ? (total - rank + world - 1) / world : 0;
+}
 
 struct Caster;
 
@@ -184,6 +193,7 @@ struct Caster {
     // sharding
     uint32_t shardRank = 0, shardWorld = 1;
     uint32_t row0 = 0, row1 = 0;
+    uint32_t stripeH = 0;
     std::vector<void*> openedIpc;
     // timing
     cudaEvent_t ev[8] = {};

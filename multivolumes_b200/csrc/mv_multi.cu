@@ -119,6 +119,14 @@ int mv_set_row_band(mv_caster* h, uint32_t row0, uint32_t row1)
     return MV_OK;
 }
 
+int mv_set_row_stripes(mv_caster* h, uint32_t stripeHeight)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(stripeHeight <= c.d.height);
+    c.stripeH = stripeHeight;
+    return MV_OK;
+}
+
 int mv_exchange_block(mv_caster* h, void** p, uint64_t* bytes)
 {
     MV_ENTER(h);

@@ -142,7 +142,9 @@ class HostExchange:
 class ShardedRenderer:
     """Renders one frame of a scene on `world` ranks; rank 0 ends up with the whole frame."""
 
-    def __init__(self, caster, rank, world, mode="collective", exchange=None, group=None):
+    STRIPE_HEIGHT = 30   # + 2 halo rows = two 16-row OIT tile rows
+
+    def __init__(self, caster, rank, world, mode="collective", exchange=None, group=None, stripes=True):
         assert mode in ("fused", "collective")
         self.c, self.rank, self.world, self.mode, self.group = caster, rank, world, mode, group
         self.bands = [row_band(caster.H, r, world) for r in range(world)]
@@ -151,6 +153,9 @@ class ShardedRenderer:
         caster.SetRowBand(self.row0, self.row1)
         self.x = exchange
         if world > 1 and mode == "fused":
+            if stripes:   # interleaved row stripes instead of one band: the expensive pixels (direct marches) cluster
+                caster.SetRowBand(0, caster.H)
+                caster.SetRowStripes(self.STRIPE_HEIGHT)
             self._map_peers()
 
     def _map_peers(self):
