@@ -63,6 +63,21 @@ MV_D float get_tmax(V3 clipPos, V3 rayOrigin, V3 rayDir, const float* wvpi)
     return max3(t.x, t.y, t.z);
 }
 
+// Conservative early-out for the ray / unit-box tests: true only when the ray o + u d (u >= 0, d not
+// normalised) certainly misses the box, because it stays outside the box's bounding sphere (radius
+// sqrt(3)) by a margin far above the fp32 error of these few operations. Whenever it returns true the
+// exact slab test (compute_ray_origin, the OIT exit test) would have reported a miss as well, so using
+// it changes no result; NaNs fall through to the exact test.
+MV_D bool ray_misses_box_for_sure(V3 o, V3 d)
+{
+    const float oo = dot(o, o);
+    const float slack = 3.2f + 1.0e-4f * oo;      // sphere radius^2 + absolute and relative safety margins
+    if (!(oo > slack)) return false;              // origin inside the (inflated) sphere
+    const float tca = -dot(o, d);                 // projection of (centre - o) on d, times |d|
+    if (tca < 0.0f) return true;                  // sphere entirely behind the ray
+    return (oo - slack) * dot(d, d) > tca * tca;  // closest approach of the line outside the sphere
+}
+
 struct MarchCount { uint32_t samples, lightFetches; };
 
 // The per-ray loop of CSRayMarch.hlsl:112-155 and RayCast.hlsli:57-105 (identical bodies).

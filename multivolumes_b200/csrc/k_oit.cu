@@ -91,11 +91,12 @@ MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, ui
     const float flx = floorf(fx), fly = floorf(fy);
     const int i0 = (int)flx, j0 = (int)fly;
     V4 smp[4]; float zs[4];
+    const bool interior = i0 >= 0 && j0 >= 0 && i0 + 1 < S && j0 + 1 < S;   // all four taps on this face (the common case)
 #pragma unroll
     for (int k = 0; k < 4; ++k) {    // Gather order (-,+), (+,+), (+,-), (-,-)
         const int ti = (k == 1 || k == 2) ? i0 + 1 : i0, tj = (k < 2) ? j0 + 1 : j0;
-        int f, i, j;
-        cube_resolve_texel(S, face, ti, tj, f, i, j);
+        int f = face, i = ti, j = tj;
+        if (!interior) cube_resolve_texel(S, face, ti, tj, f, i, j);
         const size_t idx = ((size_t)f * S + j) * S + i;
         smp[k] = unpack_half4(__ldg(colors + idx));
         zs[k] = __ldg(depths + idx);
@@ -197,6 +198,7 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
                 const PerObject* po = s.perObject + volumeId;
                 const V3 o = {s_cand[ci].eyeL[0], s_cand[ci].eyeL[1], s_cand[ci].eyeL[2]};   // mul(float4(g_eyePt, 1), WorldI)
                 const V3 d = mul_v33(dirW, po->worldI);
+                if (ray_misses_box_for_sure(o, d)) continue;    // the tile overlaps the volume's rectangle, this pixel's ray does not come near
                 float tmin = -kFltMax, tmax = kFltMax; int exitAxis = -1; bool miss = false;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {

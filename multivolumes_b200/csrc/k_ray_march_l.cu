@@ -65,8 +65,22 @@ struct LightTarget {
     uint32_t numPeers;
 };
 
+constexpr uint32_t kMaxSharedDirs = 1024;   // volumes whose light direction is staged in shared memory
+
 __global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
 {
+    // The light is directional (CSRayMarchL.hlsl:91-92): normalize(mul(g_lightPos.xyz, (float3x3)WorldI)) depends on
+    // the volume only. It is evaluated once per CTA and volume here instead of once per voxel and volume.
+    extern __shared__ float s_dirS[];
+    {
+        const V3 lightPos = {cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]};
+        const uint32_t nShared = min(cb.numVolumes, kMaxSharedDirs);
+        for (uint32_t n = threadIdx.x; n < nShared; n += kLightThreads) {
+            const V3 d = normalize(mul_v33(lightPos, s.perObject[n].worldI));
+            s_dirS[3 * n] = d.x; s_dirS[3 * n + 1] = d.y; s_dirS[3 * n + 2] = d.z;
+        }
+        __syncthreads();
+    }
     const uint32_t z0 = tgt.z0, z1 = tgt.z1;
     const uint32_t L = cb.lightGridSize, N = cb.numVolumes;
     // 8x4x4 voxel bricks: a warp is an 8x4 slice, neighbouring rays stay coherent in the texture cache
@@ -113,12 +127,16 @@ __global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, Fr
                 const cudaTextureObject_t grid = s.volumeTex[s.volumeDescs[n] & 0x3fffu];
                 V3 localRayOrigin = mul_p43(rayOrigin, po->worldI);                                 // :83
                 if (shadow >= kZeroThreshold) {
-                    const V3 rayDir = normalize(mul_v33(lightPos, po->worldI));                     // :91-92 (directional)
+                    const V3 rayDir = n < kMaxSharedDirs ? V3{s_dirS[3 * n], s_dirS[3 * n + 1], s_dirS[3 * n + 2]}
+                                                         : normalize(mul_v33(lightPos, po->worldI));   // :91-92 (directional)
+                    if (ray_misses_box_for_sure(localRayOrigin, rayDir)) continue;                  // most volumes: far off the ray
                     if (!compute_ray_origin(localRayOrigin, rayDir)) continue;                      // :95
                     cast_light_ray(shadow, grid, localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
                 }
                 if (cb.hasSH) {                                                                     // :100-108
-                    const V3 rayDir = normalize(mul_v33(aoRayDir, po->worldI));
+                    const V3 dirU = mul_v33(aoRayDir, po->worldI);
+                    if (ray_misses_box_for_sure(localRayOrigin, dirU)) continue;
+                    const V3 rayDir = normalize(dirU);
                     if (!compute_ray_origin(localRayOrigin, rayDir)) continue;
                     float transm = 1.0f;
                     cast_light_ray(transm, grid, localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
@@ -168,7 +186,8 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
     }
     if (tgt.z1 <= tgt.z0) return;
     const uint32_t bricks = ((L + 7) / 8) * ((L + 3) / 4) * ((tgt.z1 - tgt.z0 + 3) / 4);
-    k_ray_march_l<<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    const size_t smem = (size_t)min(c.d.num_volumes, kMaxSharedDirs) * 3 * sizeof(float);
+    k_ray_march_l<<<bricks, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
 }
 
 } // namespace mv
