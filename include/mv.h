@@ -127,6 +127,16 @@ int mv_read_cubemap(mv_caster* c, uint32_t volume, uint32_t mip, uint16_t* rgba1
 int mv_read_lightmap(mv_caster* c, uint32_t volume, uint16_t* rgba16f);
 int mv_read_frame(mv_caster* c, uint16_t* rgba16f);
 int mv_read_post(mv_caster* c, uint16_t* taa_rgba16f, uint8_t* rgba8);
+/* Present (the swap-chain Present of the reference's frame loop, MultiVolumes.cpp:OnRender, with
+ * FrameCount = 3 frames in flight): asynchronous read-back of the RGBA8 back buffer of the frame
+ * rendered so far into PINNED host memory, on a copy stream, overlapping the next frame's passes.
+ * slot < MV_PRESENT_SLOTS names the in-flight copy; mv_present_wait(slot) blocks until that copy has
+ * landed. The next frame's post-process (or, sharded, its first peer barrier) waits for the copy on
+ * the device, so the back buffer is never overwritten under it. host_rgba8 = NULL only marks the
+ * frame's end (ranks that hold no frame use it to bound their queue depth). */
+#define MV_PRESENT_SLOTS 3
+int mv_present_async(mv_caster* c, uint8_t* host_rgba8_pinned, uint32_t slot);
+int mv_present_wait(mv_caster* c, uint32_t slot);
 int mv_get_stats(mv_caster* c, mv_stats* out);
 int mv_get_timings(mv_caster* c, mv_timings* out);
 int mv_set_frame_index(mv_caster* c, uint32_t frame_idx);

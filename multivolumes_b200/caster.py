@@ -52,6 +52,8 @@ _EXTRA = {
     "set_stream": (C.c_int, [_vp, _vp]),
     "get_stream": (C.c_int, [_vp, P(_vp)]),
     "frame_buffers": (C.c_int, [_vp, P(_vp), P(_vp), P(_vp)]),
+    "present_async": (C.c_int, [_vp, _vp, u32]),
+    "present_wait": (C.c_int, [_vp, u32]),
 }
 
 _binding = None
@@ -123,6 +125,13 @@ class MultiRayCaster(CasterBase):
     def ReadPostInto(self, rgba8_ptr=None, taa_ptr=None):
         """Read-back into caller-owned (pinned) memory; pointers are integers."""
         self._ck(self.b.read_post(self.h, taa_ptr, rgba8_ptr), "read_post")
+
+    def PresentAsync(self, rgba8_ptr, slot):
+        """Swap-chain Present: asynchronous read-back of the back buffer into pinned memory (slot < 3 in flight)."""
+        self._ck(self.b.present_async(self.h, rgba8_ptr, slot), "present_async")
+
+    def PresentWait(self, slot):
+        self._ck(self.b.present_wait(self.h, slot), "present_wait")
 
     # --- multi-GPU ---
     def SetRowStripes(self, stripe_height):

@@ -171,6 +171,12 @@ static void record(Caster& c, int i)
     if (c.d.flags & MV_FLAG_TIME_PASSES) { cudaEventRecord(c.ev[i], c.stream); c.evValid[i] = true; }
 }
 
+// The back buffer may still be read by an mv_present_async copy: order the next writer after it.
+static void wait_back_buffer_free(Caster& c)
+{
+    if (c.backBufferBusy >= 0) { cudaStreamWaitEvent(c.stream, c.presentDone[c.backBufferBusy], 0); c.backBufferBusy = -1; }
+}
+
 static int check_launch(const char* what)
 {
     const cudaError_t e = cudaGetLastError();
@@ -196,6 +202,9 @@ static void destroy_caster(Caster& c)
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
     for (auto& e : c.ev) if (e) cudaEventDestroy(e);
     for (auto& e : c.uploadDone) if (e) cudaEventDestroy(e);
+    for (auto& e : c.presentDone) if (e) cudaEventDestroy(e);
+    if (c.frameDone) cudaEventDestroy(c.frameDone);
+    if (c.copyStream) { cudaStreamSynchronize(c.copyStream); cudaStreamDestroy(c.copyStream); }
     if (c.ownStream) cudaStreamDestroy(c.ownStream);
 }
 
@@ -254,6 +263,9 @@ int mv_create(const mv_desc* d, mv_caster** out)
     MV_CUDA_C(cudaStreamCreateWithFlags(&c.ownStream, cudaStreamNonBlocking));
     c.stream = c.ownStream;
     for (auto& e : c.ev) MV_CUDA_C(cudaEventCreate(&e));
+    MV_CUDA_C(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+    MV_CUDA_C(cudaEventCreateWithFlags(&c.frameDone, cudaEventDisableTiming));
+    for (auto& e : c.presentDone) MV_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     // MultiRayCaster.cpp:99-126 — per-source volumes, per-instance light maps and cube maps
     c.volumes.resize(S);
@@ -608,7 +620,8 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         return MV_ERR_INVALID;
     }
     launch_ray_march_light(c, -1);
-    if (c.shardWorld > 1) { launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
+    // sharded: once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
+    if (c.shardWorld > 1) { wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
     record(c, 2);
     launch_ray_march_view(c);
     if (c.shardWorld > 1) launch_peer_barrier(c);                                // every owner's cube maps have landed
@@ -624,6 +637,7 @@ int mv_postprocess(mv_caster* h, uint32_t taa)
 {
     MV_ENTER(h);
     if (!c.evValid[4]) record(c, 4);
+    wait_back_buffer_free(c);
     launch_postprocess(c, taa != 0);
     record(c, 5);
     return check_launch("k_postprocess");
@@ -735,6 +749,28 @@ int mv_read_post(mv_caster* h, uint16_t* taa, uint8_t* rgba8)
     if (taa) MV_CUDA(cudaMemcpyAsync(taa, c.dHistory[c.frameParity], px * 8, cudaMemcpyDeviceToHost, c.stream));
     if (rgba8) MV_CUDA(cudaMemcpyAsync(rgba8, c.dBackBuffer, px * 4, cudaMemcpyDeviceToHost, c.stream));
     MV_CUDA(cudaStreamSynchronize(c.stream));
+    return MV_OK;
+}
+
+int mv_present_async(mv_caster* h, uint8_t* host, uint32_t slot)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(slot < MV_PRESENT_SLOTS);
+    if (c.presentPending[slot]) { MV_CUDA(cudaEventSynchronize(c.presentDone[slot])); c.presentPending[slot] = false; }
+    MV_CUDA(cudaEventRecord(c.frameDone, c.stream));
+    MV_CUDA(cudaStreamWaitEvent(c.copyStream, c.frameDone, 0));
+    if (host) MV_CUDA(cudaMemcpyAsync(host, c.dBackBuffer, (size_t)c.d.width * c.d.height * 4, cudaMemcpyDeviceToHost, c.copyStream));
+    MV_CUDA(cudaEventRecord(c.presentDone[slot], c.copyStream));
+    c.presentPending[slot] = true;
+    if (host) c.backBufferBusy = (int)slot;
+    return MV_OK;
+}
+
+int mv_present_wait(mv_caster* h, uint32_t slot)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(slot < MV_PRESENT_SLOTS);
+    if (c.presentPending[slot]) { MV_CUDA(cudaEventSynchronize(c.presentDone[slot])); c.presentPending[slot] = false; }
     return MV_OK;
 }
 

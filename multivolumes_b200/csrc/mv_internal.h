@@ -179,6 +179,11 @@ struct Caster {
     cudaStream_t ownStream = nullptr;
     cudaEvent_t uploadDone[3] = {};
     bool uploadPending[3] = {};
+    cudaStream_t copyStream = nullptr;   // mv_present_async: back-buffer read-back overlapping the next frame
+    cudaEvent_t frameDone = nullptr;     // main stream -> copy stream
+    cudaEvent_t presentDone[MV_PRESENT_SLOTS] = {};
+    bool presentPending[MV_PRESENT_SLOTS] = {};
+    int backBufferBusy = -1;             // slot whose copy still reads the back buffer (device-side wait before it is rewritten)
     float* dDepth = nullptr;
     uint16_t* dShadow = nullptr;
     uint32_t shadowSize = 0;
