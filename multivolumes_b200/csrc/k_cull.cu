@@ -212,6 +212,13 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
             L->marchTileTotal = running;
             L->marchTileCursor = 0;
             L->oitTileCursor = 0;
+            L->lightDenseCount = 0;
+            L->lightDenseCursor = 0;
+            L->lightItemCount = 0;
+            L->lightItemCursor = 0;
+            L->lightResultCount = 0;
+            L->lightEmitCursor = 0;
+            L->lightOverflow = 0;
             // CSRayMarchL.hlsl:29-33 (visible[] was written by other threads of this CTA before the last barrier)
             L->lightVolume = visibleCount ? s.visible[cb.frameIdx % visibleCount] : cb.frameIdx % N;
         }

@@ -11,6 +11,8 @@
 // values are rounded to 11/11/10-bit floats before the store, which makes the texels identical to the
 // reference's format (every such value is exactly representable in binary16).
 #include "k_march.cuh"
+#include <cstdio>
+#include <cstdlib>
 
 namespace mv {
 
@@ -65,25 +67,33 @@ struct LightTarget {
     uint32_t numPeers;
 };
 
-constexpr uint32_t kMaxSharedDirs = 1024;   // volumes whose light direction is staged in shared memory
+#ifndef MV_LIGHT_MIN_BLOCKS
+#define MV_LIGHT_MIN_BLOCKS 8
+#endif
+constexpr uint32_t kMaxSharedDirs = 1024;   // volumes whose light direction and bounding sphere are staged in shared memory
 
-__global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
+MV_D void store_light_voxel(const DeviceScene& s, const LightTarget& tgt, uint32_t volumeId, uint32_t L, uint32_t x, uint32_t y, uint32_t z, V3 value)
 {
-    // The light is directional (CSRayMarchL.hlsl:91-92): normalize(mul(g_lightPos.xyz, (float3x3)WorldI)) depends on
-    // the volume only. It is evaluated once per CTA and volume here instead of once per voxel and volume.
-    extern __shared__ float s_dirS[];
-    {
-        const V3 lightPos = {cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]};
-        const uint32_t nShared = min(cb.numVolumes, kMaxSharedDirs);
-        for (uint32_t n = threadIdx.x; n < nShared; n += kLightThreads) {
-            const V3 d = normalize(mul_v33(lightPos, s.perObject[n].worldI));
-            s_dirS[3 * n] = d.x; s_dirS[3 * n + 1] = d.y; s_dirS[3 * n + 2] = d.z;
-        }
-        __syncthreads();
-    }
+    const V4 out = {quantize_ufloat(value.x, 6), quantize_ufloat(value.y, 6), quantize_ufloat(value.z, 5), 0.0f};
+    const uint2 packed = pack_half4(out);
+    if (tgt.staging) {
+        const size_t idx = ((size_t)z * L + y) * L + x;
+        tgt.staging[idx] = packed;
+        for (uint32_t p = 0; p < tgt.numPeers; ++p) if (tgt.peerStaging[p]) tgt.peerStaging[p][idx] = packed;
+    } else surf3Dwrite(packed, s.lightSurf[volumeId], (int)(x * 8), (int)y, (int)z);                // :120
+}
+
+// Pass 1, one thread per light-map voxel (8x4x4 bricks): density at the voxel centre and the shadow-map
+// test (CSRayMarchL.hlsl:36-51). A voxel below the density threshold casts no ray: its texel
+// (shadow * lightColor + ambient, with ao = 1 and irradiance = 0 under a light probe) is written here.
+// The others are appended, brick by brick and in thread order inside a brick, to the dense-voxel list
+// that pass 2 marches with full warps.
+__global__ void __launch_bounds__(kLightThreads) k_light_classify(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
+{
+    __shared__ uint32_t s_warpCount[kLightThreads / 32];
+    __shared__ uint32_t s_base;
     const uint32_t z0 = tgt.z0, z1 = tgt.z1;
-    const uint32_t L = cb.lightGridSize, N = cb.numVolumes;
-    // 8x4x4 voxel bricks: a warp is an 8x4 slice, neighbouring rays stay coherent in the texture cache
+    const uint32_t L = cb.lightGridSize;
     const uint32_t bricksX = (L + 7) / 8, bricksY = (L + 3) / 4;
     const uint32_t brick = blockIdx.x;
     const uint32_t bz = brick / (bricksX * bricksY), rem = brick - bz * bricksX * bricksY;
@@ -91,82 +101,423 @@ __global__ void __launch_bounds__(kLightThreads) k_ray_march_l(DeviceScene s, Fr
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t x = bx * 8 + (lane & 7), y = by * 4 + (lane >> 3), z = z0 + bz * 4 + warp;
     const bool active = x < L && y < L && z < z1;
-
     const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;   // :29-33
-    uint32_t dense = 0, samples = 0;
+
+    bool dense = false;
+    float shadow = 1.0f;
     if (active) {
         const float gridSize = (float)L;
         V3 rayOrigin = {((float)x + 0.5f) / gridSize * 2.0f - 1.0f, ((float)y + 0.5f) / gridSize * 2.0f - 1.0f,
                         ((float)z + 0.5f) / gridSize * 2.0f - 1.0f};                               // :36
-        const uint32_t volTexId0 = s.volumeDescs[volumeId] & 0x3fffu;
-        const cudaTextureObject_t grid0 = s.volumeTex[volTexId0];
+        const cudaTextureObject_t grid0 = s.volumeTex[s.volumeDescs[volumeId] & 0x3fffu];
         const V3 uvw = local_to_tex3d(rayOrigin);                                                   // :41
-        const PerObject* po0 = s.perObject + volumeId;
         const float density = tex3D<float4>(grid0, uvw.x, uvw.y, uvw.z).w;                          // :45
-        const bool hasDensity = density >= kZeroThreshold;                                          // :46
-        rayOrigin = mul_p43(rayOrigin, po0->world);                                                 // :48
-        float shadow = shadow_test(s, cb, rayOrigin);                                               // :51
-        float ao = 1.0f;
-        V3 irradiance = {0.0f, 0.0f, 0.0f};
-        if (hasDensity) {
-            ++dense;
-            const float maxDist = 2.0f * sqrtf(3.0f);
-            const float gStep = maxDist / (float)cb.maxLightSamples;                                // RayMarch.hlsli:18
-            V3 aoRayDir = {0.0f, 0.0f, 0.0f};
+        dense = density >= kZeroThreshold;                                                          // :46
+        rayOrigin = mul_p43(rayOrigin, s.perObject[volumeId].world);                                // :48
+        shadow = shadow_test(s, cb, rayOrigin);                                                     // :51
+        if (!dense) {
+            const V3 lightColor = {cb.lightColor[0] * cb.lightColor[3], cb.lightColor[1] * cb.lightColor[3], cb.lightColor[2] * cb.lightColor[3]};
+            V3 ambient = {cb.ambient[0] * cb.ambient[3], cb.ambient[1] * cb.ambient[3], cb.ambient[2] * cb.ambient[3]};
+            if (cb.hasSH) ambient = {1.0f * 0.0f, 1.0f * 0.0f, 1.0f * 0.0f};                        // ao * irradiance, :117
+            store_light_voxel(s, tgt, volumeId, L, x, y, z,
+                              V3{shadow * lightColor.x + ambient.x, shadow * lightColor.y + ambient.y, shadow * lightColor.z + ambient.z});
+        }
+    }
+    const uint32_t bits = __ballot_sync(kFull, dense);
+    if (lane == 0) s_warpCount[warp] = __popc(bits);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+#pragma unroll
+        for (int w = 0; w < kLightThreads / 32; ++w) total += s_warpCount[w];
+        s_base = total ? atomicAdd(&s.lists->lightDenseCount, total) : 0u;
+        if (s.stats && total) atomicAdd(&s.stats->light_dense_voxels, (unsigned long long)total);
+    }
+    __syncthreads();
+    if (dense) {
+        uint32_t slot = s_base + __popc(bits & ((1u << lane) - 1u));
+        for (uint32_t w = 0; w < warp; ++w) slot += s_warpCount[w];
+        s.lightDense[slot] = make_uint2((z * L + y) * L + x, __float_as_uint(shadow));
+    }
+}
+
+// Conservative early-out in world space: true only when the ray o + u d (u >= 0, |d| = 1) certainly
+// misses the sphere (centre sph.xyz, squared radius sph.w, already inflated by 2 %) that bounds a
+// volume's box. Whenever it returns true the exact local-space tests below report a miss as well, so
+// it changes no result; it only spares the transform into the volume's space. NaNs fall through.
+MV_D bool ray_misses_sphere_for_sure(V3 o, V3 d, float4 sph)
+{
+    const V3 oc = {sph.x - o.x, sph.y - o.y, sph.z - o.z};
+    const float c2 = dot(oc, oc);
+    const float r2 = sph.w + 1.0e-4f * c2;
+    if (!(c2 > r2)) return false;
+    const float b = dot(oc, d);
+    if (b < 0.0f) return true;
+    return c2 - b * b > r2;
+}
+
+// Per-volume tables of a CTA (shared memory): the world-space bounding sphere of the volume's box and
+// the light direction in its local space. The light is directional (CSRayMarchL.hlsl:91-92):
+// normalize(mul(g_lightPos.xyz, (float3x3)WorldI)) depends on the volume only, so it is evaluated once
+// per CTA and volume instead of once per voxel and volume.
+MV_D void stage_volume_tables(const DeviceScene& s, const FrameCB& cb, float4* s_sph, float* s_dirS, uint32_t nShared)
+{
+    const V3 lightPos = {cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]};
+    for (uint32_t n = threadIdx.x; n < nShared; n += kLightThreads) {
+        const PerObject* po = s.perObject + n;
+        const V3 d = normalize(mul_v33(lightPos, po->worldI));
+        s_dirS[3 * n] = d.x; s_dirS[3 * n + 1] = d.y; s_dirS[3 * n + 2] = d.z;
+        const float* W = po->world;                          // rows: the box's half-axes a, b, c and its centre
+        float r2 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float sb = (k & 1) ? -1.0f : 1.0f, sc = (k & 2) ? -1.0f : 1.0f;
+            const V3 c = {W[0] + sb * W[3] + sc * W[6], W[1] + sb * W[4] + sc * W[7], W[2] + sb * W[5] + sc * W[8]};
+            r2 = fmaxf(r2, dot(c, c));
+        }
+        s_sph[n] = make_float4(W[9], W[10], W[11], r2 * 1.02f);
+    }
+    __syncthreads();
+}
+
+MV_D V3 light_voxel_center(uint32_t voxel, uint32_t L, uint32_t& x, uint32_t& y, uint32_t& z)   // CSRayMarchL.hlsl:36
+{
+    x = voxel % L; y = (voxel / L) % L; z = voxel / (L * L);
+    const float gridSize = (float)L;
+    return {((float)x + 0.5f) / gridSize * 2.0f - 1.0f, ((float)y + 0.5f) / gridSize * 2.0f - 1.0f, ((float)z + 0.5f) / gridSize * 2.0f - 1.0f};
+}
+
+MV_D V3 shadow_dir_local(const FrameCB& cb, const PerObject* po, const float* s_dirS, uint32_t n)
+{
+    if (n < kMaxSharedDirs) return V3{s_dirS[3 * n], s_dirS[3 * n + 1], s_dirS[3 * n + 2]};
+    return normalize(mul_v33(V3{cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]}, po->worldI));      // :91-92 (directional)
+}
+
+// What the volume loop needs to know about one voxel.
+struct LightVoxel {
+    V3 rayOrigin;      // world space (:48)
+    V3 aoRayDir;       // world space, normalised (:65-75)
+};
+
+// The volume loop of CSRayMarchL.hlsl:77-110 for one voxel with the shadow ray's march left out: its
+// outcome is summarised by castEnd, the first volume at which the shadow ray was no longer cast. Calls
+// f(n, castShadow, localRayOrigin, rayDir) for every ambient-occlusion ray that hits its volume's box,
+// in ascending volume order, with exactly the geometry (origin moved by the shadow ray's entry point,
+// volume skipped when the shadow ray misses it) of the full loop.
+template <class F>
+MV_D void for_each_ao_ray(const DeviceScene& s, const FrameCB& cb, const LightVoxel& v, uint32_t castEnd, uint32_t maxRays,
+                          const float4* s_sph, const float* s_dirS, uint32_t nShared, V3 lightDirW, F&& f)
+{
+    uint32_t found = 0;
+    for (uint32_t n = 0; n < cb.numVolumes && found < maxRays; ++n) {
+        const bool castShadow = n < castEnd;
+        if (n < nShared && ray_misses_sphere_for_sure(v.rayOrigin, castShadow ? lightDirW : v.aoRayDir, s_sph[n])) continue;
+        const PerObject* po = s.perObject + n;
+        V3 localRayOrigin = mul_p43(v.rayOrigin, po->worldI);                                       // :83
+        if (castShadow) {
+            const V3 rayDir = shadow_dir_local(cb, po, s_dirS, n);
+            if (ray_misses_box_for_sure(localRayOrigin, rayDir)) continue;
+            if (!compute_ray_origin(localRayOrigin, rayDir)) continue;                              // :95
+        }
+        const V3 dirU = mul_v33(v.aoRayDir, po->worldI);                                            // :102
+        if (ray_misses_box_for_sure(localRayOrigin, dirU)) continue;
+        const V3 rayDir = normalize(dirU);
+        if (!compute_ray_origin(localRayOrigin, rayDir)) continue;                                  // :103
+        f(n, castShadow, localRayOrigin, rayDir);
+        ++found;
+    }
+}
+
+// Pass 2, persistent: warps pull 32 dense voxels at a time from the list. Per voxel the loop over the N
+// volumes of CSRayMarchL.hlsl:77-110 is walked with its exact control flow, but only the shadow ray —
+// whose transmittance chains from one volume to the next — is marched here. The ambient-occlusion ray
+// of a (voxel, volume) pair depends on nothing but geometry and on whether the shadow ray was still
+// being cast at that volume, so every AO ray that hits its box is deferred as an independent work item
+// (passes 3-5) instead of lengthening this thread's dependent fetch chain: the pass's duration is
+// bounded by its longest chain, not by its throughput (profiles/r01_notes.md). The pass counts the
+// deferred rays per volume (they are marched sorted by volume, one texture per warp).
+__global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_march_l(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
+{
+    extern __shared__ float4 s_tab[];                       // [nShared] spheres, then [nShared] x 3 floats of directions
+    const uint32_t N = cb.numVolumes, L = cb.lightGridSize;
+    const uint32_t nShared = min(N, kMaxSharedDirs);
+    float* s_dirS = reinterpret_cast<float*>(s_tab + nShared);
+    stage_volume_tables(s, cb, s_tab, s_dirS, nShared);
+    const V3 lightDirW = normalize(V3{cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]});
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;   // :29-33
+    const uint32_t count = s.lists->lightDenseCount;
+    const cudaTextureObject_t grid0 = s.volumeTex[s.volumeDescs[volumeId] & 0x3fffu];
+    const PerObject* po0 = s.perObject + volumeId;
+    const float maxDist = 2.0f * sqrtf(3.0f);
+    const float gStep = maxDist / (float)cb.maxLightSamples;                                        // RayMarch.hlsli:18
+    uint32_t samples = 0;
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s.lists->lightDenseCursor, 32u);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= count) break;
+        const bool live = base + lane < count;
+        uint32_t x = 0, y = 0, z = 0, numItems = 0;
+        LightRec rec;
+        rec.voxel = 0; rec.castEnd = N; rec.shadow = 1.0f; rec.ao = 1.0f;
+        V3 rayOrigin = {0.0f, 0.0f, 0.0f}, aoRayDir = {0.0f, 0.0f, 0.0f};
+        if (live) {
+            const uint2 item = __ldg(s.lightDense + base + lane);
+            rec.voxel = item.x;
+            float shadow = __uint_as_float(item.y);
+            rayOrigin = light_voxel_center(rec.voxel, L, x, y, z);
+            const V3 uvw = local_to_tex3d(rayOrigin);                                               // :41
+            rayOrigin = mul_p43(rayOrigin, po0->world);                                             // :48
             if (cb.hasSH) {                                                                         // :65-75
                 aoRayDir = -density_gradient(grid0, uvw, 1.0f / (float)cb.gridSize);
                 const bool nz = fabsf(aoRayDir.x) > 0.0f || fabsf(aoRayDir.y) > 0.0f || fabsf(aoRayDir.z) > 0.0f;
                 aoRayDir = nz ? aoRayDir : rayOrigin;
                 aoRayDir = mul_v33(aoRayDir, po0->world);
                 aoRayDir = normalize(aoRayDir);
-                irradiance = evaluate_sh_irradiance(cb.sh, normalize(aoRayDir));                    // GetIrradiance
             }
-            const V3 lightPos = {cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]};
             for (uint32_t n = 0; n < N; ++n) {                                                      // :77
+                const bool castShadow = shadow >= kZeroThreshold;
+                if (!castShadow) { rec.castEnd = min(rec.castEnd, n); if (!cb.hasSH) break; }
+                // a missed shadow ray skips the volume altogether (:95 `continue`), otherwise only the AO ray is cast
+                if (n < nShared && ray_misses_sphere_for_sure(rayOrigin, castShadow ? lightDirW : aoRayDir, s_tab[n])) continue;
                 const PerObject* po = s.perObject + n;
-                const cudaTextureObject_t grid = s.volumeTex[s.volumeDescs[n] & 0x3fffu];
                 V3 localRayOrigin = mul_p43(rayOrigin, po->worldI);                                 // :83
-                if (shadow >= kZeroThreshold) {
-                    const V3 rayDir = n < kMaxSharedDirs ? V3{s_dirS[3 * n], s_dirS[3 * n + 1], s_dirS[3 * n + 2]}
-                                                         : normalize(mul_v33(lightPos, po->worldI));   // :91-92 (directional)
-                    if (ray_misses_box_for_sure(localRayOrigin, rayDir)) continue;                  // most volumes: far off the ray
+                if (castShadow) {
+                    const V3 rayDir = shadow_dir_local(cb, po, s_dirS, n);
+                    if (ray_misses_box_for_sure(localRayOrigin, rayDir)) continue;
                     if (!compute_ray_origin(localRayOrigin, rayDir)) continue;                      // :95
-                    cast_light_ray(shadow, grid, localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
+                    cast_light_ray(shadow, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
                 }
-                if (cb.hasSH) {                                                                     // :100-108
+                if (cb.hasSH) {                                                                     // :100-108, geometry only
                     const V3 dirU = mul_v33(aoRayDir, po->worldI);
                     if (ray_misses_box_for_sure(localRayOrigin, dirU)) continue;
-                    const V3 rayDir = normalize(dirU);
-                    if (!compute_ray_origin(localRayOrigin, rayDir)) continue;
-                    float transm = 1.0f;
-                    cast_light_ray(transm, grid, localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
-                    ao *= (n == volumeId) ? transm : pow025(saturate(transm + 0.5f));
+                    if (!compute_ray_origin(localRayOrigin, normalize(dirU))) continue;
+                    const uint32_t hit = n | (castShadow ? 0x80000000u : 0u);
+#pragma unroll
+                    for (uint32_t j = 0; j < kLightRecHits; ++j) if (j == numItems) rec.hits[j] = hit;
+                    ++numItems;
+                    // per-volume ray count, one atomic per group of lanes that are at the same volume together
+                    const uint32_t grp = __match_any_sync(__activemask(), n);
+                    if (lane == (uint32_t)__ffs(grp) - 1u) atomicAdd(s.lightSeg + n, (uint32_t)__popc(grp));
                 }
             }
+            rec.shadow = shadow;
         }
-        const V3 lightColor = {cb.lightColor[0] * cb.lightColor[3], cb.lightColor[1] * cb.lightColor[3], cb.lightColor[2] * cb.lightColor[3]};
-        V3 ambient = {cb.ambient[0] * cb.ambient[3], cb.ambient[1] * cb.ambient[3], cb.ambient[2] * cb.ambient[3]};
-        if (cb.hasSH) ambient = {ao * irradiance.x, ao * irradiance.y, ao * irradiance.z};         // :117
-        const V4 out = {quantize_ufloat(shadow * lightColor.x + ambient.x, 6), quantize_ufloat(shadow * lightColor.y + ambient.y, 6),
-                        quantize_ufloat(shadow * lightColor.z + ambient.z, 5), 0.0f};
-        const uint2 packed = pack_half4(out);
-        if (tgt.staging) {
-            const size_t idx = ((size_t)z * L + y) * L + x;
-            tgt.staging[idx] = packed;
-            for (uint32_t p = 0; p < tgt.numPeers; ++p) if (tgt.peerStaging[p]) tgt.peerStaging[p][idx] = packed;
-        } else surf3Dwrite(packed, s.lightSurf[volumeId], (int)(x * 8), (int)y, (int)z);           // :120
+        if (!cb.hasSH) {
+            if (live) {
+                const V3 lightColor = {cb.lightColor[0] * cb.lightColor[3], cb.lightColor[1] * cb.lightColor[3], cb.lightColor[2] * cb.lightColor[3]};
+                const V3 ambient = {cb.ambient[0] * cb.ambient[3], cb.ambient[1] * cb.ambient[3], cb.ambient[2] * cb.ambient[3]};
+                store_light_voxel(s, tgt, volumeId, L, x, y, z,
+                                  V3{rec.shadow * lightColor.x + ambient.x, rec.shadow * lightColor.y + ambient.y, rec.shadow * lightColor.z + ambient.z});
+            }
+            continue;
+        }
+        // reserve the warp's AO factors in one atomic; a voxel's factors are contiguous, in ascending volume order
+        uint32_t incl = numItems;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += t; }
+        const uint32_t warpTotal = __shfl_sync(kFull, incl, 31);
+        uint32_t warpBase = 0;
+        if (lane == 0 && warpTotal) warpBase = atomicAdd(&s.lists->lightResultCount, warpTotal);
+        warpBase = __shfl_sync(kFull, warpBase, 0);
+        if (live) {
+            rec.itemBase = warpBase + incl - numItems; rec.itemCount = numItems;
+            rec.aoDir[0] = aoRayDir.x; rec.aoDir[1] = aoRayDir.y; rec.aoDir[2] = aoRayDir.z; rec.pad = 0;
+            s.lightRecs[base + lane] = rec;
+        }
     }
     if (s.stats) {
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            dense += __shfl_xor_sync(kFull, dense, d);
-            samples += __shfl_xor_sync(kFull, samples, d);
+        for (int d = 16; d > 0; d >>= 1) samples += __shfl_xor_sync(kFull, samples, d);
+        if (lane == 0 && samples) atomicAdd(&s.stats->light_samples, (unsigned long long)samples);
+    }
+}
+
+constexpr uint32_t kItemSentinel = 0xffffffffu;
+
+// Pass 3, one CTA: exclusive scan of the per-volume AO-ray counts, each rounded up to a multiple of 32,
+// into segment offsets (so that a warp of pass 5 never straddles two volumes); the padding slots are
+// marked, the counts reset for the next frame, and the frame falls back to inline marching when the
+// rays do not fit the buffers.
+__global__ void __launch_bounds__(1024) k_light_scan(DeviceScene s, FrameCB cb)
+{
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_running;
+    const uint32_t N = cb.numVolumes, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_running = 0;
+    __syncthreads();
+    for (uint32_t tile = 0; tile < N; tile += 1024) {
+        const uint32_t n = tile + threadIdx.x;
+        const uint32_t c = n < N ? s.lightSeg[n] : 0u;
+        const uint32_t padded = (c + 31u) & ~31u;
+        uint32_t incl = padded;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, d); if ((int)lane >= d) incl += t; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = s_running;
+        for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
+        const uint32_t start = before + incl - padded;
+        if (n < N) {
+            s.lightSeg[N + n] = start;
+            s.lightSeg[n] = 0;
+            for (uint32_t q = start + c; q < start + padded; ++q)
+                if (q < s.lightItemCapacity) s.lightItems[q] = make_uint4(kItemSentinel, 0u, 0u, 0u);
         }
-        if (lane == 0 && (dense | samples)) {
-            atomicAdd(&s.stats->light_dense_voxels, (unsigned long long)dense);
-            atomicAdd(&s.stats->light_samples, (unsigned long long)samples);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_running = before + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        s.lists->lightItemCount = s_running;
+        s.lists->lightOverflow = (s_running > s.lightItemCapacity || s.lists->lightResultCount > s.lightItemCapacity) ? 1u : 0u;
+    }
+}
+
+// Pass 4, persistent over the dense voxels: scatter every deferred AO ray into its volume's segment of
+// the item list. (Overflow frame: march the voxel's AO rays inline instead, CSRayMarchL.hlsl:100-108.)
+__global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, FrameCB cb, int volumeOverride)
+{
+    extern __shared__ float4 s_tab[];
+    const uint32_t N = cb.numVolumes, L = cb.lightGridSize;
+    const uint32_t nShared = min(N, kMaxSharedDirs);
+    float* s_dirS = reinterpret_cast<float*>(s_tab + nShared);
+    stage_volume_tables(s, cb, s_tab, s_dirS, nShared);
+    const V3 lightDirW = normalize(V3{cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]});
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
+    const uint32_t count = s.lists->lightDenseCount;
+    const bool overflow = s.lists->lightOverflow != 0;
+    const PerObject* po0 = s.perObject + volumeId;
+    const float maxDist = 2.0f * sqrtf(3.0f);
+    const float gStep = maxDist / (float)cb.maxLightSamples;
+    uint32_t samples = 0;
+
+    auto emit = [&](uint32_t recIdx, uint32_t hit, uint32_t resultIdx) {
+        const uint32_t n = hit & 0x7fffffffu;
+        const uint32_t grp = __match_any_sync(__activemask(), n);
+        const uint32_t leader = (uint32_t)__ffs(grp) - 1u;
+        uint32_t slot = 0;
+        if (lane == leader) slot = atomicAdd(s.lightSeg + N + n, (uint32_t)__popc(grp));
+        slot = __shfl_sync(grp, slot, leader) + __popc(grp & ((1u << lane) - 1u));
+        s.lightItems[slot] = make_uint4(recIdx, hit, resultIdx, 0u);
+    };
+
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s.lists->lightEmitCursor, 32u);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= count) break;
+        if (base + lane >= count) continue;
+        const uint32_t recIdx = base + lane;
+        const LightRec rec = s.lightRecs[recIdx];
+        if (!overflow && rec.itemCount <= kLightRecHits) {
+            for (uint32_t j = 0; j < rec.itemCount; ++j) {
+                uint32_t hit = 0;
+#pragma unroll
+                for (uint32_t k = 0; k < kLightRecHits; ++k) if (k == j) hit = rec.hits[k];
+                emit(recIdx, hit, rec.itemBase + j);
+            }
+            continue;
+        }
+        uint32_t x, y, z;
+        LightVoxel v;
+        v.rayOrigin = mul_p43(light_voxel_center(rec.voxel, L, x, y, z), po0->world);               // :36, :48
+        v.aoRayDir = {rec.aoDir[0], rec.aoDir[1], rec.aoDir[2]};
+        if (!overflow) {
+            uint32_t j = 0;
+            for_each_ao_ray(s, cb, v, rec.castEnd, rec.itemCount, s_tab, s_dirS, nShared, lightDirW,
+                            [&](uint32_t n, bool castShadow, V3, V3) { emit(recIdx, n | (castShadow ? 0x80000000u : 0u), rec.itemBase + j); ++j; });
+        } else {
+            float ao = 1.0f;
+            for_each_ao_ray(s, cb, v, rec.castEnd, rec.itemCount, s_tab, s_dirS, nShared, lightDirW,
+                            [&](uint32_t n, bool, V3 localRayOrigin, V3 rayDir) {
+                                float transm = 1.0f;
+                                cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
+                                ao *= (n == volumeId) ? transm : pow025(saturate(transm + 0.5f));   // :107
+                            });
+            s.lightRecs[recIdx].ao = ao;
+            s.lightRecs[recIdx].itemCount = 0;
         }
     }
+    if (s.stats) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) samples += __shfl_xor_sync(kFull, samples, d);
+        if (lane == 0 && samples) atomicAdd(&s.stats->light_samples, (unsigned long long)samples);
+    }
+}
+
+// Pass 5, persistent: one thread per deferred ambient-occlusion ray (CSRayMarchL.hlsl:100-108), a warp's
+// 32 rays all through the same volume. The ray is rebuilt from the voxel, the volume and the
+// cast-shadow flag with the operations of pass 2.
+__global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_light_ao(DeviceScene s, FrameCB cb, int volumeOverride)
+{
+    const uint32_t L = cb.lightGridSize;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
+    const uint32_t count = s.lists->lightOverflow ? 0u : s.lists->lightItemCount;   // a multiple of 32
+    const PerObject* po0 = s.perObject + volumeId;
+    const float maxDist = 2.0f * sqrtf(3.0f);
+    const float gStep = maxDist / (float)cb.maxLightSamples;
+    uint32_t samples = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(&s.lists->lightItemCursor, 32u);
+        base = __shfl_sync(kFull, base, 0);
+        if (base >= count) break;
+        const uint4 item = __ldg(s.lightItems + base + lane);
+        const bool valid = item.x != kItemSentinel;
+        const uint32_t validMask = __ballot_sync(kFull, valid);
+        if (!validMask) continue;
+        const uint32_t n = __shfl_sync(kFull, item.y & 0x7fffffffu, __ffs(validMask) - 1);          // the segment's volume
+        if (!valid) continue;
+        const bool castShadow = (item.y >> 31) != 0;
+        const LightRec* rec = s.lightRecs + item.x;
+        uint32_t x, y, z;
+        V3 rayOrigin = light_voxel_center(__ldg(&rec->voxel), L, x, y, z);
+        rayOrigin = mul_p43(rayOrigin, po0->world);                                                 // :48
+        const V3 aoRayDir = {__ldg(&rec->aoDir[0]), __ldg(&rec->aoDir[1]), __ldg(&rec->aoDir[2])};
+        const PerObject* po = s.perObject + n;
+        V3 localRayOrigin = mul_p43(rayOrigin, po->worldI);                                         // :83
+        if (castShadow) {                                                                           // the shadow ray's entry point moved the origin (:95)
+            const V3 shadowDir = normalize(mul_v33(V3{cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]}, po->worldI));
+            compute_ray_origin(localRayOrigin, shadowDir);
+        }
+        const V3 rayDir = normalize(mul_v33(aoRayDir, po->worldI));
+        compute_ray_origin(localRayOrigin, rayDir);
+        float transm = 1.0f;
+        cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
+        s.lightItemResults[item.z] = (n == volumeId) ? transm : pow025(saturate(transm + 0.5f));    // :107
+    }
+    if (s.stats) {
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) samples += __shfl_xor_sync(kFull, samples, d);
+        if (lane == 0 && samples) atomicAdd(&s.stats->light_samples, (unsigned long long)samples);
+    }
+}
+
+// Pass 6: fold each dense voxel's AO factors in ascending volume order and write its texel (:112-120).
+__global__ void __launch_bounds__(256) k_light_finalize(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
+{
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= s.lists->lightDenseCount) return;
+    const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
+    const LightRec* rec = s.lightRecs + i;
+    float ao = rec->ao;
+    const uint32_t itemBase = rec->itemBase, itemCount = rec->itemCount;
+    for (uint32_t j = 0; j < itemCount; ++j) ao *= __ldg(s.lightItemResults + itemBase + j);
+    const V3 aoRayDir = {rec->aoDir[0], rec->aoDir[1], rec->aoDir[2]};
+    const V3 irradiance = evaluate_sh_irradiance(cb.sh, normalize(aoRayDir));                       // GetIrradiance
+    const uint32_t L = cb.lightGridSize;
+    uint32_t x, y, z;
+    light_voxel_center(rec->voxel, L, x, y, z);
+    const float shadow = rec->shadow;
+    const V3 lightColor = {cb.lightColor[0] * cb.lightColor[3], cb.lightColor[1] * cb.lightColor[3], cb.lightColor[2] * cb.lightColor[3]};
+    const V3 ambient = {ao * irradiance.x, ao * irradiance.y, ao * irradiance.z};                   // :117
+    store_light_voxel(s, tgt, volumeId, L, x, y, z,
+                      V3{shadow * lightColor.x + ambient.x, shadow * lightColor.y + ambient.y, shadow * lightColor.z + ambient.z});
 }
 
 } // namespace
@@ -185,9 +536,45 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
             tgt.peerStaging[p] = (p == c.shardRank) ? nullptr : reinterpret_cast<uint2*>(c.peerBlock[p] + c.layout.light_staging_offset);
     }
     if (tgt.z1 <= tgt.z0) return;
+    const uint32_t voxels = L * L * (tgt.z1 - tgt.z0);
     const uint32_t bricks = ((L + 7) / 8) * ((L + 3) / 4) * ((tgt.z1 - tgt.z0 + 3) / 4);
-    const size_t smem = (size_t)min(c.d.num_volumes, kMaxSharedDirs) * 3 * sizeof(float);
-    k_ray_march_l<<<bricks, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    const size_t smem = (size_t)min(c.d.num_volumes, kMaxSharedDirs) * (sizeof(float4) + 3 * sizeof(float));
+    static int perSM = 0, perSMAo = 0, perSMEmit = 0;
+    if (!perSM) {
+        const size_t smemMax = (size_t)kMaxSharedDirs * (sizeof(float4) + 3 * sizeof(float));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_l, kLightThreads, smemMax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMEmit, k_light_emit, kLightThreads, smemMax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMAo, k_light_ao, kLightThreads, 0);
+        perSM = max(perSM, 1); perSMEmit = max(perSMEmit, 1); perSMAo = max(perSMAo, 1);
+    }
+    // MV_LIGHT_TIMING=1 (tuning aid): CUDA events around each pass, averages printed every 64 launches
+    static const bool timing = getenv("MV_LIGHT_TIMING") != nullptr;
+    static cudaEvent_t tev[7]; static float tacc[6]; static int tcount = 0;
+    if (timing && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
+    auto mark = [&](int i) { if (timing) cudaEventRecord(tev[i], c.stream); };
+    mark(0);
+    k_light_classify<<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    mark(1);
+    k_ray_march_l<<<c.smCount * perSM, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    mark(2);
+    if (!c.cb.hasSH) return;
+    k_light_scan<<<1, 1024, 0, c.stream>>>(c.scene(), c.cb);
+    mark(3);
+    k_light_emit<<<c.smCount * perSMEmit, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride);
+    mark(4);
+    k_light_ao<<<c.smCount * perSMAo, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride);
+    mark(5);
+    k_light_finalize<<<(voxels + 255) / 256, 256, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    mark(6);
+    if (timing) {
+        cudaEventSynchronize(tev[6]);
+        for (int i = 0; i < 6; ++i) { float ms = 0; cudaEventElapsedTime(&ms, tev[i], tev[i + 1]); tacc[i] += ms; }
+        if (++tcount % 64 == 0) {
+            fprintf(stderr, "[light] classify %.4f shadow %.4f scan %.4f emit %.4f ao %.4f finalize %.4f ms\n",
+                    tacc[0] / 64, tacc[1] / 64, tacc[2] / 64, tacc[3] / 64, tacc[4] / 64, tacc[5] / 64);
+            for (auto& t : tacc) t = 0;
+        }
+    }
 }
 
 } // namespace mv

@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <new>
 
 using namespace mv;
@@ -56,6 +57,12 @@ DeviceScene Caster::scene() const
     s.depth = dDepth;
     s.shadow = dShadow;
     s.color = dColor;
+    s.lightDense = dLightDense;
+    s.lightRecs = dLightRecs;
+    s.lightItems = dLightItems;
+    s.lightItemResults = dLightItemResults;
+    s.lightSeg = dLightSeg;
+    s.lightItemCapacity = lightItemCapacity;
     s.stats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dStats : nullptr;
     s.arena = arena;
     s.shardRank = shardRank; s.shardWorld = shardWorld;
@@ -196,7 +203,7 @@ static void destroy_caster(Caster& c)
     };
     for (auto& v : c.volumes) kill(v);
     for (auto& v : c.lightMaps) kill(v);
-    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dBlock,
+    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
                      c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
@@ -326,6 +333,14 @@ int mv_create(const mv_desc* d, mv_caster** out)
     const size_t listBytes = ((sizeof(FrameLists) + (3 * (size_t)N + 1) * sizeof(uint32_t) + 31) & ~(size_t)31) + (size_t)N * sizeof(VisInfo);
     MV_CUDA_C(cudaMalloc(&c.dLists, listBytes));
     MV_CUDA_C(cudaMemsetAsync(c.dLists, 0, listBytes, c.stream));
+    MV_CUDA_C(cudaMalloc(&c.dLightDense, (size_t)L * L * L * sizeof(uint2)));
+    MV_CUDA_C(cudaMalloc(&c.dLightRecs, (size_t)L * L * L * sizeof(LightRec)));
+    c.lightItemCapacity = 4u * L * L * L + 32u * N;   // deferred AO rays (4 per voxel + segment padding); a frame that needs more marches them inline
+    if (const char* cap = getenv("MV_LIGHT_ITEM_CAPACITY")) c.lightItemCapacity = (uint32_t)strtoul(cap, nullptr, 10) + 32u * N;   // tests: force the inline fallback
+    MV_CUDA_C(cudaMalloc(&c.dLightItems, (size_t)c.lightItemCapacity * sizeof(uint4)));
+    MV_CUDA_C(cudaMalloc(&c.dLightSeg, 2 * (size_t)N * sizeof(uint32_t)));
+    MV_CUDA_C(cudaMemsetAsync(c.dLightSeg, 0, 2 * (size_t)N * sizeof(uint32_t), c.stream));
+    MV_CUDA_C(cudaMalloc(&c.dLightItemResults, (size_t)c.lightItemCapacity * sizeof(float)));
     MV_CUDA_C(cudaMalloc(&c.dStats, sizeof(StatsDev)));
     MV_CUDA_C(cudaMemsetAsync(c.dStats, 0, sizeof(StatsDev), c.stream));
 
@@ -585,6 +600,10 @@ int mv_ray_march_light(mv_caster* h, int32_t v)
 {
     MV_ENTER(h);
     MV_REQUIRE(v < (int32_t)c.d.num_volumes);
+    if (c.d.flags & MV_FLAG_COUNT_SAMPLES)
+        MV_CUDA(cudaMemsetAsync(&c.dStats->light_voxels, 0, 3 * sizeof(unsigned long long), c.stream));
+    // stand-alone call (the frame path has the cull kernel reset these)
+    MV_CUDA(cudaMemsetAsync(&reinterpret_cast<FrameLists*>(c.dLists)->lightDenseCount, 0, 8 * sizeof(uint32_t), c.stream));
     launch_ray_march_light(c, v);
     return check_launch("k_ray_march_l");
 }

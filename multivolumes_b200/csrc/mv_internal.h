@@ -47,7 +47,14 @@ struct FrameLists {
     uint32_t marchTileCursor;   // work-stealing cursor of the persistent view-march kernel
     uint32_t lightVolume;       // CSRayMarchL.hlsl:29-33
     uint32_t oitTileCursor;
-    uint32_t pad[2];
+    uint32_t lightDenseCount;   // light march: voxels with density >= 0.01 appended by the classify pass
+    uint32_t lightDenseCursor;  // work cursor of the persistent shadow-march kernel
+    uint32_t lightItemCount;    // deferred ambient-occlusion rays: slots of the volume-sorted item list (segments padded to 32)
+    uint32_t lightItemCursor;   // work cursor of the persistent AO-march kernel
+    uint32_t lightResultCount;  // AO factors reserved, voxel-major (a voxel's factors are contiguous, ascending volume index)
+    uint32_t lightEmitCursor;   // work cursor of the item-emission kernel
+    uint32_t lightOverflow;     // the frame's AO rays do not fit the item buffers: they are marched inline instead
+    uint32_t pad0;
     // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1]
 };
 
@@ -58,6 +65,22 @@ struct VisInfo {
     uint32_t volumeId;
     int x0, y0, x1, y1;   // inclusive pixel bounds; full screen when a corner is behind the eye plane
 };
+
+// Light march, per dense voxel (k_ray_march_l.cu): what the finalize pass needs once the voxel's
+// deferred ambient-occlusion rays have been marched.
+constexpr uint32_t kLightRecHits = 6;
+struct LightRec {
+    uint32_t voxel;        // (z L + y) L + x
+    uint32_t itemBase;     // first of the voxel's AO factors (ascending volume index)
+    uint32_t itemCount;
+    float shadow;          // transmittance toward the light through all volumes
+    float aoDir[3];        // world-space AO direction (normalised negative density gradient)
+    float ao;              // AO product of the rays marched inline (1 when every ray was deferred)
+    uint32_t castEnd;      // first volume at which the shadow ray was no longer cast
+    uint32_t hits[kLightRecHits];   // the first AO rays of the voxel: volume | castShadow << 31
+    uint32_t pad;
+};
+static_assert(sizeof(LightRec) == 64, "LightRec layout");
 
 struct StatsDev {
     unsigned long long view_rays, view_samples, view_light_fetches;
@@ -103,6 +126,12 @@ struct DeviceScene {
     const cudaSurfaceObject_t* lightSurf;   // [N]
     const float* depth;                  // W*H D32
     const uint16_t* shadow;              // S*S D16
+    uint2* lightDense;                   // [L^3] {voxel index, shadow-test result} of the dense voxels of the frame's light volume
+    LightRec* lightRecs;                 // [L^3] per dense voxel, same order as lightDense
+    uint4* lightItems;                   // [lightItemCapacity] {record index, volume | castShadow << 31, result index, -}, sorted by volume
+    float* lightItemResults;             // [lightItemCapacity] AO factor of each deferred ray, voxel-major
+    uint32_t* lightSeg;                  // [2 N] per volume: AO-ray count of the frame, then the append cursor of its segment
+    uint32_t lightItemCapacity;
     uint2* color;                        // W*H RGBA16F (half4 as uint2)
     StatsDev* stats;                     // nullptr when counters are off
     CubeArena arena;
@@ -165,6 +194,12 @@ struct Caster {
     ushort4* dAttribs = nullptr;
     unsigned char* dLists = nullptr;     // FrameLists + visible + cubeVolumes + cubeTilePrefix
     StatsDev* dStats = nullptr;
+    uint2* dLightDense = nullptr;        // L^3 entries
+    LightRec* dLightRecs = nullptr;      // L^3 entries
+    uint4* dLightItems = nullptr;
+    uint32_t* dLightSeg = nullptr;
+    float* dLightItemResults = nullptr;
+    uint32_t lightItemCapacity = 0;
     unsigned char* dBlock = nullptr;     // exchange block: arena | light staging | back buffer | flags
     mv_exchange_layout layout{};
     unsigned char* dArena = nullptr;     // = dBlock + layout.arena_offset
