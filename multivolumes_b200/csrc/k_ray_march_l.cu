@@ -452,7 +452,10 @@ __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, Fra
 // Pass 5, persistent: one thread per deferred ambient-occlusion ray (CSRayMarchL.hlsl:100-108), a warp's
 // 32 rays all through the same volume. The ray is rebuilt from the voxel, the volume and the
 // cast-shadow flag with the operations of pass 2.
-__global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_light_ao(DeviceScene s, FrameCB cb, int volumeOverride)
+#ifndef MV_LIGHT_AO_MIN_BLOCKS
+#define MV_LIGHT_AO_MIN_BLOCKS 8
+#endif
+__global__ void __launch_bounds__(kLightThreads, MV_LIGHT_AO_MIN_BLOCKS) k_light_ao(DeviceScene s, FrameCB cb, int volumeOverride)
 {
     const uint32_t L = cb.lightGridSize;
     const uint32_t lane = threadIdx.x & 31;
