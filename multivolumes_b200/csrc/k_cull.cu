@@ -180,8 +180,42 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
         __syncthreads();
     }
 
-    // tile prefix of the view march over the cube-map volumes this rank owns (warp 0, shuffle scan)
     const uint32_t visibleCount = s_baseVis, cubeCount = s_baseCube;
+    // Screen-space marches (RayCast, volumes on the direct scheme: VSCube.hlsl:73): every such visible volume gets its
+    // screen rectangle as a slice of the result buffer and a run of 8x4-pixel tiles (warp 1, two shuffle scans). A
+    // rectangle that does not fit the buffer gets no slice: the resolve kernel marches that volume itself.
+    if (warp == 1) {
+        uint32_t runningPix = 0, runningTiles = 0;
+        for (uint32_t base = 0; base < visibleCount; base += 32) {
+            const uint32_t k = base + lane;
+            uint32_t pix = 0, tiles = 0;
+            if (k < visibleCount) {
+                const ushort4 a = s.attribs[s.visible[k]];
+                if (!(a.z & kCubeMapRayMarchBit) && a.y > 0) {
+                    const VisInfo vi = s.visInfo[k];
+                    const int w = vi.x1 - vi.x0 + 1, h = vi.y1 - vi.y0 + 1;
+                    if (w > 0 && h > 0) { pix = (uint32_t)w * (uint32_t)h; tiles = (uint32_t)((w + 7) / 8) * (uint32_t)((h + 3) / 4); }
+                }
+            }
+            uint32_t incl = pix;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(kFull, incl, d); if (lane >= (uint32_t)d) incl += t; }
+            const uint32_t offset = runningPix + incl - pix;
+            const bool fits = pix != 0 && offset <= s.directCapacity && pix <= s.directCapacity - offset;
+            runningPix = min(runningPix + __shfl_sync(kFull, incl, 31), 0x80000000u);   // saturate: everything after an overflow does not fit either
+            if (!fits) tiles = 0;
+            uint32_t inclT = tiles;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(kFull, inclT, d); if (lane >= (uint32_t)d) inclT += t; }
+            if (k < visibleCount) {
+                s.directOffset[k] = fits ? offset : kNoDirect;
+                s.directTilePrefix[k] = runningTiles + inclT - tiles;
+            }
+            runningTiles += __shfl_sync(kFull, inclT, 31);
+        }
+        if (lane == 0) { s.directTilePrefix[visibleCount] = runningTiles; s.lists->directTileTotal = runningTiles; }
+    }
+    // tile prefix of the view march over the cube-map volumes this rank owns (warp 0, shuffle scan)
     if (warp == 0) {
         uint32_t running = 0;
         for (uint32_t base = 0; base < cubeCount; base += 32) {
@@ -212,6 +246,7 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
             L->marchTileTotal = running;
             L->marchTileCursor = 0;
             L->oitTileCursor = 0;
+            L->directTileCursor = 0;
             L->lightDenseCount = 0;
             L->lightDenseCursor = 0;
             L->lightItemCount = 0;

@@ -135,6 +135,145 @@ MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, ui
     return col;
 }
 
+// Pixel-centre ray: unproject z = 0 through screenToWorld (RTCube.hlsl:54-70; PSCube.hlsl:38-40). Returns the world-space
+// direction from the eye (not normalised) and the pixel's clip-space x, y.
+MV_D V3 pixel_ray(const FrameCB& cb, int px, int py, float& sx, float& sy)
+{
+    sx = ((float)px + 0.5f) / cb.viewport[0]; sy = ((float)py + 0.5f) / cb.viewport[1];
+    sx = sx * 2.0f - 1.0f; sy = sy * 2.0f - 1.0f;
+    sy = -sy;
+    const V4 wh = mul_p44(V3{sx, sy, 0.0f}, cb.screenToWorld);
+    const V3 wpos = {wh.x / wh.w, wh.y / wh.w, wh.z / wh.w};
+    return wpos - V3{cb.eye[0], cb.eye[1], cb.eye[2]};
+}
+
+// The back-face fragment of a volume under a pixel: exit of the local-space ray o + t d from the unit box, with the
+// rasteriser's depth clip. false = no fragment. Shared by the resolve kernel and the screen-space march so that both
+// see exactly the same fragments.
+struct BackFace { int axis; float sgn; float z; };
+MV_D bool back_face_fragment(V3 o, V3 d, const float* wvp, BackFace& f)
+{
+    if (ray_misses_box_for_sure(o, d)) return false;    // the tile overlaps the volume's rectangle, this pixel's ray does not come near
+    float tmin = -kFltMax, tmax = kFltMax; int exitAxis = -1; bool miss = false;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const float da = comp(d, a), oa = comp(o, a);
+        if (da == 0.0f) { if (fabsf(oa) > 1.0f) miss = true; continue; }
+        const float t1 = (-1.0f - oa) / da, t2 = (1.0f - oa) / da;
+        const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
+        if (tn > tmin) tmin = tn;
+        if (tf < tmax) { tmax = tf; exitAxis = a; }
+    }
+    if (miss || exitAxis < 0 || !(tmax > 0.0f) || !(tmin < tmax)) return false;
+    V3 lpt = {clamp1(o.x + d.x * tmax), clamp1(o.y + d.y * tmax), clamp1(o.z + d.z * tmax)};
+    const float sgn = comp(d, exitAxis) > 0.0f ? 1.0f : -1.0f;
+    if (exitAxis == 0) lpt.x = sgn; else if (exitAxis == 1) lpt.y = sgn; else lpt.z = sgn;
+    const V4 clip = mul_p44(lpt, wvp);
+    if (!(clip.w > 0.0f)) return false;
+    const float z = clip.z / clip.w;
+    if (!(z >= 0.0f && z <= 1.0f)) return false;        // rasteriser depth clip
+    f.axis = exitAxis; f.sgn = sgn; f.z = z;
+    return true;
+}
+
+// The fragment's local-space position: exit point of the pixel ray on the back face (axis, sgn)
+MV_D V3 back_face_point(V3 localEye, V3 d, int axis, float sgn)
+{
+    const float tmax = (sgn - comp(localEye, axis)) / comp(d, axis);
+    V3 lpt = {clamp1(localEye.x + d.x * tmax), clamp1(localEye.y + d.y * tmax), clamp1(localEye.z + d.z * tmax)};
+    if (axis == 0) lpt.x = sgn; else if (axis == 1) lpt.y = sgn; else lpt.z = sgn;
+    return lpt;
+}
+
+// RayCast, RayCast.hlsli:42-107: screen-space march of one fragment of a direct-scheme volume
+MV_D V4 ray_cast(const DeviceScene& s, const PerObject* po, uint32_t volumeId, uint32_t volTexId, uint32_t smpCnt, V3 localEye, V3 rayDir,
+                 float sx, float sy, float sceneDepth, bool& marched, MarchCount& mc)
+{
+    V3 ro = localEye; const V3 rd = normalize(rayDir);
+    marched = compute_ray_origin(ro, rd);
+    if (!marched) return {0.0f, 0.0f, 0.0f, 0.0f};
+    const float tMax = get_tmax(V3{sx, sy, sceneDepth}, ro, rd, po->wvpi);
+    return march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCnt, ro, rd, tMax, mc);
+}
+
+// the same, kept out of line: the resolve kernel only marches volumes whose rectangle did not fit the result buffer
+__device__ __noinline__ V4 ray_cast_fallback(const DeviceScene& s, const PerObject* po, uint32_t volumeId, uint32_t volTexId, uint32_t smpCnt, V3 localEye, V3 rayDir,
+                                             float sx, float sy, float sceneDepth, uint32_t& rays, uint32_t& samples, uint32_t& light)
+{
+    bool marched; MarchCount mc = {0, 0};
+    const V4 c = ray_cast(s, po, volumeId, volTexId, smpCnt, localEye, rayDir, sx, sy, sceneDepth, marched, mc);
+    if (marched) { ++rays; samples += mc.samples; light += mc.lightFetches; }
+    return c;
+}
+
+// Does this rank resolve row py (its band or stripes, plus the one-row halo the TAA's 3x3 neighbourhood reads)?
+MV_D bool row_is_resolved_here(const DeviceScene& s, const FrameCB& cb, int py)
+{
+    if (py < 0 || py >= (int)cb.height) return false;
+    if (!s.stripeH) return py >= (int)s.row0 - 1 && py < (int)s.row1 + 1;
+    const int h = (int)s.stripeH, world = (int)s.shardWorld, rank = (int)s.shardRank;
+    const int g = py / h;
+    if (g % world == rank) return true;
+    if (py == g * h && g >= 1 && (g - 1) % world == rank) return true;          // halo below the previous stripe
+    if (py == (g + 1) * h - 1 && (g + 1) % world == rank && (g + 1) * h < (int)cb.height) return true;   // halo above the next stripe
+    return false;
+}
+
+// Screen-space march of every direct-scheme volume over its screen rectangle, persistent: warps pull 8x4-pixel tiles of
+// one volume (one texture per warp, coherent neighbouring rays) from a cursor. Replaces the RayCast branch of PSCube
+// (PSCube.hlsl:44-52) as a pass of its own: inside the per-pixel resolve the marches of different volumes shared warps
+// (a TEX per distinct texture, serialised) at 24 warps per SM. The result is stored as the K-buffer would hold it
+// (RGBA16F, zero unless 0 < alpha <= 1, PSCube.hlsl:57).
+#ifndef MV_DIRECT_MIN_BLOCKS
+#define MV_DIRECT_MIN_BLOCKS 5
+#endif
+template <bool kStats>
+__global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(DeviceScene s, FrameCB cb)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t total = s.lists->directTileTotal, nvis = s.lists->visibleCount;
+    uint32_t dRays = 0, dSamples = 0, dLight = 0;
+    for (;;) {
+        uint32_t w = 0;
+        if (lane == 0) w = atomicAdd(&s.lists->directTileCursor, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= total) break;
+        uint32_t lo = 0, hi = nvis;
+        while (hi - lo > 1) {
+            const uint32_t mid = (lo + hi) >> 1;
+            if (__ldg(s.directTilePrefix + mid) <= w) lo = mid; else hi = mid;
+        }
+        const VisInfo vi = s.visInfo[lo];
+        const uint32_t local = w - __ldg(s.directTilePrefix + lo);
+        const int rectW = vi.x1 - vi.x0 + 1;
+        const uint32_t tilesX = (uint32_t)(rectW + 7) >> 3;
+        const uint32_t ty = local / tilesX, tx = local - ty * tilesX;
+        const int px = vi.x0 + (int)(tx * 8 + (lane & 7)), py = vi.y0 + (int)(ty * 4 + (lane >> 3));
+        if (px > vi.x1 || py > vi.y1 || !row_is_resolved_here(s, cb, py)) continue;
+        const uint32_t volumeId = vi.volumeId;
+        const PerObject* po = s.perObject + volumeId;
+        const ushort4 a = s.attribs[volumeId];
+        float sx, sy;
+        const V3 dirW = pixel_ray(cb, px, py, sx, sy);
+        const V3 localEye = {vi.eyeL[0], vi.eyeL[1], vi.eyeL[2]};
+        const V3 d = mul_v33(dirW, po->worldI);
+        uint2 stored = make_uint2(0u, 0u), st = make_uint2(0u, 0u);
+        BackFace f;
+        if (back_face_fragment(localEye, d, po->wvp, f)) {
+            const V3 lpt = back_face_point(localEye, d, f.axis, f.sgn);
+            const V3 rayDir = lpt - localEye;                                    // PSCube.hlsl:34
+            const float sceneDepth = __ldg(s.depth + (size_t)py * cb.width + px);
+            bool marched; MarchCount mc = {0, 0};
+            const V4 color = ray_cast(s, po, volumeId, a.w, a.y, localEye, rayDir, sx, sy, sceneDepth, marched, mc);
+            if (color.w > 0.0f && color.w <= 1.0f) stored = pack_half4(color);
+            if (kStats && marched) st = make_uint2(mc.samples | 0x80000000u, mc.lightFetches);
+        }
+        const size_t slot = (size_t)__ldg(s.directOffset + lo) + (size_t)(py - vi.y0) * rectW + (px - vi.x0);
+        s.directColor[slot] = stored;
+        if (kStats) s.directStats[slot] = st;
+    }
+}
+
 constexpr int kOitChunk = 256;   // visible volumes binned per pass over the CTA's 16x16-pixel tile
 
 __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
@@ -161,14 +300,8 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
     const bool valid = px < W && py < rowEnd;
 
     const uint32_t nvis = s.lists->visibleCount;
-    // pixel-centre ray: unproject z = 0 through screenToWorld (RTCube.hlsl:54-70; PSCube.hlsl:38-40)
-    float sx = ((float)px + 0.5f) / cb.viewport[0], sy = ((float)py + 0.5f) / cb.viewport[1];
-    sx = sx * 2.0f - 1.0f; sy = sy * 2.0f - 1.0f;
-    sy = -sy;
-    const V4 wh = mul_p44(V3{sx, sy, 0.0f}, cb.screenToWorld);
-    const V3 wpos = {wh.x / wh.w, wh.y / wh.w, wh.z / wh.w};
-    const V3 eye = {cb.eye[0], cb.eye[1], cb.eye[2]};
-    const V3 dirW = wpos - eye;
+    float sx, sy;
+    const V3 dirW = pixel_ray(cb, px, py, sx, sy);
 
     // depth peel: the kNumOitLayers nearest back-face exits (PSDepthPeel.hlsl:12-24), sorted, stable
     uint32_t keys[kNumOitLayers], ids[kNumOitLayers];
@@ -198,28 +331,11 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
                 const PerObject* po = s.perObject + volumeId;
                 const V3 o = {s_cand[ci].eyeL[0], s_cand[ci].eyeL[1], s_cand[ci].eyeL[2]};   // mul(float4(g_eyePt, 1), WorldI)
                 const V3 d = mul_v33(dirW, po->worldI);
-                if (ray_misses_box_for_sure(o, d)) continue;    // the tile overlaps the volume's rectangle, this pixel's ray does not come near
-                float tmin = -kFltMax, tmax = kFltMax; int exitAxis = -1; bool miss = false;
-#pragma unroll
-                for (int a = 0; a < 3; ++a) {
-                    const float da = comp(d, a), oa = comp(o, a);
-                    if (da == 0.0f) { if (fabsf(oa) > 1.0f) miss = true; continue; }
-                    const float t1 = (-1.0f - oa) / da, t2 = (1.0f - oa) / da;
-                    const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
-                    if (tn > tmin) tmin = tn;
-                    if (tf < tmax) { tmax = tf; exitAxis = a; }
-                }
-                if (miss || exitAxis < 0 || !(tmax > 0.0f) || !(tmin < tmax)) continue;
-                V3 lpt = {clamp1(o.x + d.x * tmax), clamp1(o.y + d.y * tmax), clamp1(o.z + d.z * tmax)};
-                const float sgn = comp(d, exitAxis) > 0.0f ? 1.0f : -1.0f;
-                if (exitAxis == 0) lpt.x = sgn; else if (exitAxis == 1) lpt.y = sgn; else lpt.z = sgn;
-                const V4 clip = mul_p44(lpt, po->wvp);
-                if (!(clip.w > 0.0f)) continue;
-                const float z = clip.z / clip.w;
-                if (!(z >= 0.0f && z <= 1.0f)) continue;       // rasteriser depth clip
+                BackFace f;
+                if (!back_face_fragment(o, d, po->wvp, f)) continue;
                 ++frags;
                 // insert (key, visible-list index) keeping ascending keys; equal keys keep list order
-                uint32_t key = as_uint(z), id = s_candSlot[ci] | ((uint32_t)(exitAxis * 2 + (sgn > 0.0f ? 0 : 1)) << 24);
+                uint32_t key = as_uint(f.z), id = s_candSlot[ci] | ((uint32_t)(f.axis * 2 + (f.sgn > 0.0f ? 0 : 1)) << 24);
 #pragma unroll
                 for (int l = 0; l < (int)kNumOitLayers; ++l) {
                     if (key < keys[l]) {
@@ -252,26 +368,28 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
         const V3 d = mul_v33(dirW, po->worldI);
         const int axis = face >> 1;
         const float sgn = (face & 1) ? -1.0f : 1.0f;
-        const float tmax = (sgn - comp(localEye, axis)) / comp(d, axis);
-        V3 lpt = {clamp1(localEye.x + d.x * tmax), clamp1(localEye.y + d.y * tmax), clamp1(localEye.z + d.z * tmax)};
-        if (axis == 0) lpt.x = sgn; else if (axis == 1) lpt.y = sgn; else lpt.z = sgn;
+        const V3 lpt = back_face_point(localEye, d, axis, sgn);
         const V3 rayDir = lpt - localEye;                                        // PSCube.hlsl:34
         const uint32_t smpCnt = (a.z & kCubeMapRayMarchBit) ? 0u : (uint32_t)a.y;   // VSCube.hlsl:73
-        V4 color;
-        if (smpCnt > 0) {
-            // RayCast.hlsli:42-107
-            V3 ro = localEye; const V3 rd = normalize(rayDir);
-            if (!compute_ray_origin(ro, rd)) color = {0.0f, 0.0f, 0.0f, 0.0f};
-            else {
-                const float tMax = get_tmax(V3{sx, sy, sceneDepth}, ro, rd, po->wvpi);
-                MarchCount mc = {0, 0};
-                color = march_ray(s.volumeTex[a.w], s.lightTex[volumeId], smpCnt, ro, rd, tMax, mc);
-                ++dRays; dSamples += mc.samples; dLight += mc.lightFetches;
-            }
-        } else color = cube_cast(s, cb, volumeId, a.x, sceneDepth, face, lpt, rayDir);
         // K-colour layers are RGBA16F; a layer is written only if 0 < alpha <= 1 (PSCube.hlsl:57)
         V4 src = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
+        V4 color = {0.0f, 0.0f, 0.0f, 0.0f};
+        bool stored = false;
+        if (smpCnt > 0) {
+            const uint32_t slot = id & 0xffffffu;
+            const uint32_t off = __ldg(s.directOffset + slot);
+            const int x0 = __ldg(&s.visInfo[slot].x0), y0 = __ldg(&s.visInfo[slot].y0), x1 = __ldg(&s.visInfo[slot].x1), y1 = __ldg(&s.visInfo[slot].y1);
+            if (off != kNoDirect && px >= x0 && px <= x1 && py >= y0 && py <= y1) {   // marched by k_ray_cast_direct, already in K-buffer form
+                const size_t at = (size_t)off + (size_t)(py - y0) * (x1 - x0 + 1) + (px - x0);
+                src = unpack_half4(__ldg(s.directColor + at));
+                stored = true;
+                if (s.directStats) {
+                    const uint2 st = __ldg(s.directStats + at);
+                    if (st.x >> 31) { ++dRays; dSamples += st.x & 0x7fffffffu; dLight += st.y; }
+                }
+            } else color = ray_cast_fallback(s, po, volumeId, a.w, smpCnt, localEye, rayDir, sx, sy, sceneDepth, dRays, dSamples, dLight);
+        } else color = cube_cast(s, cb, volumeId, a.x, sceneDepth, face, lpt, rayDir);
+        if (!stored && color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
         const float k1 = 1.0f - result.w;
         result = {result.x + src.x * k1, result.y + src.y * k1, result.z + src.z * k1, result.w + src.w * k1};
     }
@@ -304,6 +422,19 @@ __global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
 }
 
 } // namespace
+
+void launch_ray_cast_direct(Caster& c)
+{
+    const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0;
+    static int perSM[2] = {0, 0};
+    if (!perSM[0]) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[0], k_ray_cast_direct<false>, 256, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[1], k_ray_cast_direct<true>, 256, 0);
+        perSM[0] = max(perSM[0], 1); perSM[1] = max(perSM[1], 1);
+    }
+    if (stats) k_ray_cast_direct<true><<<c.smCount * perSM[1], 256, 0, c.stream>>>(c.scene(), c.cb);
+    else k_ray_cast_direct<false><<<c.smCount * perSM[0], 256, 0, c.stream>>>(c.scene(), c.cb);
+}
 
 void launch_resolve_oit(Caster& c)
 {

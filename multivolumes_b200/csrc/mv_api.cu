@@ -5,6 +5,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <cstdlib>
 #include <new>
 
@@ -50,7 +51,12 @@ DeviceScene Caster::scene() const
     s.visible = tail;
     s.cubeVolumes = tail + N;
     s.cubeTilePrefix = tail + 2 * N;
-    s.visInfo = reinterpret_cast<VisInfo*>(dLists + ((sizeof(FrameLists) + (3 * (size_t)N + 1) * sizeof(uint32_t) + 31) & ~(size_t)31));
+    s.directTilePrefix = tail + 3 * N + 1;
+    s.directOffset = tail + 4 * N + 2;
+    s.visInfo = reinterpret_cast<VisInfo*>(dLists + frame_lists_header_bytes(N));
+    s.directColor = dDirectColor;
+    s.directStats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dDirectStats : nullptr;
+    s.directCapacity = directCapacity;
     s.volumeTex = dVolumeTex;
     s.lightTex = dLightTex;
     s.lightSurf = dLightSurf;
@@ -184,6 +190,13 @@ static void wait_back_buffer_free(Caster& c)
     if (c.backBufferBusy >= 0) { cudaStreamWaitEvent(c.stream, c.presentDone[c.backBufferBusy], 0); c.backBufferBusy = -1; }
 }
 
+// the per-result counters of the screen-space marches exist only while the sample counters are on
+#define MV_TRY_DIRECT_STATS(c)                                                                                   \
+    do {                                                                                                        \
+        if (((c).d.flags & MV_FLAG_COUNT_SAMPLES) && !(c).dDirectStats)                                         \
+            MV_CUDA(cudaMalloc(&(c).dDirectStats, std::max<size_t>((c).directCapacity, 1) * sizeof(uint2)));    \
+    } while (0)
+
 static int check_launch(const char* what)
 {
     const cudaError_t e = cudaGetLastError();
@@ -203,7 +216,7 @@ static void destroy_caster(Caster& c)
     };
     for (auto& v : c.volumes) kill(v);
     for (auto& v : c.lightMaps) kill(v);
-    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
+    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
                      c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
@@ -330,9 +343,14 @@ int mv_create(const mv_desc* d, mv_caster** out)
     MV_CUDA_C(cudaMemcpy(c.dVolumeDescs, descs.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
     MV_CUDA_C(cudaMalloc(&c.dAttribs, N * sizeof(ushort4)));
     MV_CUDA_C(cudaMemsetAsync(c.dAttribs, 0, N * sizeof(ushort4), c.stream));
-    const size_t listBytes = ((sizeof(FrameLists) + (3 * (size_t)N + 1) * sizeof(uint32_t) + 31) & ~(size_t)31) + (size_t)N * sizeof(VisInfo);
+    const size_t listBytes = frame_lists_header_bytes(N) + (size_t)N * sizeof(VisInfo);
     MV_CUDA_C(cudaMalloc(&c.dLists, listBytes));
     MV_CUDA_C(cudaMemsetAsync(c.dLists, 0, listBytes, c.stream));
+    // results of the screen-space marches (RayCast of the direct-scheme volumes), rectangle by rectangle: room for four
+    // full-screen rectangles; volumes beyond that are marched inside the resolve kernel
+    c.directCapacity = (uint32_t)std::min<size_t>(4 * px, 0x7fffffffu);
+    if (const char* cap = getenv("MV_DIRECT_CAPACITY")) c.directCapacity = (uint32_t)strtoul(cap, nullptr, 10);   // tests: force the fallback
+    MV_CUDA_C(cudaMalloc(&c.dDirectColor, std::max<size_t>(c.directCapacity, 1) * sizeof(uint2)));
     MV_CUDA_C(cudaMalloc(&c.dLightDense, (size_t)L * L * L * sizeof(uint2)));
     MV_CUDA_C(cudaMalloc(&c.dLightRecs, (size_t)L * L * L * sizeof(LightRec)));
     c.lightItemCapacity = 4u * L * L * L + 32u * N;   // deferred AO rays (4 per voxel + segment padding); a frame that needs more marches them inline
@@ -603,7 +621,7 @@ int mv_ray_march_light(mv_caster* h, int32_t v)
     if (c.d.flags & MV_FLAG_COUNT_SAMPLES)
         MV_CUDA(cudaMemsetAsync(&c.dStats->light_voxels, 0, 3 * sizeof(unsigned long long), c.stream));
     // stand-alone call (the frame path has the cull kernel reset these)
-    MV_CUDA(cudaMemsetAsync(&reinterpret_cast<FrameLists*>(c.dLists)->lightDenseCount, 0, 8 * sizeof(uint32_t), c.stream));
+    MV_CUDA(cudaMemsetAsync(&reinterpret_cast<FrameLists*>(c.dLists)->lightDenseCount, 0, 7 * sizeof(uint32_t), c.stream));
     launch_ray_march_light(c, v);
     return check_launch("k_ray_march_l");
 }
@@ -622,6 +640,8 @@ int mv_resolve_oit(mv_caster* h)
     MV_ENTER(h);
     if (c.d.flags & MV_FLAG_COUNT_SAMPLES)
         MV_CUDA(cudaMemsetAsync(&c.dStats->direct_rays, 0, 4 * sizeof(unsigned long long), c.stream));
+    MV_TRY_DIRECT_STATS(c);
+    launch_ray_cast_direct(c);
     launch_resolve_oit(c);
     return check_launch("k_resolve_oit");
 }
@@ -645,6 +665,8 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
     launch_ray_march_view(c);
     if (c.shardWorld > 1) launch_peer_barrier(c);                                // every owner's cube maps have landed
     record(c, 3);
+    MV_TRY_DIRECT_STATS(c);
+    launch_ray_cast_direct(c);
     launch_resolve_oit(c);
     record(c, 4);
     c.evValid[5] = false;

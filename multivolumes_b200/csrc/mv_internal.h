@@ -54,8 +54,10 @@ struct FrameLists {
     uint32_t lightResultCount;  // AO factors reserved, voxel-major (a voxel's factors are contiguous, ascending volume index)
     uint32_t lightEmitCursor;   // work cursor of the item-emission kernel
     uint32_t lightOverflow;     // the frame's AO rays do not fit the item buffers: they are marched inline instead
-    uint32_t pad0;
-    // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1]
+    uint32_t directTileTotal;   // 8x4-pixel tiles of the screen-space marches (direct-scheme volumes)
+    uint32_t directTileCursor;  // work cursor of the persistent direct-march kernel
+    uint32_t pad0[3];
+    // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1], directTilePrefix[N + 1], directOffset[N]
 };
 
 // Per visible volume (same order as the visible list), written by the cull for the OIT resolve: the
@@ -81,6 +83,10 @@ struct LightRec {
     uint32_t pad;
 };
 static_assert(sizeof(LightRec) == 64, "LightRec layout");
+
+constexpr uint32_t kNoDirect = 0xffffffffu;
+// bytes of the per-frame lists in front of the VisInfo records (mv_api.cu lays the block out)
+MV_HD size_t frame_lists_header_bytes(size_t N) { return (sizeof(FrameLists) + (5 * N + 2) * sizeof(uint32_t) + 31) & ~(size_t)31; }
 
 struct StatsDev {
     unsigned long long view_rays, view_samples, view_light_fetches;
@@ -121,6 +127,11 @@ struct DeviceScene {
     uint32_t* cubeVolumes;               // [N]
     uint32_t* cubeTilePrefix;            // [N + 1]
     VisInfo* visInfo;                    // [N]
+    uint32_t* directTilePrefix;          // [N + 1] over the visible list: tiles of the screen-space march of each direct-scheme volume
+    uint32_t* directOffset;              // [N] over the visible list: first pixel of the volume's rectangle in directColor (kNoDirect = none)
+    uint2* directColor;                  // RayCast results (RGBA16F as stored in the K-buffer), rectangle by rectangle
+    uint2* directStats;                  // per result {samples | marched << 31, light fetches}; nullptr when counters are off
+    uint32_t directCapacity;             // pixels
     const cudaTextureObject_t* volumeTex;   // [srcs]
     const cudaTextureObject_t* lightTex;    // [N]
     const cudaSurfaceObject_t* lightSurf;   // [N]
@@ -156,6 +167,7 @@ void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity);
 void launch_cull(Caster& c);
 void launch_ray_march_light(Caster& c, int volumeOverride);
 void launch_ray_march_view(Caster& c);
+void launch_ray_cast_direct(Caster& c);
 void launch_resolve_oit(Caster& c);
 void launch_postprocess(Caster& c, bool taaOn);
 void launch_sh_project(Caster& c, const float* devCube, uint32_t size, float* devOut27);
@@ -194,6 +206,9 @@ struct Caster {
     ushort4* dAttribs = nullptr;
     unsigned char* dLists = nullptr;     // FrameLists + visible + cubeVolumes + cubeTilePrefix
     StatsDev* dStats = nullptr;
+    uint2* dDirectColor = nullptr;       // screen-space march results, directCapacity pixels
+    uint2* dDirectStats = nullptr;       // allocated on first use with counters on
+    uint32_t directCapacity = 0;
     uint2* dLightDense = nullptr;        // L^3 entries
     LightRec* dLightRecs = nullptr;      // L^3 entries
     uint4* dLightItems = nullptr;

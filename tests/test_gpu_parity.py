@@ -247,6 +247,31 @@ def test_frame_parity(cfg):
     assert so["direct_rays"] == sp["direct_rays"] and so["direct_samples"] == sp["direct_samples"]
 
 
+@pytest.mark.parametrize("direct_capacity", [None, 0, 3000])
+def test_frame_parity_direct_scheme_volumes(direct_capacity, monkeypatch):
+    """Small, distant volumes take the screen-space march (RayCast): k_ray_cast_direct marches them rectangle by rectangle
+    ahead of the resolve. direct_capacity shrinks its result buffer so that all (0) or some (3000 pixels) of the volumes
+    fall back to the march inside the resolve kernel."""
+    if direct_capacity is not None:
+        monkeypatch.setenv("MV_DIRECT_CAPACITY", str(direct_capacity))
+    kw = dict(grid_size=64, light_grid_size=16, num_volumes=16, num_volume_srcs=4, width=320, height=180)
+    o, p = _pair(**kw)
+    monkeypatch.delenv("MV_DIRECT_CAPACITY", raising=False)
+    vp, _ = scene.default_camera(320, 180)
+    depth = scene.sphere_depth(320, 180, vp, center=(0, 0, 0), radius=12.0)
+    for c in (o, p):
+        configure(c, sh=True, depth=depth, background=checker_background(320, 180), eye=(10.0, 40.0, -160.0))
+        for _ in range(2):
+            c.Render()
+    so, sp = o.GetStats(), p.GetStats()
+    assert so["direct_rays"] > 1000, so
+    for k in ("oit_fragments", "direct_rays", "direct_samples", "direct_light_fetches", "visible_count", "cubemap_count"):
+        assert so[k] == sp[k], (k, so[k], sp[k])
+    fo, fp = o.ReadFrame(), p.ReadFrame()
+    if not _same_bits(fo, fp):
+        assert_image_close(fp, fo, "frame")
+
+
 def test_frame_parity_with_mesh_depth_and_shadow():
     kw = dict(grid_size=32, light_grid_size=16, num_volumes=16, num_volume_srcs=4, width=320, height=180)
     o, p = _pair(**kw)
