@@ -29,6 +29,8 @@ WORKLOADS = {
     "cfg2": dict(n=16, g=128, l=96, w=1920, h=1080, sh=True, taa=True, note="BASELINE.json configs[1]"),
     "cfg3": dict(n=64, g=256, l=96, w=1920, h=1080, sh=True, taa=True, note="BASELINE.json configs[2] (analytic sphere occluder)"),
     "cfg4": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, note="BASELINE.json configs[3]"),
+    "cfg5i": dict(n=512, srcs=8, g=512, l=96, w=3840, h=2160, sh=True, taa=True,
+                  note="BASELINE.json configs[4] with 8 source volumes instanced 64x (VolTexId = i % srcs): 8.6 GB instead of 512 GB of RGBA16F"),
     "tiny": dict(n=4, g=32, l=16, w=320, h=180, sh=True, taa=True, note="CI-sized"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_ray_march_v from the committed ncu --set full capture
@@ -117,7 +119,8 @@ def run_reference(args, wl, rank, world):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_binding import OracleCaster
     from multivolumes_b200 import scene
-    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], width=wl["w"], height=wl["h"])
+    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"),
+                     width=wl["w"], height=wl["h"])
     sky = o.TransformSH(scene.procedural_sky(64))
     build_scene(o, wl, scene, sky)
     cores = o.GetStats()["threads"]
@@ -160,7 +163,7 @@ def workload_config(args, wl, world):
     return {"workload": f"{args.workload}: {wl['n']} volumes x {wl['g']}^3 RGBA16F (procedural density x seeded value noise), "
                         f"{wl['w']}x{wl['h']}, light map {wl['l']}^3, SH {'on' if wl['sh'] else 'off'}, TAA {'on' if wl['taa'] else 'off'}, "
                         f"orbit camera; {wl['note']}",
-            "l2_policy": f"inputs larger than L2 ({wl['n'] * wl['g'] ** 3 * 8 / 1e6:.0f} MB of volume textures vs 126 MB)",
+            "l2_policy": f"inputs larger than L2 ({(wl.get('srcs') or wl['n']) * wl['g'] ** 3 * 8 / 1e6:.0f} MB of volume textures vs 126 MB)",
             "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: volumes v % {world}, light-map z-slabs, {world} row bands; exchange = {args.exchange}",
             "e2e_inputs": "per-frame matrices (PerObject records) from pinned host memory; result = tone-mapped RGBA8 frame read back to pinned host "
                           "memory every step (Present, 3 frames in flight as in the reference's frame loop)"}
@@ -203,7 +206,7 @@ def main():
     hbm_peak, peak_src = peaks()
 
     c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, grid_size=wl["g"], light_grid_size=wl["l"],
-                       num_volumes=wl["n"], width=wl["w"], height=wl["h"])
+                       num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
     stream = torch.cuda.Stream()
     c.SetStream(stream.cuda_stream)      # order the caster's kernels with torch's events / NCCL on one stream
     sky = c.TransformSH(scene.procedural_sky(64))
@@ -348,7 +351,8 @@ def cpu_baseline(args, wl):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_binding import OracleCaster
     from multivolumes_b200 import scene
-    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], width=wl["w"], height=wl["h"])
+    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"),
+                     width=wl["w"], height=wl["h"])
     build_scene(o, wl, scene, o.TransformSH(scene.procedural_sky(64)))
     n, t0, samples = 0, time.perf_counter(), 0
     while n < args.cpu_baseline_frames and (n == 0 or time.perf_counter() - t0 < 25.0):

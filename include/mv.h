@@ -118,6 +118,21 @@ int mv_postprocess(mv_caster* c, uint32_t taa_on);
 /* SphericalHarmonics::Transform (XUSGSphericalHarmonics.h:25-26), order 3; cube = 6 x size x size x RGB f32 (host) */
 int mv_sh_project(mv_caster* c, const float* cube_rgb_f32, uint32_t size, float* coeffs27_out);
 
+/* ---- producer of the depth inputs: the occluder mesh ----
+ * ObjectRenderer's depth-only passes: Init's OBJ import and AABB (ObjectRenderer.cpp:68-77,
+ * XUSG/Optional/XUSGObjLoader.cpp:18-40, :166-228), SetWorld (:147-153), the light's orthographic
+ * view-projection of UpdateFrame (:171-190), RenderShadow (:220-243, D16 1024^2) and the depth pre-pass
+ * (:555-570, VSDepth.hlsl:25-28, D32 W x H). mv_mesh_render_depth rasterises both maps straight into the
+ * caster's scene depth and shadow map (what SetRenderTargets borrows in the reference) and returns the
+ * light's view-projection for mv_update_frame. Rasterisation rules: mv_mesh.cu. */
+int  mv_obj_parse(const char* path, float** positions_xyz, uint32_t* num_vertices, uint32_t** indices, uint32_t* num_indices); /* host only */
+void mv_obj_free(float* positions_xyz, uint32_t* indices);
+int  mv_mesh_set(mv_caster* c, const float* positions_xyz, uint32_t num_vertices, const uint32_t* indices, uint32_t num_indices);
+int  mv_mesh_load_obj(mv_caster* c, const char* path);
+int  mv_mesh_set_world(mv_caster* c, float scale, const float pos[3]);
+int  mv_mesh_render_depth(mv_caster* c, const float view_proj[16], float shadow_vp_out[16]);
+int  mv_read_depth(mv_caster* c, float* depth, uint16_t* shadow_d16, uint32_t* shadow_size);
+
 /* read-backs (host pointers; each synchronises the stream). The reference has no read-back API. */
 int mv_read_per_object(mv_caster* c, float* out56xN);
 int mv_read_visible(mv_caster* c, uint32_t* ids, uint32_t* count);

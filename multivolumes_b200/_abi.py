@@ -65,6 +65,10 @@ _COMMON = {
     "read_post": (C.c_int, [_vp, _vp, _vp]),
     "get_stats": (C.c_int, [_vp, P(Stats)]),
     "set_frame_index": (C.c_int, [_vp, u32]),
+    "mesh_set": (C.c_int, [_vp, _vp, u32, _vp, u32]),
+    "mesh_set_world": (C.c_int, [_vp, f32, P(f32)]),
+    "mesh_render_depth": (C.c_int, [_vp, P(f32), P(f32)]),
+    "read_depth": (C.c_int, [_vp, _vp, _vp, P(u32)]),
     "set_shard": (C.c_int, [_vp, u32, u32]),
     "set_row_band": (C.c_int, [_vp, u32, u32]),
 }
@@ -201,6 +205,32 @@ class CasterBase:
     def SetAmbient(self, color, intensity):
         a, pa = _fp(color)
         self._ck(self.b.set_ambient(self.h, pa, intensity), "set_ambient")
+
+    # --- the occluder mesh: ObjectRenderer's depth-only passes (ObjectRenderer.h; .cpp:147-243, 555-570) ---
+    def SetMesh(self, positions, indices):
+        """positions (V, 3) float32 and indices (3 T,) uint32 of a triangle list (createVB / createIB)."""
+        pos = np.ascontiguousarray(positions, np.float32).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, np.uint32).reshape(-1)
+        self._ck(self.b.mesh_set(self.h, pos.ctypes.data, pos.shape[0], idx.ctypes.data, idx.shape[0]), "mesh_set")
+
+    def SetMeshWorld(self, scale, pos):
+        a, pa = _fp(pos)
+        self._ck(self.b.mesh_set_world(self.h, scale, pa), "mesh_set_world")
+
+    def RenderMeshDepth(self, view_proj):
+        """RenderShadow + depth pre-pass into the caster's shadow map / scene depth; returns the light's view-projection."""
+        a, pa = _fp(np.asarray(view_proj).reshape(16))
+        out = np.zeros(16, np.float32)
+        self._ck(self.b.mesh_render_depth(self.h, pa, out.ctypes.data_as(P(f32))), "mesh_render_depth")
+        return out.reshape(4, 4)
+
+    def ReadDepth(self):
+        depth = np.empty((self.H, self.W), np.float32)
+        size = u32(0)
+        self._ck(self.b.read_depth(self.h, None, None, C.byref(size)), "read_depth")
+        shadow = np.empty((size.value, size.value), np.uint16)
+        self._ck(self.b.read_depth(self.h, depth.ctypes.data, shadow.ctypes.data if size.value else None, C.byref(size)), "read_depth")
+        return depth, shadow
 
     def UpdateFrame(self, view_proj, shadow_vp, eye):
         a, pa = _fp(np.asarray(view_proj).reshape(16))

@@ -52,6 +52,9 @@ _EXTRA = {
     "set_stream": (C.c_int, [_vp, _vp]),
     "get_stream": (C.c_int, [_vp, P(_vp)]),
     "frame_buffers": (C.c_int, [_vp, P(_vp), P(_vp), P(_vp)]),
+    "obj_parse": (C.c_int, [C.c_char_p, P(P(f32)), P(u32), P(P(u32)), P(u32)]),
+    "obj_free": (None, [P(f32), P(u32)]),
+    "mesh_load_obj": (C.c_int, [_vp, C.c_char_p]),
     "present_async": (C.c_int, [_vp, _vp, u32]),
     "present_wait": (C.c_int, [_vp, u32]),
 }
@@ -98,6 +101,21 @@ class PinnedBuffer:
             pass
 
 
+def parse_obj(path):
+    """XUSGObjLoader::Import(forDX = true) through mv_obj_parse (host only, no device needed): z negated, index list reversed."""
+    b = binding()
+    pos, idx, nv, ni = P(f32)(), P(u32)(), u32(0), u32(0)
+    rc = b.obj_parse(os.fsencode(path), C.byref(pos), C.byref(nv), C.byref(idx), C.byref(ni))
+    if rc != 0:
+        raise RuntimeError(f"mv_obj_parse failed (rc={rc}): {b.last_error().decode()}")
+    try:
+        positions = np.ctypeslib.as_array(pos, shape=(nv.value * 3,)).copy().reshape(-1, 3) if nv.value else np.zeros((0, 3), np.float32)
+        indices = np.ctypeslib.as_array(idx, shape=(ni.value,)).copy() if ni.value else np.zeros((0,), np.uint32)
+    finally:
+        b.obj_free(pos, idx)
+    return positions, indices
+
+
 class MultiRayCaster(CasterBase):
     """MultiVolumes/Content/MultiRayCaster.h:28-50 on one B200. Method names follow the reference class."""
 
@@ -125,6 +143,9 @@ class MultiRayCaster(CasterBase):
     def ReadPostInto(self, rgba8_ptr=None, taa_ptr=None):
         """Read-back into caller-owned (pinned) memory; pointers are integers."""
         self._ck(self.b.read_post(self.h, taa_ptr, rgba8_ptr), "read_post")
+
+    def LoadMeshObj(self, path):
+        self._ck(self.b.mesh_load_obj(self.h, os.fsencode(path)), "mesh_load_obj")
 
     def PresentAsync(self, rgba8_ptr, slot):
         """Swap-chain Present: asynchronous read-back of the back buffer into pinned memory (slot < 3 in flight)."""

@@ -216,7 +216,7 @@ static void destroy_caster(Caster& c)
     };
     for (auto& v : c.volumes) kill(v);
     for (auto& v : c.lightMaps) kill(v);
-    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
+    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
                      c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);

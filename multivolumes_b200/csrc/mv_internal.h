@@ -206,6 +206,14 @@ struct Caster {
     ushort4* dAttribs = nullptr;
     unsigned char* dLists = nullptr;     // FrameLists + visible + cubeVolumes + cubeTilePrefix
     StatsDev* dStats = nullptr;
+    // occluder mesh (mv_mesh.cu): the producer of the scene depth and the shadow map
+    float* dMeshPos = nullptr;           // V x 3
+    uint32_t* dMeshIdx = nullptr;        // 3 T
+    void* dMeshTris = nullptr;           // 2 T screen-space records of the pass being rasterised
+    uint32_t* dShadowBits = nullptr;     // S x S float bit patterns (depth test target of the shadow pass)
+    uint32_t meshNumIndices = 0;
+    float meshExtent = 1.0f;             // largest AABB extent (ObjectRenderer.cpp:74-76)
+    float meshScale = 1.0f, meshPos[3] = {0.0f, 0.0f, 0.0f};
     uint2* dDirectColor = nullptr;       // screen-space march results, directCapacity pixels
     uint2* dDirectStats = nullptr;       // allocated on first use with counters on
     uint32_t directCapacity = 0;

@@ -75,6 +75,12 @@ int mvo_resolve_oit(mvo_caster* c);
 int mvo_postprocess(mvo_caster* c, uint32_t taa_on);
 int mvo_sh_project(mvo_caster* c, const float* cube_rgb_f32, uint32_t size, float* coeffs27_out);
 
+/* ObjectRenderer's depth-only passes (same semantics as mv_mesh_* of the product) */
+int mvo_mesh_set(mvo_caster* c, const float* positions_xyz, uint32_t num_vertices, const uint32_t* indices, uint32_t num_indices);
+int mvo_mesh_set_world(mvo_caster* c, float scale, const float pos[3]);
+int mvo_mesh_render_depth(mvo_caster* c, const float view_proj[16], float shadow_vp_out[16]);
+int mvo_read_depth(mvo_caster* c, float* depth, uint16_t* shadow_d16, uint32_t* shadow_size);
+
 /* read-backs */
 int mvo_read_per_object(mvo_caster* c, float* out56xN);
 int mvo_read_visible(mvo_caster* c, uint32_t* ids, uint32_t* count);

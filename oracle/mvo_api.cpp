@@ -175,6 +175,90 @@ int mvo_set_light(mvo_caster* h, const float p[3], const float col[3], float int
     h->c.lightPt = {p[0], p[1], p[2]}; h->c.lightColor = {col[0], col[1], col[2], intensity};
     return 0;
 }
+// ---- occluder mesh: ObjectRenderer.cpp:68-77 (AABB), :147-153 (SetWorld), :171-190 (light view-projection) ----
+int mvo_mesh_set(mvo_caster* h, const float* pos, uint32_t nv, const uint32_t* idx, uint32_t ni)
+{
+    if (!h || ni % 3 != 0 || (ni && (!pos || !idx))) return -1;
+    for (uint32_t i = 0; i < ni; ++i) if (idx[i] >= nv) return -1;
+    Caster& c = h->c;
+    c.meshPos.assign(pos, pos + (size_t)nv * 3);
+    c.meshIdx.assign(idx, idx + ni);
+    c.meshExtent = 1.0f;
+    if (ni) {
+        float mn[3] = {kFltMax, kFltMax, kFltMax}, mx[3] = {-kFltMax, -kFltMax, -kFltMax};
+        for (uint32_t v = 0; v < nv; ++v)
+            for (int k = 0; k < 3; ++k) { mn[k] = fminf(mn[k], pos[3 * v + k]); mx[k] = fmaxf(mx[k], pos[3 * v + k]); }
+        c.meshExtent = fmaxf(mx[0] - mn[0], fmaxf(mx[1] - mn[1], mx[2] - mn[2]));
+    }
+    return 0;
+}
+int mvo_mesh_set_world(mvo_caster* h, float scale, const float pos[3])
+{
+    if (!h || !pos) return -1;
+    h->c.meshScale = scale; h->c.meshPosition = {pos[0], pos[1], pos[2]};
+    return 0;
+}
+namespace {
+// DirectXMath call sites of ObjectRenderer.cpp:182-186, evaluated in double and rounded once to fp32
+void mul44d(const double* A, const double* B, double* R)
+{
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            double s = 0.0;
+            for (int k = 0; k < 4; ++k) s += A[i * 4 + k] * B[k * 4 + j];
+            R[i * 4 + j] = s;
+        }
+}
+void look_at_lh(const double e[3], double M[16])   // XMMatrixLookAtLH(eye, 0, (0, 1, 0))
+{
+    const double up[3] = {0.0, 1.0, 0.0};
+    double z[3] = {0.0 - e[0], 0.0 - e[1], 0.0 - e[2]};
+    double l = sqrt(z[0] * z[0] + z[1] * z[1] + z[2] * z[2]);
+    for (double& v : z) v /= l;
+    double x[3] = {up[1] * z[2] - up[2] * z[1], up[2] * z[0] - up[0] * z[2], up[0] * z[1] - up[1] * z[0]};
+    l = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+    for (double& v : x) v /= l;
+    const double y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+    auto d3 = [](const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; };
+    const double m[16] = {x[0], y[0], z[0], 0, x[1], y[1], z[1], 0, x[2], y[2], z[2], 0, -d3(x, e), -d3(y, e), -d3(z, e), 1};
+    memcpy(M, m, sizeof m);
+}
+}
+int mvo_mesh_render_depth(mvo_caster* h, const float viewProj[16], float shadowVpOut[16])
+{
+    if (!h || !viewProj) return -1;
+    Caster& c = h->c;
+    const uint32_t S = 1024;   // m_shadowMapSize
+    const double s = c.meshScale;
+    const double world[16] = {s, 0, 0, 0, 0, s, 0, 0, 0, 0, s, 0, c.meshPosition.x, c.meshPosition.y, c.meshPosition.z, 1};
+    double vp[16], wvp[16], lv[16], lvp[16], swvp[16];
+    for (int i = 0; i < 16; ++i) vp[i] = viewProj[i];
+    mul44d(world, vp, wvp);
+    const double size = (double)(c.meshExtent * c.meshScale) * 1.5, zn = 1.0, zf = 200.0;
+    const double eye[3] = {c.lightPt.x, c.lightPt.y, c.lightPt.z};
+    look_at_lh(eye, lv);
+    const double lp[16] = {2.0 / size, 0, 0, 0, 0, 2.0 / size, 0, 0, 0, 0, 1.0 / (zf - zn), 0, 0, 0, -zn / (zf - zn), 1};
+    mul44d(lv, lp, lvp);
+    mul44d(world, lvp, swvp);
+    m44 W, SW;
+    for (int i = 0; i < 16; ++i) { W.m[i / 4][i % 4] = (float)wvp[i]; SW.m[i / 4][i % 4] = (float)swvp[i]; if (shadowVpOut) shadowVpOut[i] = (float)lvp[i]; }
+    std::vector<float> sd((size_t)S * S);
+    raster_depth(c.meshPos, c.meshIdx, SW, S, S, sd.data());
+    c.shadow.resize((size_t)S * S); c.shadowSize = S;
+    for (size_t i = 0; i < sd.size(); ++i) c.shadow[i] = (uint16_t)floorf(sd[i] * 65535.0f + 0.5f);
+    c.depth.resize((size_t)c.d.width * c.d.height);
+    raster_depth(c.meshPos, c.meshIdx, W, c.d.width, c.d.height, c.depth.data());
+    return 0;
+}
+int mvo_read_depth(mvo_caster* h, float* depth, uint16_t* shadow, uint32_t* shadowSize)
+{
+    if (!h) return -1;
+    Caster& c = h->c;
+    if (depth) memcpy(depth, c.depth.data(), c.depth.size() * sizeof(float));
+    if (shadow && c.shadowSize) memcpy(shadow, c.shadow.data(), c.shadow.size() * sizeof(uint16_t));
+    if (shadowSize) *shadowSize = c.shadowSize;
+    return 0;
+}
 int mvo_set_ambient(mvo_caster* h, const float col[3], float intensity)
 {
     if (!h) return -1;

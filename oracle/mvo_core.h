@@ -73,6 +73,11 @@ struct Caster {
     // the light map is filled in z-slabs of ceil(L / world), OIT and post-process cover rows [row0, row1)
     uint32_t shardRank = 0, shardWorld = 1;
     uint32_t row0 = 0, row1 = 0;
+    // occluder mesh (mvo_mesh.cpp)
+    std::vector<float> meshPos;           // V x 3
+    std::vector<uint32_t> meshIdx;        // 3 T
+    float meshExtent = 1.0f, meshScale = 1.0f;
+    f3 meshPosition = {0.0f, 0.0f, 0.0f};
 };
 
 // passes (mvo_passes.cpp)
@@ -85,5 +90,7 @@ void tone_map(Caster& c);
 void init_grid_data(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
 void sh_project(const float* cubeRGB, uint32_t size, float out27[27]);
 f4 evaluate_sh_irradiance(const f3 sh[9], f3 norm);
+// mvo_mesh.cpp: depth-only rasterisation of an indexed triangle list under wvp into depth[width * height]
+void raster_depth(const std::vector<float>& pos, const std::vector<uint32_t>& idx, const m44& wvp, uint32_t width, uint32_t height, float* depth);
 
 } // namespace mvo

@@ -95,3 +95,28 @@ def blob_shadow(size=64):
     d = np.full((size, size), 65535, np.uint16)
     d[(x - size * 0.45) ** 2 + (y - size * 0.5) ** 2 < (size * 0.2) ** 2] = 9000
     return d
+
+
+def uv_sphere(radius=1.0, center=(0.0, 0.0, 0.0), rings=24, sectors=48):
+    """Closed triangle mesh (positions (V, 3) float32, indices (3 T,) uint32) standing in for the reference's bunny.obj."""
+    pos, idx = [], []
+    for r in range(rings + 1):
+        th = np.pi * r / rings
+        for s in range(sectors):
+            ph = 2.0 * np.pi * s / sectors
+            pos.append((center[0] + radius * np.sin(th) * np.cos(ph), center[1] + radius * np.cos(th), center[2] + radius * np.sin(th) * np.sin(ph)))
+    for r in range(rings):
+        for s in range(sectors):
+            a, b = r * sectors + s, r * sectors + (s + 1) % sectors
+            c, d = a + sectors, b + sectors
+            idx += [a, c, b, b, c, d]
+    return np.asarray(pos, np.float32), np.asarray(idx, np.uint32)
+
+
+def triangle_soup(count, seed, extent=30.0, size=6.0):
+    """Random triangles, some of them large or crossing the camera's near plane."""
+    rs = np.random.RandomState(seed)
+    c = rs.uniform(-extent, extent, (count, 1, 3))
+    c[:, 0, 2] = rs.uniform(-110.0, 60.0, count)       # the default camera sits at z = -80
+    v = c + rs.uniform(-size, size, (count, 3, 3)) * rs.choice([0.2, 1.0, 6.0], (count, 1, 1))
+    return v.reshape(-1, 3).astype(np.float32), np.arange(3 * count, dtype=np.uint32)

@@ -33,7 +33,7 @@ with torch.cuda.stream(stream):
     x = CudaExchange(c, rank, world) if mode == "collective" else None
     r = ShardedRenderer(c, rank, world, mode=mode, exchange=x)
     for i in range(4):
-        vp, eye = scene.default_camera(640, 360, eye=(4.0 + 6 * i, 16.0, -80.0))
+        vp, eye = scene.default_camera(640, 360, eye=(4.0 + 6 * i, 16.0 + 8 * i, -80.0 - 30 * i))
         r.render(vp, None, eye, taa=True)
     c.Sync()
     dist.barrier()
@@ -53,7 +53,7 @@ def _single():
     c = MultiRayCaster(**kw)
     configure(c, sh=True, background=checker_background(640, 360))
     for i in range(4):
-        vp, eye = scene.default_camera(640, 360, eye=(4.0 + 6 * i, 16.0, -80.0))
+        vp, eye = scene.default_camera(640, 360, eye=(4.0 + 6 * i, 16.0 + 8 * i, -80.0 - 30 * i))
         c.UpdateFrame(vp, None, eye); c.ResetColor(); c.Render(); c.Postprocess(True)
     return c.ReadPost()[1]
 

@@ -359,3 +359,48 @@ def test_full_size_sharded_march_equals_unsharded():
         assert _same_bits(cw, cg) and np.array_equal(dw, dg)
         other = shards[(int(v) + 1) % world].ReadCubeMap(int(v), mip)[0]
         assert not other.view(np.uint16).any()          # not marched by a non-owner
+
+
+# ---------------------------------------------------------------- depth-input producer (occluder mesh)
+@pytest.mark.parametrize("mesh", ["sphere", "soup"])
+def test_mesh_depth_and_shadow_bit_exact(mesh):
+    from harness import triangle_soup, uv_sphere
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=640, height=360)
+    o, p = _pair(**kw)
+    pos, idx = uv_sphere(radius=5.0, rings=64, sectors=128) if mesh == "sphere" else triangle_soup(2000, seed=11)
+    vp, eye = scene.default_camera(640, 360)
+    svps = []
+    for c in (o, p):
+        c.SetLight(scene.LIGHT_PT, scene.LIGHT_COLOR, scene.LIGHT_INTENSITY)
+        c.SetMesh(pos, idx)
+        c.SetMeshWorld(1.8, (0.0, -9.0, 0.0))
+        svps.append(c.RenderMeshDepth(vp))
+    assert np.array_equal(svps[0], svps[1])
+    (do, so), (dp, sp) = o.ReadDepth(), p.ReadDepth()
+    assert (do < 1.0).sum() > 2000 and (so < 65535).sum() > 2000
+    assert np.array_equal(do.view(np.uint32), dp.view(np.uint32))
+    assert np.array_equal(so, sp)
+
+
+def test_frame_parity_with_rasterised_mesh_occluder():
+    """The whole producer -> consumer chain: depth and shadow map rasterised from a mesh, the light's view-projection
+    returned by the producer, then cull / light march (PCF shadow test) / view march / OIT against that depth."""
+    from harness import uv_sphere
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=16, num_volume_srcs=4, width=320, height=180)
+    o, p = _pair(**kw)
+    pos, idx = uv_sphere(radius=5.0, rings=32, sectors=64)
+    vp, eye = scene.default_camera(320, 180)
+    for c in (o, p):
+        configure(c, sh=True, background=checker_background(320, 180))
+        c.SetMesh(pos, idx)
+        c.SetMeshWorld(3.6, (0.0, -4.0, 0.0))
+        svp = c.RenderMeshDepth(vp)
+        c.UpdateFrame(vp, svp, eye)
+        for _ in range(2):
+            c.Render()
+    so, sp = o.GetStats(), p.GetStats()
+    for k in ("oit_fragments", "view_samples", "light_samples", "direct_samples"):
+        assert so[k] == sp[k], (k, so[k], sp[k])
+    fo, fp = o.ReadFrame(), p.ReadFrame()
+    if not _same_bits(fo, fp):
+        assert_image_close(fp, fo, "frame")
