@@ -82,6 +82,19 @@ int mv_volume_init_procedural(mv_caster* c, uint32_t src, uint32_t mode, uint32_
 int mv_volume_upload_rgba16f(mv_caster* c, uint32_t src, const uint16_t* texels);
 int mv_volume_upload_r32f(mv_caster* c, uint32_t src, const float* density);
 int mv_volume_read(mv_caster* c, uint32_t src, uint16_t* texels_out);
+/* LoadVolumeData from a file (MultiRayCaster.cpp:168-209; DDS::Loader, XUSG/Advanced/XUSGDDSLoader.h:21-37): a 3-D DDS
+ * with one scalar channel, of any resolution, resampled to the G^3 grid by CSR32FToRGBA16F's LINEAR fetch at the voxel
+ * centres (CSR32FToRGBA16F.hlsl:16-26). mv_dds_parse is host-only (no device needed). */
+enum { MV_DDS_R32_FLOAT = 1, MV_DDS_R16_FLOAT = 2, MV_DDS_R16_UNORM = 3, MV_DDS_R8_UNORM = 4 };
+typedef struct mv_dds_info {
+    uint32_t width, height, depth;
+    uint32_t format;            /* MV_DDS_* */
+    uint32_t bytes_per_texel;
+    uint32_t data_offset;       /* of the top mip level in the file */
+} mv_dds_info;
+int mv_dds_parse(const char* path, mv_dds_info* out);
+int mv_volume_upload_r32f_sized(mv_caster* c, uint32_t src, const float* density, uint32_t width, uint32_t height, uint32_t depth);
+int mv_volume_load_dds(mv_caster* c, uint32_t src, const char* path);
 
 /* SetRenderTargets / SetViewport (MultiRayCaster.h:37-38): scene depth D32 WxH (NULL = 1.0),
  * shadow map D16 SxS (NULL = none -> unshadowed), colour RT RGBA16F WxH that the volumes are

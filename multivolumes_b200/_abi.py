@@ -37,6 +37,7 @@ _COMMON = {
     "volume_init_procedural": (C.c_int, [_vp, u32, u32, u32]),
     "volume_upload_rgba16f": (C.c_int, [_vp, u32, _vp]),
     "volume_upload_r32f": (C.c_int, [_vp, u32, _vp]),
+    "volume_upload_r32f_sized": (C.c_int, [_vp, u32, _vp, u32, u32, u32]),
     "volume_read": (C.c_int, [_vp, u32, _vp]),
     "set_targets": (C.c_int, [_vp, _vp, _vp, u32, _vp, _vp]),
     "reset_color": (C.c_int, [_vp]),
@@ -146,7 +147,11 @@ class CasterBase:
 
     def LoadVolumeData(self, i, data):
         data = np.ascontiguousarray(data)
-        if data.dtype == np.float32:
+        if data.dtype == np.float32 and data.ndim == 3 and data.shape != (self.G,) * 3:
+            # a scalar source of another resolution: resampled by CSR32FToRGBA16F's LINEAR fetch (array is [z][y][x])
+            d, h, w = data.shape
+            self._ck(self.b.volume_upload_r32f_sized(self.h, i, data.ctypes.data, w, h, d), "volume_upload_r32f_sized")
+        elif data.dtype == np.float32:
             assert data.size == self.G ** 3
             self._ck(self.b.volume_upload_r32f(self.h, i, data.ctypes.data), "volume_upload_r32f")
         else:

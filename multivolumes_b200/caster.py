@@ -31,6 +31,10 @@ class ExchangeLayout(C.Structure):
                [("light_slab_depth", u32), ("reserved", u32)]
 
 
+class DdsInfo(C.Structure):
+    _fields_ = [(k, u32) for k in ("width", "height", "depth", "format", "bytes_per_texel", "data_offset")]
+
+
 u64p = P(C.c_uint64)
 _EXTRA = {
     "last_error": (C.c_char_p, []),
@@ -52,6 +56,8 @@ _EXTRA = {
     "set_stream": (C.c_int, [_vp, _vp]),
     "get_stream": (C.c_int, [_vp, P(_vp)]),
     "frame_buffers": (C.c_int, [_vp, P(_vp), P(_vp), P(_vp)]),
+    "dds_parse": (C.c_int, [C.c_char_p, P(DdsInfo)]),
+    "volume_load_dds": (C.c_int, [_vp, u32, C.c_char_p]),
     "obj_parse": (C.c_int, [C.c_char_p, P(P(f32)), P(u32), P(P(u32)), P(u32)]),
     "obj_free": (None, [P(f32), P(u32)]),
     "mesh_load_obj": (C.c_int, [_vp, C.c_char_p]),
@@ -116,6 +122,16 @@ def parse_obj(path):
     return positions, indices
 
 
+def parse_dds(path):
+    """Header of a 3-D scalar DDS through mv_dds_parse (host only): dict of width, height, depth, format, bytes_per_texel, data_offset."""
+    b = binding()
+    info = DdsInfo()
+    rc = b.dds_parse(os.fsencode(path), C.byref(info))
+    if rc != 0:
+        raise RuntimeError(f"mv_dds_parse failed (rc={rc}): {b.last_error().decode()}")
+    return {k: int(getattr(info, k)) for k, _ in DdsInfo._fields_}
+
+
 class MultiRayCaster(CasterBase):
     """MultiVolumes/Content/MultiRayCaster.h:28-50 on one B200. Method names follow the reference class."""
 
@@ -143,6 +159,10 @@ class MultiRayCaster(CasterBase):
     def ReadPostInto(self, rgba8_ptr=None, taa_ptr=None):
         """Read-back into caller-owned (pinned) memory; pointers are integers."""
         self._ck(self.b.read_post(self.h, taa_ptr, rgba8_ptr), "read_post")
+
+    def LoadVolumeFile(self, i, path):
+        """MultiRayCaster::LoadVolumeData(cmdList, i, fileName): DDS import + CSR32FToRGBA16F."""
+        self._ck(self.b.volume_load_dds(self.h, i, os.fsencode(path)), "volume_load_dds")
 
     def LoadMeshObj(self, path):
         self._ck(self.b.mesh_load_obj(self.h, os.fsencode(path)), "mesh_load_obj")

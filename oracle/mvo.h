@@ -51,6 +51,7 @@ void mvo_destroy(mvo_caster* c);
 int mvo_volume_init_procedural(mvo_caster* c, uint32_t src, uint32_t mode, uint32_t seed);
 int mvo_volume_upload_rgba16f(mvo_caster* c, uint32_t src, const uint16_t* texels);
 int mvo_volume_upload_r32f(mvo_caster* c, uint32_t src, const float* density);
+int mvo_volume_upload_r32f_sized(mvo_caster* c, uint32_t src, const float* density, uint32_t width, uint32_t height, uint32_t depth);
 int mvo_volume_read(mvo_caster* c, uint32_t src, uint16_t* texels_out);
 
 /* MultiRayCaster::SetRenderTargets / SetViewport: borrowed scene depth, shadow map, colour RT */

@@ -116,6 +116,36 @@ int mvo_volume_upload_r32f(mvo_caster* h, uint32_t src, const float* density)   
     }
     return 0;
 }
+// CSR32FToRGBA16F.hlsl:16-26 on a source of any resolution: LINEAR / clamp fetch at the voxel centres. Texel
+// addressing and the 8-bit weights follow the texture-unit model of mvo_sampler.h; the fp32 texels are blended
+// in double (the unit's internal precision for 32-bit float texels is not modelled: the parity test allows
+// one fp16 ulp on resampled volumes and is exact when the source already has the grid's resolution).
+int mvo_volume_upload_r32f_sized(mvo_caster* h, uint32_t src, const float* density, uint32_t w, uint32_t hh, uint32_t d)
+{
+    if (!h || !density || !ok_src(h->c, src) || !w || !hh || !d) return -1;
+    auto& t = h->c.volumes[src];
+    const int n = (int)t.n;
+    const uint16_t one = f32_to_f16(1.0f);
+    for (int z = 0; z < n; ++z)
+        for (int y = 0; y < n; ++y)
+            for (int x = 0; x < n; ++x) {
+                const float gs = (float)n;
+                const AxisFix ax = axis_sm100(((float)x + 0.5f) / gs, (int)w), ay = axis_sm100(((float)y + 0.5f) / gs, (int)hh),
+                              az = axis_sm100(((float)z + 0.5f) / gs, (int)d);
+                int wt[8];
+                weights_sm100(ax.frac, ay.frac, az.frac, wt);
+                double acc = 0.0;
+                for (int k = 0; k < 8; ++k) {
+                    const int xi = (k & 1) ? ax.i1 : ax.i0, yi = (k & 2) ? ay.i1 : ay.i0, zi = (k & 4) ? az.i1 : az.i0;
+                    acc += (double)wt[k] * (double)density[((size_t)zi * hh + yi) * w + xi];
+                }
+                const float a = (float)(acc / 256.0);
+                const size_t i = ((size_t)z * n + y) * n + x;
+                t.texels[i * 4 + 0] = one; t.texels[i * 4 + 1] = one; t.texels[i * 4 + 2] = one;
+                t.texels[i * 4 + 3] = f32_to_f16(a * 0.25f);
+            }
+    return 0;
+}
 int mvo_volume_read(mvo_caster* h, uint32_t src, uint16_t* out)
 {
     if (!h || !out || !ok_src(h->c, src)) return -1;

@@ -404,3 +404,31 @@ def test_frame_parity_with_rasterised_mesh_occluder():
     fo, fp = o.ReadFrame(), p.ReadFrame()
     if not _same_bits(fo, fp):
         assert_image_close(fp, fo, "frame")
+
+
+# ---------------------------------------------------------------- DDS ingest
+@pytest.mark.parametrize("kind,dx10,res", [("r32f", True, 32), ("r16f", True, 32), ("r8un", False, 32), ("r32f", True, 48), ("r16f", False, 20)])
+def test_dds_volume_ingest(tmp_path, kind, dx10, res):
+    """LoadVolumeData from a file: the product parses the DDS and resamples on the texture unit, the oracle gets the same
+    texels as an array. Same resolution as the grid: bit-exact. Other resolutions: within one fp16 ulp (the filter
+    precision of the unit for 32-bit float texels is not modelled by the oracle)."""
+    from dds_util import write_dds
+    o, p = _pair(**SMALL)
+    G = o.G
+    rs = np.random.RandomState(res)
+    zz, yy, xx = np.meshgrid(*[np.linspace(-1, 1, res)] * 3, indexing="ij")
+    vol = (np.clip(1.2 - np.sqrt(xx * xx + yy * yy + zz * zz), 0, 1) * rs.uniform(0.6, 1.0, (res, res, res))).astype(np.float32)
+    path = tmp_path / "vol.dds"
+    raw = write_dds(str(path), vol, kind, dx10)
+    stored = raw.astype(np.float32) / {"r8un": 255.0, "r16un": 65535.0}.get(kind, 1.0)
+    p.LoadVolumeFile(0, str(path))
+    o.LoadVolumeData(0, stored if res != G else stored.reshape(-1))
+    vo, vp_ = o.ReadVolume(0), p.ReadVolume(0)
+    assert np.array_equal(vo[..., :3], vp_[..., :3])
+    if res == G:
+        assert np.array_equal(vo, vp_)
+    else:
+        diff = np.abs(vo[..., 3].astype(np.int32) - vp_[..., 3].astype(np.int32))      # fp16 bit patterns of non-negative values
+        assert diff.max() <= 1, diff.max()
+        assert (diff > 0).mean() < 0.2
+    assert vp_.view(np.float16)[..., 3].max() > 0.1
