@@ -341,16 +341,20 @@ constexpr uint32_t kItemSentinel = 0xffffffffu;
 // into segment offsets (so that a warp of pass 5 never straddles two volumes); the padding slots are
 // marked, the counts reset for the next frame, and the frame falls back to inline marching when the
 // rays do not fit the buffers.
-__global__ void __launch_bounds__(1024) k_light_scan(DeviceScene s, FrameCB cb)
+// The segment of the light volume itself goes last: its rays are the bulk and L2-warm (short steps), whereas the
+// rays through other volumes miss to HBM on nearly every step; started first, their long chains overlap the bulk
+// instead of forming the tail of pass 5.
+__global__ void __launch_bounds__(1024) k_light_scan(DeviceScene s, FrameCB cb, int volumeOverride)
 {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_running;
     const uint32_t N = cb.numVolumes, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t ownVolume = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
     if (threadIdx.x == 0) s_running = 0;
     __syncthreads();
     for (uint32_t tile = 0; tile < N; tile += 1024) {
         const uint32_t n = tile + threadIdx.x;
-        const uint32_t c = n < N ? s.lightSeg[n] : 0u;
+        const uint32_t c = (n < N && n != ownVolume) ? s.lightSeg[n] : 0u;
         const uint32_t padded = (c + 31u) & ~31u;
         uint32_t incl = padded;
 #pragma unroll
@@ -360,7 +364,7 @@ __global__ void __launch_bounds__(1024) k_light_scan(DeviceScene s, FrameCB cb)
         uint32_t before = s_running;
         for (uint32_t w = 0; w < warp; ++w) before += s_warp[w];
         const uint32_t start = before + incl - padded;
-        if (n < N) {
+        if (n < N && n != ownVolume) {
             s.lightSeg[N + n] = start;
             s.lightSeg[n] = 0;
             for (uint32_t q = start + c; q < start + padded; ++q)
@@ -369,6 +373,14 @@ __global__ void __launch_bounds__(1024) k_light_scan(DeviceScene s, FrameCB cb)
         __syncthreads();
         if (threadIdx.x == 1023) s_running = before + incl;
         __syncthreads();
+    }
+    if (threadIdx.x == 0 && ownVolume < N) {
+        const uint32_t c = s.lightSeg[ownVolume], padded = (c + 31u) & ~31u, start = s_running;
+        s.lightSeg[N + ownVolume] = start;
+        s.lightSeg[ownVolume] = 0;
+        for (uint32_t q = start + c; q < start + padded; ++q)
+            if (q < s.lightItemCapacity) s.lightItems[q] = make_uint4(kItemSentinel, 0u, 0u, 0u);
+        s_running = start + padded;
     }
     if (threadIdx.x == 0) {
         s.lists->lightItemCount = s_running;
@@ -561,7 +573,7 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
     k_ray_march_l<<<c.smCount * perSM, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
     mark(2);
     if (!c.cb.hasSH) return;
-    k_light_scan<<<1, 1024, 0, c.stream>>>(c.scene(), c.cb);
+    k_light_scan<<<1, 1024, 0, c.stream>>>(c.scene(), c.cb, volumeOverride);
     mark(3);
     k_light_emit<<<c.smCount * perSMEmit, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride);
     mark(4);
