@@ -181,6 +181,19 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
     }
 
     const uint32_t visibleCount = s_baseVis, cubeCount = s_baseCube;
+    // Order in which the persistent view march walks the cube-map volumes: longest rays (largest sample count) first, so
+    // that the kernel ends on short rays instead of draining the SMs behind a few 256-step chains. Rank sort over the
+    // whole CTA (cubeCount^2 / 1024 comparisons per thread); the cube-map volume LIST itself stays in ascending order.
+    for (uint32_t k = threadIdx.x; k < cubeCount; k += kCullThreads) {
+        const uint32_t key = s.attribs[s.cubeVolumes[k]].y;
+        uint32_t rank = 0;
+        for (uint32_t j = 0; j < cubeCount; ++j) {
+            const uint32_t kj = s.attribs[s.cubeVolumes[j]].y;
+            rank += (kj > key || (kj == key && j < k)) ? 1u : 0u;
+        }
+        s.marchOrder[rank] = k;
+    }
+    __syncthreads();
     // Screen-space marches (RayCast, volumes on the direct scheme: VSCube.hlsl:73): every such visible volume gets its
     // screen rectangle as a slice of the result buffer and a run of 8x4-pixel tiles (warp 1, two shuffle scans). A
     // rectangle that does not fit the buffer gets no slice: the resolve kernel marches that volume itself.
@@ -222,7 +235,7 @@ __global__ void __launch_bounds__(kCullThreads, 1) k_cull(DeviceScene s, FrameCB
             const uint32_t k = base + lane;
             uint32_t tiles = 0;
             if (k < cubeCount) {
-                const uint32_t vol = s.cubeVolumes[k];
+                const uint32_t vol = s.cubeVolumes[s.marchOrder[k]];
                 if (vol % s.shardWorld == s.shardRank) {
                     const ushort4 a = s.attribs[vol];
                     const uint32_t size = cb.gridSize >> a.x;

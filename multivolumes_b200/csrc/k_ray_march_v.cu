@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
             const uint32_t mid = (lo + hi) >> 1;
             if (__ldg(s.cubeTilePrefix + mid) <= w) lo = mid; else hi = mid;
         }
-        const uint32_t volumeId = __ldg(s.cubeVolumes + lo);
+        const uint32_t volumeId = __ldg(s.cubeVolumes + __ldg(s.marchOrder + lo));
         const uint32_t local = w - __ldg(s.cubeTilePrefix + lo);
         const ushort4 a = s.attribs[volumeId];
         const uint32_t mip = a.x, smpCount = a.y, maskBits = a.z, volTexId = a.w;

@@ -53,6 +53,7 @@ DeviceScene Caster::scene() const
     s.cubeTilePrefix = tail + 2 * N;
     s.directTilePrefix = tail + 3 * N + 1;
     s.directOffset = tail + 4 * N + 2;
+    s.marchOrder = tail + 5 * N + 2;
     s.visInfo = reinterpret_cast<VisInfo*>(dLists + frame_lists_header_bytes(N));
     s.directColor = dDirectColor;
     s.directStats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dDirectStats : nullptr;

@@ -57,7 +57,7 @@ struct FrameLists {
     uint32_t directTileTotal;   // 8x4-pixel tiles of the screen-space marches (direct-scheme volumes)
     uint32_t directTileCursor;  // work cursor of the persistent direct-march kernel
     uint32_t pad0[3];
-    // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1], directTilePrefix[N + 1], directOffset[N]
+    // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1], directTilePrefix[N + 1], directOffset[N], marchOrder[N]
 };
 
 // Per visible volume (same order as the visible list), written by the cull for the OIT resolve: the
@@ -86,7 +86,7 @@ static_assert(sizeof(LightRec) == 64, "LightRec layout");
 
 constexpr uint32_t kNoDirect = 0xffffffffu;
 // bytes of the per-frame lists in front of the VisInfo records (mv_api.cu lays the block out)
-MV_HD size_t frame_lists_header_bytes(size_t N) { return (sizeof(FrameLists) + (5 * N + 2) * sizeof(uint32_t) + 31) & ~(size_t)31; }
+MV_HD size_t frame_lists_header_bytes(size_t N) { return (sizeof(FrameLists) + (6 * N + 2) * sizeof(uint32_t) + 31) & ~(size_t)31; }
 
 struct StatsDev {
     unsigned long long view_rays, view_samples, view_light_fetches;
@@ -125,7 +125,8 @@ struct DeviceScene {
     FrameLists* lists;
     uint32_t* visible;                   // [N]
     uint32_t* cubeVolumes;               // [N]
-    uint32_t* cubeTilePrefix;            // [N + 1]
+    uint32_t* cubeTilePrefix;            // [N + 1] over marchOrder
+    uint32_t* marchOrder;                // [N] indices into cubeVolumes, longest rays first
     VisInfo* visInfo;                    // [N]
     uint32_t* directTilePrefix;          // [N + 1] over the visible list: tiles of the screen-space march of each direct-scheme volume
     uint32_t* directOffset;              // [N] over the visible list: first pixel of the volume's rectangle in directColor (kNoDirect = none)
