@@ -193,6 +193,21 @@ MV_D V3 shadow_dir_local(const FrameCB& cb, const PerObject* po, const float* s_
     return normalize(mul_v33(V3{cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]}, po->worldI));      // :91-92 (directional)
 }
 
+MV_D void store_rec(LightRec* dst, const LightRec& r)
+{
+    const uint4* w = reinterpret_cast<const uint4*>(&r);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    d[0] = w[0]; d[1] = w[1]; d[2] = w[2]; d[3] = w[3];
+}
+MV_D LightRec load_rec(const LightRec* src)
+{
+    LightRec r;
+    uint4* w = reinterpret_cast<uint4*>(&r);
+    const uint4* p = reinterpret_cast<const uint4*>(src);
+    w[0] = __ldg(p); w[1] = __ldg(p + 1); w[2] = __ldg(p + 2); w[3] = __ldg(p + 3);
+    return r;
+}
+
 // What the volume loop needs to know about one voxel.
 struct LightVoxel {
     V3 rayOrigin;      // world space (:48)
@@ -325,7 +340,7 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_marc
         if (live) {
             rec.itemBase = warpBase + incl - numItems; rec.itemCount = numItems;
             rec.aoDir[0] = aoRayDir.x; rec.aoDir[1] = aoRayDir.y; rec.aoDir[2] = aoRayDir.z; rec.pad = 0;
-            s.lightRecs[base + lane] = rec;
+            store_rec(s.lightRecs + base + lane, rec);
         }
     }
     if (s.stats) {
@@ -424,7 +439,7 @@ __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, Fra
         if (base >= count) break;
         if (base + lane >= count) continue;
         const uint32_t recIdx = base + lane;
-        const LightRec rec = s.lightRecs[recIdx];
+        const LightRec rec = load_rec(s.lightRecs + recIdx);
         if (!overflow && rec.itemCount <= kLightRecHits) {
             for (uint32_t j = 0; j < rec.itemCount; ++j) {
                 uint32_t hit = 0;
@@ -519,16 +534,18 @@ __global__ void __launch_bounds__(256) k_light_finalize(DeviceScene s, FrameCB c
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= s.lists->lightDenseCount) return;
     const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
-    const LightRec* rec = s.lightRecs + i;
-    float ao = rec->ao;
-    const uint32_t itemBase = rec->itemBase, itemCount = rec->itemCount;
+    // the first two 16-byte words of the record: {voxel, itemBase, itemCount, shadow}, {aoDir, ao}
+    const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(s.lightRecs + i));
+    const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(s.lightRecs + i) + 1);
+    float ao = __uint_as_float(w1.w);
+    const uint32_t itemBase = w0.y, itemCount = w0.z;
     for (uint32_t j = 0; j < itemCount; ++j) ao *= __ldg(s.lightItemResults + itemBase + j);
-    const V3 aoRayDir = {rec->aoDir[0], rec->aoDir[1], rec->aoDir[2]};
+    const V3 aoRayDir = {__uint_as_float(w1.x), __uint_as_float(w1.y), __uint_as_float(w1.z)};
     const V3 irradiance = evaluate_sh_irradiance(cb.sh, normalize(aoRayDir));                       // GetIrradiance
     const uint32_t L = cb.lightGridSize;
     uint32_t x, y, z;
-    light_voxel_center(rec->voxel, L, x, y, z);
-    const float shadow = rec->shadow;
+    light_voxel_center(w0.x, L, x, y, z);
+    const float shadow = __uint_as_float(w0.w);
     const V3 lightColor = {cb.lightColor[0] * cb.lightColor[3], cb.lightColor[1] * cb.lightColor[3], cb.lightColor[2] * cb.lightColor[3]};
     const V3 ambient = {ao * irradiance.x, ao * irradiance.y, ao * irradiance.z};                   // :117
     store_light_voxel(s, tgt, volumeId, L, x, y, z,

@@ -71,7 +71,7 @@ struct VisInfo {
 // Light march, per dense voxel (k_ray_march_l.cu): what the finalize pass needs once the voxel's
 // deferred ambient-occlusion rays have been marched.
 constexpr uint32_t kLightRecHits = 6;
-struct LightRec {
+struct alignas(16) LightRec {   // moved as four 16-byte words
     uint32_t voxel;        // (z L + y) L + x
     uint32_t itemBase;     // first of the voxel's AO factors (ascending volume index)
     uint32_t itemCount;
