@@ -35,7 +35,7 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_ray_march_v from the committed ncu --set full capture
 # (profiles/r01_march_v_ncu_raw.csv); only known for the workload that was profiled
-NCU_TRAFFIC_BYTES = {"cfg2": 177.6e6 + 11.5e6}
+NCU_TRAFFIC_BYTES = {"cfg2": 172.1e6 + 11.5e6}
 TEX_PEAK_GFETCH = 575.9   # measured on this pool's B200: profiles/r01_tex_probe.json (trilinear RGBA16F fetches/s, L1-resident)
 
 
@@ -70,7 +70,7 @@ class ClockSampler:
     def __init__(self, index):
         self.rows, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -157,6 +157,16 @@ def run_reference(args, wl, rank, world):
                                        f"frames/s = steps / (time x {S}); calibration full frame {t_full:.2f} s"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     return line
+
+
+def launches_per_frame(wl, world, exchange):
+    """Kernels of libmv_b200.so per frame: k_cull; the light march (k_light_classify, k_ray_march_l and, with a light probe,
+    k_light_scan, k_light_emit, k_light_ao, k_light_finalize); k_ray_march_v; k_ray_cast_direct; k_resolve_oit; k_postprocess.
+    Sharded, fused exchange: + k_light_commit and three peer barriers (k_peer_signal + k_peer_wait each)."""
+    n = 1 + (6 if wl["sh"] else 2) + 1 + 1 + 1 + 1
+    if world > 1:
+        n += 1 + (6 if exchange == "fused" else 0)
+    return n
 
 
 def workload_config(args, wl, world):
@@ -248,17 +258,25 @@ def main():
             sampler.window(t_wall0, t_wall1)
             clocks = sampler.stop()
 
-        # ---- per-pass device time and sample counts: a second, instrumented pass over the same frames ----
+        # ---- per-pass device time and work counters: two more passes over the same frames ----
+        # (a) CUDA events on the caster's stream around every pass, with the same kernels as the timed loop;
+        # (b) the counting variants of the kernels (samples, fetches, rays), not timed.
         n_prof = min(args.steps, 50)
-        c.SetInstrumentation(True, True)
-        for i in range(n_prof):
-            frame(args.warmup + i)
-            t = c.GetTimings()            # CUDA events recorded on the caster's stream around every pass
-            for k in acc:
-                acc[k] += t[k]
-            st = c.GetStats()
-            for k, v in st.items():
-                stats_acc[k] = stats_acc.get(k, 0) + v
+        for count, timed in ((False, True), (True, False)):
+            c.SetInstrumentation(count, timed)
+            for i in range(3):            # kernels are loaded on first launch (lazy module loading): keep that out of the averages
+                frame(i)
+            c.Sync()
+            for i in range(n_prof):
+                frame(args.warmup + i)
+                if timed:
+                    t = c.GetTimings()
+                    for k in acc:
+                        acc[k] += t[k]
+                else:
+                    st = c.GetStats()
+                    for k, v in st.items():
+                        stats_acc[k] = stats_acc.get(k, 0) + v
         barrier()
         c.SetInstrumentation(False, False)
         per_pass = {k: v / n_prof for k, v in acc.items()}
@@ -329,7 +347,7 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": wl["n"] * 224, "d2h_bytes_per_step": wl["w"] * wl["h"] * 4,
                         "steps": n_e2e, "checksum": checksum,
                         "frames_in_flight": 3, "blocking_readback_value": e2e_blocking_fps},
-                "gpu_launches": args.steps * (5 if world == 1 else (10 if args.exchange == "fused" else 6)),
+                "gpu_launches": args.steps * launches_per_frame(wl, world, args.exchange),
                 "clocks": clocks,
                 "per_pass_ms": per_pass, "per_pass_note": "rank 0, instrumented pass (CUDA events around each pass; at N > 1 the light and view marches include their peer barriers)",
                 "roofline": {"kernel": "k_ray_march_v", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
