@@ -38,6 +38,8 @@ public:
     // LoadVolumeData (:35-36): R32F density (the DDS payload) through the CSR32FToRGBA16F conversion, or RGBA16F texels
     bool LoadVolumeData(uint32_t i, const float* density) { return ok(mv_volume_upload_r32f(m_h, i, density)); }
     bool LoadVolumeData(uint32_t i, const uint16_t* rgba16f) { return ok(mv_volume_upload_rgba16f(m_h, i, rgba16f)); }
+    // LoadVolumeData(cmdList, i, fileName, uploaders), MultiRayCaster.h:35-36: a 3-D scalar DDS of any resolution
+    bool LoadVolumeData(uint32_t i, const char* ddsFileName) { return ok(mv_volume_load_dds(m_h, i, ddsFileName)); }
     // InitVolumeData (:40)
     bool InitVolumeData(uint32_t i, uint32_t mode = 0, uint32_t seed = 0) { return ok(mv_volume_init_procedural(m_h, i, mode, seed)); }
     // SetRenderTargets + SetViewport (:37-38): scene depth, shadow map, colour RT (device pointers, as the reference borrows GPU resources)
@@ -63,6 +65,17 @@ public:
     // ObjectRenderer::Postprocess (ObjectRenderer.h:46-48)
     bool Postprocess(bool taa = true) { return ok(mv_postprocess(m_h, taa ? 1u : 0u)); }
     // XUSG SphericalHarmonics::Transform (XUSGSphericalHarmonics.h:25-26)
+    // ObjectRenderer's depth-only passes (ObjectRenderer.h: Init's mesh import, SetWorld, RenderShadow + depth pre-pass):
+    // RenderMeshDepth fills the scene depth and the shadow map this caster reads, and returns UpdateFrame's shadowVP
+    bool LoadMesh(const char* objFileName) { return ok(mv_mesh_load_obj(m_h, objFileName)); }
+    bool SetMesh(const float* positions, uint32_t numVertices, const uint32_t* indices, uint32_t numIndices)
+    { return ok(mv_mesh_set(m_h, positions, numVertices, indices, numIndices)); }
+    bool SetMeshWorld(float scale, const float pos[3]) { return ok(mv_mesh_set_world(m_h, scale, pos)); }
+    bool RenderMeshDepth(const float viewProj[16], float shadowVP[16]) { return ok(mv_mesh_render_depth(m_h, viewProj, shadowVP)); }
+    // Present with FrameCount = 3 frames in flight: asynchronous read-back of the RGBA8 back buffer into pinned memory
+    bool Present(uint8_t* pinnedRGBA8, uint32_t slot) { return ok(mv_present_async(m_h, pinnedRGBA8, slot)); }
+    bool WaitPresent(uint32_t slot) { return ok(mv_present_wait(m_h, slot)); }
+
     bool TransformSH(const float* cubeRGB, uint32_t size, float coeffs27[27]) { return ok(mv_sh_project(m_h, cubeRGB, size, coeffs27)); }
 
     bool ReadFrame(uint16_t* rgba16f) { return ok(mv_read_frame(m_h, rgba16f)); }
