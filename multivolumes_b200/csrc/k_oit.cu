@@ -276,7 +276,10 @@ __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(D
 
 constexpr int kOitChunk = 256;   // visible volumes binned per pass over the CTA's 16x16-pixel tile
 
-__global__ void __launch_bounds__(256) k_resolve_oit(DeviceScene s, FrameCB cb)
+#ifndef MV_OIT_MIN_BLOCKS
+#define MV_OIT_MIN_BLOCKS 4   // 64 registers, 32 warps / SM: the resolve is issue-bound, measured -8 % against 3 CTAs (75 registers)
+#endif
+__global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceScene s, FrameCB cb)
 {
     __shared__ VisInfo s_cand[kOitChunk];       // volumes whose screen rectangle overlaps this tile, list order kept
     __shared__ uint32_t s_candSlot[kOitChunk];  // their index in the visible list
