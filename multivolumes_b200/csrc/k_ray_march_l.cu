@@ -567,6 +567,7 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
         for (uint32_t p = 0; p < tgt.numPeers; ++p)
             tgt.peerStaging[p] = (p == c.shardRank) ? nullptr : reinterpret_cast<uint2*>(c.peerBlock[p] + c.layout.light_staging_offset);
     }
+    if (c.lightToStaging) tgt.staging = c.dLightStaging;   // pipelined frame: the main stream commits it (mv_api.cu)
     if (tgt.z1 <= tgt.z0) return;
     const uint32_t voxels = L * L * (tgt.z1 - tgt.z0);
     const uint32_t bricks = ((L + 7) / 8) * ((L + 3) / 4) * ((tgt.z1 - tgt.z0 + 3) / 4);

@@ -198,6 +198,25 @@ static void wait_back_buffer_free(Caster& c)
             MV_CUDA(cudaMalloc(&(c).dDirectStats, std::max<size_t>((c).directCapacity, 1) * sizeof(uint2)));    \
     } while (0)
 
+static bool pipelined(const Caster& c)
+{
+    return c.overlapLight && c.shardWorld == 1 && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES));
+}
+
+// A new frame's lists and attributes go into the other buffer (the previous frame's resolve may still read its own)
+static void flip_frame_lists(Caster& c)
+{
+    c.listParity ^= 1u;
+    c.dLists = c.dLists2[c.listParity];
+    c.dAttribs = c.dAttribs2[c.listParity];
+}
+
+// The PerObject records may have been uploaded on the other stream
+static void wait_upload(Caster& c, cudaStream_t s)
+{
+    if (c.lastUpload >= 0) cudaStreamWaitEvent(s, c.uploadDone[c.lastUpload], 0);
+}
+
 static int check_launch(const char* what)
 {
     const cudaError_t e = cudaGetLastError();
@@ -217,7 +236,8 @@ static void destroy_caster(Caster& c)
     };
     for (auto& v : c.volumes) kill(v);
     for (auto& v : c.lightMaps) kill(v);
-    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject, c.dVolumeDescs, c.dAttribs, c.dLists, c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
+    void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject2[0], c.dPerObject2[1], c.dVolumeDescs, c.dAttribs2[0], c.dAttribs2[1],
+                     c.dLists2[0], c.dLists2[1], c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
                      c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
@@ -226,6 +246,9 @@ static void destroy_caster(Caster& c)
     for (auto& e : c.presentDone) if (e) cudaEventDestroy(e);
     if (c.frameDone) cudaEventDestroy(c.frameDone);
     if (c.copyStream) { cudaStreamSynchronize(c.copyStream); cudaStreamDestroy(c.copyStream); }
+    if (c.lightStream) { cudaStreamSynchronize(c.lightStream); cudaStreamDestroy(c.lightStream); }
+    for (cudaEvent_t e : {c.lightDone, c.commitDone, c.inputsReady, c.frameEnd[0], c.frameEnd[1]}) if (e) cudaEventDestroy(e);
+    c.dPerObject = nullptr; c.dAttribs = nullptr; c.dLists = nullptr;
     if (c.ownStream) cudaStreamDestroy(c.ownStream);
 }
 
@@ -285,6 +308,14 @@ int mv_create(const mv_desc* d, mv_caster** out)
     c.stream = c.ownStream;
     for (auto& e : c.ev) MV_CUDA_C(cudaEventCreate(&e));
     MV_CUDA_C(cudaStreamCreateWithFlags(&c.copyStream, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        MV_CUDA_C(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        MV_CUDA_C(cudaStreamCreateWithPriority(&c.lightStream, cudaStreamNonBlocking, hi));
+        for (cudaEvent_t* e : {&c.lightDone, &c.commitDone, &c.inputsReady, &c.frameEnd[0], &c.frameEnd[1]})
+            MV_CUDA_C(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        if (const char* e = getenv("MV_OVERLAP")) c.overlapLight = atoi(e);
+    }
     MV_CUDA_C(cudaEventCreateWithFlags(&c.frameDone, cudaEventDisableTiming));
     for (auto& e : c.presentDone) MV_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
@@ -334,19 +365,28 @@ int mv_create(const mv_desc* d, mv_caster** out)
     c.arena.numPeers = 0;
 
     // createVolumeInfoBuffers, MultiRayCaster.cpp:455-549
-    MV_CUDA_C(cudaMalloc(&c.dPerObject, N * sizeof(PerObject)));
-    MV_CUDA_C(cudaMemsetAsync(c.dPerObject, 0, N * sizeof(PerObject), c.stream));
+    for (int q = 0; q < 2; ++q) {
+        MV_CUDA_C(cudaMalloc(&c.dPerObject2[q], N * sizeof(PerObject)));
+        MV_CUDA_C(cudaMemsetAsync(c.dPerObject2[q], 0, N * sizeof(PerObject), c.stream));
+    }
+    c.dPerObject = c.dPerObject2[0];
     MV_CUDA_C(cudaMallocHost(&c.hPerObjectPinned, (size_t)kUploadRing * N * sizeof(PerObject)));
     for (auto& e : c.uploadDone) MV_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     std::vector<uint32_t> descs(N);
     for (uint32_t i = 0; i < N; ++i) descs[i] = (i % S) | (kNumCubeMip << 14) | (G << 18);   // :470-479
     MV_CUDA_C(cudaMalloc(&c.dVolumeDescs, N * sizeof(uint32_t)));
     MV_CUDA_C(cudaMemcpy(c.dVolumeDescs, descs.data(), N * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    MV_CUDA_C(cudaMalloc(&c.dAttribs, N * sizeof(ushort4)));
-    MV_CUDA_C(cudaMemsetAsync(c.dAttribs, 0, N * sizeof(ushort4), c.stream));
+    for (int q = 0; q < 2; ++q) {
+        MV_CUDA_C(cudaMalloc(&c.dAttribs2[q], N * sizeof(ushort4)));
+        MV_CUDA_C(cudaMemsetAsync(c.dAttribs2[q], 0, N * sizeof(ushort4), c.stream));
+    }
+    c.dAttribs = c.dAttribs2[0];
     const size_t listBytes = frame_lists_header_bytes(N) + (size_t)N * sizeof(VisInfo);
-    MV_CUDA_C(cudaMalloc(&c.dLists, listBytes));
-    MV_CUDA_C(cudaMemsetAsync(c.dLists, 0, listBytes, c.stream));
+    for (int q = 0; q < 2; ++q) {
+        MV_CUDA_C(cudaMalloc(&c.dLists2[q], listBytes));
+        MV_CUDA_C(cudaMemsetAsync(c.dLists2[q], 0, listBytes, c.stream));
+    }
+    c.dLists = c.dLists2[0];
     // results of the screen-space marches (RayCast of the direct-scheme volumes), rectangle by rectangle: room for four
     // full-screen rectangles; volumes beyond that are marched inside the resolve kernel
     c.directCapacity = (uint32_t)std::min<size_t>(4 * px, 0x7fffffffu);
@@ -414,6 +454,7 @@ void mv_destroy(mv_caster* h)
 int mv_volume_init_procedural(mv_caster* h, uint32_t src, uint32_t mode, uint32_t seed)
 {
     MV_ENTER(h);
+    c.inputsDirty = true;
     MV_REQUIRE(src < c.d.num_volume_srcs && mode <= 1);
     launch_init_grid(c, src, mode, seed);
     return check_launch("k_init_grid");
@@ -422,6 +463,7 @@ int mv_volume_init_procedural(mv_caster* h, uint32_t src, uint32_t mode, uint32_
 int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
 {
     MV_ENTER(h);
+    c.inputsDirty = true;
     MV_REQUIRE(texels && src < c.d.num_volume_srcs);
     const uint32_t n = c.d.grid_size;
     cudaMemcpy3DParms p{};
@@ -437,6 +479,7 @@ int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
 int mv_volume_upload_r32f(mv_caster* h, uint32_t src, const float* density)
 {
     MV_ENTER(h);
+    c.inputsDirty = true;
     MV_REQUIRE(density && src < c.d.num_volume_srcs);
     const uint32_t n = c.d.grid_size;
     const size_t bytes = (size_t)n * n * n * sizeof(float);
@@ -468,6 +511,7 @@ int mv_volume_read(mv_caster* h, uint32_t src, uint16_t* out)
 static int set_targets_impl(Caster& c, const float* depth, const uint16_t* shadow, uint32_t shadowSize, const uint16_t* color,
                             const uint16_t* velocity, cudaMemcpyKind kind)
 {
+    c.inputsDirty = true;
     const size_t px = (size_t)c.d.width * c.d.height;
     if (depth) MV_CUDA(cudaMemcpyAsync(c.dDepth, depth, px * sizeof(float), kind, c.stream));
     else {
@@ -602,15 +646,28 @@ int mv_update_frame(mv_caster* h, const float viewProj[16], const float shadowVP
         to43(worldI, po.worldI);
         to43(world, po.world);
     }
-    MV_CUDA(cudaMemcpyAsync(c.dPerObject, staging, N * sizeof(PerObject), cudaMemcpyHostToDevice, c.stream));
-    MV_CUDA(cudaEventRecord(c.uploadDone[slot], c.stream));
+    // the records go into the buffer the previous frame does not use; pipelined, the copy runs on the light stream (beside
+    // the previous frame's passes) once the last frame that read this buffer has finished its resolve
+    const uint32_t q = c.poParity ^ 1u;
+    cudaStream_t up = c.stream;
+    if (pipelined(c)) {
+        up = c.lightStream;
+        if (c.poLastUse[q] >= 0 && c.frameEndValid[c.poLastUse[q]]) MV_CUDA(cudaStreamWaitEvent(up, c.frameEnd[c.poLastUse[q]], 0));
+    }
+    MV_CUDA(cudaMemcpyAsync(c.dPerObject2[q], staging, N * sizeof(PerObject), cudaMemcpyHostToDevice, up));
+    MV_CUDA(cudaEventRecord(c.uploadDone[slot], up));
     c.uploadPending[slot] = true;
+    c.lastUpload = (int)slot;
+    c.poParity = q;
+    c.dPerObject = c.dPerObject2[q];
     return MV_OK;
 }
 
 int mv_cull(mv_caster* h)
 {
     MV_ENTER(h);
+    wait_upload(c, c.stream);
+    flip_frame_lists(c);
     launch_cull(c);
     return check_launch("k_cull");
 }
@@ -651,26 +708,59 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
 {
     MV_ENTER(h);
     (void)oit;   // one OIT implementation: the K-buffer semantics of the default branch (:377-381)
-    if (c.d.flags & MV_FLAG_COUNT_SAMPLES) MV_CUDA(cudaMemsetAsync(c.dStats, 0, sizeof(StatsDev), c.stream));
-    record(c, 0);
-    launch_cull(c);
-    record(c, 1);
     if (c.shardWorld > 1 && !c.peersMapped) {
         set_error("sharded caster without mapped peers: run the passes and the collectives one by one (mv_cull, mv_ray_march_light, ...)");
         return MV_ERR_INVALID;
     }
-    launch_ray_march_light(c, -1);
-    // sharded: once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
-    if (c.shardWorld > 1) { wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
-    record(c, 2);
-    launch_ray_march_view(c);
-    if (c.shardWorld > 1) launch_peer_barrier(c);                                // every owner's cube maps have landed
-    record(c, 3);
-    MV_TRY_DIRECT_STATS(c);
-    launch_ray_cast_direct(c);
-    launch_resolve_oit(c);
-    record(c, 4);
-    c.evValid[5] = false;
+    flip_frame_lists(c);
+    const uint32_t slot = c.listParity;             // frameEnd slot of this frame
+    c.poLastUse[c.poParity] = (int)slot;
+    if (pipelined(c)) {
+        // light stream: cull -> light march into the staging buffer. Waits: the PerObject upload; inputs changed on the main
+        // stream since the last frame (volumes, depth / shadow targets); the frame before last, whose lists this frame
+        // overwrites; the previous frame's commit, which reads the staging buffer.
+        cudaStream_t mainStream = c.stream, B = c.lightStream;
+        wait_upload(c, B);
+        if (c.inputsDirty) { MV_CUDA(cudaEventRecord(c.inputsReady, mainStream)); MV_CUDA(cudaStreamWaitEvent(B, c.inputsReady, 0)); c.inputsDirty = false; }
+        if (c.frameEndValid[slot]) MV_CUDA(cudaStreamWaitEvent(B, c.frameEnd[slot], 0));
+        if (c.commitValid) MV_CUDA(cudaStreamWaitEvent(B, c.commitDone, 0));
+        c.stream = B;
+        c.lightToStaging = true;
+        launch_cull(c);
+        launch_ray_march_light(c, -1);
+        c.lightToStaging = false;
+        c.stream = mainStream;
+        MV_CUDA(cudaEventRecord(c.lightDone, B));
+        // main stream: commit the light map, then the passes that read it
+        MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
+        launch_light_commit(c);
+        MV_CUDA(cudaEventRecord(c.commitDone, mainStream));
+        c.commitValid = true;
+        launch_ray_march_view(c);
+        launch_ray_cast_direct(c);
+        launch_resolve_oit(c);
+    } else {
+        wait_upload(c, c.stream);
+        c.inputsDirty = true;                       // the next pipelined frame orders its light stream after this one
+        if (c.d.flags & MV_FLAG_COUNT_SAMPLES) MV_CUDA(cudaMemsetAsync(c.dStats, 0, sizeof(StatsDev), c.stream));
+        record(c, 0);
+        launch_cull(c);
+        record(c, 1);
+        launch_ray_march_light(c, -1);
+        // sharded: once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
+        if (c.shardWorld > 1) { wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
+        record(c, 2);
+        launch_ray_march_view(c);
+        if (c.shardWorld > 1) launch_peer_barrier(c);                                // every owner's cube maps have landed
+        record(c, 3);
+        MV_TRY_DIRECT_STATS(c);
+        launch_ray_cast_direct(c);
+        launch_resolve_oit(c);
+        record(c, 4);
+        c.evValid[5] = false;
+    }
+    MV_CUDA(cudaEventRecord(c.frameEnd[slot], c.stream));
+    c.frameEndValid[slot] = true;
     if (c.frameIdx != 0xffffffffu) ++c.frameIdx;
     return check_launch("render");
 }
@@ -714,6 +804,7 @@ int mv_read_per_object(mv_caster* h, float* out)
 {
     MV_ENTER(h);
     MV_REQUIRE(out);
+    wait_upload(c, c.stream);
     return d2h(c, out, c.dPerObject, c.d.num_volumes * sizeof(PerObject));
 }
 
@@ -863,6 +954,7 @@ int mv_set_flags(mv_caster* h, uint32_t flags)
     MV_ENTER(h);
     MV_REQUIRE((flags & ~(MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES)) == 0);
     c.d.flags = flags;
+    c.inputsDirty = true;
     for (auto& v : c.evValid) v = false;
     return MV_OK;
 }
@@ -870,6 +962,7 @@ int mv_set_flags(mv_caster* h, uint32_t flags)
 int mv_sync(mv_caster* h)
 {
     MV_ENTER(h);
+    MV_CUDA(cudaStreamSynchronize(c.lightStream));
     MV_CUDA(cudaStreamSynchronize(c.stream));
     return MV_OK;
 }

@@ -98,6 +98,7 @@ int mv_volume_upload_r32f_sized(mv_caster* h, uint32_t src, const float* density
 {
     MV_ENTER(h);
     MV_REQUIRE(density && src < c.d.num_volume_srcs && w && hgt && d);
+    c.inputsDirty = true;
     cudaArray_t arr = nullptr;
     const cudaChannelFormatDesc cd = cudaCreateChannelDesc<float>();
     MV_CUDA(cudaMalloc3DArray(&arr, &cd, make_cudaExtent(w, hgt, d)));

@@ -238,6 +238,20 @@ struct Caster {
     cudaStream_t ownStream = nullptr;
     cudaEvent_t uploadDone[3] = {};
     bool uploadPending[3] = {};
+    // Frame pipelining (one GPU, uninstrumented): cull + light march of a frame run on lightStream and write the light map
+    // into the staging buffer, so they depend on nothing the previous frame's view march / resolve / post-process (main
+    // stream) still use; the main stream commits the staging buffer into the light volume's array before its view march.
+    // Per-frame device state is double-buffered: PerObject records by upload, lists + attributes by render.
+    cudaStream_t lightStream = nullptr;
+    cudaEvent_t lightDone = nullptr, commitDone = nullptr, inputsReady = nullptr, frameEnd[2] = {};
+    bool commitValid = false, frameEndValid[2] = {false, false}, inputsDirty = true, lightToStaging = false;
+    int overlapLight = 1;                // MV_OVERLAP=0: every pass on the main stream
+    PerObject* dPerObject2[2] = {};      // dPerObject points at the one of the last mv_update_frame
+    ushort4* dAttribs2[2] = {};
+    unsigned char* dLists2[2] = {};
+    uint32_t poParity = 0, listParity = 0;
+    int poLastUse[2] = {-1, -1};         // frameEnd slot of the last render that read dPerObject2[q]
+    int lastUpload = -1;                 // upload-ring slot of the last PerObject upload
     cudaStream_t copyStream = nullptr;   // mv_present_async: back-buffer read-back overlapping the next frame
     cudaEvent_t frameDone = nullptr;     // main stream -> copy stream
     cudaEvent_t presentDone[MV_PRESENT_SLOTS] = {};

@@ -361,6 +361,7 @@ int mv_mesh_render_depth(mv_caster* h, const float viewProj[16], float shadowVpO
 {
     MV_ENTER(h);
     MV_REQUIRE(viewProj);
+    c.inputsDirty = true;
     const uint32_t S = 1024;                                  // m_shadowMapSize, ObjectRenderer.cpp:42
     const size_t px = (size_t)c.d.width * c.d.height;
     if (c.shadowSize != S) {

@@ -199,8 +199,10 @@ int mv_light_commit(mv_caster* h)
 int mv_set_stream(mv_caster* h, void* stream)
 {
     MV_ENTER(h);
+    MV_CUDA(cudaStreamSynchronize(c.lightStream));
     MV_CUDA(cudaStreamSynchronize(c.stream));
     c.stream = stream ? static_cast<cudaStream_t>(stream) : c.ownStream;
+    c.inputsDirty = true;
     return MV_OK;
 }
 

@@ -432,3 +432,32 @@ def test_dds_volume_ingest(tmp_path, kind, dx10, res):
         assert diff.max() <= 1, diff.max()
         assert (diff > 0).mean() < 0.2
     assert vp_.view(np.float16)[..., 3].max() > 0.1
+
+
+# ---------------------------------------------------------------- frame pipelining
+@pytest.mark.parametrize("update_every", [1, 2])
+def test_pipelined_frames_equal_oracle(update_every):
+    """Uninstrumented casters pipeline frames: cull + light march of frame i + 1 run on a second stream beside frame i's
+    view march / resolve / post-process, with double-buffered per-frame state and the light map committed from a staging
+    buffer. Every frame of an animated sequence (TAA on, so errors would accumulate) must still equal the oracle's."""
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=9, num_volume_srcs=3, width=320, height=180)
+    from multivolumes_b200 import MultiRayCaster
+    o = OracleCaster(filter_model=1, **kw)
+    p = MultiRayCaster(count_samples=False, **kw)          # no instrumentation -> the pipelined path
+    bg = checker_background(320, 180)
+    rs = np.random.RandomState(7)
+    vel = (rs.uniform(-1, 1, (180, 320, 2)) * 0.002).astype(np.float16)
+    for c in (o, p):
+        configure(c, sh=True, background=bg, velocity=vel)
+    for f in range(7):
+        vp, eye = scene.default_camera(320, 180, eye=(4.0 + 5 * f, 16.0 + 6 * f, -80.0 - 14 * f))
+        for c in (o, p):
+            if f % update_every == 0:
+                c.UpdateFrame(vp, None, eye)
+            c.ResetColor(); c.Render(); c.Postprocess(True)
+        if f in (2, 6):
+            (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
+            assert _same_bits(to, tp) and np.array_equal(bo, bp), f
+            assert np.array_equal(o.ReadVisible(), p.ReadVisible())
+            lv = o.GetStats()["light_volume"]
+            assert _same_bits(o.ReadLightMap(lv), p.ReadLightMap(lv))
