@@ -31,6 +31,11 @@ WORKLOADS = {
     "cfg4": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, note="BASELINE.json configs[3]"),
     "cfg5i": dict(n=512, srcs=8, g=512, l=96, w=3840, h=2160, sh=True, taa=True,
                   note="BASELINE.json configs[4] with 8 source volumes instanced 64x (VolTexId = i % srcs): 8.6 GB instead of 512 GB of RGBA16F"),
+    "cfg5": dict(n=512, g=512, l=96, w=3840, h=2160, sh=True, taa=True, density_only=True,
+                 note="BASELINE.json configs[4]: 512 distinct source volumes in the density-only R16F storage SURVEY.md 8(d) names for it "
+                      "(137 GB resident on every GPU; colour (1, 1, 1) as for the reference's file assets)"),
+    "cfg2d": dict(n=16, g=128, l=96, w=1920, h=1080, sh=True, taa=True, density_only=True, note="cfg2's densities in the density-only R16F storage"),
+    "cfg4d": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, density_only=True, note="cfg4's densities in the density-only R16F storage"),
     "tiny": dict(n=4, g=32, l=16, w=320, h=180, sh=True, taa=True, note="CI-sized"),
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_ray_march_v from the committed ncu --set full capture
@@ -51,6 +56,11 @@ def peaks():
 def build_scene(c, wl, scene, sky_coeffs):
     for i in range(c.srcs):
         c.InitVolumeData(i, 1, (0x9E3779B9 * (i + 1)) & 0xffffffff)
+        if wl.get("density_only") and not getattr(c, "density_only", False):
+            # the oracle has one storage format: give it the same volume, (1, 1, 1, a) as RGBA16F
+            v = c.ReadVolume(i).copy()
+            v[..., :3] = 1.0
+            c.LoadVolumeData(i, v)
     c.SetLight(scene.LIGHT_PT, scene.LIGHT_COLOR, scene.LIGHT_INTENSITY)
     c.SetAmbient(scene.AMBIENT_COLOR, scene.AMBIENT_INTENSITY)
     c.SetVolumesWorld(20.0, (0, 0, 0))
@@ -170,10 +180,12 @@ def launches_per_frame(wl, world, exchange):
 
 
 def workload_config(args, wl, world):
-    return {"workload": f"{args.workload}: {wl['n']} volumes x {wl['g']}^3 RGBA16F (procedural density x seeded value noise), "
+    fmt = "R16F density-only" if wl.get("density_only") else "RGBA16F"
+    return {"workload": f"{args.workload}: {wl['n']} volumes x {wl['g']}^3 {fmt} (procedural density x seeded value noise), "
                         f"{wl['w']}x{wl['h']}, light map {wl['l']}^3, SH {'on' if wl['sh'] else 'off'}, TAA {'on' if wl['taa'] else 'off'}, "
                         f"orbit camera; {wl['note']}",
-            "l2_policy": f"inputs larger than L2 ({(wl.get('srcs') or wl['n']) * wl['g'] ** 3 * 8 / 1e6:.0f} MB of volume textures vs 126 MB)",
+            "l2_policy": f"inputs larger than L2 ({((wl.get('srcs') or wl['n']) * wl['g'] ** 3 * (2 if wl.get('density_only') else 8) + wl['n'] * wl['l'] ** 3 * 8) / 1e6:.0f} MB "
+                         f"of volume and light-map textures vs 126 MB)",
             "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: volumes v % {world}, light-map z-slabs, {world} row bands; exchange = {args.exchange}",
             "e2e_inputs": "per-frame matrices (PerObject records) from pinned host memory; result = tone-mapped RGBA8 frame read back to pinned host "
                           "memory every step (Present, 3 frames in flight as in the reference's frame loop)"}
@@ -215,7 +227,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = peaks()
 
-    c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, grid_size=wl["g"], light_grid_size=wl["l"],
+    c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, density_only=bool(wl.get("density_only")), grid_size=wl["g"], light_grid_size=wl["l"],
                        num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
     stream = torch.cuda.Stream()
     c.SetStream(stream.cuda_stream)      # order the caster's kernels with torch's events / NCCL on one stream
@@ -335,9 +347,9 @@ def main():
         fps = args.steps / (ms_total / 1000.0)
         view_ms = per_pass["ray_march_view"]
         vs, vl, vr = (stats_acc[k] / n_prof for k in ("view_samples", "view_light_fetches", "view_rays"))
-        # 8 B density texel per sample (+ 8 B RGBA16F light texel when alpha > 0.01); per ray 4 B depth read,
+        # 8 B density texel per sample (2 B in the density-only storage) (+ 8 B RGBA16F light texel when alpha > 0.01); per ray 4 B depth read,
         # 8 B colour + 4 B cube-depth write
-        alg_bytes = vs * 8 + vl * 8 + vr * 16
+        alg_bytes = vs * (2 if wl.get("density_only") else 8) + vl * 8 + vr * 16
         achieved = alg_bytes / (view_ms / 1000.0) / 1e9 if view_ms > 0 else 0.0
         fetches = (vs + vl) / (view_ms / 1000.0) / 1e9 if view_ms > 0 else 0.0
         line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

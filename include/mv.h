@@ -13,7 +13,7 @@
  *   - matrices are row-major float arrays in the reference's row-vector convention
  *     (v' = v * M, DirectXMath layout before the reference's XMMatrixTranspose for upload);
  *   - images are tightly packed, row-major, top row first; RGBA16F = 4 x IEEE binary16;
- *   - volumes are RGBA16F, x fastest then y then z; cube maps are [face][y][x] with the D3D face
+ *   - volumes are RGBA16F (R16F density with MV_FLAG_DENSITY_ONLY), x fastest then y then z; cube maps are [face][y][x] with the D3D face
  *     order +X,-X,+Y,-Y,+Z,-Z;
  *   - there is NO CPU fallback: mv_create fails with MV_ERR_NO_DEVICE when no sm_100 device exists.
  */
@@ -38,6 +38,12 @@ enum mv_status {
 /* mv_desc.flags */
 #define MV_FLAG_COUNT_SAMPLES   1u   /* keep exact ray/sample counters (mv_get_stats); small cost */
 #define MV_FLAG_TIME_PASSES     2u   /* bracket every pass with CUDA events (mv_get_timings) */
+/* creation-time only: the volumes are stored as R16F 3-D textures holding the density alone, 2 B / voxel instead of 8.
+ * The colour of such a volume is (1, 1, 1) — what the reference's own file ingest produces for every asset it ships
+ * (CSR32FToRGBA16F.hlsl:26: rgb = 1, a = 0.25 src) — so a frame equals, bit for bit, the frame of the RGBA16F storage
+ * holding (1, 1, 1, a). Uploads keep the alpha channel only; mv_volume_read expands to (1, 1, 1, a).
+ * SURVEY.md 8(d) cfg 5: 512 x 512^3 = 137 GB instead of 550 GB. */
+#define MV_FLAG_DENSITY_ONLY    4u
 
 /* MultiRayCaster::Init arguments (MultiRayCaster.h:31-34) + viewport (SetViewport, :38) +
  * SetMaxSamples defaults (MultiVolumes.cpp:27-68). */

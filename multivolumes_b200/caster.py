@@ -16,6 +16,7 @@ LIB_PATH = os.environ.get("MV_B200_LIB") or os.path.join(HERE, "libmv_b200.so")
 
 FLAG_COUNT_SAMPLES = 1
 FLAG_TIME_PASSES = 2
+FLAG_DENSITY_ONLY = 4   # MV_FLAG_DENSITY_ONLY: R16F density volumes, colour (1, 1, 1)
 
 
 class Timings(C.Structure):
@@ -135,10 +136,12 @@ def parse_dds(path):
 class MultiRayCaster(CasterBase):
     """MultiVolumes/Content/MultiRayCaster.h:28-50 on one B200. Method names follow the reference class."""
 
-    def __init__(self, device=0, count_samples=True, time_passes=False, **kw):
-        flags = (FLAG_COUNT_SAMPLES if count_samples else 0) | (FLAG_TIME_PASSES if time_passes else 0)
+    def __init__(self, device=0, count_samples=True, time_passes=False, density_only=False, **kw):
+        flags = (FLAG_COUNT_SAMPLES if count_samples else 0) | (FLAG_TIME_PASSES if time_passes else 0) | \
+                (FLAG_DENSITY_ONLY if density_only else 0)
         super().__init__(binding(), opt0=device, opt1=flags, **kw)
         self.device = device
+        self.density_only = bool(density_only)
 
     # --- product-only calls ---
     def SetRenderTargetsDevice(self, depth=0, shadow=0, shadow_size=0, color=0, velocity=0):

@@ -6,7 +6,7 @@
 // sources of a synthetic scene differ. k_r32f_to_rgba16f replaces CSR32FToRGBA16F
 // (CSR32FToRGBA16F.hlsl:16-26; host MultiRayCaster.cpp:168-209): rgb = 1, a = 0.25 * density.
 // Both write the 3-D CUDA array through a surface object, 8 B per voxel, x fastest.
-#include "mv_internal.h"
+#include "k_march.cuh"
 
 namespace mv {
 
@@ -37,7 +37,7 @@ MV_D float value_noise(V3 p, uint32_t seed)   // p in lattice units, p >= 0; smo
     return lerp(lerp(x00, x10, ty), lerp(x01, x11, ty), tz);
 }
 
-__global__ void __launch_bounds__(256) k_init_grid(cudaSurfaceObject_t surf, uint32_t n, uint32_t mode, uint32_t seed)
+__global__ void __launch_bounds__(256) k_init_grid(cudaSurfaceObject_t surf, uint32_t n, uint32_t mode, uint32_t seed, bool densityOnly)
 {
     const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
     const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -60,17 +60,17 @@ __global__ void __launch_bounds__(256) k_init_grid(cudaSurfaceObject_t surf, uin
     const V3 colorU = {1.0f, 0.6f, 0.0f}, colorD = {0.5f, 0.8f, 1.0f};  // :23-24
     const float t = saturate(pos.y * 0.5f + 0.2f);                      // :25
     const V4 out = {lerp(colorD.x, colorU.x, t), lerp(colorD.y, colorU.y, t), lerp(colorD.z, colorU.z, t), a};
-    surf3Dwrite(pack_half4(out), surf, (int)(x * 8), (int)y, (int)z);
+    store_volume_texel(surf, x, y, z, out, densityOnly);
 }
 
-__global__ void __launch_bounds__(256) k_r32f_to_rgba16f(cudaSurfaceObject_t surf, const float* __restrict__ density, uint32_t n)
+__global__ void __launch_bounds__(256) k_r32f_to_rgba16f(cudaSurfaceObject_t surf, const float* __restrict__ density, uint32_t n, bool densityOnly)
 {
     const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
     const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
     const uint32_t z = blockIdx.z;
     if (x >= n || y >= n) return;
     const float d = density[((size_t)z * n + y) * n + x];
-    surf3Dwrite(pack_half4(V4{1.0f, 1.0f, 1.0f, d * 0.25f}), surf, (int)(x * 8), (int)y, (int)z);
+    store_volume_texel(surf, x, y, z, V4{1.0f, 1.0f, 1.0f, d * 0.25f}, densityOnly);
 }
 
 } // namespace
@@ -79,14 +79,14 @@ void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed)
 {
     const uint32_t n = c.d.grid_size;
     dim3 grid((n + 31) / 32, (n + 7) / 8, n);
-    k_init_grid<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, n, mode, seed);
+    k_init_grid<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, n, mode, seed, c.volumes[src].channels == 1);
 }
 
 void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity)
 {
     const uint32_t n = c.d.grid_size;
     dim3 grid((n + 31) / 32, (n + 7) / 8, n);
-    k_r32f_to_rgba16f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, devDensity, n);
+    k_r32f_to_rgba16f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, devDensity, n, c.volumes[src].channels == 1);
 }
 
 } // namespace mv

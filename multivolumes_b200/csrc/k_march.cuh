@@ -1,7 +1,7 @@
 // k_march.cuh — device functions shared by the light march, the view march and the direct
 // screen-space ray cast: RayMarch.hlsli of the reference restated for sm_100a.
 //
-// Volumes and light maps are CUDA 3-D arrays of RGBA16F sampled through texture objects with
+// Volumes (RGBA16F, or R16F density alone) and light maps (RGBA16F) are CUDA 3-D arrays sampled through texture objects with
 // normalised coordinates, clamp addressing and hardware trilinear filtering — the LINEAR_CLAMP
 // sampler of the reference (MultiRayCaster.cpp:556-560).
 #pragma once
@@ -22,6 +22,21 @@ MV_D float4 tex3d_issue(cudaTextureObject_t tex, float x, float y, float z)
     asm volatile("tex.3d.v4.f32.f32 {%0, %1, %2, %3}, [%4, {%5, %6, %7, %7}];"
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(tex), "f"(x), "f"(y), "f"(z));
     return r;
+}
+
+// The density of a fetched volume texel: alpha of an RGBA16F volume, the only channel of an R16F one
+// (MV_FLAG_DENSITY_ONLY; `densityOnly` is uniform over a launch).
+MV_D float texel_density(float4 c, bool densityOnly) { return densityOnly ? c.x : c.w; }
+MV_D float fetch_density(cudaTextureObject_t tex, float x, float y, float z, bool densityOnly)
+{
+    return texel_density(tex3D<float4>(tex, x, y, z), densityOnly);
+}
+
+// Store of one volume texel by the ingest kernels: RGBA16F, or the alpha channel alone into an R16F volume
+MV_D void store_volume_texel(cudaSurfaceObject_t surf, uint32_t x, uint32_t y, uint32_t z, V4 rgba, bool densityOnly)
+{
+    if (densityOnly) surf3Dwrite((unsigned short)f32_to_f16(rgba.w), surf, (int)(x * 2), (int)y, (int)z);
+    else surf3Dwrite(pack_half4(rgba), surf, (int)(x * 8), (int)y, (int)z);
 }
 
 MV_D V3 local_to_tex3d(V3 pos)   // LocalToTex3DSpace, RayMarch.hlsli:170-177
@@ -93,7 +108,7 @@ struct MarchCount { uint32_t samples, lightFetches; };
 // One trilinear density fetch per step, one trilinear light-map fetch when the sample is non-empty,
 // adaptive step from the density change, front-to-back accumulation, early out at transmittance < 0.01.
 MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t smpCount, V3 rayOrigin, V3 rayDir,
-                  float tMax, MarchCount& mc)
+                  float tMax, bool densityOnly, MarchCount& mc)
 {
     const float maxDist = 2.0f * sqrtf(3.0f);            // g_maxDist, RayMarch.hlsli:17
     const float stepScale = maxDist / (float)smpCount;
@@ -115,6 +130,7 @@ MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t 
         float4 l = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (wasDense) l = tex3d_issue(light, uvw.x, uvw.y, uvw.z);
         V4 color = {c4.x, c4.y, c4.z, c4.w};
+        if (densityOnly) color = {1.0f, 1.0f, 1.0f, c4.x};
         ++mc.samples;
         float newStep = stepScale;
         if (color.w > kZeroThreshold) {                  // skip empty space
@@ -144,7 +160,7 @@ MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t 
 
 // CastLightRay, RayMarch.hlsli:197-230 (mip 0): transmittance toward the light / along the AO direction
 MV_D void cast_light_ray(float& transm, cudaTextureObject_t grid, V3 rayOrigin, V3 rayDir, float stepScale,
-                         uint32_t numSamples, uint32_t& samples)
+                         uint32_t numSamples, bool densityOnly, uint32_t& samples)
 {
     float t = stepScale;
     float step = stepScale;
@@ -153,7 +169,7 @@ MV_D void cast_light_ray(float& transm, cudaTextureObject_t grid, V3 rayOrigin, 
         const V3 pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
         if (outside_unit_box(pos)) break;
         const V3 uvw = local_to_tex3d(pos);
-        const float density = tex3D<float4>(grid, uvw.x, uvw.y, uvw.z).w;
+        const float density = fetch_density(grid, uvw.x, uvw.y, uvw.z, densityOnly);
         ++samples;
         const float dDensity = density - prevDensity;
         const float opacity = saturate(density * step);

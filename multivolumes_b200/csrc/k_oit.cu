@@ -187,21 +187,21 @@ MV_D V3 back_face_point(V3 localEye, V3 d, int axis, float sgn)
 
 // RayCast, RayCast.hlsli:42-107: screen-space march of one fragment of a direct-scheme volume
 MV_D V4 ray_cast(const DeviceScene& s, const PerObject* po, uint32_t volumeId, uint32_t volTexId, uint32_t smpCnt, V3 localEye, V3 rayDir,
-                 float sx, float sy, float sceneDepth, bool& marched, MarchCount& mc)
+                 float sx, float sy, float sceneDepth, bool densityOnly, bool& marched, MarchCount& mc)
 {
     V3 ro = localEye; const V3 rd = normalize(rayDir);
     marched = compute_ray_origin(ro, rd);
     if (!marched) return {0.0f, 0.0f, 0.0f, 0.0f};
     const float tMax = get_tmax(V3{sx, sy, sceneDepth}, ro, rd, po->wvpi);
-    return march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCnt, ro, rd, tMax, mc);
+    return march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCnt, ro, rd, tMax, densityOnly, mc);
 }
 
 // the same, kept out of line: the resolve kernel only marches volumes whose rectangle did not fit the result buffer
 __device__ __noinline__ V4 ray_cast_fallback(const DeviceScene& s, const PerObject* po, uint32_t volumeId, uint32_t volTexId, uint32_t smpCnt, V3 localEye, V3 rayDir,
-                                             float sx, float sy, float sceneDepth, uint32_t& rays, uint32_t& samples, uint32_t& light)
+                                             float sx, float sy, float sceneDepth, bool densityOnly, uint32_t& rays, uint32_t& samples, uint32_t& light)
 {
     bool marched; MarchCount mc = {0, 0};
-    const V4 c = ray_cast(s, po, volumeId, volTexId, smpCnt, localEye, rayDir, sx, sy, sceneDepth, marched, mc);
+    const V4 c = ray_cast(s, po, volumeId, volTexId, smpCnt, localEye, rayDir, sx, sy, sceneDepth, densityOnly, marched, mc);
     if (marched) { ++rays; samples += mc.samples; light += mc.lightFetches; }
     return c;
 }
@@ -227,7 +227,7 @@ MV_D bool row_is_resolved_here(const DeviceScene& s, const FrameCB& cb, int py)
 #ifndef MV_DIRECT_MIN_BLOCKS
 #define MV_DIRECT_MIN_BLOCKS 5
 #endif
-template <bool kStats>
+template <bool kStats, bool kDensityOnly>
 __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(DeviceScene s, FrameCB cb)
 {
     const uint32_t lane = threadIdx.x & 31;
@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(D
             const V3 rayDir = lpt - localEye;                                    // PSCube.hlsl:34
             const float sceneDepth = __ldg(s.depth + (size_t)py * cb.width + px);
             bool marched; MarchCount mc = {0, 0};
-            const V4 color = ray_cast(s, po, volumeId, a.w, a.y, localEye, rayDir, sx, sy, sceneDepth, marched, mc);
+            const V4 color = ray_cast(s, po, volumeId, a.w, a.y, localEye, rayDir, sx, sy, sceneDepth, kDensityOnly, marched, mc);
             if (color.w > 0.0f && color.w <= 1.0f) stored = pack_half4(color);
             if (kStats && marched) st = make_uint2(mc.samples | 0x80000000u, mc.lightFetches);
         }
@@ -279,7 +279,7 @@ constexpr int kOitChunk = 256;   // visible volumes binned per pass over the CTA
 #ifndef MV_OIT_MIN_BLOCKS
 #define MV_OIT_MIN_BLOCKS 4   // 64 registers, 32 warps / SM: the resolve is issue-bound, measured -8 % against 3 CTAs (75 registers)
 #endif
-__global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceScene s, FrameCB cb)
+__global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceScene s, FrameCB cb, bool densityOnly)
 {
     __shared__ VisInfo s_cand[kOitChunk];       // volumes whose screen rectangle overlaps this tile, list order kept
     __shared__ uint32_t s_candSlot[kOitChunk];  // their index in the visible list
@@ -390,7 +390,7 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
                     const uint2 st = __ldg(s.directStats + at);
                     if (st.x >> 31) { ++dRays; dSamples += st.x & 0x7fffffffu; dLight += st.y; }
                 }
-            } else color = ray_cast_fallback(s, po, volumeId, a.w, smpCnt, localEye, rayDir, sx, sy, sceneDepth, dRays, dSamples, dLight);
+            } else color = ray_cast_fallback(s, po, volumeId, a.w, smpCnt, localEye, rayDir, sx, sy, sceneDepth, densityOnly, dRays, dSamples, dLight);
         } else color = cube_cast(s, cb, volumeId, a.x, sceneDepth, face, lpt, rayDir);
         if (!stored && color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
         const float k1 = 1.0f - result.w;
@@ -428,15 +428,16 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
 
 void launch_ray_cast_direct(Caster& c)
 {
-    const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0;
-    static int perSM[2] = {0, 0};
-    if (!perSM[0]) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[0], k_ray_cast_direct<false>, 256, 0);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[1], k_ray_cast_direct<true>, 256, 0);
-        perSM[0] = max(perSM[0], 1); perSM[1] = max(perSM[1], 1);
+    const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0, densityOnly = (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0;
+    using Kernel = void (*)(DeviceScene, FrameCB);
+    static const Kernel kernels[4] = {k_ray_cast_direct<false, false>, k_ray_cast_direct<true, false>, k_ray_cast_direct<false, true>, k_ray_cast_direct<true, true>};
+    static int perSM[4] = {0, 0, 0, 0};
+    const int v = (stats ? 1 : 0) | (densityOnly ? 2 : 0);
+    if (!perSM[v]) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[v], kernels[v], 256, 0);
+        perSM[v] = max(perSM[v], 1);
     }
-    if (stats) k_ray_cast_direct<true><<<c.smCount * perSM[1], 256, 0, c.stream>>>(c.scene(), c.cb);
-    else k_ray_cast_direct<false><<<c.smCount * perSM[0], 256, 0, c.stream>>>(c.scene(), c.cb);
+    kernels[v]<<<c.smCount * perSM[v], 256, 0, c.stream>>>(c.scene(), c.cb);
 }
 
 void launch_resolve_oit(Caster& c)
@@ -450,7 +451,7 @@ void launch_resolve_oit(Caster& c)
     }
     if (tileRows == 0) return;
     dim3 grid((c.d.width + 15) / 16, tileRows);
-    k_resolve_oit<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb);
+    k_resolve_oit<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb, (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0);
 }
 
 } // namespace mv

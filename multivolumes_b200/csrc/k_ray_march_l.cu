@@ -45,14 +45,14 @@ MV_D float shadow_test(const DeviceScene& s, const FrameCB& cb, V3 pos)
 }
 
 // GetDensityGradient, RayMarch.hlsli:55-77: six taps at +-1 texel (SampleLevel with integer offsets)
-MV_D V3 density_gradient(cudaTextureObject_t grid, V3 uvw, float invGrid)
+MV_D V3 density_gradient(cudaTextureObject_t grid, V3 uvw, float invGrid, bool densityOnly)
 {
-    const float q0 = tex3D<float4>(grid, uvw.x + -1.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + 0.0f * invGrid).w;
-    const float q1 = tex3D<float4>(grid, uvw.x + 1.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + 0.0f * invGrid).w;
-    const float q2 = tex3D<float4>(grid, uvw.x + 0.0f * invGrid, uvw.y + -1.0f * invGrid, uvw.z + 0.0f * invGrid).w;
-    const float q3 = tex3D<float4>(grid, uvw.x + 0.0f * invGrid, uvw.y + 1.0f * invGrid, uvw.z + 0.0f * invGrid).w;
-    const float q4 = tex3D<float4>(grid, uvw.x + 0.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + -1.0f * invGrid).w;
-    const float q5 = tex3D<float4>(grid, uvw.x + 0.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + 1.0f * invGrid).w;
+    const float q0 = fetch_density(grid, uvw.x + -1.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + 0.0f * invGrid, densityOnly);
+    const float q1 = fetch_density(grid, uvw.x + 1.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + 0.0f * invGrid, densityOnly);
+    const float q2 = fetch_density(grid, uvw.x + 0.0f * invGrid, uvw.y + -1.0f * invGrid, uvw.z + 0.0f * invGrid, densityOnly);
+    const float q3 = fetch_density(grid, uvw.x + 0.0f * invGrid, uvw.y + 1.0f * invGrid, uvw.z + 0.0f * invGrid, densityOnly);
+    const float q4 = fetch_density(grid, uvw.x + 0.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + -1.0f * invGrid, densityOnly);
+    const float q5 = fetch_density(grid, uvw.x + 0.0f * invGrid, uvw.y + 0.0f * invGrid, uvw.z + 1.0f * invGrid, densityOnly);
     return {q1 - q0, q3 - q2, q5 - q4};
 }
 
@@ -88,6 +88,7 @@ MV_D void store_light_voxel(const DeviceScene& s, const LightTarget& tgt, uint32
 // (shadow * lightColor + ambient, with ao = 1 and irradiance = 0 under a light probe) is written here.
 // The others are appended, brick by brick and in thread order inside a brick, to the dense-voxel list
 // that pass 2 marches with full warps.
+template <bool kDensityOnly>
 __global__ void __launch_bounds__(kLightThreads) k_light_classify(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
 {
     __shared__ uint32_t s_warpCount[kLightThreads / 32];
@@ -111,7 +112,7 @@ __global__ void __launch_bounds__(kLightThreads) k_light_classify(DeviceScene s,
                         ((float)z + 0.5f) / gridSize * 2.0f - 1.0f};                               // :36
         const cudaTextureObject_t grid0 = s.volumeTex[s.volumeDescs[volumeId] & 0x3fffu];
         const V3 uvw = local_to_tex3d(rayOrigin);                                                   // :41
-        const float density = tex3D<float4>(grid0, uvw.x, uvw.y, uvw.z).w;                          // :45
+        const float density = fetch_density(grid0, uvw.x, uvw.y, uvw.z, kDensityOnly);                          // :45
         dense = density >= kZeroThreshold;                                                          // :46
         rayOrigin = mul_p43(rayOrigin, s.perObject[volumeId].world);                                // :48
         shadow = shadow_test(s, cb, rayOrigin);                                                     // :51
@@ -251,6 +252,7 @@ MV_D void for_each_ao_ray(const DeviceScene& s, const FrameCB& cb, const LightVo
 // (passes 3-5) instead of lengthening this thread's dependent fetch chain: the pass's duration is
 // bounded by its longest chain, not by its throughput (profiles/r01_notes.md). The pass counts the
 // deferred rays per volume (they are marched sorted by volume, one texture per warp).
+template <bool kDensityOnly>
 __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_march_l(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
 {
     extern __shared__ float4 s_tab[];                       // [nShared] spheres, then [nShared] x 3 floats of directions
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_marc
             const V3 uvw = local_to_tex3d(rayOrigin);                                               // :41
             rayOrigin = mul_p43(rayOrigin, po0->world);                                             // :48
             if (cb.hasSH) {                                                                         // :65-75
-                aoRayDir = -density_gradient(grid0, uvw, 1.0f / (float)cb.gridSize);
+                aoRayDir = -density_gradient(grid0, uvw, 1.0f / (float)cb.gridSize, kDensityOnly);
                 const bool nz = fabsf(aoRayDir.x) > 0.0f || fabsf(aoRayDir.y) > 0.0f || fabsf(aoRayDir.z) > 0.0f;
                 aoRayDir = nz ? aoRayDir : rayOrigin;
                 aoRayDir = mul_v33(aoRayDir, po0->world);
@@ -303,7 +305,7 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_marc
                     const V3 rayDir = shadow_dir_local(cb, po, s_dirS, n);
                     if (ray_misses_box_for_sure(localRayOrigin, rayDir)) continue;
                     if (!compute_ray_origin(localRayOrigin, rayDir)) continue;                      // :95
-                    cast_light_ray(shadow, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
+                    cast_light_ray(shadow, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, kDensityOnly, samples);
                 }
                 if (cb.hasSH) {                                                                     // :100-108, geometry only
                     const V3 dirU = mul_v33(aoRayDir, po->worldI);
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__(1024) k_light_scan(DeviceScene s, FrameCB cb, 
 
 // Pass 4, persistent over the dense voxels: scatter every deferred AO ray into its volume's segment of
 // the item list. (Overflow frame: march the voxel's AO rays inline instead, CSRayMarchL.hlsl:100-108.)
+template <bool kDensityOnly>
 __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, FrameCB cb, int volumeOverride)
 {
     extern __shared__ float4 s_tab[];
@@ -462,7 +465,7 @@ __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, Fra
             for_each_ao_ray(s, cb, v, rec.castEnd, rec.itemCount, s_tab, s_dirS, nShared, lightDirW,
                             [&](uint32_t n, bool, V3 localRayOrigin, V3 rayDir) {
                                 float transm = 1.0f;
-                                cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
+                                cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, kDensityOnly, samples);
                                 ao *= (n == volumeId) ? transm : pow025(saturate(transm + 0.5f));   // :107
                             });
             s.lightRecs[recIdx].ao = ao;
@@ -482,6 +485,7 @@ __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, Fra
 #ifndef MV_LIGHT_AO_MIN_BLOCKS
 #define MV_LIGHT_AO_MIN_BLOCKS 8
 #endif
+template <bool kDensityOnly>
 __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_AO_MIN_BLOCKS) k_light_ao(DeviceScene s, FrameCB cb, int volumeOverride)
 {
     const uint32_t L = cb.lightGridSize;
@@ -518,7 +522,7 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_AO_MIN_BLOCKS) k_light
         const V3 rayDir = normalize(mul_v33(aoRayDir, po->worldI));
         compute_ray_origin(localRayOrigin, rayDir);
         float transm = 1.0f;
-        cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, samples);
+        cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, kDensityOnly, samples);
         s.lightItemResults[item.z] = (n == volumeId) ? transm : pow025(saturate(transm + 0.5f));    // :107
     }
     if (s.stats) {
@@ -575,9 +579,9 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
     static int perSM = 0, perSMAo = 0, perSMEmit = 0;
     if (!perSM) {
         const size_t smemMax = (size_t)kMaxSharedDirs * (sizeof(float4) + 3 * sizeof(float));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_l, kLightThreads, smemMax);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMEmit, k_light_emit, kLightThreads, smemMax);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMAo, k_light_ao, kLightThreads, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_l<false>, kLightThreads, smemMax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMEmit, k_light_emit<false>, kLightThreads, smemMax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMAo, k_light_ao<false>, kLightThreads, 0);
         perSM = max(perSM, 1); perSMEmit = max(perSMEmit, 1); perSMAo = max(perSMAo, 1);
     }
     // MV_LIGHT_TIMING=1 (tuning aid): CUDA events around each pass, averages printed every 64 launches
@@ -586,16 +590,21 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
     if (timing && !tev[0]) for (auto& e : tev) cudaEventCreate(&e);
     auto mark = [&](int i) { if (timing) cudaEventRecord(tev[i], c.stream); };
     mark(0);
-    k_light_classify<<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    const bool densityOnly = (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0;   // same register budgets in both instantiations
+    if (densityOnly) k_light_classify<true><<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    else k_light_classify<false><<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
     mark(1);
-    k_ray_march_l<<<c.smCount * perSM, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    if (densityOnly) k_ray_march_l<true><<<c.smCount * perSM, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    else k_ray_march_l<false><<<c.smCount * perSM, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
     mark(2);
     if (!c.cb.hasSH) return;
     k_light_scan<<<1, 1024, 0, c.stream>>>(c.scene(), c.cb, volumeOverride);
     mark(3);
-    k_light_emit<<<c.smCount * perSMEmit, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride);
+    if (densityOnly) k_light_emit<true><<<c.smCount * perSMEmit, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride);
+    else k_light_emit<false><<<c.smCount * perSMEmit, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride);
     mark(4);
-    k_light_ao<<<c.smCount * perSMAo, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride);
+    if (densityOnly) k_light_ao<true><<<c.smCount * perSMAo, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride);
+    else k_light_ao<false><<<c.smCount * perSMAo, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride);
     mark(5);
     k_light_finalize<<<(voxels + 255) / 256, 256, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
     mark(6);

@@ -56,7 +56,7 @@ MV_D uint32_t nth_set_bit(uint32_t mask, uint32_t n)
     return __ffs(mask) - 1;
 }
 
-template <bool kStats>
+template <bool kStats, bool kDensityOnly>
 __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_march_v(DeviceScene s, FrameCB cb)
 {
     __shared__ TileConst s_tc[kMarchWarps];
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
                 tMax = fminf(get_tmax(V3{cx, cy, z}, rayOrigin, rayDir, tc.po + 16), tMax);   // :106
 
                 MarchCount mc = {0, 0};
-                const V4 scatter = march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCount, rayOrigin, rayDir, tMax, mc);
+                const V4 scatter = march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCount, rayOrigin, rayDir, tMax, kDensityOnly, mc);
 
                 const size_t idx = ((size_t)face * size + y) * size + x;
                 const unsigned long long cOfs = arena_color_offset(s.arena, volumeId, mip) + idx * 8ull;
@@ -167,13 +167,16 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
 
 void launch_ray_march_view(Caster& c)
 {
-    const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0;
-    int perSM = 0;
-    if (stats) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_v<true>, kMarchThreads, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_v<false>, kMarchThreads, 0);
-    if (perSM < 1) perSM = 1;
-    if (stats) k_ray_march_v<true><<<c.smCount * perSM, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
-    else k_ray_march_v<false><<<c.smCount * perSM, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
+    const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0, densityOnly = (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0;
+    using Kernel = void (*)(DeviceScene, FrameCB);
+    static const Kernel kernels[4] = {k_ray_march_v<false, false>, k_ray_march_v<true, false>, k_ray_march_v<false, true>, k_ray_march_v<true, true>};
+    static int perSM[4] = {0, 0, 0, 0};
+    const int v = (stats ? 1 : 0) | (densityOnly ? 2 : 0);
+    if (!perSM[v]) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[v], kernels[v], kMarchThreads, 0);
+        if (perSM[v] < 1) perSM[v] = 1;
+    }
+    kernels[v]<<<c.smCount * perSM[v], kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
 }
 
 } // namespace mv

@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <new>
+#include <vector>
 
 using namespace mv;
 
@@ -145,9 +146,10 @@ static void set_volumes_world(Caster& c, float size, const float center[3])   //
     }
 }
 
-static int make_volume3d(Volume3D& v, uint32_t n)
+static int make_volume3d(Volume3D& v, uint32_t n, uint32_t channels = 4)
 {
-    const cudaChannelFormatDesc cd = cudaCreateChannelDescHalf4();
+    v.channels = channels;
+    const cudaChannelFormatDesc cd = channels == 1 ? cudaCreateChannelDescHalf() : cudaCreateChannelDescHalf4();
     MV_CUDA(cudaMalloc3DArray(&v.array, &cd, make_cudaExtent(n, n, n), cudaArraySurfaceLoadStore));
     cudaResourceDesc rd{};
     rd.resType = cudaResourceTypeArray;
@@ -165,12 +167,13 @@ static int make_volume3d(Volume3D& v, uint32_t n)
 static int clear_volume3d(Caster& c, Volume3D& v, uint32_t n)
 {
     // zero-fill through a device staging row-block (cudaMemset3D does not take arrays)
-    const size_t bytes = (size_t)n * n * n * 8;
+    const size_t texel = 2 * (size_t)v.channels;
+    const size_t bytes = (size_t)n * n * n * texel;
     void* z = nullptr;
     MV_CUDA(cudaMalloc(&z, bytes));
     MV_CUDA(cudaMemsetAsync(z, 0, bytes, c.stream));
     cudaMemcpy3DParms p{};
-    p.srcPtr = make_cudaPitchedPtr(z, (size_t)n * 8, n, n);
+    p.srcPtr = make_cudaPitchedPtr(z, (size_t)n * texel, n, n);
     p.dstArray = v.array;
     p.extent = make_cudaExtent(n, n, n);
     p.kind = cudaMemcpyDeviceToDevice;
@@ -321,7 +324,7 @@ int mv_create(const mv_desc* d, mv_caster** out)
 
     // MultiRayCaster.cpp:99-126 — per-source volumes, per-instance light maps and cube maps
     c.volumes.resize(S);
-    for (auto& v : c.volumes) { MV_TRY(make_volume3d(v, G)); MV_TRY(clear_volume3d(c, v, G)); }
+    for (auto& v : c.volumes) { MV_TRY(make_volume3d(v, G, (c.d.flags & MV_FLAG_DENSITY_ONLY) ? 1u : 4u)); MV_TRY(clear_volume3d(c, v, G)); }
     c.lightMaps.resize(N);
     for (auto& v : c.lightMaps) { MV_TRY(make_volume3d(v, L)); MV_TRY(clear_volume3d(c, v, L)); }
     std::vector<cudaTextureObject_t> vt(S), lt(N);
@@ -467,7 +470,13 @@ int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
     MV_REQUIRE(texels && src < c.d.num_volume_srcs);
     const uint32_t n = c.d.grid_size;
     cudaMemcpy3DParms p{};
-    p.srcPtr = make_cudaPitchedPtr((void*)texels, (size_t)n * 8, n, n);
+    std::vector<uint16_t> alpha;
+    if (c.volumes[src].channels == 1) {   // density-only storage keeps the alpha channel
+        const size_t count = (size_t)n * n * n;
+        alpha.resize(count);
+        for (size_t i = 0; i < count; ++i) alpha[i] = texels[4 * i + 3];
+        p.srcPtr = make_cudaPitchedPtr(alpha.data(), (size_t)n * 2, n, n);
+    } else p.srcPtr = make_cudaPitchedPtr((void*)texels, (size_t)n * 8, n, n);
     p.dstArray = c.volumes[src].array;
     p.extent = make_cudaExtent(n, n, n);
     p.kind = cudaMemcpyHostToDevice;
@@ -500,11 +509,21 @@ int mv_volume_read(mv_caster* h, uint32_t src, uint16_t* out)
     const uint32_t n = c.d.grid_size;
     cudaMemcpy3DParms p{};
     p.srcArray = c.volumes[src].array;
-    p.dstPtr = make_cudaPitchedPtr(out, (size_t)n * 8, n, n);
+    const bool densityOnly = c.volumes[src].channels == 1;
+    const size_t count = (size_t)n * n * n;
+    // density-only storage: the halves land in the tail of the caller's buffer and are expanded in place, front to back
+    uint16_t* packed = densityOnly ? out + 3 * count : out;
+    p.dstPtr = make_cudaPitchedPtr(packed, (size_t)n * (densityOnly ? 2 : 8), n, n);
     p.extent = make_cudaExtent(n, n, n);
     p.kind = cudaMemcpyDeviceToHost;
     MV_CUDA(cudaMemcpy3DAsync(&p, c.stream));
     MV_CUDA(cudaStreamSynchronize(c.stream));
+    if (densityOnly)
+        for (size_t i = 0; i < count; ++i) {
+            const uint16_t a = packed[i];
+            out[4 * i] = out[4 * i + 1] = out[4 * i + 2] = 0x3c00u;   // 1.0
+            out[4 * i + 3] = a;
+        }
     return MV_OK;
 }
 
@@ -953,7 +972,7 @@ int mv_set_flags(mv_caster* h, uint32_t flags)
 {
     MV_ENTER(h);
     MV_REQUIRE((flags & ~(MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES)) == 0);
-    c.d.flags = flags;
+    c.d.flags = flags | (c.d.flags & MV_FLAG_DENSITY_ONLY);   // the storage mode is fixed at creation
     c.inputsDirty = true;
     for (auto& v : c.evValid) v = false;
     return MV_OK;

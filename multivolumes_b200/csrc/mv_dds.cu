@@ -11,7 +11,7 @@
 // The resampling runs on the texture unit: the source goes into an R32F CUDA 3-D array with a
 // linear / clamp texture object and k_resample_r32f fetches it at (id + 0.5) / G. When the source already
 // has the grid's resolution every fetch lands on a texel centre, and the result is the texel itself.
-#include "mv_internal.h"
+#include "k_march.cuh"
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -24,7 +24,7 @@ namespace mv {
 
 namespace {
 
-__global__ void __launch_bounds__(256) k_resample_r32f(cudaSurfaceObject_t surf, cudaTextureObject_t src, uint32_t n)
+__global__ void __launch_bounds__(256) k_resample_r32f(cudaSurfaceObject_t surf, cudaTextureObject_t src, uint32_t n, bool densityOnly)
 {
     const uint32_t x = blockIdx.x * 32 + (threadIdx.x & 31);
     const uint32_t y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(256) k_resample_r32f(cudaSurfaceObject_t surf,
     if (x >= n || y >= n) return;
     const float gridSize = (float)n;
     const float a = tex3D<float>(src, ((float)x + 0.5f) / gridSize, ((float)y + 0.5f) / gridSize, ((float)z + 0.5f) / gridSize);   // :23-24
-    surf3Dwrite(pack_half4(V4{1.0f, 1.0f, 1.0f, a * 0.25f}), surf, (int)(x * 8), (int)y, (int)z);                                 // :26
+    store_volume_texel(surf, x, y, z, V4{1.0f, 1.0f, 1.0f, a * 0.25f}, densityOnly);                                               // :26
 }
 
 uint32_t rd32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
@@ -126,7 +126,7 @@ int mv_volume_upload_r32f_sized(mv_caster* h, uint32_t src, const float* density
     if (e == cudaSuccess) {
         const uint32_t n = c.d.grid_size;
         dim3 grid((n + 31) / 32, (n + 7) / 8, n);
-        k_resample_r32f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, tex, n);
+        k_resample_r32f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, tex, n, c.volumes[src].channels == 1);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);

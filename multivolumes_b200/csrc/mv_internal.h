@@ -176,6 +176,7 @@ void launch_light_commit(Caster& c);
 void launch_peer_barrier(Caster& c);
 
 struct Volume3D {
+    uint32_t channels = 4;               // 4 = RGBA16F, 1 = R16F (density-only storage of the source volumes)
     cudaArray_t array = nullptr;
     cudaTextureObject_t tex = 0;
     cudaSurfaceObject_t surf = 0;

@@ -461,3 +461,78 @@ def test_pipelined_frames_equal_oracle(update_every):
             assert np.array_equal(o.ReadVisible(), p.ReadVisible())
             lv = o.GetStats()["light_volume"]
             assert _same_bits(o.ReadLightMap(lv), p.ReadLightMap(lv))
+
+
+# ---------------------------------------------------------------- density-only (R16F) volume storage
+def _density_only_pair(**kw):
+    """Oracle and RGBA16F product holding (1, 1, 1, a); product with R16F storage holding a alone."""
+    from multivolumes_b200 import MultiRayCaster
+    return OracleCaster(filter_model=1, **kw), MultiRayCaster(**kw), MultiRayCaster(density_only=True, **kw)
+
+
+def test_density_only_ingest_keeps_alpha_and_reads_back_white():
+    kw = dict(SMALL)
+    _, rgba, r16 = _density_only_pair(**kw)
+    for c in (rgba, r16):
+        c.InitVolumeData(1, 1, 1234567)
+    a, d = rgba.ReadVolume(1), r16.ReadVolume(1)
+    assert _same_bits(a[..., 3], d[..., 3])                        # same density, bit for bit
+    assert (d[..., :3].view(np.uint16) == 0x3c00).all()           # colour (1, 1, 1)
+    dens = np.random.RandomState(3).uniform(0, 4, (32, 32, 32)).astype(np.float32)
+    for c in (rgba, r16):
+        c.LoadVolumeData(0, dens)                                  # CSR32FToRGBA16F: rgb = 1, a = 0.25 src
+    assert _same_bits(rgba.ReadVolume(0), r16.ReadVolume(0))
+    t = np.random.RandomState(4).uniform(0, 1, (32, 32, 32, 4)).astype(np.float16)
+    r16.LoadVolumeData(2, t)
+    assert _same_bits(r16.ReadVolume(2)[..., 3], t[..., 3])
+
+
+@pytest.mark.parametrize("cfg", [dict(sh=True, random_transforms=9, eye=(0, 40, -90)), dict(eye=(10.0, 40.0, -160.0), sh=True), dict()])
+def test_density_only_frame_equals_rgba_storage_and_oracle(cfg):
+    """MV_FLAG_DENSITY_ONLY: volumes are R16F textures (2 B / voxel). The frame must equal, bit for bit, the frame of the
+    RGBA16F storage (and of the oracle) holding (1, 1, 1, a): light maps, cube maps, frame, counters. Scenes with
+    cube-map and direct-scheme volumes."""
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=9, num_volume_srcs=3, width=320, height=180)
+    o, rgba, r16 = _density_only_pair(**kw)
+    bg = checker_background(320, 180)
+    vp, _ = scene.default_camera(320, 180)
+    depth = scene.sphere_depth(320, 180, vp, center=(0, 0, 0), radius=10.0)
+    configure(r16, background=bg, depth=depth, **cfg)
+    vols = [r16.ReadVolume(i) for i in range(3)]
+    for c in (o, rgba):
+        configure(c, background=bg, depth=depth, **cfg)
+        for i in range(3):
+            c.LoadVolumeData(i, vols[i])                           # (1, 1, 1, a) as RGBA16F
+    for c in (o, rgba, r16):
+        for _ in range(3):
+            c.Render()
+        c.Postprocess(taa=False)
+    so, sa, sd = o.GetStats(), rgba.GetStats(), r16.GetStats()
+    for k in ("visible_count", "cubemap_count", "view_rays", "view_samples", "view_light_fetches", "light_samples", "direct_rays", "direct_samples", "oit_fragments"):
+        assert so[k] == sa[k] == sd[k], (k, so[k], sa[k], sd[k])
+    assert so["view_samples"] > 0
+    lv = so["light_volume"]
+    assert _same_bits(o.ReadLightMap(lv), r16.ReadLightMap(lv))
+    for v in o.ReadCubeVolumes():
+        mip = int(o.ReadAttribs()[v][0])
+        (co, do), (cd, dd) = o.ReadCubeMap(v, mip), r16.ReadCubeMap(v, mip)
+        assert _same_bits(co, cd) and np.array_equal(do.view(np.uint32), dd.view(np.uint32))
+    fo, fa, fd = o.ReadFrame(), rgba.ReadFrame(), r16.ReadFrame()
+    assert _same_bits(fa, fd)
+    if not _same_bits(fo, fd):
+        assert_image_close(fd, fo, "frame")
+    assert np.array_equal(o.ReadPost()[1], r16.ReadPost()[1])
+
+
+def test_density_only_dds_ingest(tmp_path):
+    from dds_util import write_dds
+    from multivolumes_b200 import MultiRayCaster
+    kw = dict(SMALL)
+    rs = np.random.RandomState(11)
+    src = rs.uniform(0, 4, (24, 20, 28)).astype(np.float32)
+    path = str(tmp_path / "v.dds")
+    write_dds(path, src, "r32f", True)
+    rgba, r16 = MultiRayCaster(**kw), MultiRayCaster(density_only=True, **kw)
+    for c in (rgba, r16):
+        c.LoadVolumeFile(0, path)
+    assert _same_bits(rgba.ReadVolume(0), r16.ReadVolume(0))

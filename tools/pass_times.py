@@ -9,7 +9,7 @@ from multivolumes_b200 import MultiRayCaster, scene
 wl = dict(bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"])
 wl.update(json.loads(os.environ.get("MV_WL", "{}")))
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-c = MultiRayCaster(count_samples=not os.environ.get("MV_NOSTATS"), time_passes=True, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
+c = MultiRayCaster(count_samples=not os.environ.get("MV_NOSTATS"), time_passes=True, density_only=bool(wl.get("density_only")), grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
 bench.build_scene(c, wl, scene, c.TransformSH(scene.procedural_sky(64)))
 acc = {}
 for i in range(30 + frames):

@@ -8,7 +8,7 @@ import bench
 from multivolumes_b200 import MultiRayCaster, scene
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "cfg2"]
 frames = int(sys.argv[2]) if len(sys.argv) > 2 else 48
-kw = dict(count_samples=False, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
+kw = dict(count_samples=False, density_only=bool(wl.get("density_only")), grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
 os.environ["MV_OVERLAP"] = "0"
 serial = MultiRayCaster(**kw)
 os.environ["MV_OVERLAP"] = "1"
