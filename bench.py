@@ -173,7 +173,7 @@ def launches_per_frame(wl, world, exchange):
     """Kernels of libmv_b200.so per frame: k_cull; the light march (k_light_classify, k_ray_march_l and, with a light probe,
     k_light_scan, k_light_emit, k_light_ao, k_light_finalize); k_ray_march_v; k_ray_cast_direct; k_resolve_oit; k_postprocess.
     Sharded, fused exchange: + k_light_commit and three peer barriers (k_peer_signal + k_peer_wait each)."""
-    n = 1 + (6 if wl["sh"] else 2) + 1 + 1 + 1 + 1
+    n = 1 + (6 if wl["sh"] else 2) + 1 + 1 + 1 + 1   # --work-graph: the same count (k_pick_light_volume instead of k_cull)
     if world > 1:
         n += 1 + (6 if exchange == "fused" else 0)
     return n
@@ -199,6 +199,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--exchange", default="fused", choices=["fused", "collective"])
+    ap.add_argument("--work-graph", action="store_true", help="Render(..., useWorkGraph = true): cull inside the view-march launch (one GPU, not pipelined)")
     ap.add_argument("--cpu-baseline-frames", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU time the reference arm may use")
@@ -235,7 +236,7 @@ def main():
     build_scene(c, wl, scene, sky)
     with torch.cuda.stream(stream):
         x = CudaExchange(c, rank, world) if world > 1 and args.exchange == "collective" else None
-        r = ShardedRenderer(c, rank, world, mode=args.exchange, exchange=x)
+        r = ShardedRenderer(c, rank, world, mode=args.exchange, exchange=x, use_work_graph=args.work_graph)
 
         def barrier():
             if world > 1:

@@ -61,7 +61,10 @@ public:
     void UpdateFrame(const float viewProj[16], const float shadowVP[16], const Float3& eyePt)
     { const float e[3] = {eyePt.x, eyePt.y, eyePt.z}; mv_update_frame(m_h, viewProj, shadowVP, e); }
     // Render (:49-50)
-    bool Render(OITMethod oitMethod = OIT_K_BUFFER) { return ok(mv_render(m_h, oitMethod)); }
+    bool Render(OITMethod oitMethod = OIT_K_BUFFER, bool useWorkGraph = false)
+    {
+        return ok(useWorkGraph ? mv_render_work_graph(m_h, oitMethod) : mv_render(m_h, oitMethod));
+    }
     // ObjectRenderer::Postprocess (ObjectRenderer.h:46-48)
     bool Postprocess(bool taa = true) { return ok(mv_postprocess(m_h, taa ? 1u : 0u)); }
     // XUSG SphericalHarmonics::Transform (XUSGSphericalHarmonics.h:25-26)

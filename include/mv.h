@@ -128,6 +128,11 @@ int mv_update_frame(mv_caster* c, const float view_proj[16], const float shadow_
  * view march -> OIT resolve into the colour RT; frame index++. The individual passes are exported
  * for the parity tests. */
 int mv_render(mv_caster* c, uint32_t oit_method);
+/* Render with useWorkGraph = true (MultiRayCaster.h:49-50, MultiRayCaster.cpp:358-362, rayMarchWG :1370-1438,
+ * LibRayMarch.hlsl:39-134): the light march runs first and takes its volume from the PREVIOUS frame's visible list,
+ * then cull and view march run as ONE launch (the cull on CTA 0 of the persistent march kernel, which releases the
+ * lists to the other CTAs), then the OIT passes. One GPU; not pipelined across frames. */
+int mv_render_work_graph(mv_caster* c, uint32_t oit_method);
 int mv_cull(mv_caster* c);                                   /* cullVolumes, MultiRayCaster.cpp:1249-1285 */
 int mv_ray_march_light(mv_caster* c, int32_t volume_override); /* rayMarchL, :1299-1327; -1 = round-robin */
 int mv_ray_march_view(mv_caster* c);                         /* rayMarchV, :1329-1368 */

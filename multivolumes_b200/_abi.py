@@ -50,6 +50,7 @@ _COMMON = {
     "set_ambient": (C.c_int, [_vp, P(f32), f32]),
     "update_frame": (C.c_int, [_vp, P(f32), P(f32), P(f32)]),
     "render": (C.c_int, [_vp, u32]),
+    "render_work_graph": (C.c_int, [_vp, u32]),
     "cull": (C.c_int, [_vp]),
     "ray_march_light": (C.c_int, [_vp, i32]),
     "ray_march_view": (C.c_int, [_vp]),
@@ -246,8 +247,12 @@ class CasterBase:
         self._ck(self.b.update_frame(self.h, pa, pb, pc), "update_frame")
 
     # --- passes ---
-    def Render(self, oit_method=0):
-        self._ck(self.b.render(self.h, oit_method), "render")
+    def Render(self, oit_method=0, use_work_graph=False):
+        """MultiRayCaster::Render (MultiRayCaster.h:49-50); use_work_graph = the reference's useWorkGraph argument."""
+        if use_work_graph:
+            self._ck(self.b.render_work_graph(self.h, oit_method), "render_work_graph")
+        else:
+            self._ck(self.b.render(self.h, oit_method), "render")
 
     def Cull(self):
         self._ck(self.b.cull(self.h), "cull")

@@ -11,8 +11,12 @@
 //   * the per-volume constants (PerObject record, attributes, output addresses) are staged once per
 //     tile in shared memory;
 //   * with peers mapped (multi-GPU), each texel is stored straight into every peer's cube-map arena
-//     over NVLink from this kernel — the all-gather of the per-volume cube maps is fused into the march.
+//     over NVLink from this kernel — the all-gather of the per-volume cube maps is fused into the march;
+//   * kFusedCull (mv_render_work_graph): the cull runs inside this launch, on CTA 0, and the other CTAs pick up the
+//     lists it wrote once it publishes the frame's serial number — the work-graph path of the reference
+//     (LibRayMarch.hlsl:39-134: VolumeCull node -> RayMarch node in one DispatchGraph, MultiRayCaster.cpp:1370-1438).
 #include "k_march.cuh"
+#include "k_cull.cuh"
 
 namespace mv {
 
@@ -56,14 +60,34 @@ MV_D uint32_t nth_set_bit(uint32_t mask, uint32_t n)
     return __ffs(mask) - 1;
 }
 
-template <bool kStats, bool kDensityOnly>
-__global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_march_v(DeviceScene s, FrameCB cb)
+// Loads of the lists the cull wrote: through the read-only path when an earlier launch wrote them, from L2 (ld.cg) when
+// CTA 0 of this very launch did.
+template <bool kFusedCull, class T>
+MV_D T ld_list(const T* p) { return kFusedCull ? __ldcg(p) : __ldg(p); }
+
+template <bool kStats, bool kDensityOnly, bool kFusedCull>
+__global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_march_v(DeviceScene s, FrameCB cb, uint32_t serial)
 {
     __shared__ TileConst s_tc[kMarchWarps];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     TileConst& tc = s_tc[warp];
-    const uint32_t total = s.lists->marchTileTotal;
-    const uint32_t cubeCount = s.lists->cubeCount;
+    if (kFusedCull) {
+        // CTA 0 is the cull node; it releases the frame's lists by storing the serial number after a fence. The launch is
+        // sized to the resident capacity and CTA 0 is dispatched first, so the spinning CTAs cannot starve it.
+        volatile uint32_t* ready = &s.lists->cullSerial;
+        if (blockIdx.x == 0) {
+            cull_body<kMarchThreads>(s, cb, false);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) *ready = serial;
+        } else {
+            if (threadIdx.x == 0) while (*ready != serial) __nanosleep(64);
+            __syncthreads();
+        }
+        __threadfence();
+    }
+    const uint32_t total = ld_list<kFusedCull>(&s.lists->marchTileTotal);
+    const uint32_t cubeCount = ld_list<kFusedCull>(&s.lists->cubeCount);
     uint32_t nRays = 0, nSamples = 0, nLight = 0;
     uint32_t stagedVolume = 0xffffffffu;
 
@@ -77,11 +101,11 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
         uint32_t lo = 0, hi = cubeCount;
         while (hi - lo > 1) {
             const uint32_t mid = (lo + hi) >> 1;
-            if (__ldg(s.cubeTilePrefix + mid) <= w) lo = mid; else hi = mid;
+            if (ld_list<kFusedCull>(s.cubeTilePrefix + mid) <= w) lo = mid; else hi = mid;
         }
-        const uint32_t volumeId = __ldg(s.cubeVolumes + __ldg(s.marchOrder + lo));
-        const uint32_t local = w - __ldg(s.cubeTilePrefix + lo);
-        const ushort4 a = s.attribs[volumeId];
+        const uint32_t volumeId = ld_list<kFusedCull>(s.cubeVolumes + ld_list<kFusedCull>(s.marchOrder + lo));
+        const uint32_t local = w - ld_list<kFusedCull>(s.cubeTilePrefix + lo);
+        const ushort4 a = kFusedCull ? __ldcg(s.attribs + volumeId) : s.attribs[volumeId];
         const uint32_t mip = a.x, smpCount = a.y, maskBits = a.z, volTexId = a.w;
         const uint32_t size = cb.gridSize >> mip;
         const uint32_t tilesX = (size + 7) >> 3, tilesY = (size + 3) >> 2;
@@ -165,18 +189,25 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
 
 } // namespace
 
-void launch_ray_march_view(Caster& c)
+static void launch_view(Caster& c, bool fusedCull)
 {
     const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0, densityOnly = (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0;
-    using Kernel = void (*)(DeviceScene, FrameCB);
-    static const Kernel kernels[4] = {k_ray_march_v<false, false>, k_ray_march_v<true, false>, k_ray_march_v<false, true>, k_ray_march_v<true, true>};
-    static int perSM[4] = {0, 0, 0, 0};
-    const int v = (stats ? 1 : 0) | (densityOnly ? 2 : 0);
+    using Kernel = void (*)(DeviceScene, FrameCB, uint32_t);
+    static const Kernel kernels[8] = {k_ray_march_v<false, false, false>, k_ray_march_v<true, false, false>, k_ray_march_v<false, true, false>, k_ray_march_v<true, true, false>,
+                                      k_ray_march_v<false, false, true>,  k_ray_march_v<true, false, true>,  k_ray_march_v<false, true, true>,  k_ray_march_v<true, true, true>};
+    static int perSM[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const int v = (stats ? 1 : 0) | (densityOnly ? 2 : 0) | (fusedCull ? 4 : 0);
     if (!perSM[v]) {
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM[v], kernels[v], kMarchThreads, 0);
         if (perSM[v] < 1) perSM[v] = 1;
     }
-    kernels[v]<<<c.smCount * perSM[v], kMarchThreads, 0, c.stream>>>(c.scene(), c.cb);
+    if (fusedCull) ++c.cullSerial;
+    kernels[v]<<<c.smCount * perSM[v], kMarchThreads, 0, c.stream>>>(c.scene(), c.cb, c.cullSerial);
 }
+
+void launch_ray_march_view(Caster& c) { launch_view(c, false); }
+
+// cull + view march in one launch (the work-graph path)
+void launch_cull_and_ray_march_view(Caster& c) { launch_view(c, true); }
 
 } // namespace mv

@@ -750,6 +750,7 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         c.lightToStaging = false;
         c.stream = mainStream;
         MV_CUDA(cudaEventRecord(c.lightDone, B));
+        c.lightDoneValid = true;
         // main stream: commit the light map, then the passes that read it
         MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
         launch_light_commit(c);
@@ -782,6 +783,39 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
     c.frameEndValid[slot] = true;
     if (c.frameIdx != 0xffffffffu) ++c.frameIdx;
     return check_launch("render");
+}
+
+// Render(..., useWorkGraph = true), MultiRayCaster.cpp:358-362: the light march runs first, on the visible list of the
+// previous frame, then ONE launch culls and marches the cube maps (rayMarchWG, :1370-1438), then the OIT passes.
+int mv_render_work_graph(mv_caster* h, uint32_t oit)
+{
+    MV_ENTER(h);
+    (void)oit;
+    if (c.shardWorld > 1) { set_error("mv_render_work_graph: one GPU only (the sharded frame drives the passes one by one)"); return MV_ERR_INVALID; }
+    flip_frame_lists(c);
+    const uint32_t slot = c.listParity;
+    c.poLastUse[c.poParity] = (int)slot;
+    wait_upload(c, c.stream);
+    // pipelined frames of mv_render may still be in flight on the light stream: this path is serial on the main stream
+    if (c.lightDoneValid) MV_CUDA(cudaStreamWaitEvent(c.stream, c.lightDone, 0));
+    c.inputsDirty = true;
+    if (c.d.flags & MV_FLAG_COUNT_SAMPLES) MV_CUDA(cudaMemsetAsync(c.dStats, 0, sizeof(StatsDev), c.stream));
+    record(c, 0);
+    record(c, 1);                       // the cull has no pass of its own here: it is timed with the view march
+    launch_pick_light_volume(c);
+    launch_ray_march_light(c, -1);
+    record(c, 2);
+    launch_cull_and_ray_march_view(c);
+    record(c, 3);
+    MV_TRY_DIRECT_STATS(c);
+    launch_ray_cast_direct(c);
+    launch_resolve_oit(c);
+    record(c, 4);
+    c.evValid[5] = false;
+    MV_CUDA(cudaEventRecord(c.frameEnd[slot], c.stream));
+    c.frameEndValid[slot] = true;
+    if (c.frameIdx != 0xffffffffu) ++c.frameIdx;
+    return check_launch("render_work_graph");
 }
 
 int mv_postprocess(mv_caster* h, uint32_t taa)

@@ -56,7 +56,8 @@ struct FrameLists {
     uint32_t lightOverflow;     // the frame's AO rays do not fit the item buffers: they are marched inline instead
     uint32_t directTileTotal;   // 8x4-pixel tiles of the screen-space marches (direct-scheme volumes)
     uint32_t directTileCursor;  // work cursor of the persistent direct-march kernel
-    uint32_t pad0[3];
+    uint32_t cullSerial;        // fused cull -> view march: the launch whose cull results these lists hold (k_ray_march_v.cu)
+    uint32_t pad0[2];
     // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1], directTilePrefix[N + 1], directOffset[N], marchOrder[N]
 };
 
@@ -168,6 +169,8 @@ void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity);
 void launch_cull(Caster& c);
 void launch_ray_march_light(Caster& c, int volumeOverride);
 void launch_ray_march_view(Caster& c);
+void launch_cull_and_ray_march_view(Caster& c);
+void launch_pick_light_volume(Caster& c);
 void launch_ray_cast_direct(Caster& c);
 void launch_resolve_oit(Caster& c);
 void launch_postprocess(Caster& c, bool taaOn);
@@ -245,7 +248,8 @@ struct Caster {
     // Per-frame device state is double-buffered: PerObject records by upload, lists + attributes by render.
     cudaStream_t lightStream = nullptr;
     cudaEvent_t lightDone = nullptr, commitDone = nullptr, inputsReady = nullptr, frameEnd[2] = {};
-    bool commitValid = false, frameEndValid[2] = {false, false}, inputsDirty = true, lightToStaging = false;
+    bool lightDoneValid = false, commitValid = false, frameEndValid[2] = {false, false}, inputsDirty = true, lightToStaging = false;
+    uint32_t cullSerial = 0;             // serial number of the last fused cull + view-march launch
     int overlapLight = 1;                // MV_OVERLAP=0: every pass on the main stream
     PerObject* dPerObject2[2] = {};      // dPerObject points at the one of the last mv_update_frame
     ushort4* dAttribs2[2] = {};

@@ -144,9 +144,11 @@ class ShardedRenderer:
 
     STRIPE_HEIGHT = 30   # + 2 halo rows = two 16-row OIT tile rows
 
-    def __init__(self, caster, rank, world, mode="collective", exchange=None, group=None, stripes=True):
+    def __init__(self, caster, rank, world, mode="collective", exchange=None, group=None, stripes=True, use_work_graph=False):
         assert mode in ("fused", "collective")
+        assert not (use_work_graph and world > 1), "the work-graph path (cull inside the march launch) is a one-GPU path"
         self.c, self.rank, self.world, self.mode, self.group = caster, rank, world, mode, group
+        self.use_work_graph = use_work_graph
         self.bands = [row_band(caster.H, r, world) for r in range(world)]
         self.row0, self.row1 = self.bands[rank]
         caster.SetShard(rank, world)
@@ -173,7 +175,7 @@ class ShardedRenderer:
         if reset_color:
             c.ResetColor()
         if self.world == 1:
-            c.Render()
+            c.Render(use_work_graph=self.use_work_graph)
             c.Postprocess(taa)
             return
         if self.mode == "fused":

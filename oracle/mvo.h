@@ -69,6 +69,8 @@ int mvo_update_frame(mvo_caster* c, const float view_proj[16], const float shado
 
 /* passes; mvo_render = cull -> light march (one volume, round-robin) -> view march -> OIT, frame++ */
 int mvo_render(mvo_caster* c, uint32_t oit_method);
+/* Render(..., useWorkGraph = true), MultiRayCaster.cpp:358-362: light march (volume from the previous frame's visible list) -> cull -> view march -> OIT */
+int mvo_render_work_graph(mvo_caster* c, uint32_t oit_method);
 int mvo_cull(mvo_caster* c);
 int mvo_ray_march_light(mvo_caster* c, int32_t volume_override);   /* -1: reference round-robin */
 int mvo_ray_march_view(mvo_caster* c);

@@ -345,6 +345,20 @@ int mvo_render(mvo_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
     if (c.frameIdx != 0xffffffffu) ++c.frameIdx;
     return 0;
 }
+int mvo_render_work_graph(mvo_caster* h, uint32_t oit)   // MultiRayCaster.cpp:358-362 (useWorkGraph), rayMarchWG :1370-1438
+{
+    if (!h) return -1;
+    (void)oit;
+    Caster& c = h->c;
+    // rayMarchL first: CSRayMarchL.hlsl:29-33 reads the visible list and its counter as the previous frame's graph left
+    // them (c.visible is only rewritten by cull_volumes); then the graph: VolumeCull node -> RayMarch node
+    ray_march_light(c, -1);
+    cull_volumes(c);
+    ray_march_view(c);
+    resolve_oit(c);
+    if (c.frameIdx != 0xffffffffu) ++c.frameIdx;
+    return 0;
+}
 int mvo_postprocess(mvo_caster* h, uint32_t taa) { if (!h) return -1; temporal_aa(h->c, taa != 0); tone_map(h->c); return 0; }
 int mvo_sh_project(mvo_caster* h, const float* cube, uint32_t size, float* out27)
 {

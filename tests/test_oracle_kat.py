@@ -240,3 +240,29 @@ def test_set_volumes_world_grid_rule():
     world = c.ReadPerObject()[:, 44:56].reshape(16, 4, 3)
     assert np.allclose(world[:, 0, 0], 10.0) and np.allclose(world[:, 1, 1], 10.0)
     assert np.allclose(world[0, 3], [-45, 0, -45]) and np.allclose(world[5, 3], [-15, 0, -15]) and np.allclose(world[15, 3], [45, 0, 45])
+
+
+def test_work_graph_order_lights_from_previous_visible_list():
+    """Render(..., useWorkGraph = true), MultiRayCaster.cpp:358-362: rayMarchL runs before the graph that culls, so the
+    light volume of frame f is visible_{f-1}[f % |visible_{f-1}|] (CSRayMarchL.hlsl:29-33), f % N on the first frame;
+    everything downstream of the cull (lists, cube maps) is that of the plain order."""
+    kw = dict(grid_size=16, light_grid_size=8, num_volumes=9, num_volume_srcs=1, width=160, height=90)
+    wg, plain = OracleCaster(**kw), OracleCaster(**kw)
+    for c in (wg, plain):
+        c.InitVolumeData(0, 1, 5)
+        c.SetVolumesWorld(20.0, (0, 0, 0))
+        c.SetRenderTargets()
+    prev_visible = np.zeros(0, np.uint32)
+    for f in range(5):
+        vp, eye = scene.default_camera(160, 90, eye=(4.0 + 25 * f, 16.0, -80.0 + 20 * f), focus=(12.0 * f, 0, 0))
+        for c in (wg, plain):
+            c.UpdateFrame(vp, None, eye)
+        wg.Render(use_work_graph=True)
+        plain.Render()
+        want = int(prev_visible[f % len(prev_visible)]) if len(prev_visible) else f % 9
+        assert wg.GetStats()["light_volume"] == want, (f, wg.GetStats()["light_volume"], want)
+        vis = plain.ReadVisible()
+        assert np.array_equal(wg.ReadVisible(), vis)
+        assert plain.GetStats()["light_volume"] == int(vis[f % len(vis)])
+        prev_visible = vis
+    assert len(set(map(len, [prev_visible]))) == 1 and len(prev_visible) > 0
