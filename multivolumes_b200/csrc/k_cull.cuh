@@ -226,19 +226,30 @@ MV_D void cull_body(const DeviceScene& s, const FrameCB& cb, bool pickLightVolum
         }
         if (lane == 0) { s.directTilePrefix[visibleCount] = runningTiles; s.lists->directTileTotal = runningTiles; }
     }
-    // tile prefix of the view march over the cube-map volumes this rank owns (warp 0, shuffle scan)
+    // Tile prefix of the view march over the cube-map volumes (warp 0, shuffle scan), in march order. One GPU: every tile.
+    // Sharded, peers unmapped (collective exchange: whole cube maps are broadcast by their owner): the tiles of the
+    // volumes v % world == rank. Sharded, peers mapped (every texel is stored into all arenas by whoever marches it, so
+    // ownership can be as fine as a tile): every volume's tile list (face-major, row-major) is cut into `world` equal
+    // contiguous parts and rank r marches part (r - k) mod world of the k-th volume. Each rank then carries 1 / world
+    // of every volume's rays — whatever the content makes them cost (sample counts per ray differ 2x between volumes:
+    // profiles/r01_notes.md) — while still reading only the wedge of each volume its own rays cross, and the rotation
+    // keeps one rank from always getting the same face. Every rank evaluates the same integers: the parts tile the list.
     if (warp == 0) {
+        const bool balanced = s.shardWorld > 1 && s.arena.numPeers != 0;
         uint32_t running = 0;
         for (uint32_t base = 0; base < cubeCount; base += 32) {
             const uint32_t k = base + lane;
-            uint32_t tiles = 0;
+            uint32_t tiles = 0, begin = 0;
             if (k < cubeCount) {
                 const uint32_t vol = s.cubeVolumes[s.marchOrder[k]];
-                if (vol % s.shardWorld == s.shardRank) {
-                    const ushort4 a = s.attribs[vol];
-                    const uint32_t size = cb.gridSize >> a.x;
-                    tiles = ((size + 7) / 8) * ((size + 3) / 4) * __popc(a.z & 0x3fu);
-                }
+                const ushort4 a = s.attribs[vol];
+                const uint32_t size = cb.gridSize >> a.x;
+                const uint32_t all = ((size + 7) / 8) * ((size + 3) / 4) * __popc(a.z & 0x3fu);
+                if (balanced) {
+                    const uint32_t part = (s.shardRank + s.shardWorld - k % s.shardWorld) % s.shardWorld;
+                    begin = (uint32_t)((unsigned long long)all * part / s.shardWorld);
+                    tiles = (uint32_t)((unsigned long long)all * (part + 1) / s.shardWorld) - begin;
+                } else if (vol % s.shardWorld == s.shardRank) tiles = all;
             }
             uint32_t incl = tiles;
 #pragma unroll
@@ -246,7 +257,7 @@ MV_D void cull_body(const DeviceScene& s, const FrameCB& cb, bool pickLightVolum
                 const uint32_t t = __shfl_up_sync(kFull, incl, d);
                 if (lane >= (uint32_t)d) incl += t;
             }
-            if (k < cubeCount) s.cubeTilePrefix[k] = running + incl - tiles;
+            if (k < cubeCount) { s.cubeTilePrefix[k] = running + incl - tiles; s.cubeTileBegin[k] = begin; }
             running += __shfl_sync(kFull, incl, 31);
         }
         if (lane == 0) {
@@ -256,6 +267,7 @@ MV_D void cull_body(const DeviceScene& s, const FrameCB& cb, bool pickLightVolum
             L->cubeCount = cubeCount;
             L->marchTileTotal = running;
             L->marchTileCursor = 0;
+            L->marchTileCursor2 = 0;
             L->oitTileCursor = 0;
             L->directTileCursor = 0;
             L->lightDenseCount = 0;

@@ -66,7 +66,7 @@ template <bool kFusedCull, class T>
 MV_D T ld_list(const T* p) { return kFusedCull ? __ldcg(p) : __ldg(p); }
 
 template <bool kStats, bool kDensityOnly, bool kFusedCull>
-__global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_march_v(DeviceScene s, FrameCB cb, uint32_t serial)
+__global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_march_v(DeviceScene s, FrameCB cb, uint32_t serial, uint32_t phase)
 {
     __shared__ TileConst s_tc[kMarchWarps];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -91,9 +91,14 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
     uint32_t nRays = 0, nSamples = 0, nLight = 0;
     uint32_t stagedVolume = 0xffffffffu;
 
+    // phase (sharded frame, mv_api.cu): 1 = every volume but the frame's light volume, whose light map is still being
+    // marched on the light stream; 2 = the light volume alone, once its light map is committed; 0 = all
+    uint32_t* cursor = phase == 2 ? &s.lists->marchTileCursor2 : &s.lists->marchTileCursor;
+    const uint32_t lightVolume = phase ? s.lists->lightVolume : 0xffffffffu;
+
     for (;;) {
         uint32_t w = 0;
-        if (lane == 0) w = atomicAdd(&s.lists->marchTileCursor, 1u);
+        if (lane == 0) w = atomicAdd(cursor, 1u);
         w = __shfl_sync(kFull, w, 0);
         if (w >= total) break;
 
@@ -104,7 +109,8 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
             if (ld_list<kFusedCull>(s.cubeTilePrefix + mid) <= w) lo = mid; else hi = mid;
         }
         const uint32_t volumeId = ld_list<kFusedCull>(s.cubeVolumes + ld_list<kFusedCull>(s.marchOrder + lo));
-        const uint32_t local = w - ld_list<kFusedCull>(s.cubeTilePrefix + lo);
+        if (phase && (volumeId == lightVolume) != (phase == 2)) continue;
+        const uint32_t local = w - ld_list<kFusedCull>(s.cubeTilePrefix + lo) + ld_list<kFusedCull>(s.cubeTileBegin + lo);
         const ushort4 a = kFusedCull ? __ldcg(s.attribs + volumeId) : s.attribs[volumeId];
         const uint32_t mip = a.x, smpCount = a.y, maskBits = a.z, volTexId = a.w;
         const uint32_t size = cb.gridSize >> mip;
@@ -189,10 +195,10 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
 
 } // namespace
 
-static void launch_view(Caster& c, bool fusedCull)
+static void launch_view(Caster& c, bool fusedCull, uint32_t phase, int blocksPerSM)
 {
     const bool stats = (c.d.flags & MV_FLAG_COUNT_SAMPLES) != 0, densityOnly = (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0;
-    using Kernel = void (*)(DeviceScene, FrameCB, uint32_t);
+    using Kernel = void (*)(DeviceScene, FrameCB, uint32_t, uint32_t);
     static const Kernel kernels[8] = {k_ray_march_v<false, false, false>, k_ray_march_v<true, false, false>, k_ray_march_v<false, true, false>, k_ray_march_v<true, true, false>,
                                       k_ray_march_v<false, false, true>,  k_ray_march_v<true, false, true>,  k_ray_march_v<false, true, true>,  k_ray_march_v<true, true, true>};
     static int perSM[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -202,12 +208,13 @@ static void launch_view(Caster& c, bool fusedCull)
         if (perSM[v] < 1) perSM[v] = 1;
     }
     if (fusedCull) ++c.cullSerial;
-    kernels[v]<<<c.smCount * perSM[v], kMarchThreads, 0, c.stream>>>(c.scene(), c.cb, c.cullSerial);
+    const int blocks = blocksPerSM > 0 ? min(blocksPerSM, perSM[v]) : perSM[v];
+    kernels[v]<<<c.smCount * blocks, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb, c.cullSerial, phase);
 }
 
-void launch_ray_march_view(Caster& c) { launch_view(c, false); }
+void launch_ray_march_view(Caster& c, uint32_t phase, int blocksPerSM) { launch_view(c, false, phase, blocksPerSM); }
 
 // cull + view march in one launch (the work-graph path)
-void launch_cull_and_ray_march_view(Caster& c) { launch_view(c, true); }
+void launch_cull_and_ray_march_view(Caster& c) { launch_view(c, true, 0, 0); }
 
 } // namespace mv

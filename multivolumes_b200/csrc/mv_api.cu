@@ -55,6 +55,7 @@ DeviceScene Caster::scene() const
     s.directTilePrefix = tail + 3 * N + 1;
     s.directOffset = tail + 4 * N + 2;
     s.marchOrder = tail + 5 * N + 2;
+    s.cubeTileBegin = tail + 6 * N + 2;
     s.visInfo = reinterpret_cast<VisInfo*>(dLists + frame_lists_header_bytes(N));
     s.directColor = dDirectColor;
     s.directStats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dDirectStats : nullptr;
@@ -250,7 +251,7 @@ static void destroy_caster(Caster& c)
     if (c.frameDone) cudaEventDestroy(c.frameDone);
     if (c.copyStream) { cudaStreamSynchronize(c.copyStream); cudaStreamDestroy(c.copyStream); }
     if (c.lightStream) { cudaStreamSynchronize(c.lightStream); cudaStreamDestroy(c.lightStream); }
-    for (cudaEvent_t e : {c.lightDone, c.commitDone, c.inputsReady, c.frameEnd[0], c.frameEnd[1]}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c.lightDone, c.commitDone, c.inputsReady, c.cullDone, c.frameEnd[0], c.frameEnd[1]}) if (e) cudaEventDestroy(e);
     c.dPerObject = nullptr; c.dAttribs = nullptr; c.dLists = nullptr;
     if (c.ownStream) cudaStreamDestroy(c.ownStream);
 }
@@ -318,6 +319,8 @@ int mv_create(const mv_desc* d, mv_caster** out)
         for (cudaEvent_t* e : {&c.lightDone, &c.commitDone, &c.inputsReady, &c.frameEnd[0], &c.frameEnd[1]})
             MV_CUDA_C(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         if (const char* e = getenv("MV_OVERLAP")) c.overlapLight = atoi(e);
+        if (const char* e = getenv("MV_SHARD_V_BLOCKS")) c.shardViewBlocks = atoi(e);
+        MV_CUDA_C(cudaEventCreateWithFlags(&c.cullDone, cudaEventDisableTiming));
     }
     MV_CUDA_C(cudaEventCreateWithFlags(&c.frameDone, cudaEventDisableTiming));
     for (auto& e : c.presentDone) MV_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -766,12 +769,32 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         record(c, 0);
         launch_cull(c);
         record(c, 1);
-        launch_ray_march_light(c, -1);
-        // sharded: once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
-        if (c.shardWorld > 1) { wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
-        record(c, 2);
-        launch_ray_march_view(c);
-        if (c.shardWorld > 1) launch_peer_barrier(c);                                // every owner's cube maps have landed
+        if (c.shardWorld > 1 && c.peersMapped && c.overlapLight && c.shardViewBlocks > 0 && !(c.d.flags & MV_FLAG_TIME_PASSES)) {
+            // Sharded frame, uninstrumented: the light march fills ONE volume's light map, so the view march of every other
+            // volume does not depend on it. The rank's slab is marched on the light stream while the main stream marches
+            // the other volumes' tiles (a few CTAs per SM fewer, so that both are resident: with 1 / world of the frame
+            // per GPU both are latency-bound, not throughput-bound); the light volume's own tiles follow the commit.
+            cudaStream_t mainStream = c.stream, B = c.lightStream;
+            MV_CUDA(cudaEventRecord(c.cullDone, mainStream));
+            MV_CUDA(cudaStreamWaitEvent(B, c.cullDone, 0));
+            c.stream = B;
+            launch_ray_march_light(c, -1);
+            c.stream = mainStream;
+            MV_CUDA(cudaEventRecord(c.lightDone, B));
+            c.lightDoneValid = true;
+            launch_ray_march_view(c, 1, c.shardViewBlocks);
+            MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
+            wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c);
+            launch_ray_march_view(c, 2);
+            launch_peer_barrier(c);
+        } else {
+            launch_ray_march_light(c, -1);
+            // sharded: once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
+            if (c.shardWorld > 1) { wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
+            record(c, 2);
+            launch_ray_march_view(c);
+            if (c.shardWorld > 1) launch_peer_barrier(c);                            // every owner's cube maps have landed
+        }
         record(c, 3);
         MV_TRY_DIRECT_STATS(c);
         launch_ray_cast_direct(c);

@@ -57,8 +57,9 @@ struct FrameLists {
     uint32_t directTileTotal;   // 8x4-pixel tiles of the screen-space marches (direct-scheme volumes)
     uint32_t directTileCursor;  // work cursor of the persistent direct-march kernel
     uint32_t cullSerial;        // fused cull -> view march: the launch whose cull results these lists hold (k_ray_march_v.cu)
-    uint32_t pad0[2];
-    // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1], directTilePrefix[N + 1], directOffset[N], marchOrder[N]
+    uint32_t marchTileCursor2;  // cursor of the second view-march launch of a sharded frame (the light volume's own tiles)
+    uint32_t pad0[1];
+    // followed in memory by: visible[N], cubeVolumes[N], cubeTilePrefix[N + 1], directTilePrefix[N + 1], directOffset[N], marchOrder[N], cubeTileBegin[N]
 };
 
 // Per visible volume (same order as the visible list), written by the cull for the OIT resolve: the
@@ -87,7 +88,7 @@ static_assert(sizeof(LightRec) == 64, "LightRec layout");
 
 constexpr uint32_t kNoDirect = 0xffffffffu;
 // bytes of the per-frame lists in front of the VisInfo records (mv_api.cu lays the block out)
-MV_HD size_t frame_lists_header_bytes(size_t N) { return (sizeof(FrameLists) + (6 * N + 2) * sizeof(uint32_t) + 31) & ~(size_t)31; }
+MV_HD size_t frame_lists_header_bytes(size_t N) { return (sizeof(FrameLists) + (7 * N + 2) * sizeof(uint32_t) + 31) & ~(size_t)31; }
 
 struct StatsDev {
     unsigned long long view_rays, view_samples, view_light_fetches;
@@ -128,6 +129,7 @@ struct DeviceScene {
     uint32_t* cubeVolumes;               // [N]
     uint32_t* cubeTilePrefix;            // [N + 1] over marchOrder
     uint32_t* marchOrder;                // [N] indices into cubeVolumes, longest rays first
+    uint32_t* cubeTileBegin;             // [N] over marchOrder: first tile of the volume this rank marches (tile-balanced sharding)
     VisInfo* visInfo;                    // [N]
     uint32_t* directTilePrefix;          // [N + 1] over the visible list: tiles of the screen-space march of each direct-scheme volume
     uint32_t* directOffset;              // [N] over the visible list: first pixel of the volume's rectangle in directColor (kNoDirect = none)
@@ -168,7 +170,9 @@ void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
 void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity);
 void launch_cull(Caster& c);
 void launch_ray_march_light(Caster& c, int volumeOverride);
-void launch_ray_march_view(Caster& c);
+// phase 0: every cube-map volume; 1: all but the frame's light volume (at most blocksPerSM CTAs per SM, 0 = all that fit);
+// 2: the light volume alone
+void launch_ray_march_view(Caster& c, uint32_t phase = 0, int blocksPerSM = 0);
 void launch_cull_and_ray_march_view(Caster& c);
 void launch_pick_light_volume(Caster& c);
 void launch_ray_cast_direct(Caster& c);
@@ -250,6 +254,8 @@ struct Caster {
     cudaEvent_t lightDone = nullptr, commitDone = nullptr, inputsReady = nullptr, frameEnd[2] = {};
     bool lightDoneValid = false, commitValid = false, frameEndValid[2] = {false, false}, inputsDirty = true, lightToStaging = false;
     uint32_t cullSerial = 0;             // serial number of the last fused cull + view-march launch
+    int shardViewBlocks = 0;             // sharded frame, opt-in (MV_SHARD_V_BLOCKS = 1..5): view-march CTAs per SM while the light march runs beside it; 0 = the passes run one after the other (faster at N = 2: profiles/r01_notes.md)
+    cudaEvent_t cullDone = nullptr;      // sharded frame: main stream -> light stream
     int overlapLight = 1;                // MV_OVERLAP=0: every pass on the main stream
     PerObject* dPerObject2[2] = {};      // dPerObject points at the one of the last mv_update_frame
     ushort4* dAttribs2[2] = {};

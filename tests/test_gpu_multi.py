@@ -40,6 +40,12 @@ with torch.cuda.stream(stream):
     if rank == 0:
         taa, rgba8 = c.ReadPost()
         np.savez(out, rgba8=rgba8)
+    else:
+        # the last rank's arena must hold every cube map of the frame: whole maps from their owners (collective) or tile
+        # ranges stored by whichever rank marched them (fused, tile-balanced split)
+        att = c.ReadAttribs()
+        cubes = {f"cube{v}": c.ReadCubeMap(int(v), int(att[v][0]))[0].view(np.uint16) for v in c.ReadCubeVolumes()}
+        np.savez(out + f".r{rank}.npz", **cubes)
     dist.barrier()
 dist.destroy_process_group()
 '''
@@ -55,10 +61,12 @@ def _single():
     for i in range(4):
         vp, eye = scene.default_camera(640, 360, eye=(4.0 + 6 * i, 16.0 + 8 * i, -80.0 - 30 * i))
         c.UpdateFrame(vp, None, eye); c.ResetColor(); c.Render(); c.Postprocess(True)
-    return c.ReadPost()[1]
+    att = c.ReadAttribs()
+    cubes = {f"cube{v}": c.ReadCubeMap(int(v), int(att[v][0]))[0].view(np.uint16) for v in c.ReadCubeVolumes()}
+    return c.ReadPost()[1], cubes
 
 
-@pytest.mark.parametrize("mode", ["fused", "collective"])
+@pytest.mark.parametrize("mode", ["fused", "fused-overlap", "collective"])
 def test_two_gpu_frame_equals_single_gpu(mode, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
@@ -68,6 +76,15 @@ def test_two_gpu_frame_equals_single_gpu(mode, tmp_path):
     out = str(tmp_path / "out.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + os.getpid() % 300), str(script), mode, out]
-    subprocess.run(cmd, check=True, timeout=600)
+    env = dict(os.environ)
+    if mode == "fused-overlap":      # light march of the frame's light volume beside the view march of the other volumes
+        env["MV_SHARD_V_BLOCKS"] = "3"
+        cmd[cmd.index(mode)] = "fused"
+    subprocess.run(cmd, check=True, timeout=600, env=env)
     got = np.load(out)["rgba8"]
-    assert np.array_equal(got, _single())
+    want, cubes = _single()
+    assert np.array_equal(got, want)
+    peer = np.load(out + ".r1.npz")
+    assert len(cubes) > 0 and sorted(peer.files) == sorted(cubes)
+    for k, v in cubes.items():
+        assert np.array_equal(peer[k], v), k
