@@ -40,7 +40,11 @@ WORKLOADS = {
 }
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of k_ray_march_v from the committed ncu --set full capture
 # (profiles/r01_march_v_ncu_raw.csv); only known for the workload that was profiled
-NCU_TRAFFIC_BYTES = {"cfg2": 172.1e6 + 11.5e6}
+NCU_TRAFFIC_BYTES = {"cfg2": 178.8e6 + 14.9e6}
+# l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed of the same capture: the texture data pipe (what the
+# tex_probe peak saturates at 98.7 %) counts wavefronts, i.e. also the idle lanes of partly active quads and the 2.5
+# wavefronts per quad request of this access pattern, which a fetch count does not see
+NCU_TEX_PIPE_PCT = {"cfg2": 61.4}
 TEX_PEAK_GFETCH = 575.9   # measured on this pool's B200: profiles/r01_tex_probe.json (trilinear RGBA16F fetches/s, L1-resident)
 
 
@@ -169,13 +173,18 @@ def run_reference(args, wl, rank, world):
     return line
 
 
-def launches_per_frame(wl, world, exchange):
+def launches_per_frame(wl, world, exchange, work_graph=False):
     """Kernels of libmv_b200.so per frame: k_cull; the light march (k_light_classify, k_ray_march_l and, with a light probe,
     k_light_scan, k_light_emit, k_light_ao, k_light_finalize); k_ray_march_v; k_ray_cast_direct; k_resolve_oit; k_postprocess.
-    Sharded, fused exchange: + k_light_commit and three peer barriers (k_peer_signal + k_peer_wait each)."""
+    One GPU, pipelined frames: + k_light_commit. Sharded, fused exchange: + k_light_commit and three peer barriers
+    (k_peer_signal + k_peer_wait each); with the light / view overlap (8 ranks) the view march is two launches."""
     n = 1 + (6 if wl["sh"] else 2) + 1 + 1 + 1 + 1   # --work-graph: the same count (k_pick_light_volume instead of k_cull)
+    if world == 1 and not work_graph and os.environ.get("MV_OVERLAP", "1") != "0":
+        n += 1                                        # pipelined frames: k_light_commit (light map through the staging buffer)
     if world > 1:
         n += 1 + (6 if exchange == "fused" else 0)
+        if exchange == "fused" and int(os.environ.get("MV_SHARD_V_BLOCKS", "4" if world >= 8 else "0")) > 0:
+            n += 1
     return n
 
 
@@ -360,14 +369,15 @@ def main():
                 "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": wl["n"] * 224, "d2h_bytes_per_step": wl["w"] * wl["h"] * 4,
                         "steps": n_e2e, "checksum": checksum,
                         "frames_in_flight": 3, "blocking_readback_value": e2e_blocking_fps},
-                "gpu_launches": args.steps * launches_per_frame(wl, world, args.exchange),
+                "gpu_launches": args.steps * launches_per_frame(wl, world, args.exchange, args.work_graph),
                 "clocks": clocks,
                 "per_pass_ms": per_pass, "per_pass_note": "rank 0, instrumented pass (CUDA events around each pass; at N > 1 the light and view marches include their peer barriers)",
                 "roofline": {"kernel": "k_ray_march_v", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                              "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None, "peak_source": peak_src,
                              "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": view_ms,
                              "tex": {"achieved": fetches, "peak": TEX_PEAK_GFETCH, "unit": "Gfetch/s", "frac": fetches / TEX_PEAK_GFETCH,
-                                     "peak_source": "profiles/r01_tex_probe.json"}}}
+                                     "peak_source": "profiles/r01_tex_probe.json",
+                                     "ncu_tex_data_pipe_pct_of_peak": NCU_TEX_PIPE_PCT.get(args.workload) if world == 1 else None}}}
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, wl)
         print(json.dumps(line), flush=True)

@@ -769,7 +769,8 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         record(c, 0);
         launch_cull(c);
         record(c, 1);
-        if (c.shardWorld > 1 && c.peersMapped && c.overlapLight && c.shardViewBlocks > 0 && !(c.d.flags & MV_FLAG_TIME_PASSES)) {
+        const int viewBlocks = c.shardViewBlocks >= 0 ? c.shardViewBlocks : (c.shardWorld >= 8 ? 4 : 0);
+        if (c.shardWorld > 1 && c.peersMapped && c.overlapLight && viewBlocks > 0 && !(c.d.flags & MV_FLAG_TIME_PASSES)) {
             // Sharded frame, uninstrumented: the light march fills ONE volume's light map, so the view march of every other
             // volume does not depend on it. The rank's slab is marched on the light stream while the main stream marches
             // the other volumes' tiles (a few CTAs per SM fewer, so that both are resident: with 1 / world of the frame
@@ -782,7 +783,7 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
             c.stream = mainStream;
             MV_CUDA(cudaEventRecord(c.lightDone, B));
             c.lightDoneValid = true;
-            launch_ray_march_view(c, 1, c.shardViewBlocks);
+            launch_ray_march_view(c, 1, viewBlocks);
             MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
             wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c);
             launch_ray_march_view(c, 2);

@@ -254,7 +254,11 @@ struct Caster {
     cudaEvent_t lightDone = nullptr, commitDone = nullptr, inputsReady = nullptr, frameEnd[2] = {};
     bool lightDoneValid = false, commitValid = false, frameEndValid[2] = {false, false}, inputsDirty = true, lightToStaging = false;
     uint32_t cullSerial = 0;             // serial number of the last fused cull + view-march launch
-    int shardViewBlocks = 0;             // sharded frame, opt-in (MV_SHARD_V_BLOCKS = 1..5): view-march CTAs per SM while the light march runs beside it; 0 = the passes run one after the other (faster at N = 2: profiles/r01_notes.md)
+    // Sharded frame: view-march CTAs per SM while the light march of the frame's light volume runs beside it on the light
+    // stream; 0 = the passes run one after the other. -1 = by world size: 4 from 8 ranks on (1 / 8 of a frame per GPU is
+    // latency-bound: cfg4 1181 -> 1274 frames/s), 0 below (at N = 2 the GPUs are still throughput-bound and the overlap
+    // costs 0 - 14 %). MV_SHARD_V_BLOCKS overrides. profiles/r01_scaling.md
+    int shardViewBlocks = -1;
     cudaEvent_t cullDone = nullptr;      // sharded frame: main stream -> light stream
     int overlapLight = 1;                // MV_OVERLAP=0: every pass on the main stream
     PerObject* dPerObject2[2] = {};      // dPerObject points at the one of the last mv_update_frame
