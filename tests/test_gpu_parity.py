@@ -569,3 +569,60 @@ def test_work_graph_render_equals_oracle(instrumented):
             (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
             assert _same_bits(o.ReadFrame(), p.ReadFrame()) and _same_bits(to, tp) and np.array_equal(bo, bp), f
     assert len(o.ReadVisible()) > 0
+
+
+# ---------------------------------------------------------------- BASELINE.json sizes: properties that need no oracle
+def _full_size_casters(n_variants, **extra):
+    """cfg 2 of BASELINE.json (16 x 128^3, 1920x1080, SH lighting) built the way bench.py builds it."""
+    import bench
+    from multivolumes_b200 import MultiRayCaster
+    wl = bench.WORKLOADS["cfg2"]
+    kw = dict(grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], width=wl["w"], height=wl["h"])
+    cs = [MultiRayCaster(**dict(kw, **v)) for v in n_variants]
+    for c in cs:
+        bench.build_scene(c, wl, scene, c.TransformSH(scene.procedural_sky(64)))
+    return wl, cs
+
+
+def test_full_size_pipelined_work_graph_and_serial_frames_agree():
+    """At cfg 2's full size, over an orbit with TAA: the uninstrumented caster (frames pipelined on two streams) and the
+    instrumented one (every pass in order on one stream) produce the same images and cube maps; the work-graph order
+    differs from the plain order only through the light volume it picks: same visible and cube-map lists every frame."""
+    wl, (piped, serial, wg) = _full_size_casters([dict(count_samples=False), dict(count_samples=True), dict(count_samples=False)])
+    import bench
+    for f in range(10):
+        vp, eye = bench.camera(scene, wl, 11 * f)
+        for c in (piped, serial, wg):
+            c.UpdateFrame(vp, None, eye); c.ResetColor()
+            c.Render(use_work_graph=(c is wg)); c.Postprocess(True)
+        if f % 3 == 2:
+            assert np.array_equal(piped.ReadVisible(), wg.ReadVisible()) and np.array_equal(piped.ReadCubeVolumes(), wg.ReadCubeVolumes())
+    (ta, ba), (tb, bb) = piped.ReadPost(), serial.ReadPost()
+    assert np.array_equal(ba, bb) and _same_bits(ta, tb)
+    assert serial.GetStats()["view_samples"] > 10_000_000
+    a = piped.ReadAttribs()
+    assert np.array_equal(a[piped.ReadVisible()], serial.ReadAttribs()[serial.ReadVisible()])
+    for v in piped.ReadCubeVolumes():
+        mip = int(a[v][0])
+        (c0, d0), (c1, d1) = piped.ReadCubeMap(int(v), mip), serial.ReadCubeMap(int(v), mip)
+        assert _same_bits(c0, c1) and np.array_equal(d0.view(np.uint32), d1.view(np.uint32))
+
+
+def test_full_size_density_only_equals_rgba_storage():
+    """cfg 2's densities at full size: the R16F storage and the RGBA16F storage holding (1, 1, 1, a) render the same bits
+    (light maps included: the frames of an orbit with TAA accumulate every earlier frame)."""
+    wl, (r16, rgba) = _full_size_casters([dict(density_only=True), dict()])
+    import bench
+    for i in range(rgba.srcs):
+        rgba.LoadVolumeData(i, r16.ReadVolume(i))
+    for f in range(6):
+        vp, eye = bench.camera(scene, wl, 17 * f)
+        for c in (r16, rgba):
+            c.UpdateFrame(vp, None, eye); c.ResetColor(); c.Render(); c.Postprocess(True)
+    (ta, ba), (tb, bb) = r16.ReadPost(), rgba.ReadPost()
+    assert np.array_equal(ba, bb) and _same_bits(ta, tb)
+    sa, sb = r16.GetStats(), rgba.GetStats()
+    for k in ("view_samples", "view_light_fetches", "light_samples", "oit_fragments"):
+        assert sa[k] == sb[k] and sa[k] > 0, k
+    lv = sa["light_volume"]
+    assert _same_bits(r16.ReadLightMap(lv), rgba.ReadLightMap(lv))
