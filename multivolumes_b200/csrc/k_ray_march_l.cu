@@ -181,6 +181,31 @@ MV_D void stage_volume_tables(const DeviceScene& s, const FrameCB& cb, float4* s
     __syncthreads();
 }
 
+// Clusters of kLightCluster consecutive volumes with one bounding sphere each (shared memory, after the per-volume
+// tables): a voxel's ray that certainly misses the cluster's sphere certainly misses every member's, so the per-voxel
+// loop over the N volumes steps over the whole cluster. With N = 512 (BASELINE.json configs[4]) that loop, not the
+// marching, was most of the pass. The cluster sphere contains the members' (already inflated) spheres with 1 % to spare.
+constexpr uint32_t kLightCluster = 16;
+MV_D void stage_volume_clusters(const float4* s_sph, float4* s_clu, uint32_t nShared)
+{
+    const uint32_t numClusters = (nShared + kLightCluster - 1) / kLightCluster;
+    for (uint32_t c = threadIdx.x; c < numClusters; c += kLightThreads) {
+        const uint32_t n0 = c * kLightCluster, n1 = min(n0 + kLightCluster, nShared);
+        V3 ctr = {0.0f, 0.0f, 0.0f};
+        for (uint32_t n = n0; n < n1; ++n) { ctr.x += s_sph[n].x; ctr.y += s_sph[n].y; ctr.z += s_sph[n].z; }
+        const float inv = 1.0f / (float)(n1 - n0);
+        ctr = {ctr.x * inv, ctr.y * inv, ctr.z * inv};
+        float radius = 0.0f;
+        for (uint32_t n = n0; n < n1; ++n) {
+            const V3 d = {s_sph[n].x - ctr.x, s_sph[n].y - ctr.y, s_sph[n].z - ctr.z};
+            radius = fmaxf(radius, sqrtf(dot(d, d)) + sqrtf(s_sph[n].w));
+        }
+        radius *= 1.01f;
+        s_clu[c] = make_float4(ctr.x, ctr.y, ctr.z, radius * radius);
+    }
+    __syncthreads();
+}
+
 MV_D V3 light_voxel_center(uint32_t voxel, uint32_t L, uint32_t& x, uint32_t& y, uint32_t& z)   // CSRayMarchL.hlsl:36
 {
     x = voxel % L; y = (voxel / L) % L; z = voxel / (L * L);
@@ -258,8 +283,11 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_marc
     extern __shared__ float4 s_tab[];                       // [nShared] spheres, then [nShared] x 3 floats of directions
     const uint32_t N = cb.numVolumes, L = cb.lightGridSize;
     const uint32_t nShared = min(N, kMaxSharedDirs);
-    float* s_dirS = reinterpret_cast<float*>(s_tab + nShared);
+    const uint32_t numClusters = (nShared + kLightCluster - 1) / kLightCluster;
+    float4* s_clu = s_tab + nShared;                        // [numClusters] cluster spheres
+    float* s_dirS = reinterpret_cast<float*>(s_clu + numClusters);
     stage_volume_tables(s, cb, s_tab, s_dirS, nShared);
+    stage_volume_clusters(s_tab, s_clu, nShared);
     const V3 lightDirW = normalize(V3{cb.lightPos[0], cb.lightPos[1], cb.lightPos[2]});
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;   // :29-33
@@ -298,7 +326,12 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_marc
                 const bool castShadow = shadow >= kZeroThreshold;
                 if (!castShadow) { rec.castEnd = min(rec.castEnd, n); if (!cb.hasSH) break; }
                 // a missed shadow ray skips the volume altogether (:95 `continue`), otherwise only the AO ray is cast
-                if (n < nShared && ray_misses_sphere_for_sure(rayOrigin, castShadow ? lightDirW : aoRayDir, s_tab[n])) continue;
+                const V3 testDir = castShadow ? lightDirW : aoRayDir;
+                if (n % kLightCluster == 0 && n < nShared && ray_misses_sphere_for_sure(rayOrigin, testDir, s_clu[n / kLightCluster])) {
+                    n += min(kLightCluster, nShared - n) - 1;   // nothing in the cluster can be hit: `shadow` and the ray stay as they are
+                    continue;
+                }
+                if (n < nShared && ray_misses_sphere_for_sure(rayOrigin, testDir, s_tab[n])) continue;
                 const PerObject* po = s.perObject + n;
                 V3 localRayOrigin = mul_p43(rayOrigin, po->worldI);                                 // :83
                 if (castShadow) {
@@ -596,11 +629,13 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
     if (tgt.z1 <= tgt.z0) return;
     const uint32_t voxels = L * L * (tgt.z1 - tgt.z0);
     const uint32_t bricks = ((L + 7) / 8) * ((L + 3) / 4) * ((tgt.z1 - tgt.z0 + 3) / 4);
-    const size_t smem = (size_t)min(c.d.num_volumes, kMaxSharedDirs) * (sizeof(float4) + 3 * sizeof(float));
+    const uint32_t nShared = min(c.d.num_volumes, kMaxSharedDirs);
+    const size_t smem = (size_t)nShared * (sizeof(float4) + 3 * sizeof(float));
+    const size_t smemMarch = smem + (size_t)((nShared + kLightCluster - 1) / kLightCluster) * sizeof(float4);   // + cluster spheres (k_ray_march_l)
     static int perSM = 0, perSMAo = 0, perSMEmit = 0;
     if (!perSM) {
         const size_t smemMax = (size_t)kMaxSharedDirs * (sizeof(float4) + 3 * sizeof(float));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_l<false>, kLightThreads, smemMax);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, k_ray_march_l<false>, kLightThreads, smemMax + (kMaxSharedDirs / kLightCluster) * sizeof(float4));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMEmit, k_light_emit<false>, kLightThreads, smemMax);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSMAo, k_light_ao<false>, kLightThreads, 0);
         perSM = max(perSM, 1); perSMEmit = max(perSMEmit, 1); perSMAo = max(perSMAo, 1);
@@ -615,8 +650,8 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
     if (densityOnly) k_light_classify<true><<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
     else k_light_classify<false><<<bricks, kLightThreads, 0, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
     mark(1);
-    if (densityOnly) k_ray_march_l<true><<<c.smCount * perSM, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
-    else k_ray_march_l<false><<<c.smCount * perSM, kLightThreads, smem, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    if (densityOnly) k_ray_march_l<true><<<c.smCount * perSM, kLightThreads, smemMarch, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
+    else k_ray_march_l<false><<<c.smCount * perSM, kLightThreads, smemMarch, c.stream>>>(c.scene(), c.cb, volumeOverride, tgt);
     mark(2);
     if (!c.cb.hasSH) return;
     k_light_scan<<<1, 1024, 0, c.stream>>>(c.scene(), c.cb, volumeOverride);

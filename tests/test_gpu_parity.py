@@ -626,3 +626,24 @@ def test_full_size_density_only_equals_rgba_storage():
         assert sa[k] == sb[k] and sa[k] > 0, k
     lv = sa["light_volume"]
     assert _same_bits(r16.ReadLightMap(lv), rgba.ReadLightMap(lv))
+
+
+# ---------------------------------------------------------------- light march with many volumes (cluster pre-cull)
+@pytest.mark.parametrize("n,transforms,sh", [(70, 13, True), (70, 0, True), (37, 21, False), (130, 5, True)])
+def test_light_march_many_volumes_bit_exact(n, transforms, sh):
+    """The per-voxel loop over the N volumes steps over clusters of 16 volumes whose bounding sphere the ray misses. With
+    overlapping, rotated volumes (random transforms) and with the reference's grid, ragged last cluster included, the
+    light maps and the exact sample counters must not change."""
+    kw = dict(grid_size=16, light_grid_size=12, num_volumes=n, num_volume_srcs=3, width=160, height=90)
+    o, p = _pair(**kw)
+    for c in (o, p):
+        configure(c, sh=sh, random_transforms=transforms, shadow=blob_shadow())
+        c.Cull()
+    for v in (0, 15, 16, n // 2, n - 1):
+        for c in (o, p):
+            c.RayMarchL(v)
+        so, sp = o.GetStats(), p.GetStats()
+        for k in ("light_voxels", "light_dense_voxels", "light_samples"):
+            assert sp[k] == so[k], (v, k, sp[k], so[k])
+        assert _same_bits(o.ReadLightMap(v), p.ReadLightMap(v)), v
+    assert so["light_samples"] > 0
