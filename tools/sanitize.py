@@ -1,20 +1,25 @@
 #!/usr/bin/env python
-"""Small frames through every pass, for compute-sanitizer: compute-sanitizer --tool memcheck python tools/sanitize.py"""
+"""Small frames through every pass, for compute-sanitizer: compute-sanitizer --tool memcheck python tools/sanitize.py
+Covers: instrumented (serial) and uninstrumented (frames pipelined on two streams) casters, RGBA16F and density-only
+storage, the plain and the work-graph order, cube-map and direct-scheme volumes, the mesh depth producer, 40 volumes
+(three clusters of the light march's pre-cull)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import numpy as np
 from multivolumes_b200 import MultiRayCaster, scene
 from harness import checker_background, configure, uv_sphere
-c = MultiRayCaster(grid_size=32, light_grid_size=16, num_volumes=16, num_volume_srcs=4, width=320, height=180, count_samples=True)
 pos, idx = uv_sphere(radius=5.0, rings=16, sectors=32)
-for eye in ((4.0, 16.0, -80.0), (10.0, 40.0, -160.0)):       # near: cube-map volumes; far: direct-scheme volumes
-    configure(c, sh=True, background=checker_background(320, 180), eye=eye)
-    c.SetMesh(pos, idx); c.SetMeshWorld(1.8, (0.0, -9.0, 0.0))
-    vp, e = scene.default_camera(320, 180, eye=eye)
-    svp = c.RenderMeshDepth(vp)
-    for i in range(3):
-        c.UpdateFrame(vp, svp, e); c.ResetColor(); c.Render(); c.Postprocess(True)
-    print(eye, c.GetStats())
-c.Sync()
+for variant in (dict(count_samples=True), dict(count_samples=False), dict(count_samples=False, density_only=True)):
+    c = MultiRayCaster(grid_size=32, light_grid_size=16, num_volumes=40, num_volume_srcs=4, width=320, height=180, **variant)
+    for eye in ((4.0, 16.0, -80.0), (10.0, 40.0, -160.0)):       # near: cube-map volumes; far: direct-scheme volumes
+        configure(c, sh=True, background=checker_background(320, 180), eye=eye)
+        c.SetMesh(pos, idx); c.SetMeshWorld(1.8, (0.0, -9.0, 0.0))
+        vp, e = scene.default_camera(320, 180, eye=eye)
+        svp = c.RenderMeshDepth(vp)
+        for i in range(4):
+            c.UpdateFrame(vp, svp, e); c.ResetColor(); c.Render(use_work_graph=(i == 2)); c.Postprocess(True)
+        print(variant, eye, {k: v for k, v in c.GetStats().items() if k in ("visible_count", "cubemap_count", "light_volume")})
+    c.Sync()
+    del c
 print("done")
