@@ -2,8 +2,10 @@
 
 Partition (BASELINE.json north_star; the single-adapter reference has no counterpart):
   * the cull is replicated on every rank (N <= a few hundred volumes: cheaper than any collective);
-  * by volume — rank r marches the cube maps of the volumes v with v % world == r and fills z-slab r
-    of the frame's light map;
+  * by volume — rank r marches the cube maps of the volumes v with v % world == r (collective mode) or, with the peers
+    mapped (fused mode: every texel is stored into all arenas by whoever marches it), one contiguous part of EVERY
+    cube-map volume's tile list (``view_march_tile_range``; the cull kernel evaluates the same integers); rank r also
+    fills z-slab r of the frame's light map;
   * by screen band — rank r resolves the OIT and post-processes rows [H r / world, H (r + 1) / world).
 Exchange steps: the light-map slabs and the marched cube maps must reach every rank before the
 resolve; the finished bands must reach rank 0.
@@ -35,6 +37,15 @@ def light_slab(L, rank, world):
 
 def owner_of(volume, world):
     return volume % world
+
+
+def view_march_tile_range(tiles, k, rank, world):
+    """Fused mode: the 8x4-texel tiles [begin, end) of the k-th cube-map volume (in march order) that `rank` marches. The
+    volume's tile list (face-major, row-major; `tiles` = tiles per face x visible faces) is cut into `world` contiguous
+    parts and the parts are handed out rotated by k, so that no rank always gets the same face of every volume. Mirrors
+    cull_body in csrc/k_cull.cuh (same integer arithmetic); the parts of the `world` ranks tile [0, tiles) exactly."""
+    part = (rank + world - k % world) % world
+    return tiles * part // world, tiles * (part + 1) // world
 
 
 class CudaExchange:

@@ -72,3 +72,25 @@ def test_partition_helpers():
         assert slabs[0][0] == 0 and max(s[1] for s in slabs) == L
         assert sum(s[1] - s[0] for s in slabs) == L
     assert [owner_of(v, 4) for v in range(6)] == [0, 1, 2, 3, 0, 1]
+
+
+def test_view_march_tile_ranges_tile_every_volume_exactly():
+    """Fused-mode split of the view march (multivolumes_b200.dist.view_march_tile_range, mirrored by the cull kernel): for
+    any tile count, volume position and world size the ranks' ranges are disjoint, cover [0, tiles), differ by at most one
+    tile, and rotate with the volume's position in the march order."""
+    sys.path.insert(0, os.path.dirname(HERE))
+    from multivolumes_b200.dist import view_march_tile_range
+    rs = np.random.RandomState(3)
+    cases = [(0, 0, 2), (1, 5, 8), (7, 3, 8), (6 * 32 * 64, 11, 8), (3 * 16 * 32, 0, 3)] + \
+            [(int(rs.randint(0, 60000)), int(rs.randint(0, 600)), int(rs.randint(1, 9))) for _ in range(300)]
+    for tiles, k, world in cases:
+        ranges = [view_march_tile_range(tiles, k, r, world) for r in range(world)]
+        covered = np.zeros(tiles, np.int32)
+        for b, e in ranges:
+            assert 0 <= b <= e <= tiles
+            covered[b:e] += 1
+        assert (covered == 1).all(), (tiles, k, world)
+        sizes = [e - b for b, e in ranges]
+        assert max(sizes) - min(sizes) <= 1
+        # rank r of volume k holds the part rank r + 1 holds of volume k + 1
+        assert ranges[0] == view_march_tile_range(tiles, k + 1, 1 % world, world)
