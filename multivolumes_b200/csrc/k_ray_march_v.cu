@@ -77,9 +77,9 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
         volatile uint32_t* ready = &s.lists->cullSerial;
         if (blockIdx.x == 0) {
             cull_body<kMarchThreads>(s, cb, false);
-            __threadfence();
-            __syncthreads();
-            if (threadIdx.x == 0) *ready = serial;
+            __threadfence();                                // every writer: its list entries are visible device-wide ...
+            __syncthreads();                                // ... before thread 0 learns that they were written
+            if (threadIdx.x == 0) { __threadfence(); *ready = serial; }   // release: fence, then the flag
         } else {
             if (threadIdx.x == 0) while (*ready != serial) __nanosleep(64);
             __syncthreads();
