@@ -266,3 +266,194 @@ def test_work_graph_order_lights_from_previous_visible_list():
         assert plain.GetStats()["light_volume"] == int(vis[f % len(vis)])
         prev_visible = vis
     assert len(set(map(len, [prev_visible]))) == 1 and len(prev_visible) > 0
+
+
+# ---------------------------------------------------------------- more closed forms: resolve, tone map, TAA, light march
+def _write_constant_cube(c, v, rgba, depth=1.0):
+    b = c.b
+    for mip in range(5):
+        s = c.G >> mip
+        col = np.empty((6, s, s, 4), np.float16); col[...] = np.asarray(rgba, np.float16)
+        dep = np.full((6, s, s), depth, np.float32)
+        assert b.write_cubemap(c.h, v, mip, col.view(np.uint16).ctypes.data, dep.ctypes.data) == 0
+
+
+def test_oit_resolve_constant_cube_maps_closed_form():
+    """CubeCast of a constant cube map is that constant (its weights are normalised, PSCube.hlsli:93-105), so with constant
+    cube maps the frame is a closed form of the layer order: one layer  -> c + bg (1 - a); two volumes in a row along the
+    view axis -> front-to-back resolve c_near + c_far (1 - a_near) (PSResolveOIT.hlsl:12-26), then the premultiplied blend
+    over the colour RT (MultiRayCaster.cpp:931). Pins the depth-peel order and both blends."""
+    kw = dict(grid_size=32, light_grid_size=8, num_volumes=2, num_volume_srcs=1, width=640, height=360, filter_model=0)
+    c = OracleCaster(**kw)
+    near, far = (0.30, 0.20, 0.10, 0.50), (0.05, 0.25, 0.40, 0.25)
+    c.SetVolumeWorld(0, 12.0, (0.0, 0.0, 0.0))        # nearer to the eye at z = -60
+    c.SetVolumeWorld(1, 30.0, (0.0, 0.0, 60.0))       # farther and larger: visible around the near one as well
+    bg = np.full((360, 640, 4), 0.125, np.float16); bg[..., 3] = 1.0
+    c.SetRenderTargets(color=bg)
+    vp, eye = scene.default_camera(640, 360, eye=(0.0, 0.0, -60.0))
+    c.UpdateFrame(vp, None, eye)
+    c.Cull()
+    vis, att = c.ReadVisible(), c.ReadAttribs()
+    assert list(vis) == [0, 1] and all(int(att[v][2]) & 0x8000 for v in vis)      # both on the cube-map scheme
+    _write_constant_cube(c, 0, near); _write_constant_cube(c, 1, far)
+    c.ResolveOIT()
+    f = c.ReadFrame().astype(np.float32)
+    n16, f16_, b16 = (np.asarray(x, np.float16).astype(np.float32) for x in (near, far, bg[0, 0]))
+    both = n16 + f16_ * (1 - n16[3]); both[3] = min(both[3], 0.9997)
+    want_centre = np.float16(both + b16 * (1 - both[3])).astype(np.float32)
+    only_far = np.float16(f16_ + b16 * (1 - f16_[3])).astype(np.float32)
+    assert np.abs(f[180, 320] - want_centre).max() <= 1e-3, (f[180, 320], want_centre)   # the two boxes overlap at the centre
+    ring = f[180, 320 + 55]                                                           # outside the near box (48 px), inside the far one (62 px)
+    assert np.abs(ring - only_far).max() <= 1e-3, (ring, only_far)
+    assert np.array_equal(c.ReadFrame()[2, 2].view(np.uint16), bg[2, 2].view(np.uint16))   # a corner: no layer, untouched
+    st = c.GetStats()
+    assert st["oit_fragments"] > 0 and st["direct_rays"] == 0
+
+
+def test_tone_map_known_answers():
+    """PSToneMap.hlsl:19-28 on a colour RT without volumes: v' = v * 1.05 / (v + 0.7), pow(|v'|, 1.25), saturate, UNORM8
+    rounding (x 255 + 0.5, floor). Expected values are evaluated independently in float64 (the fp32 path may differ by at
+    most one code value at a rounding boundary)."""
+    c = _mk(width=16, height=4)
+    vals = np.array([0.0, 0.01, 0.1, 0.18, 0.5, 1.0, 2.0, 4.0, 16.0, 100.0, 1000.0, 0.35, 0.7, 3.0, 7.5, 60000.0], np.float16)
+    img = np.zeros((4, 16, 4), np.float16)
+    img[..., 0] = vals[None, :]; img[..., 1] = vals[None, ::-1]; img[..., 2] = np.float16(0.25); img[..., 3] = 1.0
+    c.SetRenderTargets(color=img)
+    c.LoadVolumeData(0, np.zeros((32, 32, 32, 4), np.float16))
+    _setup_single(c)
+    c.Render(); c.Postprocess(False)
+    taa, rgba8 = c.ReadPost()
+    assert np.array_equal(taa.view(np.uint16), img.view(np.uint16))                   # TAA off: the colour RT is copied
+    v = img[..., :3].astype(np.float64)
+    want = np.floor(np.clip(np.abs(v * 1.05 / (v + 0.7)) ** 1.25, 0, 1) * 255 + 0.5)
+    assert np.abs(rgba8[..., :3].astype(np.float64) - want).max() <= 1
+    assert (rgba8[..., :3].astype(np.float64) == want).mean() > 0.9
+    assert (rgba8[..., 3] == 255).all()
+
+
+def test_taa_static_image_history_weight_and_identity():
+    """CSTemporalAA.hlsl:267-330 on a static constant image with zero velocity: the history weight stored in alpha grows
+    by 1 / historyMax (= 1 / 15) per frame until it saturates at 1 (history.w * 15 + 1, then / 15, :275 / :332), and the
+    colour stays the input colour (neighbourhood box = one point, TM / ITM are inverses up to rounding)."""
+    c = _mk(width=32, height=18)
+    colour = np.array([0.6, 0.3, 0.1, 1.0], np.float16)
+    img = np.empty((18, 32, 4), np.float16); img[...] = colour
+    c.SetRenderTargets(color=img)
+    c.LoadVolumeData(0, np.zeros((32, 32, 32, 4), np.float16))
+    _setup_single(c)
+    w = np.float16(0.0)
+    for k in range(1, 19):
+        c.ResetColor(); c.Render(); c.Postprocess(True)
+        taa, _ = c.ReadPost()
+        interior = taa[4:-4, 4:-4].astype(np.float32)
+        w = np.float16(min((np.float32(w) * np.float32(15.0) + np.float32(1.0)) / np.float32(15.0), 1.0))
+        assert np.abs(interior[..., 3] - np.float32(w)).max() <= 1e-3, (k, interior[0, 0, 3], w)
+        assert np.abs(interior[..., :3] - colour[:3].astype(np.float32)).max() <= 2e-3, k
+    assert w == np.float16(1.0)
+
+
+def test_light_march_uniform_density_recurrence():
+    """CSRayMarchL.hlsl:77-110 + CastLightRay (RayMarch.hlsli:197-230) in one uniform volume, no light probe, no shadow map:
+    the texel at the box centre holds lightColor * T + ambient, where T is the shadow ray's transmittance: t starts at
+    one step, every sample multiplies T by (1 - 0.8 rho), the step grows by GetStep's factor once dDensity is 0, and the ray
+    stops when it leaves the box or T < 0.01. The recurrence is replayed here independently in numpy fp32."""
+    rho = 0.04
+    L = 16
+    c = _mk(grid_size=32, light_grid_size=L, filter_model=0)
+    tex = np.zeros((32, 32, 32, 4), np.float16); tex[..., :3] = 1.0; tex[..., 3] = rho
+    c.LoadVolumeData(0, tex)
+    c.SetSH(None)
+    c.SetLight((0.0, 50.0, 0.0), (1.0, 0.5, 0.25), 2.0)          # straight up: the ray leaves through y = +1
+    c.SetAmbient((0.1, 0.2, 0.3), 1.0)
+    c.SetVolumeWorld(0, 20.0, (0, 0, 0))
+    c.SetRenderTargets()
+    vp, eye = scene.default_camera(c.W, c.H)
+    c.UpdateFrame(vp, None, eye)
+    c.Cull(); c.RayMarchL(0)
+    lm = c.ReadLightMap(0).astype(np.float32)
+    f32 = np.float32
+    rho16 = f32(np.float16(rho))
+    g_step = f32(2) * np.sqrt(f32(3)) / f32(96)
+    for (x, y, z) in ((8, 8, 8), (3, 12, 5), (15, 0, 15)):
+        y0 = (f32(y) + f32(0.5)) / f32(L) * f32(2) - f32(1)
+        T, t, step, prev = f32(1), g_step, g_step, f32(0)
+        for _ in range(96):
+            if abs(y0 + t) > 1.0:
+                break
+            d = rho16 - prev
+            opacity = min(max(rho16 * step, f32(0)), f32(1))
+            fe = f32(2) if d == 0 else min(f32(1 / 256) / abs(d), f32(2))
+            new = g_step * max(f32(1.5) * fe * min(f32(1) - opacity, f32(1)) * (f32(1) - T), f32(1))
+            prev = rho16
+            T = T * (f32(1) - rho16 * f32(0.8))
+            if T < 0.01:
+                break
+            step = new; t = t + step
+        want = np.array([1.0 * 2.0 * T + 0.1, 0.5 * 2.0 * T + 0.2, 0.25 * 2.0 * T + 0.3], np.float32)
+        got = lm[z, y, x, :3]
+        tol = np.array([2.0 ** -6, 2.0 ** -6, 2.0 ** -5]) * np.maximum(want, 1.0)      # R11G11B10F storage: 6 / 6 / 5 mantissa bits
+        assert np.all(np.abs(got - want) <= tol), ((x, y, z), got, want, float(T))
+
+
+def test_cull_lod_and_sample_count_against_independent_evaluation():
+    """EstimateCubeMapLOD (VolumeCull.hlsli:267-294) and the face mask (GenVisibilityMask :46-66) evaluated independently in
+    float64 numpy from the same matrices: the 12 cube edges projected to pixels, s = max edge / 2, sample amount
+    2 s / sqrt(3), count = min(ceil, 256), mip = min(floor(log2(G / s')), 4). Cases away from the ceil / log2 boundaries."""
+    G, W, H = 128, 1280, 720
+    c = OracleCaster(grid_size=G, num_volumes=6, num_volume_srcs=1, width=W, height=H)
+    sizes = [20.0, 8.0, 34.0, 14.0, 50.0, 3.0]
+    poss = [(0, 0, 0), (25, 5, 10), (-40, 0, 60), (10, -12, -30), (0, 0, 140), (-8, 3, -50)]
+    for i, (sz, p) in enumerate(zip(sizes, poss)):
+        c.SetVolumeWorld(i, sz, p)
+    eye = (4.0, 16.0, -80.0)
+    vp, _ = scene.default_camera(W, H, eye=eye)
+    c.UpdateFrame(vp, None, eye)
+    c.Cull()
+    att, vis = c.ReadAttribs(), list(c.ReadVisible())
+    assert len(vis) >= 4
+    vp64 = np.asarray(vp, np.float64)
+    edges = [(a, b) for a in range(8) for b in range(a + 1, 8) if bin(a ^ b).count("1") == 1]      # the 12 cube edges
+    checked, schemes = 0, set()
+    for v in vis:
+        half = sizes[v] / 2.0
+        corners = np.array([[(1 if i & 1 else -1), (1 if i & 2 else -1), (1 if i & 4 else -1)] for i in range(8)], np.float64) * half + np.array(poss[v], np.float64)
+        clip = np.concatenate([corners, np.ones((8, 1))], 1) @ vp64
+        ndc = clip[:, :3] / clip[:, 3:4]
+        px = np.stack([(ndc[:, 0] * 0.5 + 0.5) * W, (1 - (ndc[:, 1] * 0.5 + 0.5)) * H], 1)
+        max_edge = max(np.linalg.norm(px[a] - px[b]) for a, b in edges)
+        s = max_edge / 2.0
+        amt = 2.0 * s / np.sqrt(3.0)
+        if abs(amt - round(amt)) < 0.02:
+            continue                                     # too close to the ceil boundary for a float64 / fp32 comparison
+        count = min(int(np.ceil(amt)), 256)
+        s2 = min(amt, count) / 2.0 * np.sqrt(3.0)
+        lg = np.log2(G / s2)
+        if abs(lg - round(lg)) < 0.01:
+            continue
+        mip = min(int(max(lg, 0.0)), 4)
+        local_eye = (np.array(eye, np.float64) - np.array(poss[v], np.float64)) / half
+        mask = 0
+        for f in range(6):                               # +X, -X, +Y, -Y, +Z, -Z: interior face visible unless the eye is beyond its plane
+            comp = local_eye[f >> 1]
+            mask |= (1 << f) if ((comp > -1.0) if (f & 1) else (comp < 1.0)) else 0
+        assert int(att[v][0]) == mip and int(att[v][1]) == count, (v, att[v], mip, count)
+        assert int(att[v][2]) & 0x3f == mask, (v, int(att[v][2]) & 0x3f, mask)
+        # scheme bit (CSVolumeCull.hlsl:66-67): cube map iff its visible texels do not outnumber the projected pixels
+        # (EstimateProjCoverage :299-322 = area of one projected quad per set mask bit, here by the shoelace rule). The
+        # reference's face table (:213-223, rows commented -X, +X, -Y, +Y, -Z, +Z) pairs mask bit f — the visibility of the
+        # INTERIOR of cube-map face f (+X, -X, ...) — with the geometric face on the opposite side: the face the eye sees
+        # from outside. The oracle follows the table as written.
+        cov = 0.0
+        for f in range(6):
+            if not mask & (1 << f):
+                continue
+            a, bit = f >> 1, 1 if f & 1 else 0
+            u, w = [k for k in range(3) if k != a]
+            quad = [px[(bit << a) | (i << u) | (j << w)] for i, j in ((0, 0), (1, 0), (1, 1), (0, 1))]
+            cov += 0.5 * abs(sum(quad[k][0] * quad[(k + 1) % 4][1] - quad[(k + 1) % 4][0] * quad[k][1] for k in range(4)))
+        cube_pix = float((G >> mip) ** 2 * bin(mask).count("1"))
+        if abs(cube_pix - cov) > 0.02 * cov:
+            assert bool(int(att[v][2]) & 0x8000) == (cube_pix <= cov), (v, cube_pix, cov)
+            schemes.add(cube_pix <= cov)
+        checked += 1
+    assert checked >= 3 and schemes == {True, False}      # both the cube-map and the direct scheme occur
