@@ -64,3 +64,24 @@ def test_cxx_mirror_compiles_and_links(product_lib, tmp_path):
                            "-o", exe, product_lib, "-Wl,-rpath," + os.path.dirname(product_lib)])
     out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "init=" in out.stdout
+
+
+def test_python_binding_arity_matches_header(product_lib):
+    """Every prototype of include/mv.h against the ctypes table of the Python mirror: same number of parameters (a drifted
+    binding would otherwise pass garbage through the C-ABI without any error)."""
+    from multivolumes_b200 import caster
+    from multivolumes_b200._abi import _COMMON
+    src = open(os.path.join(ROOT, "include", "mv.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\b(mv_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S))
+    table = dict(_COMMON); table.update(caster._EXTRA)
+    checked = 0
+    for name, (restype, argtypes) in table.items():
+        params = protos.get("mv_" + name)
+        if params is None:
+            continue
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(argtypes), ("mv_" + name, params, len(argtypes))
+        checked += 1
+    assert checked >= 50
