@@ -7,8 +7,9 @@
 
 A step is one frame: UpdateFrame (camera on the reference's orbit, MultiVolumes.cpp:328-337) ->
 colour-RT reset -> Render (cull, light march of one volume, view march, OIT resolve) -> Postprocess
-(TAA + tone map). Workload at every N: BASELINE.json configs[1] — 16 volumes of 128^3, 1920x1080, SH
-environment lighting — unless --workload says otherwise. Prints ONE JSON line (rank 0).
+(TAA + tone map). Workload at every N: BASELINE.json configs[3], the configuration the north_star's target is quoted
+on — 64 volumes of 256^3 at 3840x2160, animated transforms + TAA, SH environment lighting (9.5 GB, fits one GPU) —
+unless --workload says otherwise. Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
@@ -27,8 +28,10 @@ WORKLOADS = {
     # name: N, srcs, G, L, W, H, sh, taa
     "cfg1": dict(n=4, g=128, l=96, w=1280, h=720, sh=False, taa=False, note="BASELINE.json configs[0]"),
     "cfg2": dict(n=16, g=128, l=96, w=1920, h=1080, sh=True, taa=True, note="BASELINE.json configs[1]"),
-    "cfg3": dict(n=64, g=256, l=96, w=1920, h=1080, sh=True, taa=True, note="BASELINE.json configs[2] (analytic sphere occluder)"),
-    "cfg4": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, note="BASELINE.json configs[3]"),
+    "cfg3": dict(n=64, g=256, l=96, w=1920, h=1080, sh=True, taa=True, mesh=True,
+                 note="BASELINE.json configs[2]: scene depth + shadow map rasterised every frame from the occluder mesh (mv_mesh_*)"),
+    "cfg4": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, animate=True,
+                 note="BASELINE.json configs[3]: per-volume rotation about y at seeded rates (SetVolumeWorldMatrix every frame)"),
     "cfg5i": dict(n=512, srcs=8, g=512, l=96, w=3840, h=2160, sh=True, taa=True,
                   note="BASELINE.json configs[4] with 8 source volumes instanced 64x (VolTexId = i % srcs): 8.6 GB instead of 512 GB of RGBA16F"),
     "cfg5": dict(n=512, g=512, l=96, w=3840, h=2160, sh=True, taa=True, density_only=True,
@@ -38,14 +41,21 @@ WORKLOADS = {
     "cfg4d": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, density_only=True, note="cfg4's densities in the density-only R16F storage"),
     "tiny": dict(n=4, g=32, l=16, w=320, h=180, sh=True, taa=True, note="CI-sized"),
 }
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of k_ray_march_v from the committed ncu --set full capture
-# (profiles/r01_march_v_ncu_raw.csv); only known for the workload that was profiled
-NCU_TRAFFIC_BYTES = {"cfg2": 178.8e6 + 14.9e6}
-# l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed of the same capture: the texture data pipe (what the
-# tex_probe peak saturates at 98.7 %) counts wavefronts, i.e. also the idle lanes of partly active quads and the 2.5
-# wavefronts per quad request of this access pattern, which a fetch count does not see
-NCU_TEX_PIPE_PCT = {"cfg2": 61.4}
-TEX_PEAK_GFETCH = 575.9   # measured on this pool's B200: profiles/r01_tex_probe.json (trilinear RGBA16F fetches/s, L1-resident)
+def ncu_summary(workload):
+    """Numbers that only a profiler can give (DRAM traffic of the dominant kernel, texture-pipe utilisation), read from the
+    tracked summary of the committed ncu capture of this workload — never constants in this file. None when there is none."""
+    p = os.path.join(ROOT, "profiles", "ncu_summary.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload)
+    return None
+
+
+def tex_peak():
+    """Trilinear RGBA16F fetch rate measured on this pool's B200 by tools/tex_probe.cu (L1-resident, coherent quads)."""
+    with open(os.path.join(ROOT, "profiles", "r01_tex_probe.json")) as f:
+        d = json.load(f)
+    return float(d["tex_rate"]["rgba16f_32_l1"]) / 1e9, float(d["l2_read_gbs"]["64MB"])
 
 
 def peaks():
@@ -69,11 +79,50 @@ def build_scene(c, wl, scene, sky_coeffs):
     c.SetAmbient(scene.AMBIENT_COLOR, scene.AMBIENT_INTENSITY)
     c.SetVolumesWorld(20.0, (0, 0, 0))
     c.SetSH(sky_coeffs if wl["sh"] else None)
-    depth = None
-    if wl is WORKLOADS["cfg3"]:
-        vp, _ = scene.default_camera(wl["w"], wl["h"])
-        depth = scene.sphere_depth(wl["w"], wl["h"], vp, center=(0, 0, 0), radius=9.0)
-    c.SetRenderTargets(depth=depth)
+    c.SetRenderTargets(depth=None)
+    if wl.get("mesh"):
+        # the occluder of Bin/all64.bat: bunny.obj where the reference tree is at hand (this container), its stand-in of the
+        # same extent and triangle count elsewhere (the GPU box has no /root/reference). Depth and shadow map are produced
+        # from it every frame by the caster's own rasteriser (mv_mesh_render_depth).
+        pos, idx = occluder(scene)
+        c.SetMesh(pos, idx)
+        c.SetMeshWorld(*scene.MESH_WORLD)
+
+
+_OCCLUDER = None
+
+
+def occluder(scene):
+    global _OCCLUDER
+    if _OCCLUDER is None:
+        path = os.environ.get("MV_OCCLUDER_OBJ", "/root/reference/Bin/Assets/bunny.obj")
+        if os.path.exists(path):
+            from multivolumes_b200 import parse_obj
+            _OCCLUDER = parse_obj(path) + (os.path.basename(path),)
+        else:
+            _OCCLUDER = scene.occluder_mesh() + ("procedural stand-in (69 696 triangles)",)
+    return _OCCLUDER[0], _OCCLUDER[1]
+
+
+def animate(c, wl, frame):
+    """cfg4 'animated transforms': every volume of the reference's grid turns about its own y axis at a seeded rate
+    (SetVolumeWorld only places axis-aligned boxes, so the matrices go in through SetVolumeWorldMatrix)."""
+    if not wl.get("animate"):
+        return
+    t = frame / 60.0
+    n = wl["n"]
+    row = int(np.ceil(np.sqrt(n))); col = n // row
+    size = 20.0
+    i = np.arange(row * col)
+    rate = ((i * 2654435761) % 1000) / 1000.0 * 1.6 - 0.8            # rad/s, seeded by the index
+    ang = rate * t
+    cs, sn = np.cos(ang) * (size * 0.5), np.sin(ang) * (size * 0.5)
+    px = -((row / 2.0 - 0.5) * size * 1.5) + (i % row) * size * 1.5
+    pz = -((col / 2.0 - 0.5) * size * 1.5) + (i // row) * size * 1.5
+    m = np.zeros((row * col, 4, 3), np.float32)
+    m[:, 0, 0] = cs; m[:, 0, 2] = -sn; m[:, 1, 1] = size * 0.5; m[:, 2, 0] = sn; m[:, 2, 2] = cs
+    m[:, 3, 0] = px; m[:, 3, 2] = pz
+    c.SetVolumeWorldMatrices(m)
 
 
 class ClockSampler:

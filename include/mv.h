@@ -44,6 +44,15 @@ enum mv_status {
  * holding (1, 1, 1, a). Uploads keep the alpha channel only; mv_volume_read expands to (1, 1, 1, a).
  * SURVEY.md 8(d) cfg 5: 512 x 512^3 = 137 GB instead of 550 GB. */
 #define MV_FLAG_DENSITY_ONLY    4u
+/* creation-time only, opt-in: run the fast build of the two ALU-bound image passes (OIT resolve, TAA + tone map): fused
+ * multiply-adds, approximate divide / reciprocal / square root — what dxc's fast-math default does to the reference's own
+ * shaders. Without the flag every pass follows the one evaluation order stated in csrc/mv_math.cuh
+ * and every output is bit-identical to the test oracle. With it, frames stay above PSNR 50 dB but a handful of pixels per
+ * million can move by more than 2e-3 where a discrete decision (which texel a bilinear footprint starts at, whether a box
+ * silhouette covers a pixel centre) flips — so the flag is NOT covered by the bit-exact parity claim; it exists for users
+ * who prefer 10-30 % on those two passes. The marches, the light march, the cull, ingest and the mesh rasteriser have one
+ * build. */
+#define MV_FLAG_FAST_FP         8u
 
 /* MultiRayCaster::Init arguments (MultiRayCaster.h:31-34) + viewport (SetViewport, :38) +
  * SetMaxSamples defaults (MultiVolumes.cpp:27-68). */
@@ -67,6 +76,9 @@ typedef struct mv_stats {
     uint32_t visible_count, cubemap_count;
     uint32_t light_volume;      /* volume whose light map the last render filled */
     uint32_t threads;           /* CUDA: SM count of the device */
+    /* of view_samples / direct_samples: samples that fell into a brick known to be empty and needed no texture fetch
+     * (csrc/mv_internal.h, Occupancy); they are samples of the algorithm all the same, so the counters above include them */
+    uint64_t view_skipped, direct_skipped;
 } mv_stats;
 
 /* per-pass device time of the last frame, milliseconds (CUDA events on the caster's stream) */
@@ -119,6 +131,9 @@ int mv_set_max_samples(mv_caster* c, uint32_t ray, uint32_t light);          /* 
 int mv_set_volumes_world(mv_caster* c, float size, const float center[3]);   /* SetVolumesWorld, :43 */
 int mv_set_volume_world(mv_caster* c, uint32_t i, float size, const float pos[3]); /* SetVolumeWorld, :44 */
 int mv_set_volume_world_matrix(mv_caster* c, uint32_t i, const float world43[12]); /* animated transforms */
+/* the same for `count` consecutive volumes starting at `first` in one call (count x 12 floats): what a caller that animates
+ * every volume each frame does with N SetVolumeWorld calls (MultiRayCaster.h:44) */
+int mv_set_volume_world_matrices(mv_caster* c, uint32_t first, uint32_t count, const float* world43);
 int mv_set_light(mv_caster* c, const float pos[3], const float color[3], float intensity);   /* SetLight, :45 */
 int mv_set_ambient(mv_caster* c, const float color[3], float intensity);                     /* SetAmbient, :46 */
 /* UpdateFrame (:47-48, MultiRayCaster.cpp:316-353): builds CBPerFrame and the N PerObject records */

@@ -23,7 +23,8 @@ class Stats(C.Structure):
                 ("light_voxels", C.c_uint64), ("light_dense_voxels", C.c_uint64), ("light_samples", C.c_uint64),
                 ("direct_rays", C.c_uint64), ("direct_samples", C.c_uint64), ("direct_light_fetches", C.c_uint64),
                 ("oit_fragments", C.c_uint64),
-                ("visible_count", u32), ("cubemap_count", u32), ("light_volume", u32), ("threads", u32)]
+                ("visible_count", u32), ("cubemap_count", u32), ("light_volume", u32), ("threads", u32),
+                ("view_skipped", C.c_uint64), ("direct_skipped", C.c_uint64)]
 
     def as_dict(self):
         return {k: int(getattr(self, k)) for k, _ in self._fields_}
@@ -203,6 +204,16 @@ class CasterBase:
     def SetVolumeWorldMatrix(self, i, world43):
         a, p = _fp(np.asarray(world43).reshape(12))
         self._ck(self.b.set_volume_world_matrix(self.h, i, p), "set_volume_world_matrix")
+
+    def SetVolumeWorldMatrices(self, world43, first=0):
+        """(count, 4, 3) matrices for consecutive volumes; one call where the library offers it."""
+        m = np.ascontiguousarray(world43, np.float32).reshape(-1, 12)
+        fn = getattr(self.b, "set_volume_world_matrices", None)
+        if fn is not None:
+            self._ck(fn(self.h, first, m.shape[0], m.ctypes.data), "set_volume_world_matrices")
+        else:
+            for k in range(m.shape[0]):
+                self.SetVolumeWorldMatrix(first + k, m[k])
 
     def SetLight(self, pos, color, intensity):
         a, pa = _fp(pos); b, pb = _fp(color)

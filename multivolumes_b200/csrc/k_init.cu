@@ -73,13 +73,46 @@ __global__ void __launch_bounds__(256) k_r32f_to_rgba16f(cudaSurfaceObject_t sur
     store_volume_texel(surf, x, y, z, V4{1.0f, 1.0f, 1.0f, d * 0.25f}, densityOnly);
 }
 
+// One thread per brick: the brick is empty when no texel of the brick, or of the one-texel border a trilinear footprint
+// can reach from inside it, holds a density above the empty-sample threshold of the march (NaN counts as dense).
+__global__ void __launch_bounds__(128) k_build_occupancy(cudaSurfaceObject_t surf, uint32_t n, uint32_t shift, uint32_t bricks, bool densityOnly, uint32_t* bits)
+{
+    const uint32_t b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= bricks * bricks * bricks) return;
+    const uint32_t bx = b % bricks, by = (b / bricks) % bricks, bz = b / (bricks * bricks);
+    const int edge = 1 << shift;
+    const int x0 = max((int)(bx << shift) - 1, 0), x1 = min((int)(bx << shift) + edge, (int)n - 1);
+    const int y0 = max((int)(by << shift) - 1, 0), y1 = min((int)(by << shift) + edge, (int)n - 1);
+    const int z0 = max((int)(bz << shift) - 1, 0), z1 = min((int)(bz << shift) + edge, (int)n - 1);
+    bool empty = true;
+    for (int z = z0; z <= z1 && empty; ++z)
+        for (int y = y0; y <= y1 && empty; ++y)
+            for (int x = x0; x <= x1; ++x) {
+                uint16_t h;
+                if (densityOnly) h = surf3Dread<unsigned short>(surf, x * 2, y, z);
+                else h = (uint16_t)(surf3Dread<uint2>(surf, x * 8, y, z).y >> 16);
+                if (!(f16_to_f32(h) <= kZeroThreshold)) { empty = false; break; }
+            }
+    if (empty) atomicOr(bits + (b >> 5), 1u << (b & 31));
+}
+
 } // namespace
+
+void launch_build_occupancy(Caster& c, uint32_t src)
+{
+    if (!c.dOcc) return;
+    uint32_t* bits = c.dOcc + (size_t)src * c.occWords;
+    cudaMemsetAsync(bits, 0, (size_t)c.occWords * sizeof(uint32_t), c.stream);
+    const uint32_t total = c.occBricks * c.occBricks * c.occBricks;
+    k_build_occupancy<<<(total + 127) / 128, 128, 0, c.stream>>>(c.volumes[src].surf, c.d.grid_size, c.occShift, c.occBricks, c.volumes[src].channels == 1, bits);
+}
 
 void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed)
 {
     const uint32_t n = c.d.grid_size;
     dim3 grid((n + 31) / 32, (n + 7) / 8, n);
     k_init_grid<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, n, mode, seed, c.volumes[src].channels == 1);
+    launch_build_occupancy(c, src);
 }
 
 void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity)
@@ -87,6 +120,7 @@ void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity)
     const uint32_t n = c.d.grid_size;
     dim3 grid((n + 31) / 32, (n + 7) / 8, n);
     k_r32f_to_rgba16f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, devDensity, n, c.volumes[src].channels == 1);
+    launch_build_occupancy(c, src);
 }
 
 } // namespace mv

@@ -102,13 +102,30 @@ MV_D bool ray_misses_box_for_sure(V3 o, V3 d)
     return (oo - slack) * dot(d, d) > tca * tca;  // closest approach of the line outside the sphere
 }
 
-struct MarchCount { uint32_t samples, lightFetches; };
+struct MarchCount { uint32_t samples, lightFetches, skipped; };
+
+// Is the brick that holds the sample position known to be empty (Occupancy, mv_internal.h)? `bits` are the bricks of
+// the ray's source volume. The sample's texel coordinate is uvw * G; the texels its trilinear footprint touches lie
+// within half a texel of it, inside the one-texel border the brick's bit accounts for.
+MV_D bool brick_is_empty(const uint32_t* __restrict__ bits, const Occupancy& occ, V3 uvw)
+{
+    const int top = (int)occ.bricks - 1;
+    const int bx = min((int)(uvw.x * occ.gridSize) >> occ.shift, top);
+    const int by = min((int)(uvw.y * occ.gridSize) >> occ.shift, top);
+    const int bz = min((int)(uvw.z * occ.gridSize) >> occ.shift, top);
+    const uint32_t b = ((uint32_t)bz * occ.bricks + (uint32_t)by) * occ.bricks + (uint32_t)bx;
+    return (__ldg(bits + (b >> 5)) >> (b & 31)) & 1u;
+}
 
 // The per-ray loop of CSRayMarch.hlsl:112-155 and RayCast.hlsli:57-105 (identical bodies).
 // One trilinear density fetch per step, one trilinear light-map fetch when the sample is non-empty,
 // adaptive step from the density change, front-to-back accumulation, early out at transmittance < 0.01.
+// `emptyBits` (nullptr = none): the empty-space bricks of the source volume. A sample inside a brick known to be empty is an
+// empty sample (density <= ZERO_THRESHOLD) whatever its exact value: it advances t by the base step and changes nothing
+// else, so its fetch is left out. The bricks are consulted only after an empty sample — inside a dense run the lookup
+// would lengthen every step's dependent chain for nothing — so the first sample of an empty run is still fetched.
 MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t smpCount, V3 rayOrigin, V3 rayDir,
-                  float tMax, bool densityOnly, MarchCount& mc)
+                  float tMax, bool densityOnly, MarchCount& mc, const uint32_t* __restrict__ emptyBits, const Occupancy& occ)
 {
     const float maxDist = 2.0f * sqrtf(3.0f);            // g_maxDist, RayMarch.hlsli:17
     const float stepScale = maxDist / (float)smpCount;
@@ -126,6 +143,12 @@ MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t 
         const V3 pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
         if (outside_unit_box(pos)) break;
         const V3 uvw = local_to_tex3d(pos);
+        if (emptyBits && !wasDense && brick_is_empty(emptyBits, occ, uvw)) {
+            ++mc.samples; ++mc.skipped;
+            t += stepScale;
+            if (t > tMax) break;
+            continue;
+        }
         const float4 c4 = tex3d_issue(grid, uvw.x, uvw.y, uvw.z);
         float4 l = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (wasDense) l = tex3d_issue(light, uvw.x, uvw.y, uvw.z);

@@ -13,6 +13,7 @@
 #include "k_march.cuh"
 
 namespace mv {
+namespace MV_VARIANT {
 
 namespace {
 
@@ -185,23 +186,40 @@ MV_D V3 back_face_point(V3 localEye, V3 d, int axis, float sgn)
     return lpt;
 }
 
+// What the screen-space march of one volume needs, gathered by the caller so that the out-of-line fallback below does not
+// take the whole scene structure by reference (it would be copied to the stack)
+struct RayCastArgs {
+    cudaTextureObject_t grid, light;
+    const uint32_t* emptyBits;
+    Occupancy occ;
+    const float* wvpi;
+    uint32_t smpCnt;
+};
+MV_D RayCastArgs ray_cast_args(const DeviceScene& s, const PerObject* po, uint32_t volumeId, uint32_t volTexId, uint32_t smpCnt)
+{
+    RayCastArgs a;
+    a.grid = s.volumeTex[volTexId]; a.light = s.lightTex[volumeId];
+    a.emptyBits = s.occ.bits ? s.occ.bits + (size_t)volTexId * s.occ.wordsPerVolume : nullptr;
+    a.occ = s.occ; a.wvpi = po->wvpi; a.smpCnt = smpCnt;
+    return a;
+}
+
 // RayCast, RayCast.hlsli:42-107: screen-space march of one fragment of a direct-scheme volume
-MV_D V4 ray_cast(const DeviceScene& s, const PerObject* po, uint32_t volumeId, uint32_t volTexId, uint32_t smpCnt, V3 localEye, V3 rayDir,
-                 float sx, float sy, float sceneDepth, bool densityOnly, bool& marched, MarchCount& mc)
+MV_D V4 ray_cast(const RayCastArgs& a, V3 localEye, V3 rayDir, float sx, float sy, float sceneDepth, bool densityOnly, bool& marched, MarchCount& mc)
 {
     V3 ro = localEye; const V3 rd = normalize(rayDir);
     marched = compute_ray_origin(ro, rd);
     if (!marched) return {0.0f, 0.0f, 0.0f, 0.0f};
-    const float tMax = get_tmax(V3{sx, sy, sceneDepth}, ro, rd, po->wvpi);
-    return march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCnt, ro, rd, tMax, densityOnly, mc);
+    const float tMax = get_tmax(V3{sx, sy, sceneDepth}, ro, rd, a.wvpi);
+    return march_ray(a.grid, a.light, a.smpCnt, ro, rd, tMax, densityOnly, mc, a.emptyBits, a.occ);
 }
 
 // the same, kept out of line: the resolve kernel only marches volumes whose rectangle did not fit the result buffer
-__device__ __noinline__ V4 ray_cast_fallback(const DeviceScene& s, const PerObject* po, uint32_t volumeId, uint32_t volTexId, uint32_t smpCnt, V3 localEye, V3 rayDir,
-                                             float sx, float sy, float sceneDepth, bool densityOnly, uint32_t& rays, uint32_t& samples, uint32_t& light)
+__device__ __noinline__ V4 ray_cast_fallback(RayCastArgs a, V3 localEye, V3 rayDir, float sx, float sy, float sceneDepth, bool densityOnly,
+                                             uint32_t& rays, uint32_t& samples, uint32_t& light)
 {
-    bool marched; MarchCount mc = {0, 0};
-    const V4 c = ray_cast(s, po, volumeId, volTexId, smpCnt, localEye, rayDir, sx, sy, sceneDepth, densityOnly, marched, mc);
+    bool marched; MarchCount mc = {0, 0, 0};
+    const V4 c = ray_cast(a, localEye, rayDir, sx, sy, sceneDepth, densityOnly, marched, mc);
     if (marched) { ++rays; samples += mc.samples; light += mc.lightFetches; }
     return c;
 }
@@ -232,7 +250,7 @@ __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(D
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t total = s.lists->directTileTotal, nvis = s.lists->visibleCount;
-    uint32_t dRays = 0, dSamples = 0, dLight = 0;
+    uint32_t dSkipped = 0;
     for (;;) {
         uint32_t w = 0;
         if (lane == 0) w = atomicAdd(&s.lists->directTileCursor, 1u);
@@ -263,14 +281,19 @@ __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(D
             const V3 lpt = back_face_point(localEye, d, f.axis, f.sgn);
             const V3 rayDir = lpt - localEye;                                    // PSCube.hlsl:34
             const float sceneDepth = __ldg(s.depth + (size_t)py * cb.width + px);
-            bool marched; MarchCount mc = {0, 0};
-            const V4 color = ray_cast(s, po, volumeId, a.w, a.y, localEye, rayDir, sx, sy, sceneDepth, kDensityOnly, marched, mc);
+            bool marched; MarchCount mc = {0, 0, 0};
+            const V4 color = ray_cast(ray_cast_args(s, po, volumeId, a.w, a.y), localEye, rayDir, sx, sy, sceneDepth, kDensityOnly, marched, mc);
             if (color.w > 0.0f && color.w <= 1.0f) stored = pack_half4(color);
-            if (kStats && marched) st = make_uint2(mc.samples | 0x80000000u, mc.lightFetches);
+            if (kStats && marched) { st = make_uint2(mc.samples | 0x80000000u, mc.lightFetches); dSkipped += mc.skipped; }
         }
         const size_t slot = (size_t)__ldg(s.directOffset + lo) + (size_t)(py - vi.y0) * rectW + (px - vi.x0);
         s.directColor[slot] = stored;
         if (kStats) s.directStats[slot] = st;
+    }
+    if (kStats) {   // diagnostic: samples of every marched pixel (also of fragments that end up beyond the eighth layer)
+#pragma unroll
+        for (int dd = 16; dd > 0; dd >>= 1) dSkipped += __shfl_xor_sync(0xffffffffu, dSkipped, dd);
+        if (lane == 0 && dSkipped) atomicAdd(&s.stats->direct_skipped, (unsigned long long)dSkipped);
     }
 }
 
@@ -390,7 +413,7 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
                     const uint2 st = __ldg(s.directStats + at);
                     if (st.x >> 31) { ++dRays; dSamples += st.x & 0x7fffffffu; dLight += st.y; }
                 }
-            } else color = ray_cast_fallback(s, po, volumeId, a.w, smpCnt, localEye, rayDir, sx, sy, sceneDepth, densityOnly, dRays, dSamples, dLight);
+            } else color = ray_cast_fallback(ray_cast_args(s, po, volumeId, a.w, smpCnt), localEye, rayDir, sx, sy, sceneDepth, densityOnly, dRays, dSamples, dLight);
         } else color = cube_cast(s, cb, volumeId, a.x, sceneDepth, face, lpt, rayDir);
         if (!stored && color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
         const float k1 = 1.0f - result.w;
@@ -454,4 +477,5 @@ void launch_resolve_oit(Caster& c)
     k_resolve_oit<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb, (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0);
 }
 
+} // namespace MV_VARIANT
 } // namespace mv

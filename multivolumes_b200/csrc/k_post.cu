@@ -9,6 +9,7 @@
 #include "mv_internal.h"
 
 namespace mv {
+namespace MV_VARIANT {
 
 namespace {
 
@@ -231,4 +232,5 @@ void launch_postprocess(Caster& c, bool taaOn)
     k_postprocess<<<grid, kPostW * kPostH, 0, c.stream>>>(a);
 }
 
+} // namespace MV_VARIANT
 } // namespace mv

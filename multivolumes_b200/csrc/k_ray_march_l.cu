@@ -589,28 +589,7 @@ __global__ void __launch_bounds__(256) k_light_finalize(DeviceScene s, FrameCB c
                       V3{shadow * lightColor.x + ambient.x, shadow * lightColor.y + ambient.y, shadow * lightColor.z + ambient.z});
 }
 
-// Work-graph order (MultiRayCaster.cpp:358-362: rayMarchL runs before the graph that culls): the light march of a frame
-// picks its volume from the visible list the PREVIOUS frame's cull left behind (CSRayMarchL.hlsl:29-33 reads
-// g_roVisibleVolumes / its counter as they are) and needs its work counters reset, which the cull otherwise does.
-__global__ void k_pick_light_volume(FrameLists* cur, const FrameLists* prev, const uint32_t* prevVisible, uint32_t frameIdx, uint32_t N)
-{
-    const uint32_t count = prev->visibleCount;
-    cur->lightVolume = count ? prevVisible[frameIdx % count] : frameIdx % N;
-    cur->lightDenseCount = 0; cur->lightDenseCursor = 0;
-    cur->lightItemCount = 0; cur->lightItemCursor = 0;
-    cur->lightResultCount = 0; cur->lightEmitCursor = 0;
-    cur->lightOverflow = 0;
-}
-
 } // namespace
-
-void launch_pick_light_volume(Caster& c)
-{
-    FrameLists* cur = reinterpret_cast<FrameLists*>(c.dLists);
-    const unsigned char* prevBase = c.dLists2[c.listParity ^ 1u];
-    k_pick_light_volume<<<1, 1, 0, c.stream>>>(cur, reinterpret_cast<const FrameLists*>(prevBase),
-                                               reinterpret_cast<const uint32_t*>(prevBase + sizeof(FrameLists)), c.cb.frameIdx, c.d.num_volumes);
-}
 
 void launch_ray_march_light(Caster& c, int volumeOverride)
 {
@@ -673,6 +652,31 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
             for (auto& t : tacc) t = 0;
         }
     }
+}
+
+
+namespace {
+// Work-graph order (MultiRayCaster.cpp:358-362: rayMarchL runs before the graph that culls): the light march of a frame
+// picks its volume from the visible list the PREVIOUS frame's cull left behind (CSRayMarchL.hlsl:29-33 reads
+// g_roVisibleVolumes / its counter as they are) and needs its work counters reset, which the cull otherwise does.
+__global__ void k_pick_light_volume(FrameLists* cur, const FrameLists* prev, const uint32_t* prevVisible, uint32_t frameIdx, uint32_t N)
+{
+    const uint32_t count = prev->visibleCount;
+    cur->lightVolume = count ? prevVisible[frameIdx % count] : frameIdx % N;
+    cur->lightDenseCount = 0; cur->lightDenseCursor = 0;
+    cur->lightItemCount = 0; cur->lightItemCursor = 0;
+    cur->lightResultCount = 0; cur->lightEmitCursor = 0;
+    cur->lightOverflow = 0;
+}
+
+} // namespace
+
+void launch_pick_light_volume(Caster& c)
+{
+    FrameLists* cur = reinterpret_cast<FrameLists*>(c.dLists);
+    const unsigned char* prevBase = c.dLists2[c.listParity ^ 1u];
+    k_pick_light_volume<<<1, 1, 0, c.stream>>>(cur, reinterpret_cast<const FrameLists*>(prevBase),
+                                               reinterpret_cast<const uint32_t*>(prevBase + sizeof(FrameLists)), c.cb.frameIdx, c.d.num_volumes);
 }
 
 } // namespace mv

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
     }
     const uint32_t total = ld_list<kFusedCull>(&s.lists->marchTileTotal);
     const uint32_t cubeCount = ld_list<kFusedCull>(&s.lists->cubeCount);
-    uint32_t nRays = 0, nSamples = 0, nLight = 0;
+    uint32_t nRays = 0, nSamples = 0, nLight = 0, nSkipped = 0;
     uint32_t stagedVolume = 0xffffffffu;
 
     // phase (sharded frame, mv_api.cu): 1 = every volume but the frame's light volume, whose light map is still being
@@ -157,8 +157,9 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
                 const float z = __ldg(s.depth + (size_t)iy * cb.width + ix);
                 tMax = fminf(get_tmax(V3{cx, cy, z}, rayOrigin, rayDir, tc.po + 16), tMax);   // :106
 
-                MarchCount mc = {0, 0};
-                const V4 scatter = march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCount, rayOrigin, rayDir, tMax, kDensityOnly, mc);
+                MarchCount mc = {0, 0, 0};
+                const uint32_t* emptyBits = s.occ.bits ? s.occ.bits + (size_t)volTexId * s.occ.wordsPerVolume : nullptr;
+                const V4 scatter = march_ray(s.volumeTex[volTexId], s.lightTex[volumeId], smpCount, rayOrigin, rayDir, tMax, kDensityOnly, mc, emptyBits, s.occ);
 
                 const size_t idx = ((size_t)face * size + y) * size + x;
                 const unsigned long long cOfs = arena_color_offset(s.arena, volumeId, mip) + idx * 8ull;
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
                         *reinterpret_cast<float*>(pb + dOfs) = z;
                     }
                 }
-                if (kStats) { ++nRays; nSamples += mc.samples; nLight += mc.lightFetches; }
+                if (kStats) { ++nRays; nSamples += mc.samples; nLight += mc.lightFetches; nSkipped += mc.skipped; }
             }
         }
     }
@@ -184,11 +185,13 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
             nRays += __shfl_xor_sync(kFull, nRays, d);
             nSamples += __shfl_xor_sync(kFull, nSamples, d);
             nLight += __shfl_xor_sync(kFull, nLight, d);
+            nSkipped += __shfl_xor_sync(kFull, nSkipped, d);
         }
         if (lane == 0 && nRays) {
             atomicAdd(&s.stats->view_rays, (unsigned long long)nRays);
             atomicAdd(&s.stats->view_samples, (unsigned long long)nSamples);
             atomicAdd(&s.stats->view_light_fetches, (unsigned long long)nLight);
+            if (nSkipped) atomicAdd(&s.stats->view_skipped, (unsigned long long)nSkipped);
         }
     }
 }

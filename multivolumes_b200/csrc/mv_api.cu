@@ -61,6 +61,7 @@ DeviceScene Caster::scene() const
     s.directStats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dDirectStats : nullptr;
     s.directCapacity = directCapacity;
     s.volumeTex = dVolumeTex;
+    s.occ.bits = dOcc; s.occ.wordsPerVolume = occWords; s.occ.shift = occShift; s.occ.bricks = occBricks; s.occ.gridSize = (float)d.grid_size;
     s.lightTex = dLightTex;
     s.lightSurf = dLightSurf;
     s.depth = dDepth;
@@ -79,6 +80,11 @@ DeviceScene Caster::scene() const
     s.stripeH = (shardWorld > 1) ? stripeH : 0;
     return s;
 }
+
+// ---- the two builds of the ALU-bound image passes (mv_internal.h) ----
+void launch_ray_cast_direct(Caster& c) { if (c.fastMask & kFastDirect) fast::launch_ray_cast_direct(c); else strict::launch_ray_cast_direct(c); }
+void launch_resolve_oit(Caster& c) { if (c.fastMask & kFastOit) fast::launch_resolve_oit(c); else strict::launch_resolve_oit(c); }
+void launch_postprocess(Caster& c, bool taaOn) { if (c.fastMask & kFastPost) fast::launch_postprocess(c, taaOn); else strict::launch_postprocess(c, taaOn); }
 
 // ---- host matrix algebra (DirectXMath call sites: MultiRayCaster.cpp:325-350) ----
 // Products and inverses are evaluated in double and rounded once to fp32.
@@ -242,7 +248,7 @@ static void destroy_caster(Caster& c)
     for (auto& v : c.lightMaps) kill(v);
     void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject2[0], c.dPerObject2[1], c.dVolumeDescs, c.dAttribs2[0], c.dAttribs2[1],
                      c.dLists2[0], c.dLists2[1], c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
-                     c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
+                     c.dOcc, c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
     for (auto& e : c.ev) if (e) cudaEventDestroy(e);
@@ -292,6 +298,8 @@ int mv_create(const mv_desc* d, mv_caster** out)
     if (c.d.max_light_samples == 0) c.d.max_light_samples = 96;
     c.device = (int)d->device;
     c.smCount = prop.multiProcessorCount;
+    c.fastMask = (c.d.flags & MV_FLAG_FAST_FP) ? kFastDefault : 0u;
+    if (const char* e = getenv("MV_FAST_MASK")) c.fastMask = (uint32_t)strtoul(e, nullptr, 0);   // tuning: which passes run their fast build
     const uint32_t G = c.d.grid_size, L = c.d.light_grid_size, N = c.d.num_volumes, S = c.d.num_volume_srcs;
     const size_t px = (size_t)c.d.width * c.d.height;
     c.row0 = 0; c.row1 = c.d.height;
@@ -328,6 +336,22 @@ int mv_create(const mv_desc* d, mv_caster** out)
     // MultiRayCaster.cpp:99-126 — per-source volumes, per-instance light maps and cube maps
     c.volumes.resize(S);
     for (auto& v : c.volumes) { MV_TRY(make_volume3d(v, G, (c.d.flags & MV_FLAG_DENSITY_ONLY) ? 1u : 4u)); MV_TRY(clear_volume3d(c, v, G)); }
+    {
+        // empty-space bricks: 64 per axis (32 KB of bits per source volume) for volumes of 256^3 and up; measured on B200
+        // (profiles/r02_notes.md): 43 % of cfg4's march samples need no fetch, view march -12 %, screen-space march -10 %.
+        // Below 256^3 the volumes are cache-friendly enough that the lookup costs more than the fetch it saves (cfg2: +5 %),
+        // so the bricks are off there. MV_OCC_BRICKS overrides (0 = off).
+        uint32_t perAxis = G >= 256 ? 64 : 0;
+        if (const char* e = getenv("MV_OCC_BRICKS")) perAxis = (uint32_t)strtoul(e, nullptr, 10);
+        if (perAxis) {
+            uint32_t shift = 1;
+            while (((G - 1) >> shift) + 1 > perAxis) ++shift;
+            c.occShift = shift; c.occBricks = ((G - 1) >> shift) + 1;
+            c.occWords = (c.occBricks * c.occBricks * c.occBricks + 31) / 32;
+            MV_CUDA_C(cudaMalloc(&c.dOcc, (size_t)S * c.occWords * sizeof(uint32_t)));
+            MV_CUDA_C(cudaMemsetAsync(c.dOcc, 0, (size_t)S * c.occWords * sizeof(uint32_t), c.stream));   // nothing known to be empty yet
+        }
+    }
     c.lightMaps.resize(N);
     for (auto& v : c.lightMaps) { MV_TRY(make_volume3d(v, L)); MV_TRY(clear_volume3d(c, v, L)); }
     std::vector<cudaTextureObject_t> vt(S), lt(N);
@@ -484,8 +508,9 @@ int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
     p.extent = make_cudaExtent(n, n, n);
     p.kind = cudaMemcpyHostToDevice;
     MV_CUDA(cudaMemcpy3DAsync(&p, c.stream));
+    launch_build_occupancy(c, src);
     MV_CUDA(cudaStreamSynchronize(c.stream));
-    return MV_OK;
+    return check_launch("k_build_occupancy");
 }
 
 int mv_volume_upload_r32f(mv_caster* h, uint32_t src, const float* density)
@@ -617,6 +642,14 @@ int mv_set_volume_world_matrix(mv_caster* h, uint32_t i, const float w[12])
     MV_ENTER(h);
     MV_REQUIRE(w && i < c.d.num_volumes);
     memcpy(&c.volumeWorlds[(size_t)i * 12], w, 12 * sizeof(float));
+    return MV_OK;
+}
+
+int mv_set_volume_world_matrices(mv_caster* h, uint32_t first, uint32_t count, const float* w)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(w && first <= c.d.num_volumes && count <= c.d.num_volumes - first);
+    memcpy(&c.volumeWorlds[(size_t)first * 12], w, (size_t)count * 12 * sizeof(float));
     return MV_OK;
 }
 
@@ -999,6 +1032,7 @@ int mv_get_stats(mv_caster* h, mv_stats* out)
     out->light_voxels = L * L * L; out->light_dense_voxels = sd.light_dense_voxels; out->light_samples = sd.light_samples;
     out->direct_rays = sd.direct_rays; out->direct_samples = sd.direct_samples; out->direct_light_fetches = sd.direct_light_fetches;
     out->oit_fragments = sd.oit_fragments;
+    out->view_skipped = sd.view_skipped; out->direct_skipped = sd.direct_skipped;
     out->visible_count = fl.visibleCount; out->cubemap_count = fl.cubeCount; out->light_volume = fl.lightVolume;
     out->threads = (uint32_t)c.smCount;
     return MV_OK;
@@ -1030,7 +1064,7 @@ int mv_set_flags(mv_caster* h, uint32_t flags)
 {
     MV_ENTER(h);
     MV_REQUIRE((flags & ~(MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES)) == 0);
-    c.d.flags = flags | (c.d.flags & MV_FLAG_DENSITY_ONLY);   // the storage mode is fixed at creation
+    c.d.flags = flags | (c.d.flags & (MV_FLAG_DENSITY_ONLY | MV_FLAG_FAST_FP));   // the storage mode and the floating-point build are fixed at creation
     c.inputsDirty = true;
     for (auto& v : c.evValid) v = false;
     return MV_OK;

@@ -127,6 +127,7 @@ int mv_volume_upload_r32f_sized(mv_caster* h, uint32_t src, const float* density
         const uint32_t n = c.d.grid_size;
         dim3 grid((n + 31) / 32, (n + 7) / 8, n);
         k_resample_r32f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, tex, n, c.volumes[src].channels == 1);
+        launch_build_occupancy(c, src);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);

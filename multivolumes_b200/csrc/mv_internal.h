@@ -95,6 +95,7 @@ struct StatsDev {
     unsigned long long light_voxels, light_dense_voxels, light_samples;
     unsigned long long direct_rays, direct_samples, direct_light_fetches;
     unsigned long long oit_fragments;
+    unsigned long long view_skipped, direct_skipped;   // samples whose texture fetch the occupancy bricks made unnecessary
 };
 
 // Cube-map arena: one device allocation holding, for every volume, the RGBA16F colour and R32F depth
@@ -119,6 +120,19 @@ MV_HD unsigned long long arena_depth_offset(const CubeArena& a, uint32_t volume,
     return a.depthBase + (unsigned long long)volume * a.depthStride + (unsigned long long)a.mipTexelOffset[mip] * 4ull;
 }
 
+// Empty-space bricks of the source volumes (k_init.cu, k_build_occupancy): one bit per brick of 2^shift texels per
+// side; a set bit means that every texel a trilinear fetch from inside the brick can touch (the brick and one texel
+// around it) holds a density <= kZeroThreshold, so the filtered density — a convex combination — cannot exceed the
+// threshold either and the march treats the sample as the empty sample it is without fetching it
+// (CSRayMarch.hlsl:128 `if (color.w > ZERO_THRESHOLD)`: an empty sample changes nothing but t). Results are unchanged.
+struct Occupancy {
+    const uint32_t* bits;          // [srcs][wordsPerVolume]; nullptr = no skipping
+    uint32_t wordsPerVolume;
+    uint32_t shift;                // log2 of the brick edge in texels
+    uint32_t bricks;               // bricks per axis
+    float gridSize;                // G as float
+};
+
 // Everything the kernels need, passed by value.
 struct DeviceScene {
     const PerObject* perObject;          // [N]
@@ -137,6 +151,7 @@ struct DeviceScene {
     uint2* directStats;                  // per result {samples | marched << 31, light fetches}; nullptr when counters are off
     uint32_t directCapacity;             // pixels
     const cudaTextureObject_t* volumeTex;   // [srcs]
+    Occupancy occ;                       // empty-space bricks of the source volumes
     const cudaTextureObject_t* lightTex;    // [N]
     const cudaSurfaceObject_t* lightSurf;   // [N]
     const float* depth;                  // W*H D32
@@ -165,22 +180,50 @@ MV_HD uint32_t num_own_stripes(uint32_t height, uint32_t stripeH, uint32_t rank,
 
 struct Caster;
 
+// passes that have a fast build (Caster::fastMask)
+constexpr uint32_t kFastDirect = 4u, kFastOit = 8u, kFastPost = 16u;
+constexpr uint32_t kFastDefault = kFastOit | kFastPost;   // with MV_FLAG_FAST_FP
+
 // kernel launchers (one translation unit per pass)
 void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
 void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity);
+void launch_build_occupancy(Caster& c, uint32_t src);   // after every write to a source volume
 void launch_cull(Caster& c);
+void launch_pick_light_volume(Caster& c);
+void launch_sh_project(Caster& c, const float* devCube, uint32_t size, float* devOut27);
+void launch_light_commit(Caster& c);
+void launch_peer_barrier(Caster& c);
+
+// The two ALU-bound image passes (OIT resolve incl. the screen-space march it shares its fragment test with, TAA + tone
+// map) are compiled twice from the same sources (csrc/Makefile):
+//   strict — --fmad=false, correctly rounded divide / reciprocal / square root, fused multiply-adds only where written as
+//            fmaf(): the evaluation-order contract of mv_math.cuh, bit-identical to the test oracle (the default);
+//   fast   — compiler-contracted FMAs, approximate divide / square root (MV_FLAG_FAST_FP, opt-in; see include/mv.h).
+// Everything else — cull, light march, view march, procedural volumes and ingest, the mesh rasteriser, the host
+// matrices — exists once and is always strict.
+#ifndef MV_FAST
+#define MV_FAST 0
+#endif
+#if MV_FAST
+#define MV_VARIANT fast
+#else
+#define MV_VARIANT strict
+#endif
+#define MV_DECLARE_VARIANT_LAUNCHERS                 \
+    void launch_ray_cast_direct(Caster& c);         \
+    void launch_resolve_oit(Caster& c);             \
+    void launch_postprocess(Caster& c, bool taaOn);
+namespace strict { MV_DECLARE_VARIANT_LAUNCHERS }
+namespace fast { MV_DECLARE_VARIANT_LAUNCHERS }
 void launch_ray_march_light(Caster& c, int volumeOverride);
 // phase 0: every cube-map volume; 1: all but the frame's light volume (at most blocksPerSM CTAs per SM, 0 = all that fit);
 // 2: the light volume alone
 void launch_ray_march_view(Caster& c, uint32_t phase = 0, int blocksPerSM = 0);
 void launch_cull_and_ray_march_view(Caster& c);
-void launch_pick_light_volume(Caster& c);
+// dispatchers (mv_api.cu): pick the build the caster was created with
 void launch_ray_cast_direct(Caster& c);
 void launch_resolve_oit(Caster& c);
 void launch_postprocess(Caster& c, bool taaOn);
-void launch_sh_project(Caster& c, const float* devCube, uint32_t size, float* devOut27);
-void launch_light_commit(Caster& c);
-void launch_peer_barrier(Caster& c);
 
 struct Volume3D {
     uint32_t channels = 4;               // 4 = RGBA16F, 1 = R16F (density-only storage of the source volumes)
@@ -193,6 +236,7 @@ struct Caster {
     mv_desc d{};
     int device = 0;
     int smCount = 0;
+    uint32_t fastMask = 0;               // kFast* bits: which passes run their fast build (MV_FLAG_FAST_FP)
     cudaStream_t stream = nullptr;
     // host scene state (MultiRayCaster.h:189-215)
     std::vector<float> volumeWorlds;     // N x 12 (float4x3)
@@ -205,6 +249,8 @@ struct Caster {
     // device resources
     std::vector<Volume3D> volumes;       // per source, RGBA16F G^3
     std::vector<Volume3D> lightMaps;     // per instance, RGBA16F L^3 holding R11G11B10F-quantised rgb
+    uint32_t* dOcc = nullptr;            // empty-space bricks of every source volume (Occupancy)
+    uint32_t occWords = 0, occShift = 0, occBricks = 0;
     cudaTextureObject_t* dVolumeTex = nullptr;
     cudaTextureObject_t* dLightTex = nullptr;
     cudaSurfaceObject_t* dLightSurf = nullptr;

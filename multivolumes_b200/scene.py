@@ -100,3 +100,30 @@ def sphere_depth(width, height, view_proj, center=(0.0, -9.0 + 9.0, 0.0), radius
     clip = np.concatenate([hp, np.ones_like(hp[..., :1])], -1) @ vp
     z = clip[..., 2] / clip[..., 3]
     return np.where(hit, z, 1.0).astype(np.float32)
+
+
+def occluder_mesh(rings=132, sectors=264):
+    """Stand-in for the reference's Bin/Assets/bunny.obj (34 835 vertices / 69 666 triangles, x in [-5, 5], y in [0, 9.9],
+    z in [-3.9, 3.9]; `-mesh bunny.obj 0 -9 0 1.8` in Bin/all64.bat), which is not redistributed with this package: a closed,
+    lobed blob of the same extent and 69 696 triangles, so the depth / shadow producer sees the same load.
+    Returns (positions (V, 3) float32, indices (3 T,) uint32) in the OBJ importer's output convention."""
+    pos, idx = [], []
+    for r in range(rings + 1):
+        th = np.pi * r / rings
+        for q in range(sectors):
+            ph = 2.0 * np.pi * q / sectors
+            d = np.array([np.sin(th) * np.cos(ph), np.cos(th), np.sin(th) * np.sin(ph)])
+            lobes = 1.0 + 0.18 * np.sin(3.0 * ph) * np.sin(th) ** 2 + 0.12 * np.cos(2.0 * th)      # ears / haunches, kept star-shaped
+            pos.append(tuple(d * lobes))
+    for r in range(rings):
+        for q in range(sectors):
+            a, b = r * sectors + q, r * sectors + (q + 1) % sectors
+            c, d = a + sectors, b + sectors
+            idx += [a, c, b, b, c, d]
+    p = np.asarray(pos, np.float64)
+    lo, hi = p.min(0), p.max(0)
+    p = (p - lo) / (hi - lo) * np.array([10.03, 9.94, 7.77]) + np.array([-5.015, -0.044, -3.887])      # the bunny's bounding box
+    return p.astype(np.float32), np.asarray(idx, np.uint32)
+
+
+MESH_WORLD = (1.8, (0.0, -9.0, 0.0))          # scale, position: Bin/all64.bat:1

@@ -42,6 +42,7 @@ typedef struct mvo_stats {
     uint32_t visible_count, cubemap_count;
     uint32_t light_volume;      /* volume whose light map the last render filled */
     uint32_t threads;
+    uint64_t view_skipped, direct_skipped;   /* layout of mv_stats; the oracle fetches every sample: always 0 */
 } mvo_stats;
 
 int  mvo_create(const mvo_desc* desc, mvo_caster** out);

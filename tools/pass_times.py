@@ -20,4 +20,4 @@ for i in range(30 + frames):
             acc[k] = acc.get(k, 0.0) + v / frames
 st = c.GetStats()
 print(json.dumps({"lib": os.path.basename(os.environ.get("MV_B200_LIB", "default")), **{k: round(v, 4) for k, v in acc.items()},
-                  "view_samples": st["view_samples"], "light_samples": st["light_samples"], "direct_samples": st["direct_samples"]}))
+                  "view_samples": st["view_samples"], "view_skipped": st["view_skipped"], "light_samples": st["light_samples"], "direct_samples": st["direct_samples"], "direct_skipped": st["direct_skipped"]}))
