@@ -172,28 +172,51 @@ def camera(scene, wl, frame):
     return scene.orbit_camera(wl["w"], wl["h"], frame)
 
 
+def host_threads():
+    """Host cores this process may use. torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arms size
+    their OpenMP team explicitly from the affinity mask instead, so that N > 1 launches time the same thing as N = 1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def make_oracle(wl, threads):
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import OracleCaster
+    return OracleCaster(filter_model=1, threads=threads, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"],
+                        num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
+
+
+def step_frame(c, wl, scene, i, render):
+    """One frame's inputs on either backend: animated transforms, occluder depth (cfg3), camera matrices; `render` draws."""
+    vp, eye = camera(scene, wl, i)
+    animate(c, wl, i)
+    svp = c.RenderMeshDepth(vp) if wl.get("mesh") else None
+    render(vp, svp, eye)
+
+
 # --------------------------------------------------------------------------------------------
 def run_reference(args, wl, rank, world):
     """--impl reference: the reference publishes no CPU implementation (HLSL on D3D12 only), so the arm
     times the scalar C++/OpenMP transliteration (the oracle) on the host cores, all threads."""
     if rank != 0:
         return None
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_binding import OracleCaster
     from multivolumes_b200 import scene
-    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"),
-                     width=wl["w"], height=wl["h"])
+    cores = host_threads()
+    o = make_oracle(wl, cores)
     sky = o.TransformSH(scene.procedural_sky(64))
     build_scene(o, wl, scene, sky)
-    cores = o.GetStats()["threads"]
 
     def frame(i, shard=None):
-        vp, eye = camera(scene, wl, i)
         if shard:
             o.SetShard(*shard)
             o.SetRowBand(*shard_band(wl["h"], *shard))
-        o.UpdateFrame(vp, None, eye); o.ResetColor(); o.Render(); o.Postprocess(wl["taa"])
+
+        def render(vp, svp, eye):
+            o.UpdateFrame(vp, svp, eye); o.ResetColor(); o.Render(); o.Postprocess(wl["taa"])
+        step_frame(o, wl, scene, i, render)
         st = o.GetStats()
         return st["view_samples"] + st["direct_samples"] + st["light_samples"]
 
@@ -215,7 +238,7 @@ def run_reference(args, wl, rank, world):
             "warmup": args.warmup, "ms_per_step": 1000.0 * dt / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, wl, world), "samples_per_s": samples / dt,
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": o.GetStats()["threads"], "kind": "port",
                              "sample": f"each step = 1/{S} of a frame (volumes v % {S} == step % {S}, light-map slab, row band {S}-th); "
                                        f"frames/s = steps / (time x {S}); calibration full frame {t_full:.2f} s"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -226,7 +249,8 @@ def launches_per_frame(wl, world, exchange, work_graph=False):
     """Kernels of libmv_b200.so per frame: k_cull; the light march (k_light_classify, k_ray_march_l and, with a light probe,
     k_light_scan, k_light_emit, k_light_ao, k_light_finalize); k_ray_march_v; k_ray_cast_direct; k_resolve_oit; k_postprocess.
     One GPU, pipelined frames: + k_light_commit. Sharded, fused exchange: + k_light_commit and three peer barriers
-    (k_peer_signal + k_peer_wait each); with the light / view overlap (8 ranks) the view march is two launches."""
+    (k_peer_signal + k_peer_wait each); with the light / view overlap (8 ranks) the view march is two launches.
+    cfg3: + the depth / shadow producer (k_mesh_setup + k_mesh_raster per pass, clears, D16 conversion)."""
     n = 1 + (6 if wl["sh"] else 2) + 1 + 1 + 1 + 1   # --work-graph: the same count (k_pick_light_volume instead of k_cull)
     if world == 1 and not work_graph and os.environ.get("MV_OVERLAP", "1") != "0":
         n += 1                                        # pipelined frames: k_light_commit (light map through the staging buffer)
@@ -234,6 +258,8 @@ def launches_per_frame(wl, world, exchange, work_graph=False):
         n += 1 + (6 if exchange == "fused" else 0)
         if exchange == "fused" and int(os.environ.get("MV_SHARD_V_BLOCKS", "4" if world >= 8 else "0")) > 0:
             n += 1
+    if wl.get("mesh"):
+        n += 7
     return n
 
 
@@ -244,7 +270,7 @@ def workload_config(args, wl, world):
                         f"orbit camera; {wl['note']}",
             "l2_policy": f"inputs larger than L2 ({((wl.get('srcs') or wl['n']) * wl['g'] ** 3 * (2 if wl.get('density_only') else 8) + wl['n'] * wl['l'] ** 3 * 8) / 1e6:.0f} MB "
                          f"of volume and light-map textures vs 126 MB)",
-            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: volumes v % {world}, light-map z-slabs, {world} row bands; exchange = {args.exchange}",
+            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: cube-map tile ranges, light-map z-slabs, interleaved row stripes; exchange = {args.exchange}",
             "e2e_inputs": "per-frame matrices (PerObject records) from pinned host memory; result = tone-mapped RGBA8 frame read back to pinned host "
                           "memory every step (Present, 3 frames in flight as in the reference's frame loop)"}
 
@@ -255,9 +281,10 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--exchange", default="fused", choices=["fused", "collective"])
     ap.add_argument("--work-graph", action="store_true", help="Render(..., useWorkGraph = true): cull inside the view-march launch (one GPU, not pipelined)")
+    ap.add_argument("--fast-fp", action="store_true", help="MV_FLAG_FAST_FP: the opt-in fast build of the OIT resolve and the TAA (not bit-exact)")
     ap.add_argument("--cpu-baseline-frames", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU time the reference arm may use")
@@ -285,13 +312,24 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     hbm_peak, peak_src = peaks()
+    tex_peak_gfetch, l2_peak_gbs = tex_peak()
 
-    c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, density_only=bool(wl.get("density_only")), grid_size=wl["g"], light_grid_size=wl["l"],
-                       num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
+    def make_caster():
+        c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, density_only=bool(wl.get("density_only")), fast_fp=args.fast_fp,
+                           grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
+        build_scene(c, wl, scene, sky_coeffs(c))
+        return c
+
+    _sky = []
+
+    def sky_coeffs(c):
+        if not _sky:
+            _sky.append(c.TransformSH(scene.procedural_sky(64)))
+        return _sky[0]
+
+    c = make_caster()
     stream = torch.cuda.Stream()
     c.SetStream(stream.cuda_stream)      # order the caster's kernels with torch's events / NCCL on one stream
-    sky = c.TransformSH(scene.procedural_sky(64))
-    build_scene(c, wl, scene, sky)
     with torch.cuda.stream(stream):
         x = CudaExchange(c, rank, world) if world > 1 and args.exchange == "collective" else None
         r = ShardedRenderer(c, rank, world, mode=args.exchange, exchange=x, use_work_graph=args.work_graph)
@@ -302,10 +340,13 @@ def main():
             torch.cuda.synchronize()
 
         def frame(i):
-            vp, eye = camera(scene, wl, i)
-            r.render(vp, None, eye, taa=wl["taa"])
+            step_frame(c, wl, scene, i, lambda vp, svp, eye: r.render(vp, svp, eye, taa=wl["taa"]))
 
         # ---- device-resident throughput ----
+        # the light march fills ONE volume's light map per frame (round robin over the visible list, CSRayMarchL.hlsl:29-33):
+        # N untimed frames first, so that the timed frames are steady-state images whatever --warmup says
+        for i in range(wl["n"]):
+            frame(i)
         for i in range(args.warmup):
             frame(i)
         barrier()
@@ -362,13 +403,15 @@ def main():
         # FrameCount = 3 frames in flight (MultiRayCaster.h:52). Present = asynchronous read-back of the tone-mapped frame
         # into pinned host memory; the host blocks on the frame presented three steps earlier before reusing its buffer.
         # Every step's H2D and D2H copies complete inside the timed region (all slots are drained before the clock stops).
+        # N > 1: every rank reads ITS rows back over its own PCIe link into one host frame shared by the ranks (POSIX shared
+        # memory, page-locked in every process), so no rank carries the whole 33 MB frame.
         slots = 3
-        outs = [PinnedBuffer((wl["h"], wl["w"], 4), np.uint8) for _ in range(slots)] if rank == 0 else [None] * slots
+        outs = r.present_buffers(slots)
         n_e2e = min(args.steps, 100)
 
         def e2e_step(i):
             frame(i)
-            c.PresentAsync(outs[i % slots].ptr if rank == 0 else None, i % slots)
+            r.present(outs, i % slots)
 
         def drain():
             for k in range(slots):
@@ -392,10 +435,8 @@ def main():
         t0 = time.perf_counter()
         for i in range(n_e2e):
             frame(args.warmup + i)
-            if rank == 0:
-                c.ReadPostInto(rgba8_ptr=outs[0].ptr)
-            else:
-                c.Sync()
+            r.present(outs, 0)
+            c.PresentWait(0)
         barrier()
         dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
         if world > 1:
@@ -405,12 +446,14 @@ def main():
     if rank == 0:
         fps = args.steps / (ms_total / 1000.0)
         view_ms = per_pass["ray_march_view"]
-        vs, vl, vr = (stats_acc[k] / n_prof for k in ("view_samples", "view_light_fetches", "view_rays"))
-        # 8 B density texel per sample (2 B in the density-only storage) (+ 8 B RGBA16F light texel when alpha > 0.01); per ray 4 B depth read,
-        # 8 B colour + 4 B cube-depth write
+        vs, vl, vr, vk = (stats_acc[k] / n_prof for k in ("view_samples", "view_light_fetches", "view_rays", "view_skipped"))
+        # SURVEY.md 8(d), per unit: a march sample = 1 trilinear density fetch (8 B texel; 2 B in the density-only storage)
+        # + 1 trilinear light-map fetch (8 B) when alpha > 0.01; per ray a 4 B depth read and 8 B + 4 B written
         alg_bytes = vs * (2 if wl.get("density_only") else 8) + vl * 8 + vr * 16
-        achieved = alg_bytes / (view_ms / 1000.0) / 1e9 if view_ms > 0 else 0.0
-        fetches = (vs + vl) / (view_ms / 1000.0) / 1e9 if view_ms > 0 else 0.0
+        sec = view_ms / 1000.0 if view_ms > 0 else float("inf")
+        fetches = (vs + vl) / sec / 1e9            # algorithmic: every sample of the reference's loop
+        issued = (vs - vk + vl) / sec / 1e9        # what the texture unit was actually asked for (empty-space bricks)
+        prof = ncu_summary(args.workload) if world == 1 else None
         line = {"metric": "frames_per_s", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": workload_config(args, wl, world),
@@ -421,39 +464,65 @@ def main():
                 "gpu_launches": args.steps * launches_per_frame(wl, world, args.exchange, args.work_graph),
                 "clocks": clocks,
                 "per_pass_ms": per_pass, "per_pass_note": "rank 0, instrumented pass (CUDA events around each pass; at N > 1 the light and view marches include their peer barriers)",
-                "roofline": {"kernel": "k_ray_march_v", "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": achieved / hbm_peak, "traffic": NCU_TRAFFIC_BYTES.get(args.workload) if world == 1 else None, "peak_source": peak_src,
-                             "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": view_ms,
-                             "tex": {"achieved": fetches, "peak": TEX_PEAK_GFETCH, "unit": "Gfetch/s", "frac": fetches / TEX_PEAK_GFETCH,
-                                     "peak_source": "profiles/r01_tex_probe.json",
-                                     "ncu_tex_data_pipe_pct_of_peak": NCU_TEX_PIPE_PCT.get(args.workload) if world == 1 else None}}}
+                # the bound BASELINE.json's north_star names for the ray march: the texture unit's filtered-fetch rate
+                "roofline": {"kernel": "k_ray_march_v", "bound": "tex", "achieved": fetches, "peak": tex_peak_gfetch, "unit": "Gfetch/s",
+                             "frac": fetches / tex_peak_gfetch, "peak_source": "profiles/r01_tex_probe.json (tools/tex_probe.cu on this pool's B200: trilinear RGBA16F, L1-resident)",
+                             "achieved_def": "(march samples + light-map fetches) of one launch, counted by the kernel's counting variant, / its CUDA-event duration; "
+                                             "SURVEY.md 8(d): 1 trilinear volume fetch per sample + 1 trilinear light fetch when alpha > 0.01",
+                             "issued": {"achieved": issued, "frac": issued / tex_peak_gfetch,
+                                        "note": "fetches the texture unit actually served: samples inside bricks known to be empty are not fetched (same results)"},
+                             "launch_ms": view_ms, "samples_per_launch": vs, "light_fetches_per_launch": vl, "rays_per_launch": vr, "skipped_per_launch": vk,
+                             "traffic": prof.get("k_ray_march_v", {}).get("dram_bytes") if prof else None,
+                             "ncu": prof.get("k_ray_march_v") if prof else None,
+                             "l2": {"achieved": issued * 64.0, "peak": l2_peak_gbs, "unit": "GB/s", "frac": issued * 64.0 / l2_peak_gbs,
+                                    "note": "64 B trilinear RGBA16F footprint per issued fetch against the measured L2 read bandwidth (an upper bound on L2 -> L1 traffic: most footprints hit L1)"},
+                             "hbm": {"achieved": alg_bytes / sec / 1e9, "peak": hbm_peak, "unit": "GB/s", "frac": alg_bytes / sec / 1e9 / hbm_peak,
+                                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes}}}
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, wl)
+            line["cpu_baseline"], line["parity_checked"], line["parity"] = cpu_baseline(args, wl, make_caster)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+    del outs
+    r.close()
+    if world > 1:
         dist.destroy_process_group()
 
 
-def cpu_baseline(args, wl):
-    """The oracle on this box's host cores, a bounded sample of the same workload (whole frames)."""
-    subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")], stdout=subprocess.DEVNULL)
-    sys.path.insert(0, os.path.join(ROOT, "tests"))
-    from oracle_binding import OracleCaster
+def cpu_baseline(args, wl, make_caster):
+    """The oracle on this box's host cores, a bounded sample of the same workload (whole frames) — and, since those frames
+    are rendered anyway, the parity check of the product on the bench's own workload: a FRESH caster renders the same
+    frames from the same start state and its composited frame / RGBA8 back buffer are compared with the oracle's."""
     from multivolumes_b200 import scene
-    o = OracleCaster(filter_model=1, grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"),
-                     width=wl["w"], height=wl["h"])
+    o = make_oracle(wl, host_threads())
     build_scene(o, wl, scene, o.TransformSH(scene.procedural_sky(64)))
-    n, t0, samples = 0, time.perf_counter(), 0
-    while n < args.cpu_baseline_frames and (n == 0 or time.perf_counter() - t0 < 25.0):
-        vp, eye = camera(scene, wl, args.warmup + n)
-        o.UpdateFrame(vp, None, eye); o.ResetColor(); o.Render(); o.Postprocess(wl["taa"])
+    p = make_caster()
+    sky = o.TransformSH(scene.procedural_sky(64)) if wl["sh"] else None
+    for c in (o, p):
+        c.SetSH(sky)                       # identical coefficients on both sides (the SH projection has its own parity test)
+    n, t_cpu, samples = 0, 0.0, 0
+    while n < args.cpu_baseline_frames and (n == 0 or t_cpu < 25.0):
+        i = args.warmup + n
+        t0 = time.perf_counter()
+        step_frame(o, wl, scene, i, lambda vp, svp, eye: (o.UpdateFrame(vp, svp, eye), o.ResetColor(), o.Render(), o.Postprocess(wl["taa"])))
+        t_cpu += time.perf_counter() - t0
+        step_frame(p, wl, scene, i, lambda vp, svp, eye: (p.UpdateFrame(vp, svp, eye), p.ResetColor(), p.Render(), p.Postprocess(wl["taa"])))
         st = o.GetStats(); samples += st["view_samples"] + st["direct_samples"] + st["light_samples"]
         n += 1
-    dt = time.perf_counter() - t0
-    return {"value": n / dt, "unit": "frames/s", "cores": o.GetStats()["threads"], "kind": "port",
-            "sample": f"{n} whole frames of the same workload (frames {args.warmup}..{args.warmup + n - 1} of the orbit)",
-            "samples_per_s": samples / dt}
+    fo, fp = o.ReadFrame().astype(np.float32), p.ReadFrame().astype(np.float32)
+    (_, bo), (_, bp) = o.ReadPost(), p.ReadPost()
+    err = np.abs(fo - fp) / np.maximum(1.0, np.abs(fo))
+    mse = float(np.mean((fo - fp) ** 2))
+    parity = {"frames": n, "visible_lists_equal": bool(np.array_equal(o.ReadVisible(), p.ReadVisible()) and np.array_equal(o.ReadCubeVolumes(), p.ReadCubeVolumes())),
+              "frame_bit_exact": bool(np.array_equal(o.ReadFrame().view(np.uint16), p.ReadFrame().view(np.uint16))),
+              "frame_max_abs": float(err.max()), "frame_psnr_db": None if mse == 0 else float(10 * np.log10(max(float(np.abs(fo).max()), 1.0) ** 2 / mse)),
+              "rgba8_max_diff": int(np.abs(bo.astype(int) - bp.astype(int)).max()),
+              "bar": "visible lists bit-exact; frame max-abs <= 2e-3 and PSNR >= 50 dB (BASELINE.json north_star)"}
+    ok = parity["visible_lists_equal"] and parity["frame_max_abs"] <= 2e-3 and (parity["frame_psnr_db"] is None or parity["frame_psnr_db"] >= 50.0)
+    p.close()
+    return ({"value": n / t_cpu, "unit": "frames/s", "cores": o.GetStats()["threads"], "kind": "port",
+             "sample": f"{n} whole frames of the same workload (frames {args.warmup}..{args.warmup + n - 1} of the orbit, from a fresh caster)",
+             "samples_per_s": samples / t_cpu}, bool(ok), parity)
 
 
 if __name__ == "__main__":

@@ -32,7 +32,9 @@ enum mv_status {
     MV_ERR_INVALID = -1,     /* bad argument */
     MV_ERR_NOMEM = -2,       /* host or device allocation failed */
     MV_ERR_CUDA = -3,        /* a CUDA call failed; see mv_last_error */
-    MV_ERR_NO_DEVICE = -4    /* no usable CUDA device (the product has no CPU path) */
+    MV_ERR_NO_DEVICE = -4,   /* no usable CUDA device (the product has no CPU path) */
+    MV_ERR_PEER_TIMEOUT = -5 /* multi-GPU: a peer did not reach a device-side barrier within ~2 s; the frames rendered since the
+                                last successful mv_sync / mv_present_wait / mv_peer_barrier are not valid */
 };
 
 /* mv_desc.flags */
@@ -200,6 +202,13 @@ int mv_sync(mv_caster* c);
 /* pinned host memory for the read-backs / uploads of a frame loop */
 void* mv_host_alloc(size_t bytes);
 void  mv_host_free(void* p);
+/* page-lock memory the caller owns (e.g. a POSIX shared-memory frame that the ranks of a multi-GPU run all map) */
+int   mv_host_register(void* p, size_t bytes);
+int   mv_host_unregister(void* p);
+/* Present of a sharded frame: like mv_present_async, but copies only the rows THIS rank resolved (its band or stripes) to
+ * their place in `host_frame_rgba8` (the whole H x W frame, e.g. shared by all ranks' processes), over this rank's own
+ * PCIe link — no rank has to carry the whole frame. */
+int   mv_present_rows_async(mv_caster* c, uint8_t* host_frame_rgba8_pinned, uint32_t slot);
 
 /* ---- multi-GPU (one process per GPU; no counterpart in the single-adapter reference) ----
  * Partition (BASELINE.json north_star): the cull is replicated; volume v's cube map is marched by
@@ -222,6 +231,10 @@ typedef struct mv_exchange_layout {
     uint64_t flags_offset, flags_bytes;
     uint32_t light_slab_depth;                          /* ceil(L / world) */
     uint32_t reserved;
+    uint64_t light_staging2_offset;                     /* second staging buffer (frames pipelined across ranks alternate) */
+    uint64_t history_offset[2], history_bytes;          /* the two TAA history images, H x W RGBA16F: a rank's TAA output rows
+                                                           are stored into every peer's image too, because the next frame's
+                                                           history fetch (uv - velocity, bilinear) may land on any row */
 } mv_exchange_layout;
 
 int mv_set_shard(mv_caster* c, uint32_t rank, uint32_t world);

@@ -30,7 +30,8 @@ class Timings(C.Structure):
 class ExchangeLayout(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("block_bytes", "arena_offset", "arena_bytes", "light_staging_offset", "light_staging_bytes",
                                           "back_buffer_offset", "back_buffer_bytes", "flags_offset", "flags_bytes")] + \
-               [("light_slab_depth", u32), ("reserved", u32)]
+               [("light_slab_depth", u32), ("reserved", u32), ("light_staging2_offset", C.c_uint64),
+                ("history_offset", C.c_uint64 * 2), ("history_bytes", C.c_uint64)]
 
 
 class DdsInfo(C.Structure):
@@ -65,6 +66,9 @@ _EXTRA = {
     "obj_free": (None, [P(f32), P(u32)]),
     "mesh_load_obj": (C.c_int, [_vp, C.c_char_p]),
     "present_async": (C.c_int, [_vp, _vp, u32]),
+    "present_rows_async": (C.c_int, [_vp, _vp, u32]),
+    "host_register": (C.c_int, [_vp, C.c_size_t]),
+    "host_unregister": (C.c_int, [_vp]),
     "present_wait": (C.c_int, [_vp, u32]),
 }
 
@@ -176,6 +180,10 @@ class MultiRayCaster(CasterBase):
     def PresentAsync(self, rgba8_ptr, slot):
         """Swap-chain Present: asynchronous read-back of the back buffer into pinned memory (slot < 3 in flight)."""
         self._ck(self.b.present_async(self.h, rgba8_ptr, slot), "present_async")
+
+    def PresentRowsAsync(self, frame_ptr, slot):
+        """Present of a sharded frame: this rank's rows into the whole-frame host buffer (shared by the ranks)."""
+        self._ck(self.b.present_rows_async(self.h, frame_ptr, slot), "present_rows_async")
 
     def PresentWait(self, slot):
         self._ck(self.b.present_wait(self.h, slot), "present_wait")

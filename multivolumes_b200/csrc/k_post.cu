@@ -13,36 +13,39 @@ namespace MV_VARIANT {
 
 namespace {
 
-MV_D V3 rgb_to_ycocg(V3 rgb)   // :78-85
+// Stated evaluation order of this pass (the test oracle states the same one): YCoCg as sums and doublings, every division as a
+// multiplication by the correctly rounded reciprocal (rcp, mv_math.cuh) or by the reciprocal constant, fused multiply-adds
+// (fma1) exactly where written. dxc compiles the reference with fast-math: its DXIL multiplies by reciprocals too.
+MV_D V3 rgb_to_ycocg(V3 rgb)   // :78-85: (1 2 1; 2 0 -2; -1 2 -1)
 {
-    const float y = (rgb.x * 1.0f + rgb.y * 2.0f) + rgb.z * 1.0f;
-    const float co = (rgb.x * 2.0f + rgb.y * 0.0f) + rgb.z * -2.0f;
-    const float cg = (rgb.x * -1.0f + rgb.y * 2.0f) + rgb.z * -1.0f;
-    return {y, co, cg};
+    const float g2 = rgb.y + rgb.y;
+    return {(rgb.x + g2) + rgb.z, (rgb.x - rgb.z) + (rgb.x - rgb.z), (g2 - rgb.x) - rgb.z};
 }
-MV_D V3 ycocg_to_rgb(V3 v)     // :90-101
-{
-    const float y = v.x * 0.25f, co = v.y * 0.25f, cg = v.z * 0.25f;
-    return {y + co - cg, y + cg, y - co - cg};
-}
-MV_D V3 TM(V3 hdr) { const V3 c = rgb_to_ycocg(hdr); const float d = 4.0f + c.x; return {c.x / d, c.y / d, c.z / d}; }   // :106-114
-MV_D V3 ITM(V3 c) { const float s = 4.0f / (1.0f - c.x); return ycocg_to_rgb(V3{c.x * s, c.y * s, c.z * s}); }         // :119-128
+MV_D V3 TM(V3 hdr) { const V3 c = rgb_to_ycocg(hdr); const float q = rcp(4.0f + c.x); return {c.x * q, c.y * q, c.z * q}; }   // :106-114
+// :119-128 with :90-101 folded in: (c * (4 / (1 - c.x))) * 0.25 = c * rcp(1 - c.x) — scaling by 4 and by 0.25 is exact
+MV_D V3 ITM(V3 c) { const float q = rcp(1.0f - c.x); const float y = c.x * q, co = c.y * q, cg = c.z * q; return {y + co - cg, y + cg, y - co - cg}; }
+MV_D float lerpf(float a, float b, float t) { return fma1(b - a, t, a); }   // lerp as one fused multiply-add
 
-MV_D uchar4 tone_map(uint2 taaTexel)   // PSToneMap.hlsl:19-28 + RGBA8_UNORM render-target write
+// PSToneMap.hlsl:19-28 + the RGBA8_UNORM render-target write, for ONE channel value. The tone map's input is an RGBA16F
+// texel, so the whole function is a table over the 65536 half patterns (k_build_tone_lut fills it with exactly this code).
+MV_D unsigned char tone_map_channel(float v)
 {
-    const V4 src = unpack_half4(taaTexel);
-    const float in[3] = {src.x, src.y, src.z};
-    unsigned char out[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        float v = in[k];
-        v *= 1.05f / (v + 0.7f);
-        v = pow125(fabsf(v));
-        float sat = saturate(v);
-        if (!(v == v)) sat = 0.0f;
-        out[k] = (unsigned char)floorf(sat * 255.0f + 0.5f);
-    }
-    return make_uchar4(out[0], out[1], out[2], 255);
+    v *= 1.05f / (v + 0.7f);
+    v = pow125(fabsf(v));
+    float sat = saturate(v);
+    if (!(v == v)) sat = 0.0f;
+    return (unsigned char)floorf(sat * 255.0f + 0.5f);
+}
+
+__global__ void __launch_bounds__(256) k_build_tone_lut(unsigned char* lut)
+{
+    const uint32_t h = blockIdx.x * 256 + threadIdx.x;
+    lut[h] = tone_map_channel(f16_to_f32((uint16_t)h));
+}
+
+MV_D uchar4 tone_map(uint2 taaTexel, const unsigned char* __restrict__ lut)
+{
+    return make_uchar4(__ldg(lut + (taaTexel.x & 0xffffu)), __ldg(lut + (taaTexel.x >> 16)), __ldg(lut + (taaTexel.y & 0xffffu)), 255);
 }
 
 struct PostArgs {
@@ -52,9 +55,12 @@ struct PostArgs {
     uint2* out;               // TAA output (next frame's history)
     uchar4* backBuffer;       // RGBA8
     uchar4* peerBackBuffer;   // rank 0's back buffer when this rank resolves a band of a multi-GPU frame
+    uint2* peerOut[kMaxPeers]; // the peers' copies of `out` (multi-GPU, peers mapped): the next frame's history fetch of ANY rank may land on these rows
+    int numPeers;
     int W, H, row0, row1;
     int stripeH, rank, world;   // stripeH > 0: interleaved stripes instead of the band
     int taaOn;
+    const unsigned char* toneLut;   // [65536] tone map + RGBA8 quantisation of every half pattern
 };
 
 MV_D V4 load_c(const uint2* img, int x, int y, int W, int H)   // Texture2D[] load: out of bounds -> 0
@@ -96,7 +102,8 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
             const size_t pix = (size_t)y * W + x;
             const uint2 t = __ldg(a.color + pix);
             a.out[pix] = t;
-            const uchar4 bb = tone_map(t);
+            for (int p = 0; p < a.numPeers; ++p) if (a.peerOut[p]) a.peerOut[p][pix] = t;
+            const uchar4 bb = tone_map(t, a.toneLut);
             a.backBuffer[pix] = bb;
             if (a.peerBackBuffer) a.peerBackBuffer[pix] = bb;
         }
@@ -116,39 +123,40 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
     const int offs[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};   // :46-50
     const float historyMax = 15.0f;                                                                   // :41-43
     const V2 texSize = {(float)W, (float)H};
-    const V2 uv = {((float)x + 0.5f) / texSize.x, ((float)y + 0.5f) / texSize.y};
+    const V2 invSize = {1.0f / texSize.x, 1.0f / texSize.y};
+    const V2 uv = {((float)x + 0.5f) * invSize.x, ((float)y + 0.5f) * invSize.y};
     const float4 own = s_tm[ty + 1][tx + 1];
     // VelocityMax :133-161
     V2 vmax = load_v(a.velocity, x, y, W, H);
-    float speedSq = dot(vmax, vmax);
+    float speedSq = fma1(vmax.x, vmax.x, vmax.y * vmax.y);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const V2 nb = load_v(a.velocity, x + offs[i + 4][0], y + offs[i + 4][1], W, H);
-        const float sq = dot(nb, nb);
+        const float sq = fma1(nb.x, nb.x, nb.y * nb.y);
         if (sq > speedSq) { vmax = nb; speedSq = sq; }
     }
     const V2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
     // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp, fp32 weights
     V4 history;
     {
-        const float fx = uvBack.x * texSize.x - 0.5f, fy = uvBack.y * texSize.y - 0.5f;
+        const float fx = fma1(uvBack.x, texSize.x, -0.5f), fy = fma1(uvBack.y, texSize.y, -0.5f);
         const float flx = floorf(fx), fly = floorf(fy);
         const float wx = fx - flx, wy = fy - fly;
         const int ix = (int)flx, iy = (int)fly;
         const int xa = min(max(ix, 0), W - 1), xb = min(max(ix + 1, 0), W - 1);
         const int ya = min(max(iy, 0), H - 1), yb = min(max(iy + 1, 0), H - 1);
-        const V4 t00 = load_c(a.history, xa, ya, W, H), t10 = load_c(a.history, xb, ya, W, H);
-        const V4 t01 = load_c(a.history, xa, yb, W, H), t11 = load_c(a.history, xb, yb, W, H);
-        history = {lerp(lerp(t00.x, t10.x, wx), lerp(t01.x, t11.x, wx), wy), lerp(lerp(t00.y, t10.y, wx), lerp(t01.y, t11.y, wx), wy),
-                   lerp(lerp(t00.z, t10.z, wx), lerp(t01.z, t11.z, wx), wy), lerp(lerp(t00.w, t10.w, wx), lerp(t01.w, t11.w, wx), wy)};
+        const uint2* rowA = a.history + (size_t)ya * W;
+        const uint2* rowB = a.history + (size_t)yb * W;
+        const V4 t00 = unpack_half4(__ldg(rowA + xa)), t10 = unpack_half4(__ldg(rowA + xb));
+        const V4 t01 = unpack_half4(__ldg(rowB + xa)), t11 = unpack_half4(__ldg(rowB + xb));
+        history = {lerpf(lerpf(t00.x, t10.x, wx), lerpf(t01.x, t11.x, wx), wy), lerpf(lerpf(t00.y, t10.y, wx), lerpf(t01.y, t11.y, wx), wy),
+                   lerpf(lerpf(t00.z, t10.z, wx), lerpf(t01.z, t11.z, wx), wy), lerpf(lerpf(t00.w, t10.w, wx), lerpf(t01.w, t11.w, wx), wy)};
     }
     // :267-275
-    const V2 historyBlurAmp = {4.0f * texSize.x, 4.0f * texSize.y};
-    const V2 historyBlurs = {fabsf(vmax.x) * historyBlurAmp.x, fabsf(vmax.y) * historyBlurAmp.y};
-    float curHistoryBlur = historyBlurs.x + historyBlurs.y;
+    float curHistoryBlur = fma1(fabsf(vmax.x), 4.0f * texSize.x, fabsf(vmax.y) * (4.0f * texSize.y));
     float historyBlur = 1.0f - history.w;
     historyBlur = fmaxf(historyBlur, curHistoryBlur);
-    history.w = history.w * historyMax + 1.0f;
+    history.w = fma1(history.w, historyMax, 1.0f);
     // :278-287 (ALPHA_BOUND = 1.0)
     const V4 currentTM = {own.x, own.y, own.z, own.w};
     const float gamma = (historyBlur > 0.0f || own.w < 1.0f) ? 1.0f : 16.0f;
@@ -161,16 +169,16 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
     for (int i = 0; i < 8; ++i) {
         const float wgt = i < 4 ? 0.5f : 0.25f;
         const float4 nb = s_tm[ty + 1 + offs[i][1]][tx + 1 + offs[i][0]];
-        const V3 ntm = {nb.x, nb.y, nb.z};
-        const V4 neighbor = {ntm.x, ntm.y, ntm.z, nb.w < 1.0f ? 0.0f : 1.0f};
-        cur = cur + neighbor * wgt;
-        mu = mu + ntm;
-        m2 = m2 + ntm * ntm;
+        const float na = nb.w < 1.0f ? 0.0f : 1.0f;
+        cur = {fma1(nb.x, wgt, cur.x), fma1(nb.y, wgt, cur.y), fma1(nb.z, wgt, cur.z), fma1(na, wgt, cur.w)};
+        mu = {mu.x + nb.x, mu.y + nb.y, mu.z + nb.z};
+        m2 = {fma1(nb.x, nb.x, m2.x), fma1(nb.y, nb.y, m2.y), fma1(nb.z, nb.z, m2.z)};
     }
-    cur = {cur.x / 4.0f, cur.y / 4.0f, cur.z / 4.0f, cur.w / 4.0f};
-    mu = mu / 9.0f;
-    const V3 m2n = m2 / 9.0f;
-    const V3 sigma = {sqrtf(fabsf(m2n.x - mu.x * mu.x)), sqrtf(fabsf(m2n.y - mu.y * mu.y)), sqrtf(fabsf(m2n.z - mu.z * mu.z))};
+    const float ninth = 1.0f / 9.0f;
+    cur = cur * 0.25f;
+    mu = mu * ninth;
+    const V3 m2n = m2 * ninth;
+    const V3 sigma = {sqrtf(fabsf(fma1(-mu.x, mu.x, m2n.x))), sqrtf(fabsf(fma1(-mu.y, mu.y, m2n.y))), sqrtf(fabsf(fma1(-mu.z, mu.z, m2n.z)))};
     const V3 gsigma = sigma * gamma;
     V4 nmin, nmax;
     nmin.x = fminf(mu.x - gsigma.x, cur.x); nmin.y = fminf(mu.y - gsigma.y, cur.y); nmin.z = fminf(mu.z - gsigma.z, cur.z);
@@ -186,29 +194,34 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
     const float contrast = nmax.w - nmin.w;
     // :304-311
     const float lumContrastFactor = 32.0f * 4.0f;
-    float addAlias = historyBlur * 0.5f + 0.25f;
-    addAlias = saturate(addAlias + 1.0f / (1.0f + contrast * lumContrastFactor));
-    filtered.x = lerp(filtered.x, currentTM.x, addAlias); filtered.y = lerp(filtered.y, currentTM.y, addAlias);
-    filtered.z = lerp(filtered.z, currentTM.z, addAlias);
+    float addAlias = fma1(historyBlur, 0.5f, 0.25f);
+    addAlias = saturate(addAlias + rcp(fma1(contrast, lumContrastFactor, 1.0f)));
+    filtered.x = lerpf(filtered.x, currentTM.x, addAlias); filtered.y = lerpf(filtered.y, currentTM.y, addAlias);
+    filtered.z = lerpf(filtered.z, currentTM.z, addAlias);
     // :314-326
     const float lumHist = historyTM.x;
     const float distToClamp = fminf(fabsf(nmin.w - lumHist), fabsf(nmax.w - lumHist));
-    const float historyAmt = fminf(1.0f / history.w + historyBlur / 8.0f, 1.0f);
-    float blend = 0.25f / lerp(8.0f, distToClamp + contrast, historyAmt);
+    const float historyAmt = fminf(fma1(historyBlur, 0.125f, rcp(history.w)), 1.0f);
+    float blend = 0.25f * rcp(lerpf(8.0f, distToClamp + contrast, historyAmt));
     blend = fminf(blend, 0.25f);
     blend = filtered.w > 0.0f ? blend : 1.0f;
     // :328-330
-    V3 result = ITM(V3{lerp(historyTM.x, filtered.x, blend), lerp(historyTM.y, filtered.y, blend), lerp(historyTM.z, filtered.z, blend)});
+    V3 result = ITM(V3{lerpf(historyTM.x, filtered.x, blend), lerpf(historyTM.y, filtered.y, blend), lerpf(historyTM.z, filtered.z, blend)});
     if (result.x != result.x || result.y != result.y || result.z != result.z) result = ITM(V3{filtered.x, filtered.y, filtered.z});
-    history.w = fminf(history.w / historyMax, 1.0f - curHistoryBlur);
+    history.w = fminf(history.w * (1.0f / historyMax), 1.0f - curHistoryBlur);
     const uint2 outTexel = pack_half4(V4{result.x, result.y, result.z, history.w});
     a.out[pix] = outTexel;
-    const uchar4 bb = tone_map(outTexel);
+    for (int p = 0; p < a.numPeers; ++p) if (a.peerOut[p]) a.peerOut[p][pix] = outTexel;
+    const uchar4 bb = tone_map(outTexel, a.toneLut);
     a.backBuffer[pix] = bb;
     if (a.peerBackBuffer) a.peerBackBuffer[pix] = bb;
 }
 
 } // namespace
+
+#if !MV_FAST
+void build_tone_lut(Caster& c) { k_build_tone_lut<<<256, 256, 0, c.stream>>>(c.dToneLut); }
+#endif
 
 void launch_postprocess(Caster& c, bool taaOn)
 {
@@ -220,9 +233,12 @@ void launch_postprocess(Caster& c, bool taaOn)
     a.out = c.dHistory[c.frameParity];
     a.backBuffer = c.dBackBuffer;
     a.peerBackBuffer = c.dPeerBackBuffer;
+    a.numPeers = (c.shardWorld > 1 && c.peersMapped) ? (int)c.shardWorld : 0;
+    for (int p = 0; p < kMaxPeers; ++p) a.peerOut[p] = p < a.numPeers ? c.peerHistory[p][c.frameParity] : nullptr;
     a.W = (int)c.d.width; a.H = (int)c.d.height;
     a.row0 = (int)c.row0; a.row1 = (int)c.row1;
     a.taaOn = taaOn ? 1 : 0;
+    a.toneLut = c.dToneLut;
     const bool stripes = c.shardWorld > 1 && c.stripeH;
     a.stripeH = stripes ? (int)c.stripeH : 0; a.rank = (int)c.shardRank; a.world = (int)c.shardWorld;
     const uint32_t blockRows = stripes ? num_own_stripes(c.d.height, c.stripeH, c.shardRank, c.shardWorld) * ((c.stripeH + kPostH - 1) / kPostH)

@@ -602,7 +602,8 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
         tgt.staging = c.dLightStaging;
         tgt.numPeers = c.peersMapped ? c.shardWorld : 0;
         for (uint32_t p = 0; p < tgt.numPeers; ++p)
-            tgt.peerStaging[p] = (p == c.shardRank) ? nullptr : reinterpret_cast<uint2*>(c.peerBlock[p] + c.layout.light_staging_offset);
+            tgt.peerStaging[p] = (p == c.shardRank) ? nullptr
+                : reinterpret_cast<uint2*>(c.peerBlock[p] + (c.stagingParity ? c.layout.light_staging2_offset : c.layout.light_staging_offset));
     }
     if (c.lightToStaging) tgt.staging = c.dLightStaging;   // pipelined frame: the main stream commits it (mv_api.cu)
     if (tgt.z1 <= tgt.z0) return;

@@ -208,9 +208,15 @@ static void wait_back_buffer_free(Caster& c)
             MV_CUDA(cudaMalloc(&(c).dDirectStats, std::max<size_t>((c).directCapacity, 1) * sizeof(uint2)));    \
     } while (0)
 
+// Frames are pipelined (cull + light march of frame i + 1 on the light stream beside frame i's view march / resolve /
+// post-process on the main stream) on one GPU and, with the peers mapped, across the ranks of a sharded frame.
+static bool pipelined_sharded(const Caster& c)
+{
+    return c.overlapLight && c.shardPipeline && c.shardWorld > 1 && c.peersMapped && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES));
+}
 static bool pipelined(const Caster& c)
 {
-    return c.overlapLight && c.shardWorld == 1 && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES));
+    return (c.overlapLight && c.shardWorld == 1 && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES))) || pipelined_sharded(c);
 }
 
 // A new frame's lists and attributes go into the other buffer (the previous frame's resolve may still read its own)
@@ -248,9 +254,10 @@ static void destroy_caster(Caster& c)
     for (auto& v : c.lightMaps) kill(v);
     void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject2[0], c.dPerObject2[1], c.dVolumeDescs, c.dAttribs2[0], c.dAttribs2[1],
                      c.dLists2[0], c.dLists2[1], c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
-                     c.dOcc, c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dHistory[0], c.dHistory[1], c.dScratch, c.dPeerFlagPtrs};
+                     c.dOcc, c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dScratch, c.dPeerFlagPtrs, c.dToneLut};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
+    if (c.hTimeout) cudaFreeHost(c.hTimeout);
     for (auto& e : c.ev) if (e) cudaEventDestroy(e);
     for (auto& e : c.uploadDone) if (e) cudaEventDestroy(e);
     for (auto& e : c.presentDone) if (e) cudaEventDestroy(e);
@@ -328,6 +335,7 @@ int mv_create(const mv_desc* d, mv_caster** out)
             MV_CUDA_C(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         if (const char* e = getenv("MV_OVERLAP")) c.overlapLight = atoi(e);
         if (const char* e = getenv("MV_SHARD_V_BLOCKS")) c.shardViewBlocks = atoi(e);
+        if (const char* e = getenv("MV_SHARD_PIPELINE")) c.shardPipeline = atoi(e);
         MV_CUDA_C(cudaEventCreateWithFlags(&c.cullDone, cudaEventDisableTiming));
     }
     MV_CUDA_C(cudaEventCreateWithFlags(&c.frameDone, cudaEventDisableTiming));
@@ -383,12 +391,23 @@ int mv_create(const mv_desc* d, mv_caster** out)
     lay.back_buffer_bytes = (uint64_t)px * 4ull;
     lay.flags_offset = align256(lay.back_buffer_offset + lay.back_buffer_bytes);
     lay.flags_bytes = 256;
-    lay.block_bytes = lay.flags_offset + lay.flags_bytes;
+    lay.light_staging2_offset = align256(lay.flags_offset + lay.flags_bytes);
+    lay.history_bytes = (uint64_t)px * 8ull;
+    lay.history_offset[0] = align256(lay.light_staging2_offset + lay.light_staging_bytes);
+    lay.history_offset[1] = align256(lay.history_offset[0] + lay.history_bytes);
+    lay.block_bytes = lay.history_offset[1] + lay.history_bytes;
     lay.light_slab_depth = L;
     MV_CUDA_C(cudaMalloc(&c.dBlock, lay.block_bytes));
     MV_CUDA_C(cudaMemsetAsync(c.dBlock, 0, lay.block_bytes, c.stream));
     c.dArena = c.dBlock + lay.arena_offset;
-    c.dLightStaging = reinterpret_cast<uint2*>(c.dBlock + lay.light_staging_offset);
+    c.dLightStaging2[0] = reinterpret_cast<uint2*>(c.dBlock + lay.light_staging_offset);
+    c.dLightStaging2[1] = reinterpret_cast<uint2*>(c.dBlock + lay.light_staging2_offset);
+    c.dLightStaging = c.dLightStaging2[0];
+    c.dHistory[0] = reinterpret_cast<uint2*>(c.dBlock + lay.history_offset[0]);
+    c.dHistory[1] = reinterpret_cast<uint2*>(c.dBlock + lay.history_offset[1]);
+    MV_CUDA_C(cudaHostAlloc(&c.hTimeout, sizeof(uint32_t), cudaHostAllocMapped));
+    *c.hTimeout = 0;
+    MV_CUDA_C(cudaHostGetDevicePointer(&c.dTimeout, c.hTimeout, 0));
     c.dBackBuffer = reinterpret_cast<uchar4*>(c.dBlock + lay.back_buffer_offset);
     c.dFlags = reinterpret_cast<uint32_t*>(c.dBlock + lay.flags_offset);
     c.arena.base = c.dArena;
@@ -438,8 +457,6 @@ int mv_create(const mv_desc* d, mv_caster** out)
     MV_CUDA_C(cudaMalloc(&c.dColor, px * 8));
     MV_CUDA_C(cudaMalloc(&c.dBackground, px * 8));
     MV_CUDA_C(cudaMalloc(&c.dVelocity, px * 4));
-    MV_CUDA_C(cudaMalloc(&c.dHistory[0], px * 8));
-    MV_CUDA_C(cudaMalloc(&c.dHistory[1], px * 8));
     {
         std::vector<float> ones(px, 1.0f);
         MV_CUDA_C(cudaMemcpy(c.dDepth, ones.data(), px * sizeof(float), cudaMemcpyHostToDevice));
@@ -447,8 +464,8 @@ int mv_create(const mv_desc* d, mv_caster** out)
     MV_CUDA_C(cudaMemsetAsync(c.dColor, 0, px * 8, c.stream));
     MV_CUDA_C(cudaMemsetAsync(c.dBackground, 0, px * 8, c.stream));
     MV_CUDA_C(cudaMemsetAsync(c.dVelocity, 0, px * 4, c.stream));
-    MV_CUDA_C(cudaMemsetAsync(c.dHistory[0], 0, px * 8, c.stream));
-    MV_CUDA_C(cudaMemsetAsync(c.dHistory[1], 0, px * 8, c.stream));
+    MV_CUDA_C(cudaMalloc(&c.dToneLut, 65536));
+    strict::build_tone_lut(c);
     c.scratchBytes = (size_t)c.smCount * 4 * 8 * 28 * sizeof(float);
     MV_CUDA_C(cudaMalloc(&c.dScratch, c.scratchBytes));
 
@@ -767,10 +784,43 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         set_error("sharded caster without mapped peers: run the passes and the collectives one by one (mv_cull, mv_ray_march_light, ...)");
         return MV_ERR_INVALID;
     }
+    if (const int rc = check_peer_timeout(c)) return rc;
     flip_frame_lists(c);
     const uint32_t slot = c.listParity;             // frameEnd slot of this frame
     c.poLastUse[c.poParity] = (int)slot;
-    if (pipelined(c)) {
+    if (pipelined_sharded(c)) {
+        // Sharded frame, pipelined across frames. Light stream: cull -> this rank's z-slab of the light map, stored into every
+        // rank's staging buffer (two buffers, alternating) -> signal on the light channel. Main stream: wait for every
+        // rank's slab -> commit -> view march (texels into every arena) -> barrier -> screen-space march + resolve of this
+        // rank's rows; mv_postprocess ends the frame with the closing barrier. What keeps the streams and ranks apart:
+        //   * lists, attributes and PerObject records are double-buffered; the light stream waits for the frame before last
+        //     (frameEnd), whose buffers it overwrites;
+        //   * by then every rank has committed the staging buffer this frame's slabs go into: a rank's resolve of frame
+        //     i - 2 follows the barrier after that frame's view march, which every rank signals after its commit;
+        //   * peers store frame i's cube-map texels into this rank's arena only after the closing barrier of frame i - 1,
+        //     i.e. after this rank's resolve of frame i - 1 has read it.
+        cudaStream_t mainStream = c.stream, B = c.lightStream;
+        wait_upload(c, B);
+        if (c.inputsDirty) { MV_CUDA(cudaEventRecord(c.inputsReady, mainStream)); MV_CUDA(cudaStreamWaitEvent(B, c.inputsReady, 0)); c.inputsDirty = false; }
+        if (c.frameEndValid[slot]) MV_CUDA(cudaStreamWaitEvent(B, c.frameEnd[slot], 0));
+        c.stagingParity ^= 1u;
+        c.dLightStaging = c.dLightStaging2[c.stagingParity];
+        c.stream = B;
+        launch_cull(c);
+        launch_ray_march_light(c, -1);
+        launch_peer_signal(c, kBarrierLight);
+        c.stream = mainStream;
+        MV_CUDA(cudaEventRecord(c.lightDone, B));
+        c.lightDoneValid = true;
+        MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
+        launch_peer_wait(c, kBarrierLight);
+        launch_light_commit(c);
+        launch_ray_march_view(c);
+        wait_back_buffer_free(c);                   // once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
+        launch_peer_barrier(c);                     // every rank's cube-map texels have landed
+        launch_ray_cast_direct(c);
+        launch_resolve_oit(c);
+    } else if (pipelined(c)) {
         // light stream: cull -> light march into the staging buffer. Waits: the PerObject upload; inputs changed on the main
         // stream since the last frame (volumes, depth / shadow targets); the frame before last, whose lists this frame
         // overwrites; the previous frame's commit, which reads the staging buffer.
@@ -881,6 +931,10 @@ int mv_postprocess(mv_caster* h, uint32_t taa)
     if (!c.evValid[4]) record(c, 4);
     wait_back_buffer_free(c);
     launch_postprocess(c, taa != 0);
+    // Sharded, peers mapped: the frame ends with a barrier — rank 0 holds every rank's rows, every peer's TAA history holds
+    // this rank's rows, and no rank starts storing the next frame's cube-map texels into a peer's arena while that peer's
+    // resolve still reads it. Part of the call, so that a C-ABI user cannot leave it out.
+    if (c.shardWorld > 1 && c.peersMapped) launch_peer_barrier(c);
     record(c, 5);
     return check_launch("k_postprocess");
 }
@@ -1014,7 +1068,7 @@ int mv_present_wait(mv_caster* h, uint32_t slot)
     MV_ENTER(h);
     MV_REQUIRE(slot < MV_PRESENT_SLOTS);
     if (c.presentPending[slot]) { MV_CUDA(cudaEventSynchronize(c.presentDone[slot])); c.presentPending[slot] = false; }
-    return MV_OK;
+    return check_peer_timeout(c);
 }
 
 int mv_get_stats(mv_caster* h, mv_stats* out)
@@ -1075,7 +1129,7 @@ int mv_sync(mv_caster* h)
     MV_ENTER(h);
     MV_CUDA(cudaStreamSynchronize(c.lightStream));
     MV_CUDA(cudaStreamSynchronize(c.stream));
-    return MV_OK;
+    return check_peer_timeout(c);
 }
 
 void* mv_host_alloc(size_t bytes)

@@ -192,7 +192,11 @@ void launch_cull(Caster& c);
 void launch_pick_light_volume(Caster& c);
 void launch_sh_project(Caster& c, const float* devCube, uint32_t size, float* devOut27);
 void launch_light_commit(Caster& c);
-void launch_peer_barrier(Caster& c);
+constexpr uint32_t kBarrierMain = 0, kBarrierLight = 1;
+void launch_peer_barrier(Caster& c);                       // signal + wait on the main channel
+void launch_peer_signal(Caster& c, uint32_t channel);
+void launch_peer_wait(Caster& c, uint32_t channel);
+int check_peer_timeout(Caster& c);                          // MV_ERR_PEER_TIMEOUT once after a k_peer_wait gave up
 
 // The two ALU-bound image passes (OIT resolve incl. the screen-space march it shares its fragment test with, TAA + tone
 // map) are compiled twice from the same sources (csrc/Makefile):
@@ -213,7 +217,7 @@ void launch_peer_barrier(Caster& c);
     void launch_ray_cast_direct(Caster& c);         \
     void launch_resolve_oit(Caster& c);             \
     void launch_postprocess(Caster& c, bool taaOn);
-namespace strict { MV_DECLARE_VARIANT_LAUNCHERS }
+namespace strict { MV_DECLARE_VARIANT_LAUNCHERS void build_tone_lut(Caster& c); }
 namespace fast { MV_DECLARE_VARIANT_LAUNCHERS }
 void launch_ray_march_light(Caster& c, int volumeOverride);
 // phase 0: every cube-map volume; 1: all but the frame's light volume (at most blocksPerSM CTAs per SM, 0 = all that fit);
@@ -283,8 +287,13 @@ struct Caster {
     unsigned char* dArena = nullptr;     // = dBlock + layout.arena_offset
     size_t arenaBytes = 0;
     CubeArena arena{};
-    uint2* dLightStaging = nullptr;      // inside the block
-    uint32_t* dFlags = nullptr;          // inside the block: [kMaxPeers] arrival counters
+    uint2* dLightStaging = nullptr;      // inside the block: the staging buffer the current light march fills
+    uint2* dLightStaging2[2] = {};       // the two staging buffers (frames pipelined across ranks alternate)
+    uint32_t stagingParity = 0;
+    uint32_t* dFlags = nullptr;          // inside the block: arrival counters, [channel][kMaxPeers] (kBarrierMain, kBarrierLight)
+    uint32_t* hTimeout = nullptr;        // mapped pinned word a timed-out k_peer_wait sets (read by the host without a copy)
+    uint32_t* dTimeout = nullptr;        // its device address
+    uint32_t barrierSeqCh[2] = {0, 0};
     unsigned char* peerBlock[kMaxPeers] = {};
     uint32_t barrierSeq = 0;
     uint32_t** dPeerFlagPtrs = nullptr;  // [kMaxPeers] flag arrays of every rank (peer-mapped)
@@ -307,6 +316,7 @@ struct Caster {
     int shardViewBlocks = -1;
     cudaEvent_t cullDone = nullptr;      // sharded frame: main stream -> light stream
     int overlapLight = 1;                // MV_OVERLAP=0: every pass on the main stream
+    int shardPipeline = 1;               // MV_SHARD_PIPELINE=0: sharded frames are not pipelined across frames (mv_api.cu)
     PerObject* dPerObject2[2] = {};      // dPerObject points at the one of the last mv_update_frame
     ushort4* dAttribs2[2] = {};
     unsigned char* dLists2[2] = {};
@@ -325,8 +335,10 @@ struct Caster {
     uint2* dBackground = nullptr;        // copy of the colour RT given to set_targets
     uint32_t* dVelocity = nullptr;       // RG16F
     uint2* dHistory[2] = {nullptr, nullptr};
+    unsigned char* dToneLut = nullptr;   // [65536] PSToneMap + RGBA8 write of every half pattern (k_post.cu)
     uchar4* dBackBuffer = nullptr;
     uchar4* dPeerBackBuffer = nullptr;   // rank 0's back buffer (peer-mapped) in a multi-GPU run
+    uint2* peerHistory[kMaxPeers][2] = {};   // the peers' TAA history images (peer-mapped; nullptr for this rank)
     float* dScratch = nullptr;           // SH projection partial sums
     size_t scratchBytes = 0;
     // sharding

@@ -61,6 +61,26 @@ MV_HD float sign(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0
 MV_HD float frac(float x) { return x - floorf(x); }
 MV_HD float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 MV_HD float clamp1(float x) { return fminf(fmaxf(x, -1.0f), 1.0f); }
+// Division, where the image passes (OIT resolve, TAA) divide: x / d is evaluated as x * rcp(d) with rcp the CORRECTLY ROUNDED
+// reciprocal — reproducible by any IEEE implementation as 1.0f / d — which is also what dxc's fast-math default turns the
+// reference's divisions into (the shipped DXIL multiplies by reciprocals). Half the cost of an IEEE divide.
+MV_HD float rcp(float d)
+{
+#ifdef __CUDA_ARCH__
+    return __frcp_rn(d);
+#else
+    return 1.0f / d;
+#endif
+}
+// a * b + c with ONE rounding, where the image passes fuse (written explicitly: the library is compiled without contraction)
+MV_HD float fma1(float a, float b, float c)
+{
+#ifdef __CUDA_ARCH__
+    return __fmaf_rn(a, b, c);
+#else
+    return fmaf(a, b, c);
+#endif
+}
 // pow(x, 0.25), pow(x, 1.25) through correctly rounded square roots
 MV_HD float pow025(float x) { return sqrtf(sqrtf(x)); }
 MV_HD float pow125(float x) { return x * sqrtf(sqrtf(x)); }

@@ -13,16 +13,19 @@ namespace mv {
 
 namespace {
 
-// Arrival counters: flags[r] on rank q is written by rank r. Each barrier bumps a sequence number;
-// a rank signals every peer (system-scope release after a system fence, so that the peer stores of
-// the kernels before it on this stream are visible first), then spins until every peer has signalled
-// the same sequence. A bounded spin (about 2 s) turns a dead peer into an error flag instead of a hang.
-__global__ void k_peer_signal(uint32_t* const* peerFlags, uint32_t world, uint32_t rank, uint32_t seq)
+// Arrival counters: flags[channel][r] on rank q is written by rank r. Each barrier of a channel bumps that channel's
+// sequence number; a rank signals every peer (system-scope release after a system fence, so that the peer stores of
+// the kernels before it on this stream are visible first), then spins until every peer has signalled the same
+// sequence. Two channels, because a pipelined sharded frame runs its light march (slab stores into the peers' staging
+// buffers, channel kBarrierLight) on the light stream beside the previous frame's passes on the main stream (cube-map
+// and back-buffer stores, channel kBarrierMain). A bounded spin (about 2 s) turns a dead peer into an error — a mapped
+// host word that mv_sync / mv_present_wait / mv_peer_barrier / mv_render report as MV_ERR_PEER_TIMEOUT — instead of a hang.
+__global__ void k_peer_signal(uint32_t* const* peerFlags, uint32_t world, uint32_t rank, uint32_t channel, uint32_t seq)
 {
     const uint32_t p = threadIdx.x;
     if (p >= world) return;
     __threadfence_system();
-    volatile uint32_t* dst = peerFlags[p] + rank;
+    volatile uint32_t* dst = peerFlags[p] + channel * kMaxPeers + rank;
     *dst = seq;
     __threadfence_system();
 }
@@ -33,7 +36,7 @@ __global__ void k_peer_wait(volatile uint32_t* flags, uint32_t world, uint32_t s
     if (p >= world) return;
     const long long t0 = clock64();
     while ((int32_t)(flags[p] - seq) < 0) {
-        if (clock64() - t0 > 4000000000ll) { *timeoutFlag = 1; break; }
+        if (clock64() - t0 > 4000000000ll) { *timeoutFlag = 1; __threadfence_system(); break; }
         __nanosleep(100);
     }
     __threadfence_system();
@@ -59,11 +62,31 @@ void launch_light_commit(Caster& c)
     k_light_commit<<<grid, 256, 0, c.stream>>>(c.scene(), c.dLightStaging, L);
 }
 
+void launch_peer_signal(Caster& c, uint32_t channel)
+{
+    ++c.barrierSeqCh[channel];
+    k_peer_signal<<<1, 32, 0, c.stream>>>(c.dPeerFlagPtrs, c.shardWorld, c.shardRank, channel, c.barrierSeqCh[channel]);
+}
+
+void launch_peer_wait(Caster& c, uint32_t channel)
+{
+    k_peer_wait<<<1, 32, 0, c.stream>>>(c.dFlags + channel * kMaxPeers, c.shardWorld, c.barrierSeqCh[channel], c.dTimeout);
+}
+
 void launch_peer_barrier(Caster& c)
 {
-    ++c.barrierSeq;
-    k_peer_signal<<<1, 32, 0, c.stream>>>(c.dPeerFlagPtrs, c.shardWorld, c.shardRank, c.barrierSeq);
-    k_peer_wait<<<1, 32, 0, c.stream>>>(c.dFlags, c.shardWorld, c.barrierSeq, c.dFlags + 32);
+    launch_peer_signal(c, kBarrierMain);
+    launch_peer_wait(c, kBarrierMain);
+}
+
+int check_peer_timeout(Caster& c)
+{
+    if (c.hTimeout && *reinterpret_cast<volatile uint32_t*>(c.hTimeout)) {
+        *reinterpret_cast<volatile uint32_t*>(c.hTimeout) = 0;
+        set_error("multi-GPU barrier timed out on rank %u: a peer did not arrive within ~2 s; the frames since the last successful sync are not valid", c.shardRank);
+        return MV_ERR_PEER_TIMEOUT;
+    }
+    return MV_OK;
 }
 
 } // namespace mv
@@ -92,6 +115,8 @@ static int refresh_peers(Caster& c)
         unsigned char* blk = (p == c.shardRank) ? c.dBlock : c.peerBlock[p];
         c.arena.peer[p] = (all && p != c.shardRank && p < c.shardWorld) ? blk + c.layout.arena_offset : nullptr;
         flagPtrs[p] = blk ? reinterpret_cast<uint32_t*>(blk + c.layout.flags_offset) : nullptr;
+        for (int k = 0; k < 2; ++k)
+            c.peerHistory[p][k] = (all && p != c.shardRank && p < c.shardWorld) ? reinterpret_cast<uint2*>(blk + c.layout.history_offset[k]) : nullptr;
     }
     if (!c.dPeerFlagPtrs) MV_CUDA(cudaMalloc(&c.dPeerFlagPtrs, sizeof flagPtrs));
     MV_CUDA(cudaMemcpyAsync(c.dPeerFlagPtrs, flagPtrs, sizeof flagPtrs, cudaMemcpyHostToDevice, c.stream));
@@ -184,7 +209,7 @@ int mv_peer_barrier(mv_caster* h)
     launch_peer_barrier(c);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MV_FAIL(MV_ERR_CUDA, "peer barrier launch failed: %s", cudaGetErrorString(e));
-    return MV_OK;
+    return check_peer_timeout(c);   // of an earlier barrier (this one has only been enqueued)
 }
 
 int mv_light_commit(mv_caster* h)
@@ -211,6 +236,50 @@ int mv_get_stream(mv_caster* h, void** stream)
     MV_ENTER(h);
     MV_REQUIRE(stream);
     *stream = c.stream;
+    return MV_OK;
+}
+
+int mv_host_register(void* p, size_t bytes)
+{
+    MV_REQUIRE(p && bytes);
+    MV_CUDA(cudaHostRegister(p, bytes, cudaHostRegisterPortable));
+    return MV_OK;
+}
+
+int mv_host_unregister(void* p)
+{
+    MV_REQUIRE(p);
+    MV_CUDA(cudaHostUnregister(p));
+    return MV_OK;
+}
+
+// Rows this rank resolved -> their place in the caller's whole-frame host buffer, on the copy stream (see mv_present_async).
+int mv_present_rows_async(mv_caster* h, uint8_t* host, uint32_t slot)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(host && slot < MV_PRESENT_SLOTS);
+    if (c.presentPending[slot]) { MV_CUDA(cudaEventSynchronize(c.presentDone[slot])); c.presentPending[slot] = false; }
+    MV_CUDA(cudaEventRecord(c.frameDone, c.stream));
+    MV_CUDA(cudaStreamWaitEvent(c.copyStream, c.frameDone, 0));
+    const size_t rowBytes = (size_t)c.d.width * 4;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(c.dBackBuffer);
+    if (c.shardWorld > 1 && c.stripeH) {
+        // the rank's k-th stripe is rows [(k world + rank) stripeH, ... + stripeH): one strided copy, plus a ragged last stripe
+        const uint32_t H = c.d.height, sh = c.stripeH, world = c.shardWorld, rank = c.shardRank;
+        const uint32_t own = num_own_stripes(H, sh, rank, world);
+        uint32_t full = own;
+        if (own) {
+            const uint32_t lastBegin = ((own - 1) * world + rank) * sh;
+            if (lastBegin + sh > H) --full;
+            const size_t ofs = (size_t)rank * sh * rowBytes, pitch = (size_t)world * sh * rowBytes;
+            if (full) MV_CUDA(cudaMemcpy2DAsync(host + ofs, pitch, src + ofs, pitch, (size_t)sh * rowBytes, full, cudaMemcpyDeviceToHost, c.copyStream));
+            if (full < own) MV_CUDA(cudaMemcpyAsync(host + (size_t)lastBegin * rowBytes, src + (size_t)lastBegin * rowBytes, (size_t)(H - lastBegin) * rowBytes, cudaMemcpyDeviceToHost, c.copyStream));
+        }
+    } else if (c.row1 > c.row0)
+        MV_CUDA(cudaMemcpyAsync(host + (size_t)c.row0 * rowBytes, src + (size_t)c.row0 * rowBytes, (size_t)(c.row1 - c.row0) * rowBytes, cudaMemcpyDeviceToHost, c.copyStream));
+    MV_CUDA(cudaEventRecord(c.presentDone[slot], c.copyStream));
+    c.presentPending[slot] = true;
+    c.backBufferBusy = (int)slot;
     return MV_OK;
 }
 

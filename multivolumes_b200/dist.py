@@ -180,6 +180,67 @@ class ShardedRenderer:
                 self.c.IpcImport(r, h)
         dist.barrier(group=self.group)
 
+    # --- Present of the frame loop (end-to-end path) ---
+    def present_buffers(self, slots):
+        """`slots` whole-frame RGBA8 host buffers for Present. One GPU: pinned memory of this process. Sharded (fused): ONE
+        POSIX shared-memory segment mapped and page-locked by every rank's process, so that each rank reads its own rows
+        back over its own PCIe link (mv_present_rows_async) and rank 0 sees the assembled frame without carrying it."""
+        from .caster import PinnedBuffer
+        c = self.c
+        if self.world == 1 or self.mode != "fused":
+            return [PinnedBuffer((c.H, c.W, 4), np.uint8) for _ in range(slots)] if self.rank == 0 else [None] * slots
+        import ctypes
+        import torch.distributed as dist
+        from multiprocessing import shared_memory
+        nbytes = slots * c.H * c.W * 4
+        name = [None]
+        if self.rank == 0:
+            self._shm = shared_memory.SharedMemory(create=True, size=nbytes)
+            name[0] = self._shm.name
+        dist.broadcast_object_list(name, src=0, group=self.group)
+        if self.rank != 0:
+            self._shm = shared_memory.SharedMemory(name=name[0])
+            try:      # the creator unlinks the segment; attached processes must not report it as leaked
+                from multiprocessing import resource_tracker
+                resource_tracker.unregister(self._shm._name, "shared_memory")
+            except Exception:
+                pass
+        base = ctypes.addressof(ctypes.c_char.from_buffer(self._shm.buf))
+        c._ck(c.b.host_register(base, nbytes), "host_register")
+        self._shm_base = base
+        dist.barrier(group=self.group)
+
+        class _Slot:
+            pass
+        outs = []
+        for k in range(slots):
+            o = _Slot()
+            o.ptr = base + k * c.H * c.W * 4
+            o.array = np.frombuffer(self._shm.buf, dtype=np.uint8, count=c.H * c.W * 4, offset=k * c.H * c.W * 4).reshape(c.H, c.W, 4)
+            outs.append(o)
+        return outs
+
+    def present(self, outs, slot):
+        c = self.c
+        if self.world > 1 and self.mode == "fused":
+            c.PresentRowsAsync(outs[slot].ptr, slot)
+        else:
+            c.PresentAsync(outs[slot].ptr if self.rank == 0 else None, slot)
+
+    def close(self):
+        if getattr(self, "_shm", None) is not None:
+            try:
+                self.c.b.host_unregister(self._shm_base)
+            except Exception:
+                pass
+            shm, self._shm = self._shm, None
+            try:
+                shm.close()
+                if self.rank == 0:
+                    shm.unlink()
+            except Exception:
+                pass
+
     def render(self, view_proj, shadow_vp, eye, taa=True, reset_color=True):
         c = self.c
         c.UpdateFrame(view_proj, shadow_vp, eye)
@@ -191,8 +252,7 @@ class ShardedRenderer:
             return
         if self.mode == "fused":
             c.Render()              # cull -> light slab -> barrier + commit -> march (peer stores) -> barrier -> OIT band
-            c.Postprocess(taa)      # band; rank r > 0 also stores its RGBA8 rows into rank 0's back buffer
-            c.PeerBarrier()         # rank 0: every band has landed
+            c.Postprocess(taa)      # band; RGBA8 rows also into rank 0's back buffer, TAA rows into every peer's history; closing barrier
             return
         c.Cull()
         c.RayMarchL(-1)

@@ -46,6 +46,11 @@ inline float lerp1(float a, float b, float t) { return a + (b - a) * t; }   // H
 inline float signf(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }
 inline float fracf(float x) { return x - floorf(x); }
 inline float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+// Division in the image passes (OIT resolve, TAA): x / d is restated as x * rcp(d), rcp = the correctly rounded reciprocal.
+// dxc's fast-math default does the same to the reference's shaders (its DXIL multiplies by reciprocals).
+inline float rcp(float d) { return 1.0f / d; }
+// a * b + c with one rounding, exactly where the restatement says so (the file is compiled with -ffp-contract=off)
+inline float fma1(float a, float b, float c) { return std::fmaf(a, b, c); }
 // pow(x, 0.25) and pow(x, 1.25) restated through correctly-rounded sqrt so CPU and GPU agree.
 inline float pow025(float x) { return sqrtf(sqrtf(x)); }
 inline float pow125(float x) { return x * sqrtf(sqrtf(x)); }

@@ -720,20 +720,18 @@ void resolve_oit(Caster& c)
 // ------------------------------------------------------------------------------------------
 // CSTemporalAA.hlsl:254-336 (ALPHA_BOUND = 1.0, _USE_YCOCG_, _VARIANCE_AABB_) and PSToneMap.hlsl:19-28
 // ------------------------------------------------------------------------------------------
-static inline f3 rgb_to_ycocg(f3 rgb)   // :78-85
+// Stated evaluation order of this pass (the product's k_post.cu states the same one): YCoCg as sums and doublings, every
+// division as a multiplication by the correctly rounded reciprocal (rcp) or by the reciprocal constant, fused multiply-adds
+// (fma1) exactly where written. dxc compiles the reference with fast-math: its DXIL multiplies by reciprocals too.
+static inline f3 rgb_to_ycocg(f3 rgb)   // :78-85: (1 2 1; 2 0 -2; -1 2 -1)
 {
-    const float y = (rgb.x * 1.0f + rgb.y * 2.0f) + rgb.z * 1.0f;
-    const float co = (rgb.x * 2.0f + rgb.y * 0.0f) + rgb.z * -2.0f;
-    const float cg = (rgb.x * -1.0f + rgb.y * 2.0f) + rgb.z * -1.0f;
-    return {y, co, cg};
+    const float g2 = rgb.y + rgb.y;
+    return {(rgb.x + g2) + rgb.z, (rgb.x - rgb.z) + (rgb.x - rgb.z), (g2 - rgb.x) - rgb.z};
 }
-static inline f3 ycocg_to_rgb(f3 v)     // :90-101
-{
-    const float y = v.x * 0.25f, co = v.y * 0.25f, cg = v.z * 0.25f;
-    return {y + co - cg, y + cg, y - co - cg};
-}
-static inline f3 TM(f3 hdr) { const f3 c = rgb_to_ycocg(hdr); const float d = 4.0f + c.x; return {c.x / d, c.y / d, c.z / d}; }   // :106-114
-static inline f3 ITM(f3 c) { const float s = 4.0f / (1.0f - c.x); return ycocg_to_rgb({c.x * s, c.y * s, c.z * s}); }             // :119-128
+static inline f3 TM(f3 hdr) { const f3 c = rgb_to_ycocg(hdr); const float q = rcp(4.0f + c.x); return {c.x * q, c.y * q, c.z * q}; }   // :106-114
+// :119-128 with :90-101 folded in: (c * (4 / (1 - c.x))) * 0.25 = c * rcp(1 - c.x) — scaling by 4 and by 0.25 is exact
+static inline f3 ITM(f3 c) { const float q = rcp(1.0f - c.x); const float y = c.x * q, co = c.y * q, cg = c.z * q; return {y + co - cg, y + cg, y - co - cg}; }
+static inline float lerpf(float a, float b, float t) { return fma1(b - a, t, a); }   // lerp as one fused multiply-add
 
 void temporal_aa(Caster& c, bool taaOn)
 {
@@ -758,37 +756,36 @@ void temporal_aa(Caster& c, bool taaOn)
     for (int y = (int)c.row0; y < (int)c.row1; ++y)
         for (int x = 0; x < W; ++x) {
             const f2 texSize = {(float)W, (float)H};
-            const f2 uv = {((float)x + 0.5f) / texSize.x, ((float)y + 0.5f) / texSize.y};
+            const f2 invSize = {1.0f / texSize.x, 1.0f / texSize.y};
+            const f2 uv = {((float)x + 0.5f) * invSize.x, ((float)y + 0.5f) * invSize.y};
             const f4 current = loadC(c.color, x, y);
             // VelocityMax :133-161
             f2 vmax = loadV(x, y);
-            float speedSq = dot2(vmax, vmax);
+            float speedSq = fma1(vmax.x, vmax.x, vmax.y * vmax.y);
             for (int i = 0; i < 4; ++i) {
                 const f2 nb = loadV(x + offs[i + 4][0], y + offs[i + 4][1]);
-                const float s = dot2(nb, nb);
+                const float s = fma1(nb.x, nb.x, nb.y * nb.y);
                 if (s > speedSq) { vmax = nb; speedSq = s; }
             }
             const f2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
             // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp, fp32 weights
             f4 history;
             {
-                const float fx = uvBack.x * texSize.x - 0.5f, fy = uvBack.y * texSize.y - 0.5f;
+                const float fx = fma1(uvBack.x, texSize.x, -0.5f), fy = fma1(uvBack.y, texSize.y, -0.5f);
                 const float flx = floorf(fx), fly = floorf(fy);
                 const float wx = fx - flx, wy = fy - fly;
                 auto cl = [&](int v, int n) { return std::min(std::max(v, 0), n - 1); };
                 const int ix = (int)flx, iy = (int)fly;
                 const f4 t00 = loadC(hist, cl(ix, W), cl(iy, H)), t10 = loadC(hist, cl(ix + 1, W), cl(iy, H));
                 const f4 t01 = loadC(hist, cl(ix, W), cl(iy + 1, H)), t11 = loadC(hist, cl(ix + 1, W), cl(iy + 1, H));
-                auto L = [&](float a, float b, float cc, float d) { return lerp1(lerp1(a, b, wx), lerp1(cc, d, wx), wy); };
+                auto L = [&](float a, float b, float cc, float d) { return lerpf(lerpf(a, b, wx), lerpf(cc, d, wx), wy); };
                 history = {L(t00.x, t10.x, t01.x, t11.x), L(t00.y, t10.y, t01.y, t11.y), L(t00.z, t10.z, t01.z, t11.z), L(t00.w, t10.w, t01.w, t11.w)};
             }
             // :267-275
-            const f2 historyBlurAmp = {4.0f * texSize.x, 4.0f * texSize.y};
-            const f2 historyBlurs = {fabsf(vmax.x) * historyBlurAmp.x, fabsf(vmax.y) * historyBlurAmp.y};
-            float curHistoryBlur = historyBlurs.x + historyBlurs.y;
+            float curHistoryBlur = fma1(fabsf(vmax.x), 4.0f * texSize.x, fabsf(vmax.y) * (4.0f * texSize.y));
             float historyBlur = 1.0f - history.w;
             historyBlur = fmaxf(historyBlur, curHistoryBlur);
-            history.w = history.w * historyMax + 1.0f;
+            history.w = fma1(history.w, historyMax, 1.0f);
             // :278-287 (ALPHA_BOUND = 1.0)
             const f3 ctm = TM({current.x, current.y, current.z});
             const f4 currentTM = {ctm.x, ctm.y, ctm.z, current.w};
@@ -802,15 +799,16 @@ void temporal_aa(Caster& c, bool taaOn)
             for (int i = 0; i < 8; ++i) {
                 const f4 nbr = loadC(c.color, x + offs[i][0], y + offs[i][1]);
                 const f3 ntm = TM({nbr.x, nbr.y, nbr.z});
-                const f4 neighbor = {ntm.x, ntm.y, ntm.z, nbr.w < 1.0f ? 0.0f : 1.0f};
-                cur = cur + neighbor * weights[i];
+                const float na = nbr.w < 1.0f ? 0.0f : 1.0f;
+                cur = {fma1(ntm.x, weights[i], cur.x), fma1(ntm.y, weights[i], cur.y), fma1(ntm.z, weights[i], cur.z), fma1(na, weights[i], cur.w)};
                 mu = mu + ntm;
-                m2 = m2 + ntm * ntm;
+                m2 = {fma1(ntm.x, ntm.x, m2.x), fma1(ntm.y, ntm.y, m2.y), fma1(ntm.z, ntm.z, m2.z)};
             }
-            cur = {cur.x / 4.0f, cur.y / 4.0f, cur.z / 4.0f, cur.w / 4.0f};
-            mu = mu / 9.0f;
-            const f3 m2n = m2 / 9.0f;
-            const f3 sigma = {sqrtf(fabsf(m2n.x - mu.x * mu.x)), sqrtf(fabsf(m2n.y - mu.y * mu.y)), sqrtf(fabsf(m2n.z - mu.z * mu.z))};
+            const float ninth = 1.0f / 9.0f;
+            cur = cur * 0.25f;
+            mu = mu * ninth;
+            const f3 m2n = m2 * ninth;
+            const f3 sigma = {sqrtf(fabsf(fma1(-mu.x, mu.x, m2n.x))), sqrtf(fabsf(fma1(-mu.y, mu.y, m2n.y))), sqrtf(fabsf(fma1(-mu.z, mu.z, m2n.z)))};
             const f3 gsigma = sigma * gamma;
             f4 neighborMin, neighborMax;
             neighborMin.x = fminf(mu.x - gsigma.x, cur.x); neighborMin.y = fminf(mu.y - gsigma.y, cur.y); neighborMin.z = fminf(mu.z - gsigma.z, cur.z);
@@ -827,20 +825,20 @@ void temporal_aa(Caster& c, bool taaOn)
             const float contrast = neighborMax.w - neighborMin.w;
             // :304-311
             const float lumContrastFactor = 32.0f * 4.0f;
-            float addAlias = historyBlur * 0.5f + 0.25f;
-            addAlias = saturate(addAlias + 1.0f / (1.0f + contrast * lumContrastFactor));
-            filtered.x = lerp1(filtered.x, currentTM.x, addAlias); filtered.y = lerp1(filtered.y, currentTM.y, addAlias); filtered.z = lerp1(filtered.z, currentTM.z, addAlias);
+            float addAlias = fma1(historyBlur, 0.5f, 0.25f);
+            addAlias = saturate(addAlias + rcp(fma1(contrast, lumContrastFactor, 1.0f)));
+            filtered.x = lerpf(filtered.x, currentTM.x, addAlias); filtered.y = lerpf(filtered.y, currentTM.y, addAlias); filtered.z = lerpf(filtered.z, currentTM.z, addAlias);
             // :314-326
             const float lumHist = historyTM.x;
             const float distToClamp = fminf(fabsf(neighborMin.w - lumHist), fabsf(neighborMax.w - lumHist));
-            const float historyAmt = fminf(1.0f / history.w + historyBlur / 8.0f, 1.0f);
-            float blend = 0.25f / lerp1(8.0f, distToClamp + contrast, historyAmt);
+            const float historyAmt = fminf(fma1(historyBlur, 0.125f, rcp(history.w)), 1.0f);
+            float blend = 0.25f * rcp(lerpf(8.0f, distToClamp + contrast, historyAmt));
             blend = fminf(blend, 0.25f);
             blend = filtered.w > 0.0f ? blend : 1.0f;
             // :328-330
-            f3 result = ITM({lerp1(historyTM.x, filtered.x, blend), lerp1(historyTM.y, filtered.y, blend), lerp1(historyTM.z, filtered.z, blend)});
+            f3 result = ITM({lerpf(historyTM.x, filtered.x, blend), lerpf(historyTM.y, filtered.y, blend), lerpf(historyTM.z, filtered.z, blend)});
             if (result.x != result.x || result.y != result.y || result.z != result.z) result = ITM({filtered.x, filtered.y, filtered.z});
-            history.w = fminf(history.w / historyMax, 1.0f - curHistoryBlur);
+            history.w = fminf(history.w * (1.0f / historyMax), 1.0f - curHistoryBlur);
             uint16_t* o = &out[((size_t)y * W + x) * 4];
             o[0] = f32_to_f16(result.x); o[1] = f32_to_f16(result.y); o[2] = f32_to_f16(result.z); o[3] = f32_to_f16(history.w);
         }

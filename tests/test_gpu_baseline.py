@@ -1,0 +1,224 @@
+"""Oracle parity at the sizes BASELINE.json names (run on the B200 box: pytest -m gpu).
+
+  cfg1  4 x 128^3, 1280x720, no SH, TAA off ....... every output of whole frames, all four light maps filled
+  cfg2  16 x 128^3, 1920x1080, SH, TAA on ......... every output of whole frames (lists, attributes, light map, every cube
+                                                    map, composited frame, TAA image, RGBA8, work counters)
+  cfg3  64 x 256^3, 1920x1080, occluder mesh ...... sampled: whole cull; depth + shadow map of the mesh producer; three light
+  cfg4  64 x 256^3, 3840x2160, animated ........... maps; two cube-map volumes marched by the oracle (shard v % 64); a 64-row
+                                                    band of the OIT resolve (with every direct-scheme march it contains) and
+                                                    of the post-process — the oracle's SetShard / SetRowBand, so that the CPU
+                                                    side stays within seconds
+
+The scenes are built by bench.py's own build_scene / step_frame, i.e. they are the bench workloads. The 64 source volumes
+of cfg3 / cfg4 (8.6 GB) are generated once on the GPU and handed to the oracle as texels — the two generators are compared
+bit for bit by test_procedural_volume_bit_exact — because evaluating 1 G voxels of value noise on the host would take
+longer than everything else in this file. The default build must match bit for bit; the bar the task states (visible
+lists exact, max-abs 2e-3, PSNR >= 50 dB) is asserted as well, so that a future non-bit-exact change is held to it."""
+import numpy as np
+import pytest
+
+import bench
+from harness import assert_image_close
+from oracle_binding import OracleCaster
+from multivolumes_b200 import scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(oracle_lib):
+    return oracle_lib
+
+
+def _pair(name, share_volumes=False):
+    from multivolumes_b200 import MultiRayCaster
+    wl = bench.WORKLOADS[name]
+    kw = dict(grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
+    p = MultiRayCaster(**kw)
+    o = OracleCaster(filter_model=1, threads=bench.host_threads(), **kw)
+    sky = o.TransformSH(scene.procedural_sky(64)) if wl["sh"] else None      # the same coefficients on both sides
+    bench.build_scene(p, wl, scene, sky)
+    if share_volumes:
+        class _NoInit:      # build_scene without the host-side procedural fill
+            def __getattr__(self, k):
+                return (lambda *a, **kw_: None) if k == "InitVolumeData" else getattr(o, k)
+        bench.build_scene(_NoInit(), wl, scene, sky)
+        for i in range(o.srcs):
+            o.LoadVolumeData(i, p.ReadVolume(i))
+    else:
+        bench.build_scene(o, wl, scene, sky)
+    return wl, o, p
+
+
+def _exact(a, b, what):
+    a, b = np.asarray(a), np.asarray(b)
+    if a.dtype == np.float16:
+        if not np.array_equal(a.view(np.uint16), b.view(np.uint16)):
+            d = a.view(np.uint16) != b.view(np.uint16)
+            assert_image_close(a, b, what)       # the stated bar first, for the message
+            raise AssertionError(f"{what}: within tolerance but not bit-exact ({int(d.sum())} of {d.size} halves differ)")
+    else:
+        assert np.array_equal(a, b), what
+
+
+def _frame(c, wl, i, taa):
+    bench.step_frame(c, wl, scene, i, lambda vp, svp, eye: (c.UpdateFrame(vp, svp, eye), c.ResetColor(), c.Render(), c.Postprocess(taa)))
+
+
+COUNTERS = ("view_rays", "view_samples", "view_light_fetches", "light_dense_voxels", "light_samples", "direct_rays", "direct_samples",
+            "direct_light_fetches", "oit_fragments", "visible_count", "cubemap_count", "light_volume")
+
+
+def _compare_whole_frame(o, p, what):
+    vo = o.ReadVisible()
+    _exact(p.ReadVisible(), vo, f"{what}: visible list")
+    _exact(p.ReadCubeVolumes(), o.ReadCubeVolumes(), f"{what}: cube-map list")
+    ao, ap = o.ReadAttribs(), p.ReadAttribs()
+    _exact(ap[vo], ao[vo], f"{what}: attributes")
+    so, sp = o.GetStats(), p.GetStats()
+    for k in COUNTERS:
+        assert so[k] == sp[k], (what, k, so[k], sp[k])
+    _exact(p.ReadLightMap(so["light_volume"]), o.ReadLightMap(so["light_volume"]), f"{what}: light map")
+    for v in o.ReadCubeVolumes():
+        mip = int(ao[v][0])
+        (co, do), (cp, dp) = o.ReadCubeMap(int(v), mip), p.ReadCubeMap(int(v), mip)
+        _exact(cp, co, f"{what}: cube map {v}")
+        _exact(dp.view(np.uint32), do.view(np.uint32), f"{what}: cube depth {v}")
+    _exact(p.ReadFrame(), o.ReadFrame(), f"{what}: frame")
+    (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
+    _exact(tp, to, f"{what}: TAA image")
+    _exact(bp, bo, f"{what}: RGBA8")
+    return so
+
+
+def test_baseline_cfg1_whole_frames():
+    wl, o, p = _pair("cfg1")
+    for i in range(4):                       # four frames: the round robin fills all four light maps
+        for c in (o, p):
+            _frame(c, wl, 20 * i, wl["taa"])
+    so = _compare_whole_frame(o, p, "cfg1")
+    assert so["visible_count"] == 4 and so["view_samples"] + so["direct_samples"] > 1_000_000
+    for v in range(4):
+        _exact(p.ReadLightMap(v), o.ReadLightMap(v), f"cfg1: light map {v}")
+
+
+def test_baseline_cfg2_whole_frames():
+    wl, o, p = _pair("cfg2")
+    for i in range(3):
+        for c in (o, p):
+            _frame(c, wl, 30 * i, wl["taa"])
+    so = _compare_whole_frame(o, p, "cfg2")
+    assert so["visible_count"] >= 12 and so["view_samples"] > 20_000_000
+
+
+def _sampled(name, frame_index, band):
+    wl, o, p = _pair(name, share_volumes=True)
+    W, H, N = wl["w"], wl["h"], wl["n"]
+    vp, eye = bench.camera(scene, wl, frame_index)
+    svp = None
+    for c in (o, p):
+        bench.animate(c, wl, frame_index)
+        if wl.get("mesh"):
+            svp = c.RenderMeshDepth(vp)
+        c.UpdateFrame(vp, svp, eye)
+        c.Cull()
+    if wl.get("mesh"):
+        (do, so_), (dp, sp_) = o.ReadDepth(), p.ReadDepth()
+        assert (do < 1.0).sum() > 10_000 and (so_ < 65535).sum() > 10_000
+        _exact(dp.view(np.uint32), do.view(np.uint32), f"{name}: scene depth")
+        _exact(sp_, so_, f"{name}: shadow map")
+    # whole cull
+    vis = o.ReadVisible()
+    _exact(p.ReadVisible(), vis, f"{name}: visible list")
+    cubes = o.ReadCubeVolumes()
+    _exact(p.ReadCubeVolumes(), cubes, f"{name}: cube-map list")
+    att = o.ReadAttribs()
+    _exact(p.ReadAttribs()[vis], att[vis], f"{name}: attributes")
+    direct = [int(v) for v in vis if not (att[v][2] & 0x8000)]
+    assert len(cubes) >= 8 and len(direct) >= 4, (len(cubes), len(direct))
+    # three light maps: two cube-map volumes (the ones the oracle will march) and one direct-scheme volume
+    picks = [int(cubes[0]), int(cubes[len(cubes) // 2])]
+    for v in picks + [direct[0]]:
+        for c in (o, p):
+            c.RayMarchL(v)
+        so, sp = o.GetStats(), p.GetStats()
+        assert so["light_samples"] == sp["light_samples"] and so["light_dense_voxels"] == sp["light_dense_voxels"] and so["light_samples"] > 0
+        _exact(p.ReadLightMap(v), o.ReadLightMap(v), f"{name}: light map {v}")
+    # product: the whole view march; oracle: volume v alone (shard v of N ranks marches the volumes v' % N == v)
+    p.RayMarchV()
+    sp = p.GetStats()
+    assert sp["view_samples"] > 50_000_000
+    if p.G >= 256:
+        assert sp["view_skipped"] > 0.2 * sp["view_samples"]        # the empty-space bricks are at work at this size
+    total = 0
+    for v in picks:
+        o.SetShard(v, N)
+        o.RayMarchV()
+        total += o.GetStats()["view_samples"]
+        mip = int(att[v][0])
+        (co, do), (cp, dp) = o.ReadCubeMap(v, mip), p.ReadCubeMap(v, mip)
+        _exact(cp, co, f"{name}: cube map {v} (mip {mip})")
+        _exact(dp.view(np.uint32), do.view(np.uint32), f"{name}: cube depth {v}")
+    assert total > 2_000_000
+    o.SetShard(0, 1)
+    # every other cube map crosses over as the multi-rank exchange would move it, then one band of the resolve
+    for v in cubes:
+        if int(v) in picks:
+            continue
+        mip = int(att[v][0])
+        cp, dp = p.ReadCubeMap(int(v), mip)
+        a, b = np.ascontiguousarray(cp.view(np.uint16)), np.ascontiguousarray(dp)
+        o._ck(o.b.write_cubemap(o.h, int(v), mip, a.ctypes.data, b.ctypes.data), "write_cubemap")
+    o.SetRowBand(*band)
+    for c in (o, p):
+        c.ResolveOIT()
+        c.Postprocess(taa=False)
+    r0, r1 = band
+    so, sp = o.GetStats(), p.GetStats()
+    assert so["oit_fragments"] > 100_000 and so["direct_rays"] > 10_000, so      # the band holds cube-map and direct-scheme fragments
+    _exact(p.ReadFrame()[r0:r1], o.ReadFrame()[r0:r1], f"{name}: frame rows {r0}..{r1}")
+    (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
+    _exact(tp[r0:r1], to[r0:r1], f"{name}: post rows")
+    _exact(bp[r0:r1], bo[r0:r1], f"{name}: RGBA8 rows")
+
+
+def test_baseline_cfg3_sampled():
+    H = bench.WORKLOADS["cfg3"]["h"]
+    _sampled("cfg3", 40, (H // 2 - 40, H // 2 + 24))
+
+
+def test_baseline_cfg4_sampled():
+    H = bench.WORKLOADS["cfg4"]["h"]
+    _sampled("cfg4", 120, (H // 2 - 70, H // 2 - 6))
+
+
+@pytest.mark.parametrize("bricks,g", [(8, 32), (16, 64), (5, 40)])
+def test_empty_space_bricks_change_nothing(bricks, g, monkeypatch):
+    """The bricks are on by default from 256^3 up; here they are forced on for small, ragged grids (40 is not a multiple
+    of the brick edge) so that the whole suite of outputs is compared with them at work."""
+    from harness import checker_background, configure
+    from multivolumes_b200 import MultiRayCaster
+    kw = dict(grid_size=g, light_grid_size=16, num_volumes=9, num_volume_srcs=3, width=320, height=180)
+    monkeypatch.setenv("MV_OCC_BRICKS", str(bricks))
+    p = MultiRayCaster(**kw)
+    monkeypatch.delenv("MV_OCC_BRICKS")
+    o = OracleCaster(filter_model=1, **kw)
+    vp, _ = scene.default_camera(320, 180)
+    depth = scene.sphere_depth(320, 180, vp, center=(0, 0, 0), radius=9.0)
+    # volumes with a wide empty margin (a blob of radius 0.62 in the [-1, 1] box; the procedural shell is too thin for
+    # bricks at these sizes), plus one of the procedural ones
+    ax = (np.arange(g) + 0.5) / g * 2 - 1
+    zz, yy, xx = np.meshgrid(ax, ax, ax, indexing="ij")
+    vol = np.zeros((g, g, g, 4), np.float16)
+    vol[..., 0], vol[..., 1], vol[..., 2] = 0.9, 0.6, 0.3
+    vol[..., 3] = np.clip(1.0 - np.sqrt(xx * xx + yy * yy + zz * zz) * 1.6, 0, 1) * (0.6 + 0.4 * np.sin(7 * xx) * np.cos(5 * yy))
+    for c in (o, p):
+        configure(c, sh=True, depth=depth, background=checker_background(320, 180), random_transforms=3, eye=(6.0, 30.0, -110.0))
+        c.LoadVolumeData(0, vol)
+        c.LoadVolumeData(2, vol[::-1].copy())
+        for _ in range(2):
+            c.Render()
+        c.Postprocess(False)
+    _compare_whole_frame(o, p, f"bricks {bricks}")
+    sp = p.GetStats()
+    assert sp["view_skipped"] + sp["direct_skipped"] > 0

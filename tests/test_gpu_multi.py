@@ -1,6 +1,8 @@
 """Multi-GPU parity on real devices (needs >= 2 GPUs; skipped otherwise): the sharded frame — by
 volume for the march, by z-slab for the light map, by row band for OIT + post-process — must equal the
-single-GPU frame bit for bit, in both exchange modes (fused peer stores / NCCL collectives)."""
+single-GPU frame bit for bit, in both exchange modes (fused peer stores / NCCL collectives). The scene has a non-zero
+velocity field and TAA on over four frames, so the history fetch (uv - velocity, bilinear) of one rank's rows lands on
+rows another rank wrote: the fused mode must have exchanged the TAA output as well as the cube maps."""
 import os
 import subprocess
 import sys
@@ -25,10 +27,12 @@ mode, out = sys.argv[1], sys.argv[2]
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
 kw = dict(grid_size=64, light_grid_size=24, num_volumes=9, num_volume_srcs=3, width=640, height=360)
-c = MultiRayCaster(device=rank, **kw)
+# uninstrumented casters take the pipelined paths (frames in flight on two streams); "fused-serial" keeps the counters on
+c = MultiRayCaster(device=rank, count_samples=(os.environ.get("MV_TEST_VARIANT") == "fused-serial"), **kw)
 stream = torch.cuda.Stream()
 c.SetStream(stream.cuda_stream)
-configure(c, sh=True, background=checker_background(640, 360))
+vel = (np.random.RandomState(7).uniform(-1, 1, (360, 640, 2)) * (0.02 if mode != "collective" else 0.0)).astype(np.float16)
+configure(c, sh=True, background=checker_background(640, 360), velocity=vel)
 with torch.cuda.stream(stream):
     x = CudaExchange(c, rank, world) if mode == "collective" else None
     r = ShardedRenderer(c, rank, world, mode=mode, exchange=x)
@@ -51,13 +55,14 @@ dist.destroy_process_group()
 '''
 
 
-def _single():
+def _single(velocity_scale):
     sys.path.insert(0, HERE)
     from harness import checker_background, configure
     from multivolumes_b200 import MultiRayCaster, scene
     kw = dict(grid_size=64, light_grid_size=24, num_volumes=9, num_volume_srcs=3, width=640, height=360)
     c = MultiRayCaster(**kw)
-    configure(c, sh=True, background=checker_background(640, 360))
+    vel = (np.random.RandomState(7).uniform(-1, 1, (360, 640, 2)) * velocity_scale).astype(np.float16)
+    configure(c, sh=True, background=checker_background(640, 360), velocity=vel)
     for i in range(4):
         vp, eye = scene.default_camera(640, 360, eye=(4.0 + 6 * i, 16.0 + 8 * i, -80.0 - 30 * i))
         c.UpdateFrame(vp, None, eye); c.ResetColor(); c.Render(); c.Postprocess(True)
@@ -66,7 +71,7 @@ def _single():
     return c.ReadPost()[1], cubes
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused-overlap", "collective"])
+@pytest.mark.parametrize("mode", ["fused", "fused-overlap", "fused-serial", "collective"])
 def test_two_gpu_frame_equals_single_gpu(mode, tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
@@ -76,13 +81,18 @@ def test_two_gpu_frame_equals_single_gpu(mode, tmp_path):
     out = str(tmp_path / "out.npz")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + os.getpid() % 300), str(script), mode, out]
-    env = dict(os.environ)
-    if mode == "fused-overlap":      # light march of the frame's light volume beside the view march of the other volumes
-        env["MV_SHARD_V_BLOCKS"] = "3"
+    # "fused": frames pipelined across the ranks (light march of frame i + 1 beside frame i, two barrier channels);
+    # "fused-overlap": not pipelined, light march of the frame's light volume beside the view march of the other volumes;
+    # "fused-serial": every pass in order on one stream
+    env = dict(os.environ, MV_TEST_VARIANT=mode)
+    if mode == "fused-overlap":
+        env["MV_SHARD_V_BLOCKS"] = "3"; env["MV_SHARD_PIPELINE"] = "0"
+    if mode.startswith("fused-"):
         cmd[cmd.index(mode)] = "fused"
     subprocess.run(cmd, check=True, timeout=600, env=env)
     got = np.load(out)["rgba8"]
-    want, cubes = _single()
+    # the collective mode gathers finished bands only (no history exchange): it is the baseline, run with a static field
+    want, cubes = _single(0.02 if mode != "collective" else 0.0)
     assert np.array_equal(got, want)
     peer = np.load(out + ".r1.npz")
     assert len(cubes) > 0 and sorted(peer.files) == sorted(cubes)
