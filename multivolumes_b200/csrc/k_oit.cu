@@ -17,9 +17,15 @@ namespace MV_VARIANT {
 
 namespace {
 
+// Stated evaluation order of the OIT passes (the test oracle states the same one): divisions as multiplications by the
+// correctly rounded reciprocal (rcp, mv_math.cuh), fused multiply-adds (fma1) exactly where written.
 MV_D float unproject_z(float depth)   // UnprojectZ, PSCube.hlsli:21-26
 {
-    return (kZNear * kZFar) / (depth * (kZNear - kZFar) + kZFar);
+    return (kZNear * kZFar) * rcp(fma1(depth, kZNear - kZFar, kZFar));
+}
+MV_D V3 mul_v33_f(V3 v, const float* M)   // mul(v, (float3x3)M), fused
+{
+    return {fma1(v.z, M[6], fma1(v.y, M[3], v.x * M[0])), fma1(v.z, M[7], fma1(v.y, M[4], v.x * M[1])), fma1(v.z, M[8], fma1(v.y, M[5], v.x * M[2]))};
 }
 
 // D3D cube-map convention: (u, v) in [0, 1] of point p on face `face` of the unit cube
@@ -80,7 +86,8 @@ MV_D void cube_resolve_texel(int S, int face, int i, int j, int& oface, int& oi,
 }
 
 // CubeCast, PSCube.hlsli:51-108
-MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, uint32_t mip, float sceneDepth, int face, V3 pos, V3 rayDir)
+// `depth` = UnprojectZ of the pixel's scene depth (the same for every layer of the pixel, :83)
+MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, uint32_t mip, float depth, int face, V3 pos, V3 rayDir)
 {
     const int S = (int)(cb.gridSize >> mip);
     const float gridSize = (float)S;
@@ -88,23 +95,29 @@ MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, ui
     const float* depths = reinterpret_cast<const float*>(s.arena.base + arena_depth_offset(s.arena, volumeId, mip));
     float u, v;
     cube_face_uv(pos, face, u, v);
-    const float fx = u * gridSize - 0.5f, fy = v * gridSize - 0.5f;
+    const float fx = fma1(u, gridSize, -0.5f), fy = fma1(v, gridSize, -0.5f);
     const float flx = floorf(fx), fly = floorf(fy);
     const int i0 = (int)flx, j0 = (int)fly;
     V4 smp[4]; float zs[4];
-    const bool interior = i0 >= 0 && j0 >= 0 && i0 + 1 < S && j0 + 1 < S;   // all four taps on this face (the common case)
+    if (i0 >= 0 && j0 >= 0 && i0 + 1 < S && j0 + 1 < S) {   // all four taps on this face (the common case): one base index
+        const uint32_t base = ((uint32_t)face * (uint32_t)S + (uint32_t)j0) * (uint32_t)S + (uint32_t)i0;
+        const uint32_t idx[4] = {base + (uint32_t)S, base + (uint32_t)S + 1u, base + 1u, base};   // Gather order (-,+), (+,+), (+,-), (-,-)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {    // Gather order (-,+), (+,+), (+,-), (-,-)
-        const int ti = (k == 1 || k == 2) ? i0 + 1 : i0, tj = (k < 2) ? j0 + 1 : j0;
-        int f = face, i = ti, j = tj;
-        if (!interior) cube_resolve_texel(S, face, ti, tj, f, i, j);
-        const size_t idx = ((size_t)f * S + j) * S + i;
-        smp[k] = unpack_half4(__ldg(colors + idx));
-        zs[k] = __ldg(depths + idx);
+        for (int k = 0; k < 4; ++k) { smp[k] = unpack_half4(__ldg(colors + idx[k])); zs[k] = __ldg(depths + idx[k]); }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int ti = (k == 1 || k == 2) ? i0 + 1 : i0, tj = (k < 2) ? j0 + 1 : j0;
+            int f, i, j;
+            cube_resolve_texel(S, face, ti, tj, f, i, j);
+            const uint32_t idx = ((uint32_t)f * (uint32_t)S + (uint32_t)j) * (uint32_t)S + (uint32_t)i;
+            smp[k] = unpack_half4(__ldg(colors + idx));
+            zs[k] = __ldg(depths + idx);
+        }
     }
     // GetDomain, :31-46
     float uvx = u * gridSize, uvy = v * gridSize;
-    float domx = frac(uvx + 0.5f), domy = frac(uvy + 0.5f);
+    float domx = frac(fma1(u, gridSize, 0.5f)), domy = frac(fma1(v, gridSize, 0.5f));
     const float bound = gridSize - 1.0f;
     const V3 axes = pos * gridSize;
     const bool edge = (fabsf(axes.x) > bound && axes.x * rayDir.x < 0.0f) || (fabsf(axes.y) > bound && axes.y * rayDir.y < 0.0f) ||
@@ -115,24 +128,23 @@ MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, ui
     }
     const float dix = 1.0f - domx, diy = 1.0f - domy;
     const float wb[4] = {dix * domy, domx * domy, domx * diy, dix * diy};
-    const float depth = unproject_z(sceneDepth);
     V4 result = {0.0f, 0.0f, 0.0f, 0.0f};
     float ws = 0.0f;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const float zi = unproject_z(zs[k]);
-        float w = fmaxf(1.0f - 0.5f * fabsf(depth - zi), 0.0f);
+        float w = fmaxf(fma1(-0.5f, fabsf(depth - zi), 1.0f), 0.0f);
         w *= wb[k];
-        result.x += smp[k].x * w; result.y += smp[k].y * w; result.z += smp[k].z * w; result.w += smp[k].w * w;
+        result = {fma1(smp[k].x, w, result.x), fma1(smp[k].y, w, result.y), fma1(smp[k].z, w, result.z), fma1(smp[k].w, w, result.w)};
         ws += w;
     }
-    if (ws > 0.0f) return {result.x / ws, result.y / ws, result.z / ws, result.w / ws};
+    if (ws > 0.0f) { const float iw = rcp(ws); return {result.x * iw, result.y * iw, result.z * iw, result.w * iw}; }
     // all taps rejected by depth: plain bilinear SampleLevel of the same footprint (:57, :105)
     const float bx = fx - flx, by = fy - fly;
     const float bw[4] = {(1.0f - bx) * by, bx * by, bx * (1.0f - by), (1.0f - bx) * (1.0f - by)};
     V4 col = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { col.x += smp[k].x * bw[k]; col.y += smp[k].y * bw[k]; col.z += smp[k].z * bw[k]; col.w += smp[k].w * bw[k]; }
+    for (int k = 0; k < 4; ++k) col = {fma1(smp[k].x, bw[k], col.x), fma1(smp[k].y, bw[k], col.y), fma1(smp[k].z, bw[k], col.z), fma1(smp[k].w, bw[k], col.w)};
     return col;
 }
 
@@ -140,12 +152,12 @@ MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, ui
 // direction from the eye (not normalised) and the pixel's clip-space x, y.
 MV_D V3 pixel_ray(const FrameCB& cb, int px, int py, float& sx, float& sy)
 {
-    sx = ((float)px + 0.5f) / cb.viewport[0]; sy = ((float)py + 0.5f) / cb.viewport[1];
-    sx = sx * 2.0f - 1.0f; sy = sy * 2.0f - 1.0f;
-    sy = -sy;
-    const V4 wh = mul_p44(V3{sx, sy, 0.0f}, cb.screenToWorld);
-    const V3 wpos = {wh.x / wh.w, wh.y / wh.w, wh.z / wh.w};
-    return wpos - V3{cb.eye[0], cb.eye[1], cb.eye[2]};
+    sx = fma1((float)px + 0.5f, 2.0f / cb.viewport[0], -1.0f); sy = fma1((float)py + 0.5f, -(2.0f / cb.viewport[1]), 1.0f);   // uniform divisions: once per launch
+    const float* S = cb.screenToWorld;
+    const float whx = fma1(sx, S[0], fma1(sy, S[4], S[12])), why = fma1(sx, S[1], fma1(sy, S[5], S[13]));
+    const float whz = fma1(sx, S[2], fma1(sy, S[6], S[14])), whw = fma1(sx, S[3], fma1(sy, S[7], S[15]));
+    const float iw = rcp(whw);
+    return V3{whx * iw, why * iw, whz * iw} - V3{cb.eye[0], cb.eye[1], cb.eye[2]};
 }
 
 // The back-face fragment of a volume under a pixel: exit of the local-space ray o + t d from the unit box, with the
@@ -160,18 +172,20 @@ MV_D bool back_face_fragment(V3 o, V3 d, const float* wvp, BackFace& f)
     for (int a = 0; a < 3; ++a) {
         const float da = comp(d, a), oa = comp(o, a);
         if (da == 0.0f) { if (fabsf(oa) > 1.0f) miss = true; continue; }
-        const float t1 = (-1.0f - oa) / da, t2 = (1.0f - oa) / da;
+        const float inv = rcp(da);
+        const float t1 = (-1.0f - oa) * inv, t2 = (1.0f - oa) * inv;
         const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
         if (tn > tmin) tmin = tn;
         if (tf < tmax) { tmax = tf; exitAxis = a; }
     }
     if (miss || exitAxis < 0 || !(tmax > 0.0f) || !(tmin < tmax)) return false;
-    V3 lpt = {clamp1(o.x + d.x * tmax), clamp1(o.y + d.y * tmax), clamp1(o.z + d.z * tmax)};
+    V3 lpt = {clamp1(fma1(d.x, tmax, o.x)), clamp1(fma1(d.y, tmax, o.y)), clamp1(fma1(d.z, tmax, o.z))};
     const float sgn = comp(d, exitAxis) > 0.0f ? 1.0f : -1.0f;
     if (exitAxis == 0) lpt.x = sgn; else if (exitAxis == 1) lpt.y = sgn; else lpt.z = sgn;
-    const V4 clip = mul_p44(lpt, wvp);
-    if (!(clip.w > 0.0f)) return false;
-    const float z = clip.z / clip.w;
+    const float clipZ = fma1(lpt.z, wvp[10], fma1(lpt.y, wvp[6], fma1(lpt.x, wvp[2], wvp[14])));
+    const float clipW = fma1(lpt.z, wvp[11], fma1(lpt.y, wvp[7], fma1(lpt.x, wvp[3], wvp[15])));
+    if (!(clipW > 0.0f)) return false;
+    const float z = clipZ * rcp(clipW);
     if (!(z >= 0.0f && z <= 1.0f)) return false;        // rasteriser depth clip
     f.axis = exitAxis; f.sgn = sgn; f.z = z;
     return true;
@@ -180,8 +194,8 @@ MV_D bool back_face_fragment(V3 o, V3 d, const float* wvp, BackFace& f)
 // The fragment's local-space position: exit point of the pixel ray on the back face (axis, sgn)
 MV_D V3 back_face_point(V3 localEye, V3 d, int axis, float sgn)
 {
-    const float tmax = (sgn - comp(localEye, axis)) / comp(d, axis);
-    V3 lpt = {clamp1(localEye.x + d.x * tmax), clamp1(localEye.y + d.y * tmax), clamp1(localEye.z + d.z * tmax)};
+    const float tmax = (sgn - comp(localEye, axis)) * rcp(comp(d, axis));
+    V3 lpt = {clamp1(fma1(d.x, tmax, localEye.x)), clamp1(fma1(d.y, tmax, localEye.y)), clamp1(fma1(d.z, tmax, localEye.z))};
     if (axis == 0) lpt.x = sgn; else if (axis == 1) lpt.y = sgn; else lpt.z = sgn;
     return lpt;
 }
@@ -274,7 +288,7 @@ __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(D
         float sx, sy;
         const V3 dirW = pixel_ray(cb, px, py, sx, sy);
         const V3 localEye = {vi.eyeL[0], vi.eyeL[1], vi.eyeL[2]};
-        const V3 d = mul_v33(dirW, po->worldI);
+        const V3 d = mul_v33_f(dirW, po->worldI);
         uint2 stored = make_uint2(0u, 0u), st = make_uint2(0u, 0u);
         BackFace f;
         if (back_face_fragment(localEye, d, po->wvp, f)) {
@@ -352,11 +366,14 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
         if (overlap) { const uint32_t slot = off + __popc(bits & ((1u << lane) - 1u)); s_cand[slot] = vi; s_candSlot[slot] = k; }
         __syncthreads();
         if (valid) {
+            const int wx0 = tileX0 + (int)((warp & 1) * 8), wy0 = tileY0 + (int)((warp >> 1) * 4);   // this warp's 8x4 pixels
             for (uint32_t ci = 0; ci < total; ++ci) {
+                // the volume's rectangle overlaps the CTA's tile; does it reach this warp's pixels? (uniform over the warp)
+                if (s_cand[ci].x0 > wx0 + 7 || s_cand[ci].x1 < wx0 || s_cand[ci].y0 > wy0 + 3 || s_cand[ci].y1 < wy0) continue;
                 const uint32_t volumeId = s_cand[ci].volumeId;
                 const PerObject* po = s.perObject + volumeId;
                 const V3 o = {s_cand[ci].eyeL[0], s_cand[ci].eyeL[1], s_cand[ci].eyeL[2]};   // mul(float4(g_eyePt, 1), WorldI)
-                const V3 d = mul_v33(dirW, po->worldI);
+                const V3 d = mul_v33_f(dirW, po->worldI);
                 BackFace f;
                 if (!back_face_fragment(o, d, po->wvp, f)) continue;
                 ++frags;
@@ -376,6 +393,7 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
 
     // shade + resolve front to back (PSCube.hlsl:30-60, PSResolveOIT.hlsl:12-26)
     const float sceneDepth = valid ? __ldg(s.depth + (size_t)py * W + px) : 1.0f;
+    const float sceneZ = unproject_z(sceneDepth);
     V4 result = {0.0f, 0.0f, 0.0f, 0.0f};
     uint32_t dRays = 0, dSamples = 0, dLight = 0;
 #pragma unroll 1
@@ -391,7 +409,7 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
         const ushort4 a = s.attribs[volumeId];
         const V3 localEye = {__ldg(&s.visInfo[id & 0xffffffu].eyeL[0]), __ldg(&s.visInfo[id & 0xffffffu].eyeL[1]), __ldg(&s.visInfo[id & 0xffffffu].eyeL[2])};
         // the fragment's local-space position: exit point of the pixel ray on the back face
-        const V3 d = mul_v33(dirW, po->worldI);
+        const V3 d = mul_v33_f(dirW, po->worldI);
         const int axis = face >> 1;
         const float sgn = (face & 1) ? -1.0f : 1.0f;
         const V3 lpt = back_face_point(localEye, d, axis, sgn);
@@ -414,10 +432,10 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
                     if (st.x >> 31) { ++dRays; dSamples += st.x & 0x7fffffffu; dLight += st.y; }
                 }
             } else color = ray_cast_fallback(ray_cast_args(s, po, volumeId, a.w, smpCnt), localEye, rayDir, sx, sy, sceneDepth, densityOnly, dRays, dSamples, dLight);
-        } else color = cube_cast(s, cb, volumeId, a.x, sceneDepth, face, lpt, rayDir);
+        } else color = cube_cast(s, cb, volumeId, a.x, sceneZ, face, lpt, rayDir);
         if (!stored && color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
         const float k1 = 1.0f - result.w;
-        result = {result.x + src.x * k1, result.y + src.y * k1, result.z + src.z * k1, result.w + src.w * k1};
+        result = {fma1(src.x, k1, result.x), fma1(src.y, k1, result.y), fma1(src.z, k1, result.z), fma1(src.w, k1, result.w)};
     }
     result.w = fminf(result.w, 0.9997f);                                         // PSResolveOIT.hlsl:22
     if (valid) {
@@ -425,7 +443,7 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
         uint2* dst = s.color + (size_t)py * W + px;
         const V4 d4 = unpack_half4(*dst);
         const float ia = 1.0f - result.w;
-        *dst = pack_half4(V4{result.x + d4.x * ia, result.y + d4.y * ia, result.z + d4.z * ia, result.w + d4.w * ia});
+        *dst = pack_half4(V4{fma1(d4.x, ia, result.x), fma1(d4.y, ia, result.y), fma1(d4.z, ia, result.z), fma1(d4.w, ia, result.w)});
     }
 
     if (s.stats) {

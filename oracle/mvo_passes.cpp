@@ -507,9 +507,16 @@ void ray_march_light(Caster& c, int volumeOverride)
 // The hardware rasteriser of the reference is replaced by the analytic exit point of the pixel-centre
 // ray on each visible volume's box (what RTCube.hlsl:72-98 does with ray queries).
 // ------------------------------------------------------------------------------------------
+// Stated evaluation order of the OIT passes (the product's k_oit.cu states the same one): divisions as multiplications by the
+// correctly rounded reciprocal (rcp), fused multiply-adds (fma1) exactly where written — see the note above rgb_to_ycocg.
 static inline float unproject_z(float depth)   // PSCube.hlsli:21-26
 {
-    return (kZNear * kZFar) / (depth * (kZNear - kZFar) + kZFar);
+    return (kZNear * kZFar) * rcp(fma1(depth, kZNear - kZFar, kZFar));
+}
+static inline f3 mul_v33_f(f3 v, const m43& M)   // mul(v, (float3x3)M), fused
+{
+    return {fma1(v.z, M.m[2][0], fma1(v.y, M.m[1][0], v.x * M.m[0][0])), fma1(v.z, M.m[2][1], fma1(v.y, M.m[1][1], v.x * M.m[0][1])),
+            fma1(v.z, M.m[2][2], fma1(v.y, M.m[1][2], v.x * M.m[0][2]))};
 }
 
 // D3D cube-map convention: face index and (u, v) in [0,1] of a point on the unit cube surface.
@@ -573,7 +580,7 @@ static f4 cube_cast(const Caster& c, uint32_t volumeId, uint32_t mip, int px, in
     float u, v;
     cube_face_uv(pos, face, u, v);
     // gather footprint
-    const float fx = u * gridSize - 0.5f, fy = v * gridSize - 0.5f;
+    const float fx = fma1(u, gridSize, -0.5f), fy = fma1(v, gridSize, -0.5f);
     const float flx = floorf(fx), fly = floorf(fy);
     const int i0 = (int)flx, j0 = (int)fly;
     const int ti[4] = {i0, i0 + 1, i0 + 1, i0}, tj[4] = {j0 + 1, j0 + 1, j0, j0};   // Gather order (-,+),(+,+),(+,-),(-,-)
@@ -588,7 +595,7 @@ static f4 cube_cast(const Caster& c, uint32_t volumeId, uint32_t mip, int px, in
     }
     // GetDomain :31-46
     float uvx = u * gridSize, uvy = v * gridSize;
-    float domx = fracf(uvx + 0.5f), domy = fracf(uvy + 0.5f);
+    float domx = fracf(fma1(u, gridSize, 0.5f)), domy = fracf(fma1(v, gridSize, 0.5f));
     const float bound = gridSize - 1.0f;
     const f3 axes = pos * gridSize;
     const bool edge = (fabsf(axes.x) > bound && axes.x * rayDir.x < 0.0f) || (fabsf(axes.y) > bound && axes.y * rayDir.y < 0.0f) ||
@@ -605,17 +612,17 @@ static f4 cube_cast(const Caster& c, uint32_t volumeId, uint32_t mip, int px, in
     float ws = 0.0f;
     for (int k = 0; k < 4; ++k) {
         const float zi = unproject_z(zs[k]);
-        float w = fmaxf(1.0f - 0.5f * fabsf(depth - zi), 0.0f);
+        float w = fmaxf(fma1(-0.5f, fabsf(depth - zi), 1.0f), 0.0f);
         w *= wb[k];
-        result.x += samples[k].x * w; result.y += samples[k].y * w; result.z += samples[k].z * w; result.w += samples[k].w * w;
+        result = {fma1(samples[k].x, w, result.x), fma1(samples[k].y, w, result.y), fma1(samples[k].z, w, result.z), fma1(samples[k].w, w, result.w)};
         ws += w;
     }
-    if (ws > 0.0f) return {result.x / ws, result.y / ws, result.z / ws, result.w / ws};
+    if (ws > 0.0f) { const float iw = rcp(ws); return {result.x * iw, result.y * iw, result.z * iw, result.w * iw}; }
     // fallback: plain bilinear SampleLevel of the same footprint (:57)
     const float bx = fx - flx, by = fy - fly;
     const float bw[4] = {(1.0f - bx) * by, bx * by, bx * (1.0f - by), (1.0f - bx) * (1.0f - by)};
     f4 col = {0, 0, 0, 0};
-    for (int k = 0; k < 4; ++k) { col.x += samples[k].x * bw[k]; col.y += samples[k].y * bw[k]; col.z += samples[k].z * bw[k]; col.w += samples[k].w * bw[k]; }
+    for (int k = 0; k < 4; ++k) col = {fma1(samples[k].x, bw[k], col.x), fma1(samples[k].y, bw[k], col.y), fma1(samples[k].z, bw[k], col.z), fma1(samples[k].w, bw[k], col.w)};
     return col;
 }
 
@@ -634,11 +641,14 @@ void resolve_oit(Caster& c)
     for (int py = rowBegin; py < rowEnd; ++py)
         for (int px = 0; px < W; ++px) {
             // pixel-centre ray (RTCube.hlsl GenerateCameraRay: unproject z = 0 through screenToWorld)
-            f2 xy = {((float)px + 0.5f) / c.cb.viewport.x, ((float)py + 0.5f) / c.cb.viewport.y};   // PSCube.hlsl:38-40
-            xy = {xy.x * 2.0f - 1.0f, xy.y * 2.0f - 1.0f};
-            xy.y = -xy.y;
-            const f4 wh = mul_p44({xy.x, xy.y, 0.0f}, c.cb.screenToWorld);
-            const f3 wpos = {wh.x / wh.w, wh.y / wh.w, wh.z / wh.w};
+            // PSCube.hlsl:38-40: xy = (pixel centre / viewport) * 2 - 1, y up; unprojected at z = 0
+            const f2 xy = {fma1((float)px + 0.5f, 2.0f / c.cb.viewport.x, -1.0f), fma1((float)py + 0.5f, -(2.0f / c.cb.viewport.y), 1.0f)};
+            const m44& S = c.cb.screenToWorld;
+            f4 wh;
+            wh.x = fma1(xy.x, S.m[0][0], fma1(xy.y, S.m[1][0], S.m[3][0])); wh.y = fma1(xy.x, S.m[0][1], fma1(xy.y, S.m[1][1], S.m[3][1]));
+            wh.z = fma1(xy.x, S.m[0][2], fma1(xy.y, S.m[1][2], S.m[3][2])); wh.w = fma1(xy.x, S.m[0][3], fma1(xy.y, S.m[1][3], S.m[3][3]));
+            const float iwh = rcp(wh.w);
+            const f3 wpos = {wh.x * iwh, wh.y * iwh, wh.z * iwh};
             const f3 dirW = wpos - c.cb.eyePt;
             // depth peel: the 8 nearest back-face fragments (PSDepthPeel.hlsl:12-24)
             Fragment layers[kNumOitLayers];
@@ -647,24 +657,27 @@ void resolve_oit(Caster& c)
                 const uint32_t volumeId = c.visible[k];
                 const PerObject& po = c.perObject[volumeId];
                 const f3 o = eyeL[k];
-                const f3 d = mul_v33(dirW, po.WorldI);
+                const f3 d = mul_v33_f(dirW, po.WorldI);
                 float tmin = -kFltMax, tmax = kFltMax; int exitAxis = -1; bool miss = false;
                 for (int a = 0; a < 3; ++a) {
                     const float da = comp(d, a), oa = comp(o, a);
                     if (da == 0.0f) { if (fabsf(oa) > 1.0f) miss = true; continue; }
-                    const float t1 = (-1.0f - oa) / da, t2 = (1.0f - oa) / da;
+                    const float inv = rcp(da);
+                    const float t1 = (-1.0f - oa) * inv, t2 = (1.0f - oa) * inv;
                     const float tn = fminf(t1, t2), tf = fmaxf(t1, t2);
                     if (tn > tmin) tmin = tn;
                     if (tf < tmax) { tmax = tf; exitAxis = a; }
                 }
                 if (miss || exitAxis < 0 || !(tmax > 0.0f) || !(tmin < tmax)) continue;
-                f3 lpt = {fminf(fmaxf(o.x + d.x * tmax, -1.0f), 1.0f), fminf(fmaxf(o.y + d.y * tmax, -1.0f), 1.0f),
-                          fminf(fmaxf(o.z + d.z * tmax, -1.0f), 1.0f)};
+                f3 lpt = {fminf(fmaxf(fma1(d.x, tmax, o.x), -1.0f), 1.0f), fminf(fmaxf(fma1(d.y, tmax, o.y), -1.0f), 1.0f),
+                          fminf(fmaxf(fma1(d.z, tmax, o.z), -1.0f), 1.0f)};
                 const float sgn = comp(d, exitAxis) > 0.0f ? 1.0f : -1.0f;
                 if (exitAxis == 0) lpt.x = sgn; else if (exitAxis == 1) lpt.y = sgn; else lpt.z = sgn;
-                const f4 clip = mul_p44(lpt, po.WorldViewProj);
-                if (!(clip.w > 0.0f)) continue;
-                const float z = clip.z / clip.w;
+                const m44& M = po.WorldViewProj;
+                const float clipZ = fma1(lpt.z, M.m[2][2], fma1(lpt.y, M.m[1][2], fma1(lpt.x, M.m[0][2], M.m[3][2])));
+                const float clipW = fma1(lpt.z, M.m[2][3], fma1(lpt.y, M.m[1][3], fma1(lpt.x, M.m[0][3], M.m[3][3])));
+                if (!(clipW > 0.0f)) continue;
+                const float z = clipZ * rcp(clipW);
                 if (!(z >= 0.0f && z <= 1.0f)) continue;       // rasteriser depth clip
                 ++frags;
                 Fragment fr = {as_uint(z), volumeId, exitAxis * 2 + (sgn > 0.0f ? 0 : 1), lpt};
@@ -704,15 +717,15 @@ void resolve_oit(Caster& c)
                 if (color.w > 0.0f && color.w <= 1.0f)
                     src = {f16_to_f32(f32_to_f16(color.x)), f16_to_f32(f32_to_f16(color.y)), f16_to_f32(f32_to_f16(color.z)), f16_to_f32(f32_to_f16(color.w))};
                 const float k = 1.0f - result.w;
-                result = {result.x + src.x * k, result.y + src.y * k, result.z + src.z * k, result.w + src.w * k};
+                result = {fma1(src.x, k, result.x), fma1(src.y, k, result.y), fma1(src.z, k, result.z), fma1(src.w, k, result.w)};
             }
             result.w = fminf(result.w, 0.9997f);
             // premultiplied-alpha blend onto the colour RT (MultiRayCaster.cpp:931)
             uint16_t* dst = &c.color[((size_t)py * W + px) * 4];
             const float ia = 1.0f - result.w;
             const f4 d4 = {f16_to_f32(dst[0]), f16_to_f32(dst[1]), f16_to_f32(dst[2]), f16_to_f32(dst[3])};
-            dst[0] = f32_to_f16(result.x + d4.x * ia); dst[1] = f32_to_f16(result.y + d4.y * ia);
-            dst[2] = f32_to_f16(result.z + d4.z * ia); dst[3] = f32_to_f16(result.w + d4.w * ia);
+            dst[0] = f32_to_f16(fma1(d4.x, ia, result.x)); dst[1] = f32_to_f16(fma1(d4.y, ia, result.y));
+            dst[2] = f32_to_f16(fma1(d4.z, ia, result.z)); dst[3] = f32_to_f16(fma1(d4.w, ia, result.w));
         }
     c.stats.oit_fragments = frags; c.stats.direct_rays = dRays; c.stats.direct_samples = dSamples; c.stats.direct_light_fetches = dLight;
 }
