@@ -284,7 +284,6 @@ def main():
     ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--exchange", default="fused", choices=["fused", "collective"])
     ap.add_argument("--work-graph", action="store_true", help="Render(..., useWorkGraph = true): cull inside the view-march launch (one GPU, not pipelined)")
-    ap.add_argument("--fast-fp", action="store_true", help="MV_FLAG_FAST_FP: the opt-in fast build of the OIT resolve and the TAA (not bit-exact)")
     ap.add_argument("--cpu-baseline-frames", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ref-budget", type=float, default=150.0, help="seconds of CPU time the reference arm may use")
@@ -315,7 +314,7 @@ def main():
     tex_peak_gfetch, l2_peak_gbs = tex_peak()
 
     def make_caster():
-        c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, density_only=bool(wl.get("density_only")), fast_fp=args.fast_fp,
+        c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, density_only=bool(wl.get("density_only")),
                            grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
         build_scene(c, wl, scene, sky_coeffs(c))
         return c

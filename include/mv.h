@@ -46,15 +46,6 @@ enum mv_status {
  * holding (1, 1, 1, a). Uploads keep the alpha channel only; mv_volume_read expands to (1, 1, 1, a).
  * SURVEY.md 8(d) cfg 5: 512 x 512^3 = 137 GB instead of 550 GB. */
 #define MV_FLAG_DENSITY_ONLY    4u
-/* creation-time only, opt-in: run the fast build of the two ALU-bound image passes (OIT resolve, TAA + tone map): fused
- * multiply-adds, approximate divide / reciprocal / square root — what dxc's fast-math default does to the reference's own
- * shaders. Without the flag every pass follows the one evaluation order stated in csrc/mv_math.cuh
- * and every output is bit-identical to the test oracle. With it, frames stay above PSNR 50 dB but a handful of pixels per
- * million can move by more than 2e-3 where a discrete decision (which texel a bilinear footprint starts at, whether a box
- * silhouette covers a pixel centre) flips — so the flag is NOT covered by the bit-exact parity claim; it exists for users
- * who prefer 10-30 % on those two passes. The marches, the light march, the cull, ingest and the mesh rasteriser have one
- * build. */
-#define MV_FLAG_FAST_FP         8u
 
 /* MultiRayCaster::Init arguments (MultiRayCaster.h:31-34) + viewport (SetViewport, :38) +
  * SetMaxSamples defaults (MultiVolumes.cpp:27-68). */

@@ -17,7 +17,6 @@ LIB_PATH = os.environ.get("MV_B200_LIB") or os.path.join(HERE, "libmv_b200.so")
 FLAG_COUNT_SAMPLES = 1
 FLAG_TIME_PASSES = 2
 FLAG_DENSITY_ONLY = 4   # MV_FLAG_DENSITY_ONLY: R16F density volumes, colour (1, 1, 1)
-FLAG_FAST_FP = 8        # MV_FLAG_FAST_FP: opt-in fast build of the OIT resolve and the TAA + tone map (not bit-exact)
 
 
 class Timings(C.Structure):
@@ -142,13 +141,12 @@ def parse_dds(path):
 class MultiRayCaster(CasterBase):
     """MultiVolumes/Content/MultiRayCaster.h:28-50 on one B200. Method names follow the reference class."""
 
-    def __init__(self, device=0, count_samples=True, time_passes=False, density_only=False, fast_fp=False, **kw):
+    def __init__(self, device=0, count_samples=True, time_passes=False, density_only=False, **kw):
         flags = (FLAG_COUNT_SAMPLES if count_samples else 0) | (FLAG_TIME_PASSES if time_passes else 0) | \
-                (FLAG_DENSITY_ONLY if density_only else 0) | (FLAG_FAST_FP if fast_fp else 0)
+                (FLAG_DENSITY_ONLY if density_only else 0)
         super().__init__(binding(), opt0=device, opt1=flags, **kw)
         self.device = device
         self.density_only = bool(density_only)
-        self.fast_fp = bool(fast_fp)
 
     # --- product-only calls ---
     def SetRenderTargetsDevice(self, depth=0, shadow=0, shadow_size=0, color=0, velocity=0):

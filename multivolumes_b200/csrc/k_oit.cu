@@ -13,7 +13,6 @@
 #include "k_march.cuh"
 
 namespace mv {
-namespace MV_VARIANT {
 
 namespace {
 
@@ -495,5 +494,4 @@ void launch_resolve_oit(Caster& c)
     k_resolve_oit<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb, (c.d.flags & MV_FLAG_DENSITY_ONLY) != 0);
 }
 
-} // namespace MV_VARIANT
 } // namespace mv

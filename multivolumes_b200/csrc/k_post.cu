@@ -9,7 +9,6 @@
 #include "mv_internal.h"
 
 namespace mv {
-namespace MV_VARIANT {
 
 namespace {
 
@@ -219,9 +218,7 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
 
 } // namespace
 
-#if !MV_FAST
 void build_tone_lut(Caster& c) { k_build_tone_lut<<<256, 256, 0, c.stream>>>(c.dToneLut); }
-#endif
 
 void launch_postprocess(Caster& c, bool taaOn)
 {
@@ -248,5 +245,4 @@ void launch_postprocess(Caster& c, bool taaOn)
     k_postprocess<<<grid, kPostW * kPostH, 0, c.stream>>>(a);
 }
 
-} // namespace MV_VARIANT
 } // namespace mv

@@ -81,11 +81,6 @@ DeviceScene Caster::scene() const
     return s;
 }
 
-// ---- the two builds of the ALU-bound image passes (mv_internal.h) ----
-void launch_ray_cast_direct(Caster& c) { if (c.fastMask & kFastDirect) fast::launch_ray_cast_direct(c); else strict::launch_ray_cast_direct(c); }
-void launch_resolve_oit(Caster& c) { if (c.fastMask & kFastOit) fast::launch_resolve_oit(c); else strict::launch_resolve_oit(c); }
-void launch_postprocess(Caster& c, bool taaOn) { if (c.fastMask & kFastPost) fast::launch_postprocess(c, taaOn); else strict::launch_postprocess(c, taaOn); }
-
 // ---- host matrix algebra (DirectXMath call sites: MultiRayCaster.cpp:325-350) ----
 // Products and inverses are evaluated in double and rounded once to fp32.
 static void mul44(const float* A, const float* B, float* R)
@@ -305,8 +300,6 @@ int mv_create(const mv_desc* d, mv_caster** out)
     if (c.d.max_light_samples == 0) c.d.max_light_samples = 96;
     c.device = (int)d->device;
     c.smCount = prop.multiProcessorCount;
-    c.fastMask = (c.d.flags & MV_FLAG_FAST_FP) ? kFastDefault : 0u;
-    if (const char* e = getenv("MV_FAST_MASK")) c.fastMask = (uint32_t)strtoul(e, nullptr, 0);   // tuning: which passes run their fast build
     const uint32_t G = c.d.grid_size, L = c.d.light_grid_size, N = c.d.num_volumes, S = c.d.num_volume_srcs;
     const size_t px = (size_t)c.d.width * c.d.height;
     c.row0 = 0; c.row1 = c.d.height;
@@ -465,7 +458,7 @@ int mv_create(const mv_desc* d, mv_caster** out)
     MV_CUDA_C(cudaMemsetAsync(c.dBackground, 0, px * 8, c.stream));
     MV_CUDA_C(cudaMemsetAsync(c.dVelocity, 0, px * 4, c.stream));
     MV_CUDA_C(cudaMalloc(&c.dToneLut, 65536));
-    strict::build_tone_lut(c);
+    build_tone_lut(c);
     c.scratchBytes = (size_t)c.smCount * 4 * 8 * 28 * sizeof(float);
     MV_CUDA_C(cudaMalloc(&c.dScratch, c.scratchBytes));
 
@@ -1118,7 +1111,7 @@ int mv_set_flags(mv_caster* h, uint32_t flags)
 {
     MV_ENTER(h);
     MV_REQUIRE((flags & ~(MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES)) == 0);
-    c.d.flags = flags | (c.d.flags & (MV_FLAG_DENSITY_ONLY | MV_FLAG_FAST_FP));   // the storage mode and the floating-point build are fixed at creation
+    c.d.flags = flags | (c.d.flags & (MV_FLAG_DENSITY_ONLY));   // the storage mode is fixed at creation
     c.inputsDirty = true;
     for (auto& v : c.evValid) v = false;
     return MV_OK;

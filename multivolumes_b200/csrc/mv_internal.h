@@ -180,10 +180,6 @@ MV_HD uint32_t num_own_stripes(uint32_t height, uint32_t stripeH, uint32_t rank,
 
 struct Caster;
 
-// passes that have a fast build (Caster::fastMask)
-constexpr uint32_t kFastDirect = 4u, kFastOit = 8u, kFastPost = 16u;
-constexpr uint32_t kFastDefault = kFastOit | kFastPost;   // with MV_FLAG_FAST_FP
-
 // kernel launchers (one translation unit per pass)
 void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
 void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity);
@@ -198,36 +194,15 @@ void launch_peer_signal(Caster& c, uint32_t channel);
 void launch_peer_wait(Caster& c, uint32_t channel);
 int check_peer_timeout(Caster& c);                          // MV_ERR_PEER_TIMEOUT once after a k_peer_wait gave up
 
-// The two ALU-bound image passes (OIT resolve incl. the screen-space march it shares its fragment test with, TAA + tone
-// map) are compiled twice from the same sources (csrc/Makefile):
-//   strict — --fmad=false, correctly rounded divide / reciprocal / square root, fused multiply-adds only where written as
-//            fmaf(): the evaluation-order contract of mv_math.cuh, bit-identical to the test oracle (the default);
-//   fast   — compiler-contracted FMAs, approximate divide / square root (MV_FLAG_FAST_FP, opt-in; see include/mv.h).
-// Everything else — cull, light march, view march, procedural volumes and ingest, the mesh rasteriser, the host
-// matrices — exists once and is always strict.
-#ifndef MV_FAST
-#define MV_FAST 0
-#endif
-#if MV_FAST
-#define MV_VARIANT fast
-#else
-#define MV_VARIANT strict
-#endif
-#define MV_DECLARE_VARIANT_LAUNCHERS                 \
-    void launch_ray_cast_direct(Caster& c);         \
-    void launch_resolve_oit(Caster& c);             \
-    void launch_postprocess(Caster& c, bool taaOn);
-namespace strict { MV_DECLARE_VARIANT_LAUNCHERS void build_tone_lut(Caster& c); }
-namespace fast { MV_DECLARE_VARIANT_LAUNCHERS }
 void launch_ray_march_light(Caster& c, int volumeOverride);
 // phase 0: every cube-map volume; 1: all but the frame's light volume (at most blocksPerSM CTAs per SM, 0 = all that fit);
 // 2: the light volume alone
 void launch_ray_march_view(Caster& c, uint32_t phase = 0, int blocksPerSM = 0);
 void launch_cull_and_ray_march_view(Caster& c);
-// dispatchers (mv_api.cu): pick the build the caster was created with
 void launch_ray_cast_direct(Caster& c);
 void launch_resolve_oit(Caster& c);
 void launch_postprocess(Caster& c, bool taaOn);
+void build_tone_lut(Caster& c);
 
 struct Volume3D {
     uint32_t channels = 4;               // 4 = RGBA16F, 1 = R16F (density-only storage of the source volumes)
@@ -240,7 +215,6 @@ struct Caster {
     mv_desc d{};
     int device = 0;
     int smCount = 0;
-    uint32_t fastMask = 0;               // kFast* bits: which passes run their fast build (MV_FLAG_FAST_FP)
     cudaStream_t stream = nullptr;
     // host scene state (MultiRayCaster.h:189-215)
     std::vector<float> volumeWorlds;     // N x 12 (float4x3)

@@ -28,17 +28,6 @@ def assert_image_close(got_h, want_h, what=""):
     assert psnr(g[fin], w[fin]) >= TOL_PSNR_DB, f"{what}: PSNR {psnr(g[fin], w[fin]):.1f} dB"
 
 
-def assert_image_close_fast(got_h, want_h, what="", max_outliers=2e-4):
-    """The bar of the opt-in MV_FLAG_FAST_FP build (include/mv.h): PSNR >= 50 dB, and max-abs <= 2e-3 on all but a
-    fraction `max_outliers` of the values (pixels where a discrete decision flipped)."""
-    g = got_h.astype(np.float32); w = want_h.astype(np.float32)
-    fin = np.isfinite(w) & np.isfinite(g)
-    assert fin.mean() > 1.0 - max_outliers, what
-    err = np.abs(g[fin] - w[fin]) / np.maximum(1.0, np.abs(w[fin]))
-    assert err.size == 0 or (err > TOL_MAX_ABS).mean() <= max_outliers, f"{what}: {(err > TOL_MAX_ABS).mean():.2e} of the values beyond 2e-3 (max {err.max():.3e})"
-    assert psnr(g[fin], w[fin]) >= TOL_PSNR_DB, f"{what}: PSNR {psnr(g[fin], w[fin]):.1f} dB"
-
-
 def rotation_y(angle):
     c, s = np.cos(angle), np.sin(angle)
     return np.array([[c, 0, -s], [0, 1, 0], [s, 0, c]], np.float64)

@@ -1,18 +1,16 @@
 """Parity of the CUDA path (libmv_b200.so, through the C-ABI) against the CPU oracle on the same
-seeded inputs. Every test runs twice (fixture `fp_mode`):
-  * "strict" — the default build: EVERY output (lists, attributes, light maps, cube maps, frames, RGBA8, work counters)
-    must equal the oracle bit for bit (the library pins one evaluation order, csrc/mv_math.cuh);
-  * "fast"   — MV_FLAG_FAST_FP, the opt-in fast build of the two ALU-bound image passes (OIT resolve, TAA + tone map):
-    everything upstream of them (lists, attributes, light maps, cube maps, counters of the marches) is still bit-exact;
-    frames must keep PSNR >= 50 dB and all but 2e-4 of their values within max-abs 2e-3 (harness.assert_image_close_fast:
-    a discrete decision can flip at a pixel, see include/mv.h) — this mode is NOT part of the bit-exact parity claim.
+seeded inputs. The library pins ONE evaluation order (csrc/mv_math.cuh; the oracle states the same one), so EVERY output —
+visible lists, attributes, light maps, cube maps, frames, TAA images, RGBA8, work counters — must equal the oracle's bit
+for bit; the bar the task states (lists bit-exact; max-abs 2e-3 and PSNR >= 50 dB on RGBA16F, harness.assert_image_close)
+is what a mismatch is reported against. (A fast-math build of the image passes was tried in round 2 and dropped: a few
+pixels per million flip a discrete decision and leave the max-abs bar, profiles/r02_notes.md.)
 Run on the B200 box: pytest -m gpu."""
 import os
 
 import numpy as np
 import pytest
 
-from harness import (assert_image_close, assert_image_close_fast, blob_shadow, checker_background, configure, psnr, sh_coeffs)
+from harness import (assert_image_close, blob_shadow, checker_background, configure, psnr, sh_coeffs)
 from oracle_binding import OracleCaster
 from multivolumes_b200 import scene
 
@@ -26,7 +24,7 @@ def _built(oracle_lib):
 
 def _product(**kw):
     from multivolumes_b200 import MultiRayCaster
-    return MultiRayCaster(fast_fp=not STRICT, **kw)
+    return MultiRayCaster(**kw)
 
 
 def _pair(**kw):
@@ -36,15 +34,7 @@ def _pair(**kw):
 SMALL = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=160, height=90)
 
 
-STRICT = True   # set per test by the fp_mode fixture
-
-
-@pytest.fixture(params=["strict", "fast"], autouse=True)
-def fp_mode(request):
-    global STRICT
-    STRICT = request.param == "strict"
-    yield request.param
-    STRICT = True
+STRICT = os.environ.get("MV_PARITY_STRICT", "1") != "0"   # 0: hold an experimental build to the stated tolerance only
 
 
 def _bits_equal(a, b):
@@ -61,13 +51,13 @@ def _same_bits(a, b):
 
 
 def _check_image(got, want, what):
-    """strict: bit for bit; fast: PSNR and a bounded fraction of outliers."""
+    """bit for bit (MV_PARITY_STRICT=0: the stated tolerance)."""
     if not _same_bits(want, got):
-        assert_image_close_fast(got, want, what)
+        assert_image_close(got, want, what)
 
 
 def _check_counts(so, sp, keys, what=""):
-    """Work counters: exact in the strict build; the fast build may end a ray one step earlier or later."""
+    """Work counters: exact (MV_PARITY_STRICT=0: an experimental build may end a ray one step earlier or later)."""
     for k in keys:
         if STRICT:
             assert so[k] == sp[k], (what, k, so[k], sp[k])
@@ -80,7 +70,7 @@ def _check_rgba8(want, got, what="rgba8"):
     if STRICT:
         assert d.max() == 0, (what, int(d.max()))
     else:   # 2e-3 of RGBA16F is 0.8 of an 8-bit level where the tone map is steepest (slope 1.5 at 0)
-        assert (d > 1).mean() < 2e-4, (what, int(d.max()), float((d > 1).mean()))
+        assert d.max() <= 1, (what, int(d.max()))
 
 
 # ---------------------------------------------------------------- inputs
