@@ -37,6 +37,11 @@ WORKLOADS = {
     "cfg5": dict(n=512, g=512, l=96, w=3840, h=2160, sh=True, taa=True, density_only=True,
                  note="BASELINE.json configs[4]: 512 distinct source volumes in the density-only R16F storage SURVEY.md 8(d) names for it "
                       "(137 GB resident on every GPU; colour (1, 1, 1) as for the reference's file assets)"),
+    "cfg5s": dict(n=512, g=512, l=96, w=3840, h=2160, sh=True, taa=True, shard_volumes=True, proxy=128,
+                  note="BASELINE.json configs[4] as specified: 512 distinct RGBA16F sources of 512^3 (550 GB) sharded by volume — rank r holds the "
+                       "sources s % world == r (69 GB at 8 ranks) and a 128^3 R16F density proxy of every other one (mv_create_sharded); needs >= 4 GPUs"),
+    "cfg5s-mini": dict(n=64, g=256, l=96, w=1920, h=1080, sh=True, taa=True, shard_volumes=True, proxy=64,
+                       note="volume-sharded storage at cfg3's size (for 2-GPU runs)"),
     "cfg2d": dict(n=16, g=128, l=96, w=1920, h=1080, sh=True, taa=True, density_only=True, note="cfg2's densities in the density-only R16F storage"),
     "cfg4d": dict(n=64, g=256, l=96, w=3840, h=2160, sh=True, taa=True, density_only=True, note="cfg4's densities in the density-only R16F storage"),
     "tiny": dict(n=4, g=32, l=16, w=320, h=180, sh=True, taa=True, note="CI-sized"),
@@ -270,7 +275,9 @@ def workload_config(args, wl, world):
                         f"orbit camera; {wl['note']}",
             "l2_policy": f"inputs larger than L2 ({((wl.get('srcs') or wl['n']) * wl['g'] ** 3 * (2 if wl.get('density_only') else 8) + wl['n'] * wl['l'] ** 3 * 8) / 1e6:.0f} MB "
                          f"of volume and light-map textures vs 126 MB)",
-            "parallelism": "1 GPU" if world == 1 else f"{world} GPUs: cube-map tile ranges, light-map z-slabs, interleaved row stripes; exchange = {args.exchange}",
+            "parallelism": "1 GPU" if world == 1 else (f"{world} GPUs, volume-sharded storage: light map / cube map / screen-space march of a volume by the rank that holds it, "
+                                                       f"interleaved row stripes for the resolve; exchange = {args.exchange}" if wl.get("shard_volumes") else
+                                                       f"{world} GPUs: cube-map tile ranges, light-map z-slabs, interleaved row stripes; exchange = {args.exchange}"),
             "e2e_inputs": "per-frame matrices (PerObject records) from pinned host memory; result = tone-mapped RGBA8 frame read back to pinned host "
                           "memory every step (Present, 3 frames in flight as in the reference's frame loop)"}
 
@@ -313,8 +320,12 @@ def main():
     hbm_peak, peak_src = peaks()
     tex_peak_gfetch, l2_peak_gbs = tex_peak()
 
+    if wl.get("shard_volumes") and (world < 2 or (wl["n"] * wl["g"] ** 3 * 8 / world > 150e9)):
+        raise SystemExit(f"bench.py: workload {args.workload} shards {wl['n'] * wl['g'] ** 3 * 8 / 1e9:.0f} GB of volumes over the ranks; {world} GPU(s) cannot hold it")
+
     def make_caster():
         c = MultiRayCaster(device=local_rank, count_samples=False, time_passes=False, density_only=bool(wl.get("density_only")),
+                           shard_volumes=(rank, world, wl["proxy"]) if wl.get("shard_volumes") else None,
                            grid_size=wl["g"], light_grid_size=wl["l"], num_volumes=wl["n"], num_volume_srcs=wl.get("srcs"), width=wl["w"], height=wl["h"])
         build_scene(c, wl, scene, sky_coeffs(c))
         return c

@@ -47,6 +47,9 @@ enum mv_status {
  * SURVEY.md 8(d) cfg 5: 512 x 512^3 = 137 GB instead of 550 GB. */
 #define MV_FLAG_DENSITY_ONLY    4u
 
+/* set by mv_create_sharded (do not pass it to mv_create): volume-sharded storage, see the multi-GPU section */
+#define MV_FLAG_SHARD_VOLUMES   8u
+
 /* MultiRayCaster::Init arguments (MultiRayCaster.h:31-34) + viewport (SetViewport, :38) +
  * SetMaxSamples defaults (MultiVolumes.cpp:27-68). */
 typedef struct mv_desc {
@@ -223,11 +226,29 @@ typedef struct mv_exchange_layout {
     uint32_t light_slab_depth;                          /* ceil(L / world) */
     uint32_t reserved;
     uint64_t light_staging2_offset;                     /* second staging buffer (frames pipelined across ranks alternate) */
+    uint64_t direct_offset, direct_bytes;               /* results of the screen-space marches (RGBA16F per pixel of every direct-scheme
+                                                           volume's rectangle): stored into every peer's block under volume-sharded storage */
     uint64_t history_offset[2], history_bytes;          /* the two TAA history images, H x W RGBA16F: a rank's TAA output rows
                                                            are stored into every peer's image too, because the next frame's
                                                            history fetch (uv - velocity, bilinear) may land on any row */
 } mv_exchange_layout;
 
+/* Volume-sharded storage (BASELINE.json configs[4]: 512 x 512^3 RGBA16F = 550 GB, more than one GPU holds): rank `rank` of
+ * `world` keeps the full-resolution texture of the sources s with s % world == rank only, the light maps of the instances
+ * that use them, and — for every other source — a DENSITY PROXY: the volume's density box-filtered to proxy_grid^3 (R16F;
+ * grid_size must be a multiple of proxy_grid). Every rank is given the same ingest calls (mv_volume_init_procedural,
+ * mv_volume_upload_*, mv_volume_load_dds) and keeps what it owns: no volume data crosses GPUs.
+ *   - the cull is replicated; light maps, cube maps and screen-space marches of a volume are produced by its owner alone
+ *     (cube-map texels and screen-space march results are stored into every peer's exchange block, as in the fused mode);
+ *   - the light march reads the OTHER ranks' volumes through their proxies: inter-volume shadows and ambient occlusion
+ *     cast by a remote volume are those of its box-filtered density. This is the one deviation from the replicated
+ *     storage (stated in DESIGN.md); shadows within a volume and between volumes of one rank are exact;
+ *   - a direct-scheme volume whose screen rectangle does not fit the march-result buffer is left out of the frame (the
+ *     resolve cannot march a volume it does not hold); the buffer holds four full-screen rectangles.
+ * Peers must be mapped (mv_ipc_import, or mv_set_peer_block for casters of one process) before mv_render when world > 1. */
+int mv_create_sharded(const mv_desc* desc, uint32_t rank, uint32_t world, uint32_t proxy_grid, mv_caster** out);
+/* a peer whose exchange block is directly addressable (another caster of this process on the same or a peer-enabled device) */
+int mv_set_peer_block(mv_caster* c, uint32_t peer, void* peer_exchange_block);
 int mv_set_shard(mv_caster* c, uint32_t rank, uint32_t world);
 int mv_set_row_band(mv_caster* c, uint32_t row0, uint32_t row1);     /* rows this rank resolves and post-processes */
 /* interleaved alternative to a contiguous band (better balance when the expensive pixels cluster): with

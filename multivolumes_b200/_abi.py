@@ -112,14 +112,14 @@ class CasterBase:
     """
 
     def __init__(self, binding, grid_size=128, light_grid_size=96, num_volumes=2, num_volume_srcs=None,
-                 width=1280, height=720, max_ray_samples=256, max_light_samples=96, opt0=0, opt1=0):
+                 width=1280, height=720, max_ray_samples=256, max_light_samples=96, opt0=0, opt1=0, create=None):
         self.b = binding
         self.G, self.L, self.N = grid_size, light_grid_size, num_volumes
         self.srcs = num_volume_srcs or num_volumes
         self.W, self.H = width, height
         d = Desc(grid_size, light_grid_size, num_volumes, self.srcs, width, height, max_ray_samples, max_light_samples, opt0, opt1)
         h = _vp()
-        rc = binding.create(C.byref(d), C.byref(h))
+        rc = create(C.byref(d), C.byref(h)) if create else binding.create(C.byref(d), C.byref(h))
         if rc != 0 or not h:
             raise RuntimeError(f"{binding.prefix}create failed (rc={rc}): {self._last_error()}")
         self.h = h

@@ -43,6 +43,8 @@ _EXTRA = {
     "abi_version": (u32, []),
     "set_targets_device": (C.c_int, [_vp, _vp, _vp, u32, _vp, _vp]),
     "set_volume_world_matrices": (C.c_int, [_vp, u32, u32, _vp]),
+    "create_sharded": (C.c_int, [_vp, u32, u32, u32, P(_vp)]),
+    "set_peer_block": (C.c_int, [_vp, u32, _vp]),
     "get_timings": (C.c_int, [_vp, P(Timings)]),
     "sync": (C.c_int, [_vp]),
     "set_flags": (C.c_int, [_vp, u32]),
@@ -141,10 +143,17 @@ def parse_dds(path):
 class MultiRayCaster(CasterBase):
     """MultiVolumes/Content/MultiRayCaster.h:28-50 on one B200. Method names follow the reference class."""
 
-    def __init__(self, device=0, count_samples=True, time_passes=False, density_only=False, **kw):
+    def __init__(self, device=0, count_samples=True, time_passes=False, density_only=False, shard_volumes=None, **kw):
+        """shard_volumes = (rank, world, proxy_grid): volume-sharded storage (mv_create_sharded, include/mv.h)."""
         flags = (FLAG_COUNT_SAMPLES if count_samples else 0) | (FLAG_TIME_PASSES if time_passes else 0) | \
                 (FLAG_DENSITY_ONLY if density_only else 0)
-        super().__init__(binding(), opt0=device, opt1=flags, **kw)
+        b = binding()
+        create = None
+        if shard_volumes is not None:
+            rank, world, proxy = shard_volumes
+            create = lambda d, h: b.create_sharded(d, rank, world, proxy, h)
+        super().__init__(b, opt0=device, opt1=flags, create=create, **kw)
+        self.shard_volumes = shard_volumes
         self.device = device
         self.density_only = bool(density_only)
 
@@ -213,6 +222,10 @@ class MultiRayCaster(CasterBase):
     def IpcImport(self, peer, handle):
         buf = C.create_string_buffer(bytes(handle), 64)
         self._ck(self.b.ipc_import(self.h, peer, buf), "ipc_import")
+
+    def SetPeerBlock(self, peer, block_ptr):
+        """A peer caster of THIS process (same or peer-enabled device): its exchange block is addressed directly."""
+        self._ck(self.b.set_peer_block(self.h, peer, block_ptr), "set_peer_block")
 
     def PeerBarrier(self):
         self._ck(self.b.peer_barrier(self.h), "peer_barrier")

@@ -235,7 +235,7 @@ MV_D void cull_body(const DeviceScene& s, const FrameCB& cb, bool pickLightVolum
     // profiles/r01_notes.md) — while still reading only the wedge of each volume its own rays cross, and the rotation
     // keeps one rank from always getting the same face. Every rank evaluates the same integers: the parts tile the list.
     if (warp == 0) {
-        const bool balanced = s.shardWorld > 1 && s.arena.numPeers != 0;
+        const bool balanced = s.shardWorld > 1 && s.arena.numPeers != 0 && !s.shardVolumes;   // volume-sharded storage: a volume is marched by the rank that holds it
         uint32_t running = 0;
         for (uint32_t base = 0; base < cubeCount; base += 32) {
             const uint32_t k = base + lane;
@@ -249,7 +249,7 @@ MV_D void cull_body(const DeviceScene& s, const FrameCB& cb, bool pickLightVolum
                     const uint32_t part = (s.shardRank + s.shardWorld - k % s.shardWorld) % s.shardWorld;
                     begin = (uint32_t)((unsigned long long)all * part / s.shardWorld);
                     tiles = (uint32_t)((unsigned long long)all * (part + 1) / s.shardWorld) - begin;
-                } else if (vol % s.shardWorld == s.shardRank) tiles = all;
+                } else if ((s.shardVolumes ? (uint32_t)a.w : vol) % s.shardWorld == s.shardRank) tiles = all;
             }
             uint32_t incl = tiles;
 #pragma unroll

@@ -96,7 +96,33 @@ __global__ void __launch_bounds__(128) k_build_occupancy(cudaSurfaceObject_t sur
     if (empty) atomicOr(bits + (b >> 5), 1u << (b & 31));
 }
 
+// Density proxy (volume-sharded storage, include/mv.h): one thread per proxy voxel, the mean density of its f^3 block of the
+// full-resolution volume — fp32, summed x fastest then y then z, times 1 / f^3 (a power of two) — rounded to binary16.
+__global__ void __launch_bounds__(128) k_build_proxy(cudaSurfaceObject_t full, bool fullDensityOnly, cudaSurfaceObject_t proxy, uint32_t P, uint32_t f)
+{
+    const uint32_t i = blockIdx.x * 128 + threadIdx.x;
+    if (i >= P * P * P) return;
+    const uint32_t x = i % P, y = (i / P) % P, z = i / (P * P);
+    float sum = 0.0f;
+    for (uint32_t k = 0; k < f; ++k)
+        for (uint32_t j = 0; j < f; ++j)
+            for (uint32_t q = 0; q < f; ++q) {
+                const int X = (int)(x * f + q), Y = (int)(y * f + j), Z = (int)(z * f + k);
+                uint16_t h;
+                if (fullDensityOnly) h = surf3Dread<unsigned short>(full, X * 2, Y, Z);
+                else h = (uint16_t)(surf3Dread<uint2>(full, X * 8, Y, Z).y >> 16);
+                sum += f16_to_f32(h);
+            }
+    surf3Dwrite((unsigned short)f32_to_f16(sum * (1.0f / (float)(f * f * f))), proxy, (int)(x * 2), (int)y, (int)z);
+}
+
 } // namespace
+
+void launch_build_proxy(Caster& c, const Volume3D& full, Volume3D& proxy)
+{
+    const uint32_t P = proxy.edge, f = full.edge / P;
+    k_build_proxy<<<(P * P * P + 127) / 128, 128, 0, c.stream>>>(full.surf, full.channels == 1, proxy.surf, P, f);
+}
 
 void launch_build_occupancy(Caster& c, uint32_t src)
 {
@@ -107,20 +133,18 @@ void launch_build_occupancy(Caster& c, uint32_t src)
     k_build_occupancy<<<(total + 127) / 128, 128, 0, c.stream>>>(c.volumes[src].surf, c.d.grid_size, c.occShift, c.occBricks, c.volumes[src].channels == 1, bits);
 }
 
-void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed)
+void launch_init_grid(Caster& c, Volume3D& target, uint32_t mode, uint32_t seed)
 {
     const uint32_t n = c.d.grid_size;
     dim3 grid((n + 31) / 32, (n + 7) / 8, n);
-    k_init_grid<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, n, mode, seed, c.volumes[src].channels == 1);
-    launch_build_occupancy(c, src);
+    k_init_grid<<<grid, 256, 0, c.stream>>>(target.surf, n, mode, seed, target.channels == 1);
 }
 
-void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity)
+void launch_r32f_to_rgba16f(Caster& c, Volume3D& target, const float* devDensity)
 {
     const uint32_t n = c.d.grid_size;
     dim3 grid((n + 31) / 32, (n + 7) / 8, n);
-    k_r32f_to_rgba16f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, devDensity, n, c.volumes[src].channels == 1);
-    launch_build_occupancy(c, src);
+    k_r32f_to_rgba16f<<<grid, 256, 0, c.stream>>>(target.surf, devDensity, n, target.channels == 1);
 }
 
 } // namespace mv

@@ -280,10 +280,13 @@ __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(D
         const uint32_t tilesX = (uint32_t)(rectW + 7) >> 3;
         const uint32_t ty = local / tilesX, tx = local - ty * tilesX;
         const int px = vi.x0 + (int)(tx * 8 + (lane & 7)), py = vi.y0 + (int)(ty * 4 + (lane >> 3));
-        if (px > vi.x1 || py > vi.y1 || !row_is_resolved_here(s, cb, py)) continue;
         const uint32_t volumeId = vi.volumeId;
-        const PerObject* po = s.perObject + volumeId;
         const ushort4 a = s.attribs[volumeId];
+        // which pixels of the rectangle this rank marches: the rows it resolves — or, under volume-sharded storage, all of
+        // them if it holds the volume (the results then go to every rank, which resolves its own rows from them)
+        if (px > vi.x1 || py > vi.y1) continue;
+        if (s.shardVolumes ? ((uint32_t)a.w % s.shardWorld != s.shardRank) : !row_is_resolved_here(s, cb, py)) continue;
+        const PerObject* po = s.perObject + volumeId;
         float sx, sy;
         const V3 dirW = pixel_ray(cb, px, py, sx, sy);
         const V3 localEye = {vi.eyeL[0], vi.eyeL[1], vi.eyeL[2]};
@@ -301,7 +304,8 @@ __global__ void __launch_bounds__(256, MV_DIRECT_MIN_BLOCKS) k_ray_cast_direct(D
         }
         const size_t slot = (size_t)__ldg(s.directOffset + lo) + (size_t)(py - vi.y0) * rectW + (px - vi.x0);
         s.directColor[slot] = stored;
-        if (kStats) s.directStats[slot] = st;
+        if (s.shardVolumes) for (uint32_t p = 0; p < s.shardWorld; ++p) if (s.directPeer[p]) s.directPeer[p][slot] = stored;
+        if (kStats && s.directStats) s.directStats[slot] = st;
     }
     if (kStats) {   // diagnostic: samples of every marched pixel (also of fragments that end up beyond the eighth layer)
 #pragma unroll
@@ -430,7 +434,8 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
                     const uint2 st = __ldg(s.directStats + at);
                     if (st.x >> 31) { ++dRays; dSamples += st.x & 0x7fffffffu; dLight += st.y; }
                 }
-            } else color = ray_cast_fallback(ray_cast_args(s, po, volumeId, a.w, smpCnt), localEye, rayDir, sx, sy, sceneDepth, densityOnly, dRays, dSamples, dLight);
+            } else if (!s.shardVolumes)      // (volume-sharded storage: the resolve cannot march a volume this rank does not hold; include/mv.h)
+                color = ray_cast_fallback(ray_cast_args(s, po, volumeId, a.w, smpCnt), localEye, rayDir, sx, sy, sceneDepth, densityOnly, dRays, dSamples, dLight);
         } else color = cube_cast(s, cb, volumeId, a.x, sceneZ, face, lpt, rayDir);
         if (!stored && color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
         const float k1 = 1.0f - result.w;

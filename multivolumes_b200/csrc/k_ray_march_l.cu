@@ -56,6 +56,18 @@ MV_D V3 density_gradient(cudaTextureObject_t grid, V3 uvw, float invGrid, bool d
     return {q1 - q0, q3 - q2, q5 - q4};
 }
 
+// Volume-sharded storage (mv_create_sharded): the light map of a volume is marched by the rank that holds its source — the
+// frame's light volume is picked on the device, so every rank launches the passes and the others leave at once — and the
+// volumes of other ranks are read through their R16F density proxies.
+MV_D bool light_volume_elsewhere(const DeviceScene& s, uint32_t volumeId)
+{
+    return s.shardVolumes && (s.volumeDescs[volumeId] & 0x3fffu) % s.shardWorld != s.shardRank;
+}
+MV_D bool density_in_x(const DeviceScene& s, uint32_t volTexId, bool densityOnly)
+{
+    return densityOnly || (s.srcIsProxy != nullptr && s.srcIsProxy[volTexId] != 0);
+}
+
 // Where the voxels of this launch go. One GPU: straight into the light volume's 3-D array (surface
 // store). Sharded: the rank fills the z-slab [z0, z1) into the linear staging buffer of its own
 // exchange block and, when peers are mapped, into every peer's (NVLink stores); mv_light_commit then
@@ -103,6 +115,7 @@ __global__ void __launch_bounds__(kLightThreads) k_light_classify(DeviceScene s,
     const uint32_t x = bx * 8 + (lane & 7), y = by * 4 + (lane >> 3), z = z0 + bz * 4 + warp;
     const bool active = x < L && y < L && z < z1;
     const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;   // :29-33
+    if (light_volume_elsewhere(s, volumeId)) return;
 
     bool dense = false;
     float shadow = 1.0f;
@@ -281,6 +294,7 @@ template <bool kDensityOnly>
 __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_march_l(DeviceScene s, FrameCB cb, int volumeOverride, LightTarget tgt)
 {
     extern __shared__ float4 s_tab[];                       // [nShared] spheres, then [nShared] x 3 floats of directions
+    if (light_volume_elsewhere(s, volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume)) return;
     const uint32_t N = cb.numVolumes, L = cb.lightGridSize;
     const uint32_t nShared = min(N, kMaxSharedDirs);
     const uint32_t numClusters = (nShared + kLightCluster - 1) / kLightCluster;
@@ -338,7 +352,8 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_marc
                     const V3 rayDir = shadow_dir_local(cb, po, s_dirS, n);
                     if (ray_misses_box_for_sure(localRayOrigin, rayDir)) continue;
                     if (!compute_ray_origin(localRayOrigin, rayDir)) continue;                      // :95
-                    cast_light_ray(shadow, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, kDensityOnly, samples);
+                    const uint32_t texId = s.volumeDescs[n] & 0x3fffu;
+                    cast_light_ray(shadow, s.volumeTex[texId], localRayOrigin, rayDir, gStep, cb.maxLightSamples, density_in_x(s, texId, kDensityOnly), samples);
                 }
                 if (cb.hasSH) {                                                                     // :100-108, geometry only
                     const V3 dirU = mul_v33(aoRayDir, po->worldI);
@@ -400,6 +415,7 @@ __global__ void __launch_bounds__(1024) k_light_scan(DeviceScene s, FrameCB cb, 
     __shared__ uint32_t s_running;
     const uint32_t N = cb.numVolumes, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t ownVolume = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
+    if (light_volume_elsewhere(s, ownVolume)) return;
     if (threadIdx.x == 0) s_running = 0;
     __syncthreads();
     for (uint32_t tile = 0; tile < N; tile += 1024) {
@@ -444,6 +460,7 @@ template <bool kDensityOnly>
 __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, FrameCB cb, int volumeOverride)
 {
     extern __shared__ float4 s_tab[];
+    if (light_volume_elsewhere(s, volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume)) return;
     const uint32_t N = cb.numVolumes, L = cb.lightGridSize;
     const uint32_t nShared = min(N, kMaxSharedDirs);
     float* s_dirS = reinterpret_cast<float*>(s_tab + nShared);
@@ -498,7 +515,8 @@ __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, Fra
             for_each_ao_ray(s, cb, v, rec.castEnd, rec.itemCount, s_tab, s_dirS, nShared, lightDirW,
                             [&](uint32_t n, bool, V3 localRayOrigin, V3 rayDir) {
                                 float transm = 1.0f;
-                                cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, kDensityOnly, samples);
+                                const uint32_t texId = s.volumeDescs[n] & 0x3fffu;
+                                cast_light_ray(transm, s.volumeTex[texId], localRayOrigin, rayDir, gStep, cb.maxLightSamples, density_in_x(s, texId, kDensityOnly), samples);
                                 ao *= (n == volumeId) ? transm : pow025(saturate(transm + 0.5f));   // :107
                             });
             s.lightRecs[recIdx].ao = ao;
@@ -524,6 +542,7 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_AO_MIN_BLOCKS) k_light
     const uint32_t L = cb.lightGridSize;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
+    if (light_volume_elsewhere(s, volumeId)) return;
     const uint32_t count = s.lists->lightOverflow ? 0u : s.lists->lightItemCount;   // a multiple of 32
     const PerObject* po0 = s.perObject + volumeId;
     const float maxDist = 2.0f * sqrtf(3.0f);
@@ -555,7 +574,8 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_AO_MIN_BLOCKS) k_light
         const V3 rayDir = normalize(mul_v33(aoRayDir, po->worldI));
         compute_ray_origin(localRayOrigin, rayDir);
         float transm = 1.0f;
-        cast_light_ray(transm, s.volumeTex[s.volumeDescs[n] & 0x3fffu], localRayOrigin, rayDir, gStep, cb.maxLightSamples, kDensityOnly, samples);
+        const uint32_t texId = s.volumeDescs[n] & 0x3fffu;
+        cast_light_ray(transm, s.volumeTex[texId], localRayOrigin, rayDir, gStep, cb.maxLightSamples, density_in_x(s, texId, kDensityOnly), samples);
         s.lightItemResults[item.z] = (n == volumeId) ? transm : pow025(saturate(transm + 0.5f));    // :107
     }
     if (s.stats) {
@@ -571,6 +591,7 @@ __global__ void __launch_bounds__(256) k_light_finalize(DeviceScene s, FrameCB c
     const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     if (i >= s.lists->lightDenseCount) return;
     const uint32_t volumeId = volumeOverride >= 0 ? (uint32_t)volumeOverride : s.lists->lightVolume;
+    if (light_volume_elsewhere(s, volumeId)) return;
     // the first two 16-byte words of the record: {voxel, itemBase, itemCount, shadow}, {aoDir, ao}
     const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(s.lightRecs + i));
     const uint4 w1 = __ldg(reinterpret_cast<const uint4*>(s.lightRecs + i) + 1);
@@ -596,7 +617,7 @@ void launch_ray_march_light(Caster& c, int volumeOverride)
     const uint32_t L = c.d.light_grid_size;
     LightTarget tgt{};
     tgt.z0 = 0; tgt.z1 = L;
-    if (c.shardWorld > 1) {
+    if (c.shardWorld > 1 && !c.shardVolumes) {       // (volume-sharded storage: the whole light map, by the volume's owner)
         const uint32_t slab = (L + c.shardWorld - 1) / c.shardWorld;
         tgt.z0 = min(L, c.shardRank * slab); tgt.z1 = min(L, tgt.z0 + slab);
         tgt.staging = c.dLightStaging;

@@ -58,7 +58,8 @@ DeviceScene Caster::scene() const
     s.cubeTileBegin = tail + 6 * N + 2;
     s.visInfo = reinterpret_cast<VisInfo*>(dLists + frame_lists_header_bytes(N));
     s.directColor = dDirectColor;
-    s.directStats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dDirectStats : nullptr;
+    // (volume-sharded storage: a pixel's march may have run on another rank; the per-result counters stay where they were counted)
+    s.directStats = ((d.flags & MV_FLAG_COUNT_SAMPLES) && !(shardVolumes && shardWorld > 1)) ? dDirectStats : nullptr;
     s.directCapacity = directCapacity;
     s.volumeTex = dVolumeTex;
     s.occ.bits = dOcc; s.occ.wordsPerVolume = occWords; s.occ.shift = occShift; s.occ.bricks = occBricks; s.occ.gridSize = (float)d.grid_size;
@@ -76,6 +77,11 @@ DeviceScene Caster::scene() const
     s.stats = (d.flags & MV_FLAG_COUNT_SAMPLES) ? dStats : nullptr;
     s.arena = arena;
     s.shardRank = shardRank; s.shardWorld = shardWorld;
+    s.shardVolumes = shardVolumes ? 1u : 0u;
+    s.srcIsProxy = shardVolumes ? dSrcIsProxy : nullptr;
+    for (int p = 0; p < kMaxPeers; ++p)
+        s.directPeer[p] = (shardVolumes && peersMapped && (uint32_t)p < shardWorld && (uint32_t)p != shardRank && peerBlock[p])
+                              ? reinterpret_cast<uint2*>(peerBlock[p] + layout.direct_offset) : nullptr;
     s.row0 = row0; s.row1 = row1;
     s.stripeH = (shardWorld > 1) ? stripeH : 0;
     return s;
@@ -151,6 +157,7 @@ static void set_volumes_world(Caster& c, float size, const float center[3])   //
 static int make_volume3d(Volume3D& v, uint32_t n, uint32_t channels = 4)
 {
     v.channels = channels;
+    v.edge = n;
     const cudaChannelFormatDesc cd = channels == 1 ? cudaCreateChannelDescHalf() : cudaCreateChannelDescHalf4();
     MV_CUDA(cudaMalloc3DArray(&v.array, &cd, make_cudaExtent(n, n, n), cudaArraySurfaceLoadStore));
     cudaResourceDesc rd{};
@@ -207,11 +214,11 @@ static void wait_back_buffer_free(Caster& c)
 // post-process on the main stream) on one GPU and, with the peers mapped, across the ranks of a sharded frame.
 static bool pipelined_sharded(const Caster& c)
 {
-    return c.overlapLight && c.shardPipeline && c.shardWorld > 1 && c.peersMapped && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES));
+    return c.overlapLight && c.shardPipeline && c.shardWorld > 1 && !c.shardVolumes && c.peersMapped && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES));
 }
 static bool pipelined(const Caster& c)
 {
-    return (c.overlapLight && c.shardWorld == 1 && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES))) || pipelined_sharded(c);
+    return (c.overlapLight && (c.shardWorld == 1 || c.shardVolumes) && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES))) || pipelined_sharded(c);
 }
 
 // A new frame's lists and attributes go into the other buffer (the previous frame's resolve may still read its own)
@@ -235,21 +242,49 @@ static int check_launch(const char* what)
     return MV_OK;
 }
 
+static void kill_volume3d(Volume3D& v)
+{
+    if (v.tex) cudaDestroyTextureObject(v.tex);
+    if (v.surf) cudaDestroySurfaceObject(v.surf);
+    if (v.array) cudaFreeArray(v.array);
+    v.tex = 0; v.surf = 0; v.array = nullptr;
+}
+
+int begin_ingest(Caster& c, uint32_t src, IngestTarget& t)
+{
+    Volume3D& own = c.volumes[src];
+    if (!own.proxy) { t.vol = &own; t.temporary = false; return MV_OK; }
+    // this rank keeps only the proxy of the source: the full-resolution data passes through a temporary texture
+    t.vol = new (std::nothrow) Volume3D();
+    if (!t.vol) { set_error("out of host memory"); return MV_ERR_NOMEM; }
+    t.temporary = true;
+    const int rc = make_volume3d(*t.vol, c.d.grid_size, (c.d.flags & MV_FLAG_DENSITY_ONLY) ? 1u : 4u);
+    if (rc != MV_OK) { kill_volume3d(*t.vol); delete t.vol; t.vol = nullptr; }
+    return rc;
+}
+
+int end_ingest(Caster& c, uint32_t src, IngestTarget& t)
+{
+    if (!t.vol) return MV_OK;
+    if (!t.temporary) { launch_build_occupancy(c, src); return check_launch("k_build_occupancy"); }
+    launch_build_proxy(c, *t.vol, c.volumes[src]);
+    int rc = check_launch("k_build_proxy");
+    if (cudaStreamSynchronize(c.stream) != cudaSuccess && rc == MV_OK) { set_error("proxy build failed: %s", cudaGetErrorString(cudaGetLastError())); rc = MV_ERR_CUDA; }
+    kill_volume3d(*t.vol);
+    delete t.vol; t.vol = nullptr;
+    return rc;
+}
+
 static void destroy_caster(Caster& c)
 {
     cudaSetDevice(c.device);
     if (c.stream) cudaStreamSynchronize(c.stream);
     for (void* p : c.openedIpc) cudaIpcCloseMemHandle(p);
-    auto kill = [](Volume3D& v) {
-        if (v.tex) cudaDestroyTextureObject(v.tex);
-        if (v.surf) cudaDestroySurfaceObject(v.surf);
-        if (v.array) cudaFreeArray(v.array);
-    };
-    for (auto& v : c.volumes) kill(v);
-    for (auto& v : c.lightMaps) kill(v);
+    for (auto& v : c.volumes) kill_volume3d(v);
+    for (auto& v : c.lightMaps) kill_volume3d(v);
     void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject2[0], c.dPerObject2[1], c.dVolumeDescs, c.dAttribs2[0], c.dAttribs2[1],
-                     c.dLists2[0], c.dLists2[1], c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectColor, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
-                     c.dOcc, c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dScratch, c.dPeerFlagPtrs, c.dToneLut};
+                     c.dLists2[0], c.dLists2[1], c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
+                     c.dOcc, c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dScratch, c.dPeerFlagPtrs, c.dToneLut, c.dSrcIsProxy};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);
     if (c.hTimeout) cudaFreeHost(c.hTimeout);
@@ -271,10 +306,12 @@ extern "C" {
 const char* mv_last_error(void) { return g_error; }
 uint32_t mv_abi_version(void) { return 1; }
 
-int mv_create(const mv_desc* d, mv_caster** out)
+static int create_impl(const mv_desc* d, bool shardVolumes, uint32_t shardRank, uint32_t shardWorld, uint32_t proxyGrid, mv_caster** out)
 {
     if (out) *out = nullptr;
     MV_REQUIRE(d && out);
+    MV_REQUIRE(shardVolumes || !(d->flags & MV_FLAG_SHARD_VOLUMES));
+    if (shardVolumes) MV_REQUIRE(shardWorld >= 1 && shardWorld <= (uint32_t)kMaxPeers && shardRank < shardWorld && proxyGrid >= 2 && d->grid_size % proxyGrid == 0);
     MV_REQUIRE(d->grid_size != 0 && d->num_volumes != 0 && d->num_volume_srcs != 0 && d->width != 0 && d->height != 0);
     MV_REQUIRE(d->grid_size < (1u << 14) && d->num_volume_srcs < (1u << 14) && (d->grid_size >> (kNumCubeMip - 1)) != 0);
     MV_REQUIRE(d->num_volumes < (1u << 24));
@@ -300,6 +337,7 @@ int mv_create(const mv_desc* d, mv_caster** out)
     if (c.d.max_light_samples == 0) c.d.max_light_samples = 96;
     c.device = (int)d->device;
     c.smCount = prop.multiProcessorCount;
+    if (shardVolumes) { c.shardVolumes = true; c.shardRank = shardRank; c.shardWorld = shardWorld; c.proxyGrid = proxyGrid; c.d.flags |= MV_FLAG_SHARD_VOLUMES; }
     const uint32_t G = c.d.grid_size, L = c.d.light_grid_size, N = c.d.num_volumes, S = c.d.num_volume_srcs;
     const size_t px = (size_t)c.d.width * c.d.height;
     c.row0 = 0; c.row1 = c.d.height;
@@ -336,7 +374,18 @@ int mv_create(const mv_desc* d, mv_caster** out)
 
     // MultiRayCaster.cpp:99-126 — per-source volumes, per-instance light maps and cube maps
     c.volumes.resize(S);
-    for (auto& v : c.volumes) { MV_TRY(make_volume3d(v, G, (c.d.flags & MV_FLAG_DENSITY_ONLY) ? 1u : 4u)); MV_TRY(clear_volume3d(c, v, G)); }
+    {
+        std::vector<unsigned char> isProxy(S, 0);
+        for (uint32_t i = 0; i < S; ++i) {
+            Volume3D& v = c.volumes[i];
+            if (c.owns_source(i)) { MV_TRY(make_volume3d(v, G, (c.d.flags & MV_FLAG_DENSITY_ONLY) ? 1u : 4u)); MV_TRY(clear_volume3d(c, v, G)); }
+            else { MV_TRY(make_volume3d(v, c.proxyGrid, 1u)); v.proxy = true; isProxy[i] = 1; MV_TRY(clear_volume3d(c, v, c.proxyGrid)); }
+        }
+        if (c.shardVolumes) {
+            MV_CUDA_C(cudaMalloc(&c.dSrcIsProxy, S));
+            MV_CUDA_C(cudaMemcpy(c.dSrcIsProxy, isProxy.data(), S, cudaMemcpyHostToDevice));
+        }
+    }
     {
         // empty-space bricks: 64 per axis (32 KB of bits per source volume) for volumes of 256^3 and up; measured on B200
         // (profiles/r02_notes.md): 43 % of cfg4's march samples need no fetch, view march -12 %, screen-space march -10 %.
@@ -353,8 +402,8 @@ int mv_create(const mv_desc* d, mv_caster** out)
             MV_CUDA_C(cudaMemsetAsync(c.dOcc, 0, (size_t)S * c.occWords * sizeof(uint32_t), c.stream));   // nothing known to be empty yet
         }
     }
-    c.lightMaps.resize(N);
-    for (auto& v : c.lightMaps) { MV_TRY(make_volume3d(v, L)); MV_TRY(clear_volume3d(c, v, L)); }
+    c.lightMaps.resize(N);     // volume-sharded storage: only of the instances whose source this rank holds (only their marches read them)
+    for (uint32_t i = 0; i < N; ++i) if (c.owns_source(i % S)) { MV_TRY(make_volume3d(c.lightMaps[i], L)); MV_TRY(clear_volume3d(c, c.lightMaps[i], L)); }
     std::vector<cudaTextureObject_t> vt(S), lt(N);
     std::vector<cudaSurfaceObject_t> ls(N);
     for (uint32_t i = 0; i < S; ++i) vt[i] = c.volumes[i].tex;
@@ -385,8 +434,14 @@ int mv_create(const mv_desc* d, mv_caster** out)
     lay.flags_offset = align256(lay.back_buffer_offset + lay.back_buffer_bytes);
     lay.flags_bytes = 256;
     lay.light_staging2_offset = align256(lay.flags_offset + lay.flags_bytes);
+    // results of the screen-space marches (RayCast of the direct-scheme volumes), rectangle by rectangle: room for four
+    // full-screen rectangles; volumes beyond that are marched inside the resolve kernel
+    c.directCapacity = (uint32_t)std::min<size_t>(4 * px, 0x7fffffffu);
+    if (const char* cap = getenv("MV_DIRECT_CAPACITY")) c.directCapacity = (uint32_t)strtoul(cap, nullptr, 10);   // tests: force the fallback
+    lay.direct_offset = align256(lay.light_staging2_offset + lay.light_staging_bytes);
+    lay.direct_bytes = std::max<uint64_t>(c.directCapacity, 1) * 8ull;
     lay.history_bytes = (uint64_t)px * 8ull;
-    lay.history_offset[0] = align256(lay.light_staging2_offset + lay.light_staging_bytes);
+    lay.history_offset[0] = align256(lay.direct_offset + lay.direct_bytes);
     lay.history_offset[1] = align256(lay.history_offset[0] + lay.history_bytes);
     lay.block_bytes = lay.history_offset[1] + lay.history_bytes;
     lay.light_slab_depth = L;
@@ -396,6 +451,7 @@ int mv_create(const mv_desc* d, mv_caster** out)
     c.dLightStaging2[0] = reinterpret_cast<uint2*>(c.dBlock + lay.light_staging_offset);
     c.dLightStaging2[1] = reinterpret_cast<uint2*>(c.dBlock + lay.light_staging2_offset);
     c.dLightStaging = c.dLightStaging2[0];
+    c.dDirectColor = reinterpret_cast<uint2*>(c.dBlock + lay.direct_offset);
     c.dHistory[0] = reinterpret_cast<uint2*>(c.dBlock + lay.history_offset[0]);
     c.dHistory[1] = reinterpret_cast<uint2*>(c.dBlock + lay.history_offset[1]);
     MV_CUDA_C(cudaHostAlloc(&c.hTimeout, sizeof(uint32_t), cudaHostAllocMapped));
@@ -429,11 +485,7 @@ int mv_create(const mv_desc* d, mv_caster** out)
         MV_CUDA_C(cudaMemsetAsync(c.dLists2[q], 0, listBytes, c.stream));
     }
     c.dLists = c.dLists2[0];
-    // results of the screen-space marches (RayCast of the direct-scheme volumes), rectangle by rectangle: room for four
-    // full-screen rectangles; volumes beyond that are marched inside the resolve kernel
-    c.directCapacity = (uint32_t)std::min<size_t>(4 * px, 0x7fffffffu);
-    if (const char* cap = getenv("MV_DIRECT_CAPACITY")) c.directCapacity = (uint32_t)strtoul(cap, nullptr, 10);   // tests: force the fallback
-    MV_CUDA_C(cudaMalloc(&c.dDirectColor, std::max<size_t>(c.directCapacity, 1) * sizeof(uint2)));
+    if (c.d.flags & MV_FLAG_COUNT_SAMPLES) MV_CUDA_C(cudaMalloc(&c.dDirectStats, std::max<size_t>(c.directCapacity, 1) * sizeof(uint2)));   // else on first use
     MV_CUDA_C(cudaMalloc(&c.dLightDense, (size_t)L * L * L * sizeof(uint2)));
     MV_CUDA_C(cudaMalloc(&c.dLightRecs, (size_t)L * L * L * sizeof(LightRec)));
     c.lightItemCapacity = 4u * L * L * L + 32u * N;   // deferred AO rays (4 per voxel + segment padding); a frame that needs more marches them inline
@@ -479,6 +531,13 @@ int mv_create(const mv_desc* d, mv_caster** out)
     return MV_OK;
 }
 
+int mv_create(const mv_desc* d, mv_caster** out) { return create_impl(d, false, 0, 1, 0, out); }
+
+int mv_create_sharded(const mv_desc* d, uint32_t rank, uint32_t world, uint32_t proxyGrid, mv_caster** out)
+{
+    return create_impl(d, true, rank, world, proxyGrid, out);
+}
+
 void mv_destroy(mv_caster* h)
 {
     if (!h) return;
@@ -496,8 +555,13 @@ int mv_volume_init_procedural(mv_caster* h, uint32_t src, uint32_t mode, uint32_
     MV_ENTER(h);
     c.inputsDirty = true;
     MV_REQUIRE(src < c.d.num_volume_srcs && mode <= 1);
-    launch_init_grid(c, src, mode, seed);
-    return check_launch("k_init_grid");
+    IngestTarget t;
+    int rc = begin_ingest(c, src, t);
+    if (rc != MV_OK) return rc;
+    launch_init_grid(c, *t.vol, mode, seed);
+    rc = check_launch("k_init_grid");
+    const int rc2 = end_ingest(c, src, t);
+    return rc != MV_OK ? rc : rc2;
 }
 
 int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
@@ -506,21 +570,25 @@ int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
     c.inputsDirty = true;
     MV_REQUIRE(texels && src < c.d.num_volume_srcs);
     const uint32_t n = c.d.grid_size;
+    IngestTarget t;
+    int rc = begin_ingest(c, src, t);
+    if (rc != MV_OK) return rc;
     cudaMemcpy3DParms p{};
     std::vector<uint16_t> alpha;
-    if (c.volumes[src].channels == 1) {   // density-only storage keeps the alpha channel
+    if (t.vol->channels == 1) {   // density-only storage keeps the alpha channel
         const size_t count = (size_t)n * n * n;
         alpha.resize(count);
         for (size_t i = 0; i < count; ++i) alpha[i] = texels[4 * i + 3];
         p.srcPtr = make_cudaPitchedPtr(alpha.data(), (size_t)n * 2, n, n);
     } else p.srcPtr = make_cudaPitchedPtr((void*)texels, (size_t)n * 8, n, n);
-    p.dstArray = c.volumes[src].array;
+    p.dstArray = t.vol->array;
     p.extent = make_cudaExtent(n, n, n);
     p.kind = cudaMemcpyHostToDevice;
-    MV_CUDA(cudaMemcpy3DAsync(&p, c.stream));
-    launch_build_occupancy(c, src);
+    const cudaError_t e = cudaMemcpy3DAsync(&p, c.stream);
+    rc = end_ingest(c, src, t);
+    if (e != cudaSuccess) { set_error("volume upload failed: %s", cudaGetErrorString(e)); return MV_ERR_CUDA; }
     MV_CUDA(cudaStreamSynchronize(c.stream));
-    return check_launch("k_build_occupancy");
+    return rc;
 }
 
 int mv_volume_upload_r32f(mv_caster* h, uint32_t src, const float* density)
@@ -533,17 +601,23 @@ int mv_volume_upload_r32f(mv_caster* h, uint32_t src, const float* density)
     float* dtmp = nullptr;
     MV_CUDA(cudaMalloc(&dtmp, bytes));
     cudaError_t e = cudaMemcpyAsync(dtmp, density, bytes, cudaMemcpyHostToDevice, c.stream);
-    if (e == cudaSuccess) { launch_r32f_to_rgba16f(c, src, dtmp); e = cudaGetLastError(); }
+    int rc = MV_OK;
+    if (e == cudaSuccess) {
+        IngestTarget t;
+        rc = begin_ingest(c, src, t);
+        if (rc == MV_OK) { launch_r32f_to_rgba16f(c, *t.vol, dtmp); e = cudaGetLastError(); rc = end_ingest(c, src, t); }
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
     cudaFree(dtmp);
     if (e != cudaSuccess) { set_error("volume_upload_r32f: %s", cudaGetErrorString(e)); return MV_ERR_CUDA; }
-    return MV_OK;
+    return rc;
 }
 
 int mv_volume_read(mv_caster* h, uint32_t src, uint16_t* out)
 {
     MV_ENTER(h);
     MV_REQUIRE(out && src < c.d.num_volume_srcs);
+    if (c.volumes[src].proxy) { set_error("source %u lives on rank %u: this rank holds its density proxy only", src, src % c.shardWorld); return MV_ERR_INVALID; }
     const uint32_t n = c.d.grid_size;
     cudaMemcpy3DParms p{};
     p.srcArray = c.volumes[src].array;
@@ -774,14 +848,57 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
     MV_ENTER(h);
     (void)oit;   // one OIT implementation: the K-buffer semantics of the default branch (:377-381)
     if (c.shardWorld > 1 && !c.peersMapped) {
-        set_error("sharded caster without mapped peers: run the passes and the collectives one by one (mv_cull, mv_ray_march_light, ...)");
+        set_error(c.shardVolumes ? "volume-sharded caster without mapped peers (mv_ipc_import / mv_set_peer_block)"
+                                 : "sharded caster without mapped peers: run the passes and the collectives one by one (mv_cull, mv_ray_march_light, ...)");
         return MV_ERR_INVALID;
     }
     if (const int rc = check_peer_timeout(c)) return rc;
     flip_frame_lists(c);
     const uint32_t slot = c.listParity;             // frameEnd slot of this frame
     c.poLastUse[c.poParity] = (int)slot;
-    if (pipelined_sharded(c)) {
+    if (c.shardVolumes && c.shardWorld > 1) {
+        // Volume-sharded storage (mv_create_sharded): light map, cube map and screen-space march of a volume are produced by
+        // the rank that holds it. The light march (a no-op on every rank but the light volume's owner) goes through the staging
+        // buffer, so that — uninstrumented — it can run on the light stream beside the previous frame's passes, as on one GPU;
+        // it needs no exchange. View march and screen-space march store into every peer's block; one barrier, then the resolve
+        // of this rank's rows. mv_postprocess ends the frame with the closing barrier.
+        cudaStream_t mainStream = c.stream, B = c.lightStream;
+        const bool piped = pipelined(c);
+        if (piped) {
+            wait_upload(c, B);
+            if (c.inputsDirty) { MV_CUDA(cudaEventRecord(c.inputsReady, mainStream)); MV_CUDA(cudaStreamWaitEvent(B, c.inputsReady, 0)); c.inputsDirty = false; }
+            if (c.frameEndValid[slot]) MV_CUDA(cudaStreamWaitEvent(B, c.frameEnd[slot], 0));
+            if (c.commitValid) MV_CUDA(cudaStreamWaitEvent(B, c.commitDone, 0));
+            c.stream = B;
+        } else {
+            wait_upload(c, c.stream);
+            c.inputsDirty = true;
+            if (c.d.flags & MV_FLAG_COUNT_SAMPLES) MV_CUDA(cudaMemsetAsync(c.dStats, 0, sizeof(StatsDev), c.stream));
+            record(c, 0);
+        }
+        launch_cull(c);
+        if (!piped) record(c, 1);
+        c.lightToStaging = true;
+        launch_ray_march_light(c, -1);
+        c.lightToStaging = false;
+        if (piped) {
+            c.stream = mainStream;
+            MV_CUDA(cudaEventRecord(c.lightDone, B));
+            c.lightDoneValid = true;
+            MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
+        }
+        launch_light_commit(c);
+        if (piped) { MV_CUDA(cudaEventRecord(c.commitDone, mainStream)); c.commitValid = true; }
+        else record(c, 2);
+        launch_ray_march_view(c);
+        if (!piped) record(c, 3);
+        MV_TRY_DIRECT_STATS(c);
+        launch_ray_cast_direct(c);
+        wait_back_buffer_free(c);
+        launch_peer_barrier(c);                     // every owner's cube-map texels and screen-space march results have landed
+        launch_resolve_oit(c);
+        if (!piped) { record(c, 4); c.evValid[5] = false; }
+    } else if (pipelined_sharded(c)) {
         // Sharded frame, pipelined across frames. Light stream: cull -> this rank's z-slab of the light map, stored into every
         // rank's staging buffer (two buffers, alternating) -> signal on the light channel. Main stream: wait for every
         // rank's slab -> commit -> view march (texels into every arena) -> barrier -> screen-space march + resolve of this
@@ -1014,6 +1131,7 @@ int mv_read_lightmap(mv_caster* h, uint32_t v, uint16_t* out)
 {
     MV_ENTER(h);
     MV_REQUIRE(out && v < c.d.num_volumes);
+    if (!c.lightMaps[v].array) { set_error("the light map of volume %u lives on the rank that owns its source", v); return MV_ERR_INVALID; }
     const uint32_t n = c.d.light_grid_size;
     cudaMemcpy3DParms p{};
     p.srcArray = c.lightMaps[v].array;

@@ -123,18 +123,23 @@ int mv_volume_upload_r32f_sized(mv_caster* h, uint32_t src, const float* density
         td.normalizedCoords = 1;
         e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
     }
+    int rc = MV_OK;
     if (e == cudaSuccess) {
-        const uint32_t n = c.d.grid_size;
-        dim3 grid((n + 31) / 32, (n + 7) / 8, n);
-        k_resample_r32f<<<grid, 256, 0, c.stream>>>(c.volumes[src].surf, tex, n, c.volumes[src].channels == 1);
-        launch_build_occupancy(c, src);
-        e = cudaGetLastError();
+        IngestTarget t;
+        rc = begin_ingest(c, src, t);
+        if (rc == MV_OK) {
+            const uint32_t n = c.d.grid_size;
+            dim3 grid((n + 31) / 32, (n + 7) / 8, n);
+            k_resample_r32f<<<grid, 256, 0, c.stream>>>(t.vol->surf, tex, n, t.vol->channels == 1);
+            e = cudaGetLastError();
+            rc = end_ingest(c, src, t);
+        }
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c.stream);
     if (tex) cudaDestroyTextureObject(tex);
     cudaFreeArray(arr);
     if (e != cudaSuccess) { set_error("volume_upload_r32f_sized: %s", cudaGetErrorString(e)); return MV_ERR_CUDA; }
-    return MV_OK;
+    return rc;
 }
 
 // LoadVolumeData (MultiRayCaster.h:35-36)

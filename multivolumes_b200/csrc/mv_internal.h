@@ -165,6 +165,9 @@ struct DeviceScene {
     uint2* color;                        // W*H RGBA16F (half4 as uint2)
     StatsDev* stats;                     // nullptr when counters are off
     CubeArena arena;
+    uint32_t shardVolumes;               // volume-sharded storage (mv_create_sharded): source s lives on rank s % world
+    const unsigned char* srcIsProxy;     // [srcs] 1 = this rank holds the source as an R16F density proxy only; nullptr = none
+    uint2* directPeer[kMaxPeers];        // the peers' directColor buffers (volume-sharded storage), nullptr otherwise
     uint32_t shardRank, shardWorld;      // volume v is marched by rank v % world
     uint32_t row0, row1;                 // rows of the frame this rank resolves
     uint32_t stripeH;                    // > 0: interleaved stripes (r / stripeH) % shardWorld == shardRank instead of the band
@@ -181,9 +184,17 @@ MV_HD uint32_t num_own_stripes(uint32_t height, uint32_t stripeH, uint32_t rank,
 struct Caster;
 
 // kernel launchers (one translation unit per pass)
-void launch_init_grid(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
-void launch_r32f_to_rgba16f(Caster& c, uint32_t src, const float* devDensity);
+struct Volume3D;
+void launch_init_grid(Caster& c, Volume3D& target, uint32_t mode, uint32_t seed);
+void launch_r32f_to_rgba16f(Caster& c, Volume3D& target, const float* devDensity);
 void launch_build_occupancy(Caster& c, uint32_t src);   // after every write to a source volume
+void launch_build_proxy(Caster& c, const Volume3D& full, Volume3D& proxy);
+// Every write to a source volume goes through these two: begin_ingest hands out the texture to write (the source's own, or —
+// when this rank keeps only a proxy of it — a temporary full-resolution one), end_ingest derives what the rank keeps from it
+// (empty-space bricks, or the proxy) and releases the temporary.
+struct IngestTarget { Volume3D* vol = nullptr; bool temporary = false; };
+int begin_ingest(Caster& c, uint32_t src, IngestTarget& t);
+int end_ingest(Caster& c, uint32_t src, IngestTarget& t);
 void launch_cull(Caster& c);
 void launch_pick_light_volume(Caster& c);
 void launch_sh_project(Caster& c, const float* devCube, uint32_t size, float* devOut27);
@@ -205,6 +216,8 @@ void launch_postprocess(Caster& c, bool taaOn);
 void build_tone_lut(Caster& c);
 
 struct Volume3D {
+    bool proxy = false;                  // volume-sharded storage: an R16F density proxy of another rank's source
+    uint32_t edge = 0;                   // texels per side
     uint32_t channels = 4;               // 4 = RGBA16F, 1 = R16F (density-only storage of the source volumes)
     cudaArray_t array = nullptr;
     cudaTextureObject_t tex = 0;
@@ -317,6 +330,10 @@ struct Caster {
     size_t scratchBytes = 0;
     // sharding
     uint32_t shardRank = 0, shardWorld = 1;
+    bool shardVolumes = false;           // mv_create_sharded
+    uint32_t proxyGrid = 0;
+    unsigned char* dSrcIsProxy = nullptr;
+    bool owns_source(uint32_t src) const { return !shardVolumes || src % shardWorld == shardRank; }
     uint32_t row0 = 0, row1 = 0;
     uint32_t stripeH = 0;
     std::vector<void*> openedIpc;

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) k_light_commit(DeviceScene s, const uint2
     const uint32_t z = blockIdx.z;
     if (x >= L || y >= L) return;
     const uint32_t volumeId = s.lists->lightVolume;
+    if (s.shardVolumes && (s.volumeDescs[volumeId] & 0x3fffu) % s.shardWorld != s.shardRank) return;   // committed by the volume's owner
     surf3Dwrite(__ldg(staging + ((size_t)z * L + y) * L + x), s.lightSurf[volumeId], (int)(x * 8), (int)y, (int)z);
 }
 
@@ -131,6 +132,7 @@ int mv_set_shard(mv_caster* h, uint32_t rank, uint32_t world)
 {
     MV_ENTER(h);
     MV_REQUIRE(world >= 1 && world <= (uint32_t)kMaxPeers && rank < world);
+    if (c.shardVolumes && (rank != c.shardRank || world != c.shardWorld)) MV_FAIL(MV_ERR_INVALID, "a volume-sharded caster keeps the rank / world it was created with (%u / %u)", c.shardRank, c.shardWorld);
     c.shardRank = rank; c.shardWorld = world;
     c.layout.light_slab_depth = (c.d.light_grid_size + world - 1) / world;
     return refresh_peers(c);
@@ -199,6 +201,14 @@ int mv_ipc_import(mv_caster* h, uint32_t peer, const void* handle64)
     MV_CUDA(cudaIpcOpenMemHandle(&p, hd, cudaIpcMemLazyEnablePeerAccess));
     c.openedIpc.push_back(p);
     c.peerBlock[peer] = static_cast<unsigned char*>(p);
+    return refresh_peers(c);
+}
+
+int mv_set_peer_block(mv_caster* h, uint32_t peer, void* block)
+{
+    MV_ENTER(h);
+    MV_REQUIRE(block && peer < (uint32_t)kMaxPeers && peer != c.shardRank);
+    c.peerBlock[peer] = static_cast<unsigned char*>(block);
     return refresh_peers(c);
 }
 

@@ -99,10 +99,17 @@ int mvo_set_frame_index(mvo_caster* c, uint32_t frame_idx);
 /* sharding, same semantics as mv_set_shard / mv_set_row_band */
 int mvo_set_shard(mvo_caster* c, uint32_t rank, uint32_t world);
 int mvo_set_row_band(mvo_caster* c, uint32_t row0, uint32_t row1);
+/* volume-sharded storage, same semantics as mv_create_sharded: call after the volumes are loaded (builds the proxies) */
+int mvo_set_shard_volumes(mvo_caster* c, uint32_t rank, uint32_t world, uint32_t proxy_grid);
 /* raw access for the exchange steps of the multi-rank host logic (tests): cube map / light map of a volume */
 int mvo_write_cubemap(mvo_caster* c, uint32_t volume, uint32_t mip, const uint16_t* rgba16f, const float* depth);
 int mvo_write_lightmap_slab(mvo_caster* c, uint32_t volume, uint32_t z0, uint32_t z1, const uint16_t* rgba16f_slab);
 int mvo_write_rows(mvo_caster* c, uint32_t what, uint32_t row0, uint32_t row1, const void* rows);
+
+/* MV_MIN16_CONSTS_AS_HALF: 1 = evaluate with the binary16-rounded `min16float` literals the shipped DXIL
+ * holds (g_maxDist 3.4648, ABSORPTION 0.7998, ZERO_THRESHOLD 0.010002, 1/(2 pi) 0.15918, alpha clamp 0.99951, 1/9 0.11108)
+ * instead of the fp32 source literals; process-wide. For measuring how far a real D3D12 run may sit from the oracle. */
+void mvo_set_min16_consts_as_half(int on);
 
 /* stand-alone helpers used by the known-answer tests */
 void  mvo_sample_volume(mvo_caster* c, uint32_t src, const float uvw[3], float rgba_out[4]);

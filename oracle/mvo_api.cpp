@@ -427,6 +427,51 @@ int mvo_set_shard(mvo_caster* h, uint32_t rank, uint32_t world)
     h->c.shardRank = rank; h->c.shardWorld = world;
     return 0;
 }
+// Density proxy of a source volume: the mean density of every (G / P)^3 block (fp32, summed x fastest then y then z, times
+// the reciprocal of the block size — a power of two), rounded to binary16. Same arithmetic as k_build_proxy of the product.
+static void build_proxy(const Tex3D& full, uint32_t P, Tex3D& out)
+{
+    const uint32_t G = full.n, f = G / P;
+    out.n = P;
+    out.texels.assign((size_t)P * P * P * 4, f32_to_f16(1.0f));
+    const float inv = 1.0f / (float)(f * f * f);
+    for (uint32_t z = 0; z < P; ++z)
+        for (uint32_t y = 0; y < P; ++y)
+            for (uint32_t x = 0; x < P; ++x) {
+                float sum = 0.0f;
+                for (uint32_t k = 0; k < f; ++k)
+                    for (uint32_t j = 0; j < f; ++j)
+                        for (uint32_t i = 0; i < f; ++i) sum += f16_to_f32(full.at((int)(x * f + i), (int)(y * f + j), (int)(z * f + k))[3]);
+                out.texels[(((size_t)z * P + y) * P + x) * 4 + 3] = f32_to_f16(sum * inv);
+            }
+}
+
+int mvo_set_shard_volumes(mvo_caster* h, uint32_t rank, uint32_t world, uint32_t proxyGrid)
+{
+    if (!h || world == 0 || rank >= world || proxyGrid == 0 || h->c.d.grid_size % proxyGrid != 0) return -1;
+    Caster& c = h->c;
+    c.shardRank = rank; c.shardWorld = world; c.shardVolumes = true; c.proxyGrid = proxyGrid;
+    c.proxies.assign(c.volumes.size(), Tex3D());
+    for (uint32_t s = 0; s < c.volumes.size(); ++s)
+        if (!c.owns_source(s)) build_proxy(c.volumes[s], proxyGrid, c.proxies[s]);
+    return 0;
+}
+
+// process-wide: the `min16float` literals as the shipped DXIL holds them (binary16-rounded), SURVEY.md App. B.2
+void mvo_set_min16_consts_as_half(int on)
+{
+    Min16Consts k;
+    if (on) {
+        k.absorption = f16_to_f32(0x3A66);       // 0.7998
+        k.zeroThreshold = f16_to_f32(0x211F);    // 0.010002
+        k.maxDist = f16_to_f32(0x42EE);          // 3.4648
+        k.invTwoPi = f16_to_f32(0x3118);         // 0.15918
+        k.alphaClamp = f16_to_f32(0x3BFF);       // 0.99951
+        k.ninth = f16_to_f32(0x2F1C);            // 0.11108
+    }
+    g_min16 = k;
+}
+
 int mvo_set_row_band(mvo_caster* h, uint32_t row0, uint32_t row1)
 {
     if (!h || row0 > row1 || row1 > h->c.d.height) return -1;

@@ -15,8 +15,22 @@ constexpr uint32_t kNumOitLayers = 8;
 constexpr float kZNear = 1.0f, kZFar = 1000.0f;
 // Common.hlsli:12, RayMarch.hlsli:11-12,17
 constexpr uint32_t kCubeMapRayMarchBit = 1u << 15;
-constexpr float kAbsorption = 0.8f;
-constexpr float kZeroThreshold = 0.01f;
+// RayMarch.hlsli:11-12, :17; CSRayMarch.hlsl:155; PSResolveOIT.hlsl:22; CSTemporalAA.hlsl (1 / 9). These are `min16float`
+// literals in the HLSL. The reference is compiled WITHOUT -enable-16bit-types, so min-precision is a hint and the oracle's
+// default is fp32 arithmetic with the source literals; the shipped DXIL, however, holds them rounded to binary16 (SURVEY.md
+// App. B.2), which is what a D3D12 driver would feed its ALUs. mvo_set_min16_consts_as_half(1) switches to those values so
+// that the difference can be measured (tests/test_oracle_kat.py::test_min16_consts_as_half_delta, tools/min16_delta.py).
+struct Min16Consts {
+    float absorption = 0.8f;
+    float zeroThreshold = 0.01f;
+    float maxDist = 3.4641016151377544f;     // 2 sqrt(3), = 2.0f * sqrtf(3.0f) in fp32
+    float invTwoPi = 0.0f;                   // 0 = divide by 2 pi (source form); else the baked reciprocal
+    float alphaClamp = 0.9997f;
+    float ninth = 1.0f / 9.0f;
+};
+extern Min16Consts g_min16;
+#define kAbsorption (mvo::g_min16.absorption)
+#define kZeroThreshold (mvo::g_min16.zeroThreshold)
 constexpr float kFltMax = 3.402823466e+38f;
 constexpr float kPi = 3.1415926535897f;           // SHIrradiance.hlsli:6
 
@@ -73,6 +87,14 @@ struct Caster {
     // the light map is filled in z-slabs of ceil(L / world), OIT and post-process cover rows [row0, row1)
     uint32_t shardRank = 0, shardWorld = 1;
     uint32_t row0 = 0, row1 = 0;
+    // volume-sharded storage (mirrors mv_create_sharded of the product): rank r holds the full-resolution texture of the
+    // sources s with s % world == r only; the light march reads every other volume through a density proxy (box-filtered
+    // to proxyGrid^3), marches light maps and cube maps of its own volumes only, and is not split in z-slabs
+    bool shardVolumes = false;
+    uint32_t proxyGrid = 0;
+    std::vector<Tex3D> proxies;           // per source (empty for the rank's own sources)
+    bool owns_source(uint32_t src) const { return !shardVolumes || src % shardWorld == shardRank; }
+    const Tex3D& density_source(uint32_t src) const { return owns_source(src) ? volumes[src] : proxies[src]; }
     // occluder mesh (mvo_mesh.cpp)
     std::vector<float> meshPos;           // V x 3
     std::vector<uint32_t> meshIdx;        // 3 T

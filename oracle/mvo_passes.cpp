@@ -9,6 +9,8 @@
 
 namespace mvo {
 
+Min16Consts g_min16;
+
 // ------------------------------------------------------------------------------------------
 // CSInitGridData.hlsl:10-27 — procedural density (mode 0 verbatim; mode 1 = same envelope times
 // seeded value noise so that sources differ)
@@ -230,7 +232,7 @@ static inline f3 get_light(const Caster& c, uint32_t volumeId, f3 pos)   // :235
 static f4 march_loop(const Caster& c, uint32_t volumeId, uint32_t volTexId, uint32_t smpCount, f3 rayOrigin, f3 rayDir,
                      float tMax, MarchCounters& mc)
 {
-    const float maxDist = 2.0f * sqrtf(3.0f);           // RayMarch.hlsli:17
+    const float maxDist = g_min16.maxDist;              // g_maxDist = 2 sqrt(3), RayMarch.hlsli:17
     const float stepScale = maxDist / (float)smpCount;
     f4 scatter = {0, 0, 0, 0};
     float t = 0.0f;
@@ -262,7 +264,8 @@ static f4 march_loop(const Caster& c, uint32_t volumeId, uint32_t volTexId, uint
         if (t > tMax) break;
     }
     const float twoPi = 2.0f * kPi;
-    scatter.x /= twoPi; scatter.y /= twoPi; scatter.z /= twoPi;
+    if (g_min16.invTwoPi != 0.0f) { scatter.x *= g_min16.invTwoPi; scatter.y *= g_min16.invTwoPi; scatter.z *= g_min16.invTwoPi; }
+    else { scatter.x /= twoPi; scatter.y /= twoPi; scatter.z /= twoPi; }
     return scatter;
 }
 
@@ -301,7 +304,7 @@ void ray_march_view(Caster& c)
 {
     uint64_t rays = 0, samples = 0, lightFetches = 0;
     for (uint32_t volumeId : c.cubeVolumes) {
-        if (volumeId % c.shardWorld != c.shardRank) continue;   // marched by its owner rank
+        if (c.shardVolumes ? !c.owns_source(c.volumeDescs[volumeId] & 0x3fff) : (volumeId % c.shardWorld != c.shardRank)) continue;   // marched by its owner rank
         const uint16_t* a = &c.attribs[volumeId * 4];
         const uint32_t mip = a[0], smpCount = a[1], maskBits = a[2], volTexId = a[3];
         const PerObject& po = c.perObject[volumeId];
@@ -393,7 +396,7 @@ static void cast_light_ray(const Caster& c, float& transm, uint32_t volTexId, f3
     float t = stepScale;
     float step = stepScale;
     float prevDensity = 0.0f;
-    const Tex3D& grid = c.volumes[volTexId];
+    const Tex3D& grid = c.density_source(volTexId);      // volume-sharded storage: another rank's volume is read through its proxy
     for (uint32_t i = 0; i < numSamples; ++i) {
         const f3 pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
         if (fabsf(pos.x) > 1.0f || fabsf(pos.y) > 1.0f || fabsf(pos.z) > 1.0f) break;
@@ -435,15 +438,16 @@ void ray_march_light(Caster& c, int volumeOverride)
     else volumeId = c.cb.frameIdx % N;
     c.stats.light_volume = volumeId;
     const uint32_t volTexId0 = c.volumeDescs[volumeId] & 0x3fff;
+    if (!c.owns_source(volTexId0)) { c.stats.light_voxels = 0; c.stats.light_dense_voxels = 0; c.stats.light_samples = 0; return; }   // marched by its owner
     const PerObject& po0 = c.perObject[volumeId];
     const float gridSize = (float)L;
-    const float maxDist = 2.0f * sqrtf(3.0f);
+    const float maxDist = g_min16.maxDist;
     const uint32_t numSamples = c.d.max_light_samples;
     const float gStep = maxDist / (float)numSamples;     // RayMarch.hlsli:18
     Tex3D& lm = c.lightMaps[volumeId];
     uint64_t dense = 0, samples = 0;
-    const int slab = (L + (int)c.shardWorld - 1) / (int)c.shardWorld;
-    const int zBegin = std::min(L, (int)c.shardRank * slab), zEnd = std::min(L, zBegin + slab);
+    const int slab = c.shardVolumes ? L : (L + (int)c.shardWorld - 1) / (int)c.shardWorld;
+    const int zBegin = c.shardVolumes ? 0 : std::min(L, (int)c.shardRank * slab), zEnd = std::min(L, zBegin + slab);
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : dense, samples)
     for (int z = zBegin; z < zEnd; ++z)
         for (int y = 0; y < L; ++y)
@@ -719,7 +723,7 @@ void resolve_oit(Caster& c)
                 const float k = 1.0f - result.w;
                 result = {fma1(src.x, k, result.x), fma1(src.y, k, result.y), fma1(src.z, k, result.z), fma1(src.w, k, result.w)};
             }
-            result.w = fminf(result.w, 0.9997f);
+            result.w = fminf(result.w, g_min16.alphaClamp);
             // premultiplied-alpha blend onto the colour RT (MultiRayCaster.cpp:931)
             uint16_t* dst = &c.color[((size_t)py * W + px) * 4];
             const float ia = 1.0f - result.w;
@@ -817,7 +821,7 @@ void temporal_aa(Caster& c, bool taaOn)
                 mu = mu + ntm;
                 m2 = {fma1(ntm.x, ntm.x, m2.x), fma1(ntm.y, ntm.y, m2.y), fma1(ntm.z, ntm.z, m2.z)};
             }
-            const float ninth = 1.0f / 9.0f;
+            const float ninth = g_min16.ninth;
             cur = cur * 0.25f;
             mu = mu * ninth;
             const f3 m2n = m2 * ninth;

@@ -4,6 +4,10 @@ import sys
 
 import pytest
 
+# several casters of one process meet at device-side barriers in the virtual-rank tests: their streams must not share a
+# hardware queue (set before CUDA initialises)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -19,6 +19,8 @@ _EXTRA = {
     "write_cubemap": (C.c_int, [_vp, u32, u32, _vp, _vp]),
     "write_lightmap_slab": (C.c_int, [_vp, u32, u32, u32, _vp]),
     "write_rows": (C.c_int, [_vp, u32, u32, u32, _vp]),
+    "set_shard_volumes": (C.c_int, [_vp, u32, u32, u32]),
+    "set_min16_consts_as_half": (None, [C.c_int]),
 }
 _binding = None
 
@@ -36,6 +38,10 @@ class OracleCaster(CasterBase):
 
     def __init__(self, filter_model=1, threads=0, **kw):
         super().__init__(oracle_binding(), opt0=filter_model, opt1=threads, **kw)
+
+    def SetShardVolumes(self, rank, world, proxy_grid):
+        """Volume-sharded storage as rank `rank` of `world` sees it (call after the volumes are loaded)."""
+        self._ck(self.b.set_shard_volumes(self.h, rank, world, proxy_grid), "set_shard_volumes")
 
     def SampleVolume(self, src, uvw):
         uvw = np.ascontiguousarray(uvw, np.float32).reshape(-1, 3)

@@ -222,3 +222,91 @@ def test_empty_space_bricks_change_nothing(bricks, g, monkeypatch):
     _compare_whole_frame(o, p, f"bricks {bricks}")
     sp = p.GetStats()
     assert sp["view_skipped"] + sp["direct_skipped"] > 0
+
+
+# ---------------------------------------------------------------- volume-sharded storage (BASELINE.json configs[4] as specified)
+@pytest.mark.parametrize("world,sh", [(2, True), (3, False)])
+def test_volume_sharded_storage_virtual_ranks(world, sh):
+    """mv_create_sharded on `world` virtual ranks of ONE device (the casters address each other's exchange blocks directly):
+    rank r holds the sources s % world == r at full resolution and an R16F density proxy (G / 4) of every other one; light
+    maps, cube maps and screen-space marches of a volume are produced by its owner and reach the others through peer
+    stores. Against `world` oracles that see the scene the same way (mvo_set_shard_volumes): every owner's light maps and
+    cube maps bit for bit, then the assembled frame (light maps and cube maps moved between the oracles as the exchange
+    would) bit for bit. And against the unsharded product: the proxies must actually change the light maps."""
+    from harness import blob_shadow, checker_background, configure
+    from multivolumes_b200 import MultiRayCaster
+    kw = dict(grid_size=32, light_grid_size=12, num_volumes=9, num_volume_srcs=9, width=320, height=180)
+    P = 8
+    cfg = dict(sh=sh, background=checker_background(320, 180), random_transforms=5, eye=(8.0, 34.0, -120.0), shadow=blob_shadow())
+    prods = [MultiRayCaster(shard_volumes=(r, world, P), **kw) for r in range(world)]
+    orcs = [OracleCaster(filter_model=1, **kw) for _ in range(world)]
+    for r in range(world):
+        for q in range(world):
+            if q != r:
+                prods[r].SetPeerBlock(q, prods[q].ExchangeBlock()[0])
+        configure(prods[r], **cfg)
+        configure(orcs[r], **cfg)
+        orcs[r].SetShardVolumes(r, world, P)
+        prods[r].SetRowBand(180 * r // world, 180 * (r + 1) // world)
+    frames = 4
+    for f in range(frames):
+        vp, eye = scene.default_camera(320, 180, eye=(8.0 + 3 * f, 34.0, -120.0 + 9 * f))
+        svp = scene.shadow_view_proj()
+        for r in range(world):
+            prods[r].UpdateFrame(vp, svp, eye); prods[r].ResetColor()
+            orcs[r].UpdateFrame(vp, svp, eye); orcs[r].ResetColor()
+        for r in range(world):
+            prods[r].Render()                 # asynchronous: the ranks meet at the device-side barriers
+        for r in range(world):
+            prods[r].Postprocess(False)
+        for r in range(world):
+            prods[r].Sync()
+        # the oracles, pass by pass, with the exchange done by hand
+        for o in orcs:
+            o.Cull(); o.RayMarchL(-1); o.RayMarchV()
+        lv = orcs[0].GetStats()["light_volume"]
+        owner = lv % world                                  # srcs == N: the source of volume v is v
+        lm = np.ascontiguousarray(orcs[owner].ReadLightMap(lv).view(np.uint16))
+        cubes, att = orcs[0].ReadCubeVolumes(), orcs[0].ReadAttribs()
+        for q in range(world):
+            if q != owner:
+                orcs[q]._ck(orcs[q].b.write_lightmap_slab(orcs[q].h, lv, 0, kw["light_grid_size"], lm.ctypes.data), "write_lightmap_slab")
+            for v in cubes:
+                if int(v) % world == q:
+                    continue
+                mip = int(att[v][0])
+                cc, dd = orcs[int(v) % world].ReadCubeMap(int(v), mip)
+                a, b = np.ascontiguousarray(cc.view(np.uint16)), np.ascontiguousarray(dd)
+                orcs[q]._ck(orcs[q].b.write_cubemap(orcs[q].h, int(v), mip, a.ctypes.data, b.ctypes.data), "write_cubemap")
+        for o in orcs:
+            o.ResolveOIT(); o.AdvanceFrame(); o.Postprocess(False)
+    # owners' light maps and cube maps
+    vis = orcs[0].ReadVisible()
+    assert np.array_equal(prods[0].ReadVisible(), vis) and len(vis) >= 5
+    checked = 0
+    for v in range(kw["num_volumes"]):
+        o, p = orcs[v % world], prods[v % world]
+        _exact(p.ReadLightMap(v), o.ReadLightMap(v), f"light map {v} (rank {v % world})")
+        with pytest.raises(RuntimeError):
+            prods[(v + 1) % world].ReadLightMap(v)          # lives on its owner only
+    for v in cubes:
+        mip = int(att[v][0])
+        for q in range(world):                              # every rank's arena holds the owner's texels
+            _exact(prods[q].ReadCubeMap(int(v), mip)[0], orcs[int(v) % world].ReadCubeMap(int(v), mip)[0], f"cube map {v} on rank {q}")
+        checked += 1
+    assert checked >= 2
+    # the assembled frame, rank by rank (each resolved its band)
+    for r in range(world):
+        r0, r1 = 180 * r // world, 180 * (r + 1) // world
+        _exact(prods[r].ReadFrame()[r0:r1], orcs[r].ReadFrame()[r0:r1], f"frame rows of rank {r}")
+    # the deviation is real and bounded: against the replicated storage the light maps differ (proxies), the frame stays close
+    full = MultiRayCaster(**kw)
+    configure(full, **cfg)
+    for f in range(frames):
+        vp, eye = scene.default_camera(320, 180, eye=(8.0 + 3 * f, 34.0, -120.0 + 9 * f))
+        full.UpdateFrame(vp, scene.shadow_view_proj(), eye); full.ResetColor(); full.Render(); full.Postprocess(False)
+    lvs = [v for v in range(kw["num_volumes"]) if np.abs(full.ReadLightMap(v).astype(np.float32)).max() > 0]
+    assert any(not np.array_equal(full.ReadLightMap(v).view(np.uint16), prods[v % world].ReadLightMap(v).view(np.uint16)) for v in lvs)
+    whole = np.concatenate([prods[r].ReadFrame()[180 * r // world:180 * (r + 1) // world] for r in range(world)])
+    from harness import psnr
+    assert psnr(whole.astype(np.float32), full.ReadFrame().astype(np.float32)) > 30.0

@@ -71,15 +71,15 @@ def _single(velocity_scale):
     return c.ReadPost()[1], cubes
 
 
-@pytest.mark.parametrize("mode", ["fused", "fused-overlap", "fused-serial", "collective"])
-def test_two_gpu_frame_equals_single_gpu(mode, tmp_path):
+@pytest.mark.parametrize("mode,world", [("fused", 2), ("fused-overlap", 2), ("fused-serial", 2), ("collective", 2), ("fused", 4), ("fused-serial", 4)])
+def test_multi_gpu_frame_equals_single_gpu(mode, world, tmp_path):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     script = tmp_path / "worker.py"
     script.write_text(WORKER % dict(root=ROOT, here=HERE))
     out = str(tmp_path / "out.npz")
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(29600 + os.getpid() % 300), str(script), mode, out]
     # "fused": frames pipelined across the ranks (light march of frame i + 1 beside frame i, two barrier channels);
     # "fused-overlap": not pipelined, light march of the frame's light volume beside the view march of the other volumes;
@@ -93,7 +93,9 @@ def test_two_gpu_frame_equals_single_gpu(mode, tmp_path):
     got = np.load(out)["rgba8"]
     # the collective mode gathers finished bands only (no history exchange): it is the baseline, run with a static field
     want, cubes = _single(0.02 if mode != "collective" else 0.0)
-    assert np.array_equal(got, want)
+    if not np.array_equal(got, want):
+        rows = np.nonzero((got != want).any(axis=(1, 2)))[0]
+        raise AssertionError(f"{int((got != want).any(axis=2).sum())} pixels differ, rows {rows[:40].tolist()}, max diff {int(np.abs(got.astype(int) - want.astype(int)).max())}")
     peer = np.load(out + ".r1.npz")
     assert len(cubes) > 0 and sorted(peer.files) == sorted(cubes)
     for k, v in cubes.items():
