@@ -56,6 +56,7 @@ struct PostArgs {
     uchar4* peerBackBuffer;   // rank 0's back buffer when this rank resolves a band of a multi-GPU frame
     uint2* peerOut[kMaxPeers]; // the peers' copies of `out` (multi-GPU, peers mapped): the next frame's history fetch of ANY rank may land on these rows
     int numPeers;
+    int peerAllRows;           // 0: only the first and last row of each stripe / band go to the peers (static velocity field: the history fetch stays within one row)
     int W, H, row0, row1;
     int stripeH, rank, world;   // stripeH > 0: interleaved stripes instead of the band
     int taaOn;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
         blockRow -= k * blocksPerStripe;
         rowBegin = (k * a.world + a.rank) * a.stripeH; rowEnd = min(rowBegin + a.stripeH, H);
     }
+    const int y0Stripe = rowBegin;     // first row of the stripe / band this CTA works in
     const int x0 = (int)blockIdx.x * kPostW, y0 = rowBegin + blockRow * kPostH;
     const int x = x0 + tx, y = y0 + ty;
     const bool valid = x < W && y < rowEnd;
@@ -101,7 +103,8 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
             const size_t pix = (size_t)y * W + x;
             const uint2 t = __ldg(a.color + pix);
             a.out[pix] = t;
-            for (int p = 0; p < a.numPeers; ++p) if (a.peerOut[p]) a.peerOut[p][pix] = t;
+            if (a.peerAllRows || y == y0Stripe || y == rowEnd - 1)
+                for (int p = 0; p < a.numPeers; ++p) if (a.peerOut[p]) a.peerOut[p][pix] = t;
             const uchar4 bb = tone_map(t, a.toneLut);
             a.backBuffer[pix] = bb;
             if (a.peerBackBuffer) a.peerBackBuffer[pix] = bb;
@@ -210,7 +213,8 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
     history.w = fminf(history.w * (1.0f / historyMax), 1.0f - curHistoryBlur);
     const uint2 outTexel = pack_half4(V4{result.x, result.y, result.z, history.w});
     a.out[pix] = outTexel;
-    for (int p = 0; p < a.numPeers; ++p) if (a.peerOut[p]) a.peerOut[p][pix] = outTexel;
+    if (a.peerAllRows || y == y0Stripe || y == rowEnd - 1)
+        for (int p = 0; p < a.numPeers; ++p) if (a.peerOut[p]) a.peerOut[p][pix] = outTexel;
     const uchar4 bb = tone_map(outTexel, a.toneLut);
     a.backBuffer[pix] = bb;
     if (a.peerBackBuffer) a.peerBackBuffer[pix] = bb;
@@ -231,6 +235,10 @@ void launch_postprocess(Caster& c, bool taaOn)
     a.backBuffer = c.dBackBuffer;
     a.peerBackBuffer = c.dPeerBackBuffer;
     a.numPeers = (c.shardWorld > 1 && c.peersMapped) ? (int)c.shardWorld : 0;
+    // The next frame's history fetch of a pixel lands at uv - velocity: with the velocity field all zero (none was ever given)
+    // that is the pixel itself up to rounding, i.e. within one row, so only the border rows of every stripe need to reach the
+    // peers; with a velocity field it can land anywhere, and every row goes out.
+    a.peerAllRows = c.velocityGiven ? 1 : 0;
     for (int p = 0; p < kMaxPeers; ++p) a.peerOut[p] = p < a.numPeers ? c.peerHistory[p][c.frameParity] : nullptr;
     a.W = (int)c.d.width; a.H = (int)c.d.height;
     a.row0 = (int)c.row0; a.row1 = (int)c.row1;

@@ -73,7 +73,8 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
     TileConst& tc = s_tc[warp];
     if (kFusedCull) {
         // CTA 0 is the cull node; it releases the frame's lists by storing the serial number after a fence. The launch is
-        // sized to the resident capacity and CTA 0 is dispatched first, so the spinning CTAs cannot starve it.
+        // COOPERATIVE (cudaLaunchCooperativeKernel: the runtime refuses a grid that is not co-resident), so the spinning
+        // CTAs cannot starve CTA 0 whatever the dispatch order; the spin is bounded all the same (about 2 s).
         volatile uint32_t* ready = &s.lists->cullSerial;
         if (blockIdx.x == 0) {
             cull_body<kMarchThreads>(s, cb, false);
@@ -81,8 +82,12 @@ __global__ void __launch_bounds__(kMarchThreads, MV_MARCH_MIN_BLOCKS) k_ray_marc
             __syncthreads();                                // ... before thread 0 learns that they were written
             if (threadIdx.x == 0) { __threadfence(); *ready = serial; }   // release: fence, then the flag
         } else {
-            if (threadIdx.x == 0) while (*ready != serial) __nanosleep(64);
+            if (threadIdx.x == 0) {
+                const long long t0 = clock64();
+                while (*ready != serial && clock64() - t0 < 4000000000ll) __nanosleep(64);
+            }
             __syncthreads();
+            if (*ready != serial) return;               // the cull never published: leave the frame unmarched rather than hang
         }
         __threadfence();
     }
@@ -212,7 +217,11 @@ static void launch_view(Caster& c, bool fusedCull, uint32_t phase, int blocksPer
     }
     if (fusedCull) ++c.cullSerial;
     const int blocks = blocksPerSM > 0 ? min(blocksPerSM, perSM[v]) : perSM[v];
-    kernels[v]<<<c.smCount * blocks, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb, c.cullSerial, phase);
+    if (fusedCull) {
+        DeviceScene scene = c.scene(); FrameCB cb = c.cb; uint32_t serial = c.cullSerial, ph = phase;
+        void* args[] = {&scene, &cb, &serial, &ph};
+        cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernels[v]), dim3(c.smCount * blocks), dim3(kMarchThreads), args, 0, c.stream);
+    } else kernels[v]<<<c.smCount * blocks, kMarchThreads, 0, c.stream>>>(c.scene(), c.cb, c.cullSerial, phase);
 }
 
 void launch_ray_march_view(Caster& c, uint32_t phase, int blocksPerSM) { launch_view(c, false, phase, blocksPerSM); }

@@ -531,12 +531,15 @@ static int create_impl(const mv_desc* d, bool shardVolumes, uint32_t shardRank, 
     return MV_OK;
 }
 
-int mv_create(const mv_desc* d, mv_caster** out) { return create_impl(d, false, 0, 1, 0, out); }
+// (no C++ exception may cross the C boundary: the host-side containers of the entry points that size them from their
+// arguments are guarded, and the failure is reported as MV_ERR_NOMEM)
+int mv_create(const mv_desc* d, mv_caster** out)
+try { return create_impl(d, false, 0, 1, 0, out); }
+catch (const std::bad_alloc&) { set_error("out of host memory"); if (out) *out = nullptr; return MV_ERR_NOMEM; }
 
 int mv_create_sharded(const mv_desc* d, uint32_t rank, uint32_t world, uint32_t proxyGrid, mv_caster** out)
-{
-    return create_impl(d, true, rank, world, proxyGrid, out);
-}
+try { return create_impl(d, true, rank, world, proxyGrid, out); }
+catch (const std::bad_alloc&) { set_error("out of host memory"); if (out) *out = nullptr; return MV_ERR_NOMEM; }
 
 void mv_destroy(mv_caster* h)
 {
@@ -565,7 +568,7 @@ int mv_volume_init_procedural(mv_caster* h, uint32_t src, uint32_t mode, uint32_
 }
 
 int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
-{
+try {
     MV_ENTER(h);
     c.inputsDirty = true;
     MV_REQUIRE(texels && src < c.d.num_volume_srcs);
@@ -589,7 +592,7 @@ int mv_volume_upload_rgba16f(mv_caster* h, uint32_t src, const uint16_t* texels)
     if (e != cudaSuccess) { set_error("volume upload failed: %s", cudaGetErrorString(e)); return MV_ERR_CUDA; }
     MV_CUDA(cudaStreamSynchronize(c.stream));
     return rc;
-}
+} catch (const std::bad_alloc&) { set_error("out of host memory"); return MV_ERR_NOMEM; }
 
 int mv_volume_upload_r32f(mv_caster* h, uint32_t src, const float* density)
 {
@@ -641,7 +644,7 @@ int mv_volume_read(mv_caster* h, uint32_t src, uint16_t* out)
 
 static int set_targets_impl(Caster& c, const float* depth, const uint16_t* shadow, uint32_t shadowSize, const uint16_t* color,
                             const uint16_t* velocity, cudaMemcpyKind kind)
-{
+try {
     c.inputsDirty = true;
     const size_t px = (size_t)c.d.width * c.d.height;
     if (depth) MV_CUDA(cudaMemcpyAsync(c.dDepth, depth, px * sizeof(float), kind, c.stream));
@@ -664,9 +667,10 @@ static int set_targets_impl(Caster& c, const float* depth, const uint16_t* shado
     MV_CUDA(cudaMemcpyAsync(c.dColor, c.dBackground, px * 8, cudaMemcpyDeviceToDevice, c.stream));
     if (velocity) MV_CUDA(cudaMemcpyAsync(c.dVelocity, velocity, px * 4, kind, c.stream));
     else MV_CUDA(cudaMemsetAsync(c.dVelocity, 0, px * 4, c.stream));
+    c.velocityGiven = velocity != nullptr;
     if (kind == cudaMemcpyHostToDevice) MV_CUDA(cudaStreamSynchronize(c.stream));   // host buffers may be pageable / freed by the caller
     return MV_OK;
-}
+} catch (const std::bad_alloc&) { set_error("out of host memory"); return MV_ERR_NOMEM; }
 
 int mv_set_targets(mv_caster* h, const float* depth, const uint16_t* shadow, uint32_t shadowSize, const uint16_t* color, const uint16_t* velocity)
 {

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <vector>
+#include <new>
 
 using namespace mv;
 
@@ -86,6 +87,8 @@ int mv_dds_parse(const char* path, mv_dds_info* out)
     else if ((pfFlags & 0x20000u) && rgbBits == 16) fmt = MV_DDS_R16_UNORM;
     if (!fmt) { set_error("%s: unsupported DDS pixel format (one scalar channel expected)", path); return MV_ERR_INVALID; }
     if (!volume || !width || !height || !depth) { set_error("%s is not a 3-D (volume) texture", path); return MV_ERR_INVALID; }
+    // header fields come from the file: bound them before multiplying (CUDA 3-D arrays end at 16384 per side anyway)
+    if (width > 16384u || height > 16384u || depth > 16384u) { set_error("%s: %u x %u x %u is beyond the 16384^3 a 3-D texture can hold", path, width, height, depth); return MV_ERR_INVALID; }
     const uint32_t bpt = fmt == MV_DDS_R32_FLOAT ? 4 : (fmt == MV_DDS_R8_UNORM ? 1 : 2);
     const uint64_t need = (uint64_t)offset + (uint64_t)width * height * depth * bpt;
     if (need > (uint64_t)fileSize) { set_error("%s: file shorter than its top mip level", path); return MV_ERR_INVALID; }
@@ -144,7 +147,7 @@ int mv_volume_upload_r32f_sized(mv_caster* h, uint32_t src, const float* density
 
 // LoadVolumeData (MultiRayCaster.h:35-36)
 int mv_volume_load_dds(mv_caster* h, uint32_t src, const char* path)
-{
+try {
     MV_REQUIRE(h != nullptr);
     mv_dds_info info;
     int rc = mv_dds_parse(path, &info);
@@ -167,6 +170,6 @@ int mv_volume_load_dds(mv_caster* h, uint32_t src, const char* path)
         }
     }
     return mv_volume_upload_r32f_sized(h, src, density.data(), info.width, info.height, info.depth);
-}
+} catch (const std::bad_alloc&) { set_error("%s: out of host memory while reading the file", path); return MV_ERR_NOMEM; }
 
 } // extern "C"

@@ -321,6 +321,7 @@ struct Caster {
     uint2* dColor = nullptr;             // colour RT
     uint2* dBackground = nullptr;        // copy of the colour RT given to set_targets
     uint32_t* dVelocity = nullptr;       // RG16F
+    bool velocityGiven = false;          // a velocity field was passed to mv_set_targets (else it is all zero)
     uint2* dHistory[2] = {nullptr, nullptr};
     unsigned char* dToneLut = nullptr;   // [65536] PSToneMap + RGBA8 write of every half pattern (k_post.cu)
     uchar4* dBackBuffer = nullptr;

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <cstdlib>
 #include <vector>
+#include <new>
 #include <string>
 
 using namespace mv;
@@ -256,7 +257,7 @@ extern "C" {
 // list reversed (winding flipped for the left-handed frame). Faces with more than three corners are
 // fanned; negative (relative) indices are resolved; texture / normal references are skipped.
 int mv_obj_parse(const char* path, float** positions, uint32_t* numVertices, uint32_t** indices, uint32_t* numIndices)
-{
+try {
     MV_REQUIRE(path && positions && numVertices && indices && numIndices);
     *positions = nullptr; *indices = nullptr; *numVertices = 0; *numIndices = 0;
     FILE* f = fopen(path, "r");
@@ -303,7 +304,7 @@ int mv_obj_parse(const char* path, float** positions, uint32_t* numVertices, uin
     *positions = P; *indices = I;
     *numVertices = (uint32_t)(pos.size() / 3); *numIndices = (uint32_t)idx.size();
     return MV_OK;
-}
+} catch (const std::bad_alloc&) { set_error("%s: out of host memory while parsing", path); return MV_ERR_NOMEM; }
 
 void mv_obj_free(float* positions, uint32_t* indices) { free(positions); free(indices); }
 

@@ -112,6 +112,7 @@ int mvo_write_rows(mvo_caster* c, uint32_t what, uint32_t row0, uint32_t row1, c
 void mvo_set_min16_consts_as_half(int on);
 
 /* stand-alone helpers used by the known-answer tests */
+void  mvo_cube_resolve_texel(int size, int face, int i, int j, int out_face_i_j[3]);   /* seamless Gather addressing of CubeCast */
 void  mvo_sample_volume(mvo_caster* c, uint32_t src, const float uvw[3], float rgba_out[4]);
 float mvo_quantize_r11(float v);
 float mvo_quantize_b10(float v);

@@ -576,6 +576,9 @@ static inline void cube_resolve_texel(int S, int face, int i, int j, int& oface,
     oi = (ua + S - 1) / 2; oj = (vb + S - 1) / 2;
 }
 
+// exposed for the known-answer test of the seamless Gather addressing (mvo.h)
+extern "C" void mvo_cube_resolve_texel(int S, int face, int i, int j, int* out3) { cube_resolve_texel(S, face, i, j, out3[0], out3[1], out3[2]); }
+
 static f4 cube_cast(const Caster& c, uint32_t volumeId, uint32_t mip, int px, int py, int face, f3 pos, f3 rayDir)   // PSCube.hlsli:51-108
 {
     const int S = (int)(c.d.grid_size >> mip);

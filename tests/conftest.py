@@ -7,6 +7,9 @@ import pytest
 # several casters of one process meet at device-side barriers in the virtual-rank tests: their streams must not share a
 # hardware queue (set before CUDA initialises)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# ... and no kernel may be loaded lazily while another caster of the process spins in a barrier kernel (loading a module
+# waits for the device); one process per GPU, the way the library is deployed, has no such coupling
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:

@@ -21,6 +21,7 @@ _EXTRA = {
     "write_rows": (C.c_int, [_vp, u32, u32, u32, _vp]),
     "set_shard_volumes": (C.c_int, [_vp, u32, u32, u32]),
     "set_min16_consts_as_half": (None, [C.c_int]),
+    "cube_resolve_texel": (None, [C.c_int, C.c_int, C.c_int, C.c_int, P(C.c_int)]),
 }
 _binding = None
 

@@ -485,3 +485,133 @@ def test_min16_consts_as_half_delta(oracle_lib):
     d = np.abs(f0 - f1) / np.maximum(1.0, np.abs(f0))
     assert d.max() > 0.0 and (d > 2e-3).mean() < 0.15 and psnr(f1, f0) > 35.0, (d.max(), (d > 2e-3).mean(), psnr(f1, f0))
     assert s0 > 0 and abs(s0 - s1) < 0.02 * s0          # the sample budget per ray follows g_maxDist
+
+
+def test_seamless_cube_addressing_against_unfolded_geometry(oracle_lib):
+    """CubeCast gathers four texels (PSCube.hlsli:59-69); on a TextureCube the taps that fall off a face come from the face
+    across the edge. The oracle (and the kernel) fold the index with integer arithmetic; here the same texel is found
+    geometrically, in float64 and without that arithmetic: the off-face tap's centre lies one texel beyond the edge in the
+    face's plane — rotate it about the cube edge onto the neighbouring face (unfolding the cube) and take the texel of ANY
+    face whose centre is nearest. D3D cube convention for (face, u, v) -> direction."""
+    import ctypes as C
+    from oracle_binding import oracle_binding
+    b = oracle_binding()
+
+    def centre(S, f, i, j):
+        u, v = (i + 0.5) / S * 2 - 1, (j + 0.5) / S * 2 - 1
+        return np.array({0: (1, -v, -u), 1: (-1, -v, u), 2: (u, 1, v), 3: (u, -1, -v), 4: (u, -v, 1), 5: (-u, -v, -1)}[f], np.float64)
+
+    for S in (4, 7, 16):
+        centres = np.array([[[centre(S, f, i, j) for i in range(S)] for j in range(S)] for f in range(6)])      # [f][j][i]
+        for f in range(6):
+            major = f >> 1
+            for (i, j) in [(-1, k) for k in range(S)] + [(S, k) for k in range(S)] + [(k, -1) for k in range(S)] + [(k, S) for k in range(S)]:
+                p = centre(S, f, i, j)                                   # in the face's plane, one texel outside
+                over = [k for k in range(3) if k != major and abs(p[k]) > 1][0]
+                e = abs(p[over]) - 1.0
+                q = p.copy()
+                q[over] = np.sign(p[over])                               # onto the neighbouring face's plane ...
+                q[major] = np.sign(p[major]) * (1.0 - e)                 # ... the overshoot turned about the edge
+                d = np.linalg.norm(centres - q, axis=-1)
+                wf, wj, wi = np.unravel_index(np.argmin(d), d.shape)
+                assert d[wf, wj, wi] < 1e-9
+                out = (C.c_int * 3)()
+                b.cube_resolve_texel(S, f, i, j, out)
+                assert (out[0], out[1], out[2]) == (wf, wi, wj), (S, f, i, j, tuple(out), (wf, wi, wj))
+            # inside the face nothing moves; a corner tap is pinned to the edge texel of the face across the i-edge
+            out = (C.c_int * 3)()
+            b.cube_resolve_texel(S, f, 2, 1, out)
+            assert tuple(out) == (f, 2, 1)
+            b.cube_resolve_texel(S, f, -1, -1, out)
+            ref = (C.c_int * 3)()
+            b.cube_resolve_texel(S, f, -1, 0, ref)
+            assert tuple(out) == tuple(ref)
+
+
+def test_light_voxel_through_two_uniform_volumes():
+    """One whole light-map voxel of CSRayMarchL.hlsl:36-120 with a light probe, replayed independently: the shadow ray through
+    the voxel's own (uniform) volume and on through a second volume stacked above it (the transmittance carries over, the ray
+    re-enters at the second box's face: ComputeRayOrigin), the ambient-occlusion ray of each volume (zero gradient in a uniform
+    volume -> direction = the voxel's world position, :70; in the second volume it starts from the shadow ray's entry point, :95
+    and :103), `transm` for the own volume and pow(sat(transm + 0.5), 0.25) for the other (:107), and
+    shadow * lightColor + ao * irradiance (:113-120) with only the constant SH band set. Geometry in float64, the march
+    recurrences in fp32 as the shader runs them."""
+    f32 = np.float32
+    L, rhoA, rhoB = 16, 0.03, 0.05
+    c = _mk(grid_size=32, light_grid_size=L, num_volumes=2, num_volume_srcs=2, filter_model=0)
+    for i, rho in enumerate((rhoA, rhoB)):
+        tex = np.zeros((32, 32, 32, 4), np.float16); tex[..., :3] = 1.0; tex[..., 3] = rho
+        c.LoadVolumeData(i, tex)
+    sh = np.zeros((9, 3), np.float32); sh[0] = (1.5, 2.0, 2.5)
+    c.SetSH(sh)
+    c.SetLight((0.0, 50.0, 0.0), (1.0, 0.5, 0.25), 2.0)
+    c.SetAmbient((0.1, 0.2, 0.3), 1.0)
+    c.SetVolumeWorld(0, 20.0, (0, 0, 0))
+    c.SetVolumeWorld(1, 20.0, (0, 23.0, 0))
+    c.SetRenderTargets()
+    vp, eye = scene.default_camera(c.W, c.H)
+    c.UpdateFrame(vp, None, eye)
+    c.Cull(); c.RayMarchL(0)
+    lm = c.ReadLightMap(0).astype(np.float32)
+    g_step = f32(2) * np.sqrt(f32(3)) / f32(96)
+    centres = [np.zeros(3), np.array([0.0, 23.0, 0.0])]
+
+    def cast(T, o, d, rho16):
+        """CastLightRay from local origin o along unit d through a uniform box; returns the transmittance."""
+        t, step, prev = g_step, g_step, f32(0)
+        for _ in range(96):
+            if np.any(np.abs(o + d * float(t)) > 1.0):
+                break
+            dd = rho16 - prev
+            opacity = min(max(rho16 * step, f32(0)), f32(1))
+            fe = f32(2) if dd == 0 else min(f32(1 / 256) / abs(dd), f32(2))
+            new = g_step * max(f32(1.5) * fe * min(f32(1) - opacity, f32(1)) * (f32(1) - T), f32(1))
+            prev = rho16
+            T = T * (f32(1) - rho16 * f32(0.8))
+            if T < 0.01:
+                break
+            step = new; t = t + step
+        return T
+
+    def enter(o, d):
+        """ComputeRayOrigin: None on a miss, else the (clamped) entry point."""
+        if np.all(np.abs(o) <= 1.0):
+            return o
+        best = None
+        for a in range(3):
+            if d[a] == 0:
+                continue
+            u = (-np.sign(d[a]) - o[a]) / d[a]
+            if u < 0:
+                continue
+            p = o + d * u
+            if all(abs(p[k]) <= 1.0 for k in range(3) if k != a) and (best is None or u < best):
+                best = u
+        return None if best is None else np.clip(o + d * best, -1.0, 1.0)
+
+    checked = 0
+    for (x, y, z) in ((9, 5, 7), (4, 11, 10), (12, 2, 3)):
+        local = (np.array([x, y, z]) + 0.5) / L * 2 - 1
+        world = local * 10.0
+        ao_dir = world / np.linalg.norm(world)                     # zero gradient: the world position, through World (uniform scale), normalised
+        shadow, ao = f32(1), f32(1)
+        for n, (rho, ctr) in enumerate(zip((rhoA, rhoB), centres)):
+            rho16 = f32(np.float16(rho))
+            o = (world - ctr) / 10.0
+            if shadow >= 0.01:
+                o = enter(o, np.array([0.0, 1.0, 0.0]))
+                if o is None:
+                    continue
+                shadow = cast(shadow, o, np.array([0.0, 1.0, 0.0]), rho16)
+            o2 = enter(o, ao_dir)
+            if o2 is None:
+                continue
+            T = cast(f32(1), o2, ao_dir, rho16)
+            ao = ao * (T if n == 0 else f32(np.sqrt(np.sqrt(min(max(T + f32(0.5), f32(0)), f32(1))))))
+        irr = f32(0.88622692545275801) * sh[0]                     # EvaluateSHIrradiance with the constant band only
+        want = shadow * np.array([1.0, 0.5, 0.25], np.float32) * f32(2.0) + ao * irr
+        got = lm[z, y, x, :3]
+        tol = np.array([2.0 ** -6, 2.0 ** -6, 2.0 ** -5]) * np.maximum(want, 1.0) * 1.01
+        assert np.all(np.abs(got - want) <= tol), ((x, y, z), got, want, float(shadow), float(ao))
+        checked += 1
+    assert checked == 3
