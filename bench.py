@@ -419,9 +419,12 @@ def main():
         outs = r.present_buffers(slots)
         n_e2e = min(args.steps, 100)
 
+        no_present = os.environ.get("MV_BENCH_E2E") == "nopresent"     # diagnostic: the same wall-clock loop without the read-back
+
         def e2e_step(i):
             frame(i)
-            r.present(outs, i % slots)
+            if not no_present:
+                r.present(outs, i % slots)
 
         def drain():
             for k in range(slots):
