@@ -84,6 +84,8 @@ def build_scene(c, wl, scene, sky_coeffs):
     c.SetAmbient(scene.AMBIENT_COLOR, scene.AMBIENT_INTENSITY)
     c.SetVolumesWorld(20.0, (0, 0, 0))
     c.SetSH(sky_coeffs if wl["sh"] else None)
+    if wl["sh"]:
+        c.SetEnvironment(scene.procedural_sky(64))     # the radiance map the SH coefficients come from (LightProbe): drawn behind the volumes
     c.SetRenderTargets(depth=None)
     if wl.get("mesh"):
         # the occluder of Bin/all64.bat: bunny.obj where the reference tree is at hand (this container), its stand-in of the
@@ -220,7 +222,7 @@ def run_reference(args, wl, rank, world):
             o.SetRowBand(*shard_band(wl["h"], *shard))
 
         def render(vp, svp, eye):
-            o.UpdateFrame(vp, svp, eye); o.ResetColor(); o.Render(); o.Postprocess(wl["taa"])
+            o.UpdateFrame(vp, svp, eye); o.RenderEnvironment(); o.Render(); o.Postprocess(wl["taa"])
         step_frame(o, wl, scene, i, render)
         st = o.GetStats()
         return st["view_samples"] + st["direct_samples"] + st["light_samples"]
@@ -255,14 +257,14 @@ def launches_per_frame(wl, world, exchange, work_graph=False):
     k_light_scan, k_light_emit, k_light_ao, k_light_finalize); k_ray_march_v; k_ray_cast_direct; k_resolve_oit; k_postprocess.
     One GPU, pipelined frames: + k_light_commit. Sharded, fused exchange: + k_light_commit and three peer barriers
     (k_peer_signal + k_peer_wait each); with the light / view overlap (8 ranks) the view march is two launches.
-    cfg3: + the depth / shadow producer (k_mesh_setup + k_mesh_raster per pass, clears, D16 conversion)."""
+    With a light probe: + k_environment. cfg3: + the depth / shadow producer (k_mesh_setup + k_mesh_raster per pass, clears,
+    D16 conversion). Volume-sharded storage: two barriers and a commit instead of the slab exchange."""
     n = 1 + (6 if wl["sh"] else 2) + 1 + 1 + 1 + 1   # --work-graph: the same count (k_pick_light_volume instead of k_cull)
+    n += 1 if wl["sh"] else 0
     if world == 1 and not work_graph and os.environ.get("MV_OVERLAP", "1") != "0":
         n += 1                                        # pipelined frames: k_light_commit (light map through the staging buffer)
-    if world > 1:
-        n += 1 + (6 if exchange == "fused" else 0)
-        if exchange == "fused" and int(os.environ.get("MV_SHARD_V_BLOCKS", "4" if world >= 8 else "0")) > 0:
-            n += 1
+    if world > 1:      # fused: k_light_commit + light-channel signal / wait + two barriers on the main channel (signal + wait each)
+        n += 1 + ((4 if wl.get("shard_volumes") else 6) if exchange == "fused" else 0)
     if wl.get("mesh"):
         n += 7
     return n
@@ -517,9 +519,9 @@ def cpu_baseline(args, wl, make_caster):
     while n < args.cpu_baseline_frames and (n == 0 or t_cpu < 25.0):
         i = args.warmup + n
         t0 = time.perf_counter()
-        step_frame(o, wl, scene, i, lambda vp, svp, eye: (o.UpdateFrame(vp, svp, eye), o.ResetColor(), o.Render(), o.Postprocess(wl["taa"])))
+        step_frame(o, wl, scene, i, lambda vp, svp, eye: (o.UpdateFrame(vp, svp, eye), o.RenderEnvironment(), o.Render(), o.Postprocess(wl["taa"])))
         t_cpu += time.perf_counter() - t0
-        step_frame(p, wl, scene, i, lambda vp, svp, eye: (p.UpdateFrame(vp, svp, eye), p.ResetColor(), p.Render(), p.Postprocess(wl["taa"])))
+        step_frame(p, wl, scene, i, lambda vp, svp, eye: (p.UpdateFrame(vp, svp, eye), p.RenderEnvironment(), p.Render(), p.Postprocess(wl["taa"])))
         st = o.GetStats(); samples += st["view_samples"] + st["direct_samples"] + st["light_samples"]
         n += 1
     fo, fp = o.ReadFrame().astype(np.float32), p.ReadFrame().astype(np.float32)

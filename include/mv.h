@@ -168,6 +168,18 @@ int  mv_mesh_set_world(mv_caster* c, float scale, const float pos[3]);
 int  mv_mesh_render_depth(mv_caster* c, const float view_proj[16], float shadow_vp_out[16]);
 int  mv_read_depth(mv_caster* c, float* depth, uint16_t* shadow_d16, uint32_t* shadow_size);
 
+/* ---- the environment under the volumes and the screenshot ----
+ * LightProbe (MultiVolumes/Content/LightProbe.cpp:29-61): the radiance cube map, 6 x size x size x RGB f32 (host), D3D face
+ * order; NULL / 0 = none. mv_render_environment = what the frame loop does to the colour RT before MultiRayCaster::Render
+ * (MultiVolumes.cpp:645-673): the background given to mv_set_targets (the mesh pass's output), then RenderEnvironment
+ * (LightProbe.cpp:85-97, PSEnvironment.hlsl:46-69) wherever the scene depth is 1 — the radiance along the pixel's ray,
+ * alpha 0. Use it in place of mv_reset_color. mv_screenshot = MultiVolumes::SaveImage (MultiVolumes.cpp:744-764): the RGBA8
+ * back buffer as a PNG; mv_write_png is host-only. */
+int mv_set_environment(mv_caster* c, const float* cube_rgb_f32, uint32_t size);
+int mv_render_environment(mv_caster* c);
+int mv_write_png(const char* path, const uint8_t* rgba8, uint32_t width, uint32_t height);
+int mv_screenshot(mv_caster* c, const char* path);
+
 /* read-backs (host pointers; each synchronises the stream). The reference has no read-back API. */
 int mv_read_per_object(mv_caster* c, float* out56xN);
 int mv_read_visible(mv_caster* c, uint32_t* ids, uint32_t* count);

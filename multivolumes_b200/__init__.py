@@ -5,6 +5,6 @@ is the Python mirror of the reference's MultiRayCaster operator surface plus the
 (scene set-up, multi-GPU driver). Nothing here computes on the CPU.
 """
 from . import scene  # noqa: F401
-from .caster import MultiRayCaster, PinnedBuffer, binding, parse_dds, parse_obj, LIB_PATH  # noqa: F401
+from .caster import MultiRayCaster, PinnedBuffer, binding, parse_dds, parse_obj, write_png, LIB_PATH  # noqa: F401
 
-__all__ = ["MultiRayCaster", "PinnedBuffer", "binding", "parse_dds", "parse_obj", "scene", "LIB_PATH"]
+__all__ = ["MultiRayCaster", "PinnedBuffer", "binding", "parse_dds", "parse_obj", "write_png", "scene", "LIB_PATH"]

@@ -58,6 +58,8 @@ _COMMON = {
     "resolve_oit": (C.c_int, [_vp]),
     "postprocess": (C.c_int, [_vp, u32]),
     "sh_project": (C.c_int, [_vp, _vp, u32, _vp]),
+    "set_environment": (C.c_int, [_vp, _vp, u32]),
+    "render_environment": (C.c_int, [_vp]),
     "read_per_object": (C.c_int, [_vp, _vp]),
     "read_visible": (C.c_int, [_vp, _vp, P(u32)]),
     "read_cube_volumes": (C.c_int, [_vp, _vp, P(u32)]),
@@ -279,6 +281,19 @@ class CasterBase:
 
     def Postprocess(self, taa=True):
         self._ck(self.b.postprocess(self.h, 1 if taa else 0), "postprocess")
+
+    def SetEnvironment(self, cube_rgb):
+        """LightProbe: the radiance cube map, (6, S, S, 3) float32 in the D3D face order (None = no environment)."""
+        if cube_rgb is None:
+            self._ck(self.b.set_environment(self.h, None, 0), "set_environment")
+            return
+        cube = np.ascontiguousarray(cube_rgb, dtype=np.float32)
+        assert cube.ndim == 4 and cube.shape[0] == 6 and cube.shape[1] == cube.shape[2] and cube.shape[3] == 3
+        self._ck(self.b.set_environment(self.h, cube.ctypes.data, cube.shape[1]), "set_environment")
+
+    def RenderEnvironment(self):
+        """The colour RT before the volumes: the background (mesh pass) and the environment where the depth is 1."""
+        self._ck(self.b.render_environment(self.h), "render_environment")
 
     def TransformSH(self, cube_rgb):
         cube = np.ascontiguousarray(cube_rgb, dtype=np.float32)

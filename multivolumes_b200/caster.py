@@ -66,6 +66,8 @@ _EXTRA = {
     "obj_parse": (C.c_int, [C.c_char_p, P(P(f32)), P(u32), P(P(u32)), P(u32)]),
     "obj_free": (None, [P(f32), P(u32)]),
     "mesh_load_obj": (C.c_int, [_vp, C.c_char_p]),
+    "write_png": (C.c_int, [C.c_char_p, _vp, u32, u32]),
+    "screenshot": (C.c_int, [_vp, C.c_char_p]),
     "present_async": (C.c_int, [_vp, _vp, u32]),
     "present_rows_async": (C.c_int, [_vp, _vp, u32]),
     "host_register": (C.c_int, [_vp, C.c_size_t]),
@@ -130,6 +132,16 @@ def parse_obj(path):
     return positions, indices
 
 
+def write_png(path, rgba8):
+    """mv_write_png (host only): an (H, W, 4) uint8 image as a PNG file."""
+    b = binding()
+    img = np.ascontiguousarray(rgba8, np.uint8)
+    assert img.ndim == 3 and img.shape[2] == 4
+    rc = b.write_png(os.fsencode(path), img.ctypes.data, img.shape[1], img.shape[0])
+    if rc != 0:
+        raise RuntimeError(f"mv_write_png failed (rc={rc}): {b.last_error().decode()}")
+
+
 def parse_dds(path):
     """Header of a 3-D scalar DDS through mv_dds_parse (host only): dict of width, height, depth, format, bytes_per_texel, data_offset."""
     b = binding()
@@ -183,6 +195,10 @@ class MultiRayCaster(CasterBase):
 
     def LoadMeshObj(self, path):
         self._ck(self.b.mesh_load_obj(self.h, os.fsencode(path)), "mesh_load_obj")
+
+    def Screenshot(self, path):
+        """MultiVolumes::SaveImage: the RGBA8 back buffer as a PNG file."""
+        self._ck(self.b.screenshot(self.h, os.fsencode(path)), "screenshot")
 
     def PresentAsync(self, rgba8_ptr, slot):
         """Swap-chain Present: asynchronous read-back of the back buffer into pinned memory (slot < 3 in flight)."""

@@ -214,6 +214,7 @@ void launch_ray_cast_direct(Caster& c);
 void launch_resolve_oit(Caster& c);
 void launch_postprocess(Caster& c, bool taaOn);
 void build_tone_lut(Caster& c);
+void launch_environment(Caster& c);
 
 struct Volume3D {
     bool proxy = false;                  // volume-sharded storage: an R16F density proxy of another rank's source
@@ -323,6 +324,8 @@ struct Caster {
     uint32_t* dVelocity = nullptr;       // RG16F
     bool velocityGiven = false;          // a velocity field was passed to mv_set_targets (else it is all zero)
     uint2* dHistory[2] = {nullptr, nullptr};
+    uint2* dEnvCube = nullptr;           // radiance cube map of the environment pass, RGBA16F [face][y][x] (k_env.cu)
+    uint32_t envSize = 0;
     unsigned char* dToneLut = nullptr;   // [65536] PSToneMap + RGBA8 write of every half pattern (k_post.cu)
     uchar4* dBackBuffer = nullptr;
     uchar4* dPeerBackBuffer = nullptr;   // rank 0's back buffer (peer-mapped) in a multi-GPU run

@@ -245,7 +245,7 @@ class ShardedRenderer:
         c = self.c
         c.UpdateFrame(view_proj, shadow_vp, eye)
         if reset_color:
-            c.ResetColor()
+            c.RenderEnvironment()
         if self.world == 1:
             c.Render(use_work_graph=self.use_work_graph)
             c.Postprocess(taa)

@@ -77,6 +77,9 @@ int mvo_ray_march_light(mvo_caster* c, int32_t volume_override);   /* -1: refere
 int mvo_ray_march_view(mvo_caster* c);
 int mvo_resolve_oit(mvo_caster* c);
 int mvo_postprocess(mvo_caster* c, uint32_t taa_on);
+/* LightProbe: radiance cube map + RenderEnvironment (same semantics as mv_set_environment / mv_render_environment) */
+int mvo_set_environment(mvo_caster* c, const float* cube_rgb_f32, uint32_t size);
+int mvo_render_environment(mvo_caster* c);
 int mvo_sh_project(mvo_caster* c, const float* cube_rgb_f32, uint32_t size, float* coeffs27_out);
 
 /* ObjectRenderer's depth-only passes (same semantics as mv_mesh_* of the product) */

@@ -457,6 +457,19 @@ int mvo_set_shard_volumes(mvo_caster* h, uint32_t rank, uint32_t world, uint32_t
     return 0;
 }
 
+int mvo_set_environment(mvo_caster* h, const float* cubeRGB, uint32_t size)
+{
+    if (!h || ((cubeRGB == nullptr) != (size == 0))) return -1;
+    Caster& c = h->c;
+    c.envSize = size;
+    c.envCube.assign((size_t)6 * size * size * 4, 0);
+    for (size_t i = 0; i < (size_t)6 * size * size; ++i)
+        for (int k = 0; k < 3; ++k) c.envCube[4 * i + k] = f32_to_f16(cubeRGB[3 * i + k]);
+    return 0;
+}
+
+int mvo_render_environment(mvo_caster* h) { if (!h) return -1; render_environment(h->c); return 0; }
+
 // process-wide: the `min16float` literals as the shipped DXIL holds them (binary16-rounded), SURVEY.md App. B.2
 void mvo_set_min16_consts_as_half(int on)
 {

@@ -95,6 +95,9 @@ struct Caster {
     std::vector<Tex3D> proxies;           // per source (empty for the rank's own sources)
     bool owns_source(uint32_t src) const { return !shardVolumes || src % shardWorld == shardRank; }
     const Tex3D& density_source(uint32_t src) const { return owns_source(src) ? volumes[src] : proxies[src]; }
+    // radiance cube map of the environment pass (LightProbe), RGBA16F [face][y][x]
+    std::vector<uint16_t> envCube;
+    uint32_t envSize = 0;
     // occluder mesh (mvo_mesh.cpp)
     std::vector<float> meshPos;           // V x 3
     std::vector<uint32_t> meshIdx;        // 3 T
@@ -108,6 +111,7 @@ void ray_march_light(Caster& c, int volumeOverride);
 void ray_march_view(Caster& c);
 void resolve_oit(Caster& c);
 void temporal_aa(Caster& c, bool taaOn);
+void render_environment(Caster& c);
 void tone_map(Caster& c);
 void init_grid_data(Caster& c, uint32_t src, uint32_t mode, uint32_t seed);
 void sh_project(const float* cubeRGB, uint32_t size, float out27[27]);

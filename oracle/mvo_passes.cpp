@@ -864,6 +864,57 @@ void temporal_aa(Caster& c, bool taaOn)
         }
 }
 
+// ------------------------------------------------------------------------------------------
+// LightProbe::RenderEnvironment (LightProbe.cpp:85-97: screen quad at z = 1, DEPTH_READ_LESS_EQUAL) + PSEnvironment.hlsl:46-69
+// (infinite-size branch): the radiance cube map along the pixel's ray, alpha 0, wherever the scene depth is 1. The cube lookup
+// is restated as bilinear filtering of mip 0 with fp32 weights and seamless edge taps (the sampler's fixed-point weights are
+// hardware detail); same stated order as the product's k_env.cu.
+// ------------------------------------------------------------------------------------------
+void render_environment(Caster& c)
+{
+    const int W = (int)c.d.width, H = (int)c.d.height, S = (int)c.envSize;
+    c.color = c.background;                                       // what the mesh pass left
+    if (!S) return;
+    const m44& M = c.cb.screenToWorld;
+    const int rowBegin = c.row1 > c.row0 ? std::max((int)c.row0 - 1, 0) : 0, rowEnd = c.row1 > c.row0 ? std::min((int)c.row1 + 1, H) : 0;
+#pragma omp parallel for schedule(static)
+    for (int py = rowBegin; py < rowEnd; ++py)
+        for (int px = 0; px < W; ++px) {
+            const size_t pix = (size_t)py * W + px;
+            if (!(1.0f <= c.depth[pix])) continue;
+            const float sx = fma1((float)px + 0.5f, 2.0f / c.cb.viewport.x, -1.0f), sy = fma1((float)py + 0.5f, -(2.0f / c.cb.viewport.y), 1.0f);
+            const float whx = fma1(sx, M.m[0][0], fma1(sy, M.m[1][0], M.m[2][0] + M.m[3][0])), why = fma1(sx, M.m[0][1], fma1(sy, M.m[1][1], M.m[2][1] + M.m[3][1]));
+            const float whz = fma1(sx, M.m[0][2], fma1(sy, M.m[1][2], M.m[2][2] + M.m[3][2])), whw = fma1(sx, M.m[0][3], fma1(sy, M.m[1][3], M.m[2][3] + M.m[3][3]));
+            const float iw = rcp(whw);
+            const f3 viewDir = normalize3(c.cb.eyePt - f3{whx * iw, why * iw, whz * iw});
+            const f3 d = -viewDir;
+            const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+            int face; float ma;
+            if (ax >= ay && ax >= az) { face = d.x > 0.0f ? 0 : 1; ma = ax; }
+            else if (ay >= az) { face = d.y > 0.0f ? 2 : 3; ma = ay; }
+            else { face = d.z > 0.0f ? 4 : 5; ma = az; }
+            const float im = rcp(ma);
+            float u, v;
+            cube_face_uv({d.x * im, d.y * im, d.z * im}, face, u, v);
+            const float fx = fma1(u, (float)S, -0.5f), fy = fma1(v, (float)S, -0.5f);
+            const float flx = floorf(fx), fly = floorf(fy);
+            const float wx = fx - flx, wy = fy - fly;
+            const int i0 = (int)flx, j0 = (int)fly;
+            f4 t[4];
+            for (int k = 0; k < 4; ++k) {
+                int f, i, j;
+                cube_resolve_texel(S, face, i0 + (k & 1), j0 + (k >> 1), f, i, j);
+                const uint16_t* h = &c.envCube[(((size_t)f * S + j) * S + i) * 4];
+                t[k] = {f16_to_f32(h[0]), f16_to_f32(h[1]), f16_to_f32(h[2]), f16_to_f32(h[3])};
+            }
+            uint16_t* o = &c.color[pix * 4];
+            o[0] = f32_to_f16(lerpf(lerpf(t[0].x, t[1].x, wx), lerpf(t[2].x, t[3].x, wx), wy));
+            o[1] = f32_to_f16(lerpf(lerpf(t[0].y, t[1].y, wx), lerpf(t[2].y, t[3].y, wx), wy));
+            o[2] = f32_to_f16(lerpf(lerpf(t[0].z, t[1].z, wx), lerpf(t[2].z, t[3].z, wx), wy));
+            o[3] = 0;
+        }
+}
+
 void tone_map(Caster& c)
 {
     const int W = (int)c.d.width, H = (int)c.d.height;

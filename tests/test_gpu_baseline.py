@@ -62,7 +62,7 @@ def _exact(a, b, what):
 
 
 def _frame(c, wl, i, taa):
-    bench.step_frame(c, wl, scene, i, lambda vp, svp, eye: (c.UpdateFrame(vp, svp, eye), c.ResetColor(), c.Render(), c.Postprocess(taa)))
+    bench.step_frame(c, wl, scene, i, lambda vp, svp, eye: (c.UpdateFrame(vp, svp, eye), c.RenderEnvironment(), c.Render(), c.Postprocess(taa)))
 
 
 COUNTERS = ("view_rays", "view_samples", "view_light_fetches", "light_dense_voxels", "light_samples", "direct_rays", "direct_samples",

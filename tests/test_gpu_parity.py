@@ -662,3 +662,45 @@ def test_light_march_many_volumes_bit_exact(n, transforms, sh):
         _check_counts(so, sp, ("light_samples",), v)
         _check_image(p.ReadLightMap(v), o.ReadLightMap(v), f"light map {v}")
     assert so["light_samples"] > 0
+
+
+# ---------------------------------------------------------------- environment under the volumes + screenshot
+def test_environment_pass_and_screenshot(tmp_path):
+    """LightProbe::RenderEnvironment + PSEnvironment in front of MultiRayCaster::Render, over an orbit: the procedural sky
+    behind the volumes, a depth occluder that keeps the mesh pass's colour, volumes composited over both; then the frame
+    loop's screenshot (MultiVolumes::SaveImage) decodes to the RGBA8 back buffer."""
+    import zlib, struct
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=9, num_volume_srcs=3, width=320, height=180)
+    o, p = _pair(**kw)
+    sky = scene.procedural_sky(32)
+    vp0, _ = scene.default_camera(320, 180)
+    depth = scene.sphere_depth(320, 180, vp0, center=(0, 0, 0), radius=9.0)
+    for c in (o, p):
+        configure(c, sh=True, depth=depth, background=checker_background(320, 180))
+        c.SetEnvironment(sky)
+    for f in range(4):
+        vp, eye = scene.orbit_camera(320, 180, 40 * f)
+        for c in (o, p):
+            c.UpdateFrame(vp, None, eye)
+            c.RenderEnvironment()
+        if f == 3:
+            env = o.ReadFrame()
+            _check_image(p.ReadFrame(), env, "environment")
+        for c in (o, p):
+            c.Render(); c.Postprocess(True)
+    _check_image(p.ReadFrame(), o.ReadFrame(), "frame over the environment")
+    (to, bo), (tp, bp) = o.ReadPost(), p.ReadPost()
+    _check_image(tp, to, "taa"); _check_rgba8(bo, bp)
+    sky_px = depth >= 1.0
+    assert sky_px.any() and (~sky_px).any() and np.abs(env.astype(np.float32)[sky_px][:, :3]).max() > 0.5
+    path = str(tmp_path / "shot.png")
+    p.Screenshot(path)
+    d = open(path, "rb").read()
+    pos, idat = 8, b""
+    while pos < len(d):
+        n, = struct.unpack(">I", d[pos:pos + 4])
+        if d[pos + 4:pos + 8] == b"IDAT":
+            idat += d[pos + 8:pos + 8 + n]
+        pos += 12 + n
+    rows = np.frombuffer(zlib.decompress(idat), np.uint8).reshape(180, 1 + 320 * 4)
+    assert np.array_equal(rows[:, 1:].reshape(180, 320, 4), bp)

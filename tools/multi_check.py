@@ -47,7 +47,7 @@ with torch.cuda.stream(stream):
 if rank == 0:
     s = make(0)
     for i in range(K):
-        bench.step_frame(s, wl, scene, STEP * i, lambda vp, svp, eye: (s.UpdateFrame(vp, svp, eye), s.ResetColor(), s.Render(), s.Postprocess(wl["taa"])))
+        bench.step_frame(s, wl, scene, STEP * i, lambda vp, svp, eye: (s.UpdateFrame(vp, svp, eye), s.RenderEnvironment(), s.Render(), s.Postprocess(wl["taa"])))
     taa1, want = s.ReadPost()
     d = (got != want).any(axis=2)
     print(f"world {world} {'serial' if instr else 'pipelined'}: rgba8 pixels differing {int(d.sum())}, rows {np.nonzero(d.any(axis=1))[0][:30].tolist()}, cols {np.nonzero(d.any(axis=0))[0][:20].tolist()}")

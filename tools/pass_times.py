@@ -14,7 +14,7 @@ bench.build_scene(c, wl, scene, c.TransformSH(scene.procedural_sky(64)))
 acc = {}
 for i in range(30 + frames):
     vp, eye = bench.camera(scene, wl, i)
-    c.UpdateFrame(vp, None, eye); c.ResetColor(); c.Render(); c.Postprocess(wl["taa"])
+    c.UpdateFrame(vp, None, eye); c.RenderEnvironment(); c.Render(); c.Postprocess(wl["taa"])
     if i >= 30:
         for k, v in c.GetTimings().items():
             acc[k] = acc.get(k, 0.0) + v / frames
