@@ -35,6 +35,17 @@ public:
         mv_destroy(m_h); m_h = nullptr;
         return ok(mv_create(&d, &m_h));
     }
+    // The same with volume-sharded storage (one process per GPU; no counterpart in the single-adapter reference): this rank
+    // keeps the sources s % world == rank at full resolution and a proxyGrid^3 density proxy of the others (mv.h)
+    bool InitSharded(uint32_t width, uint32_t height, uint32_t gridSize, uint32_t lightGridSize, uint32_t numVolumes,
+                     uint32_t numVolumeSrcs, uint32_t rank, uint32_t world, uint32_t proxyGrid, uint32_t device = 0, uint32_t flags = 0)
+    {
+        mv_desc d{};
+        d.grid_size = gridSize; d.light_grid_size = lightGridSize; d.num_volumes = numVolumes; d.num_volume_srcs = numVolumeSrcs;
+        d.width = width; d.height = height; d.max_ray_samples = 256; d.max_light_samples = 96; d.device = device; d.flags = flags;
+        mv_destroy(m_h); m_h = nullptr;
+        return ok(mv_create_sharded(&d, rank, world, proxyGrid, &m_h));
+    }
     // LoadVolumeData (:35-36): R32F density (the DDS payload) through the CSR32FToRGBA16F conversion, or RGBA16F texels
     bool LoadVolumeData(uint32_t i, const float* density) { return ok(mv_volume_upload_r32f(m_h, i, density)); }
     bool LoadVolumeData(uint32_t i, const uint16_t* rgba16f) { return ok(mv_volume_upload_rgba16f(m_h, i, rgba16f)); }
@@ -54,6 +65,7 @@ public:
     void SetVolumesWorld(float size, const Float3& center) { const float c[3] = {center.x, center.y, center.z}; mv_set_volumes_world(m_h, size, c); }   // :43
     void SetVolumeWorld(uint32_t i, float size, const Float3& pos) { const float p[3] = {pos.x, pos.y, pos.z}; mv_set_volume_world(m_h, i, size, p); } // :44
     void SetVolumeWorld(uint32_t i, const float world4x3[12]) { mv_set_volume_world_matrix(m_h, i, world4x3); }
+    void SetVolumeWorlds(uint32_t first, uint32_t count, const float* world4x3) { mv_set_volume_world_matrices(m_h, first, count, world4x3); }
     void SetLight(const Float3& pos, const Float3& color, float intensity)                              // :45
     { const float p[3] = {pos.x, pos.y, pos.z}, c[3] = {color.x, color.y, color.z}; mv_set_light(m_h, p, c, intensity); }
     void SetAmbient(const Float3& color, float intensity) { const float c[3] = {color.x, color.y, color.z}; mv_set_ambient(m_h, c, intensity); }       // :46
@@ -75,6 +87,12 @@ public:
     { return ok(mv_mesh_set(m_h, positions, numVertices, indices, numIndices)); }
     bool SetMeshWorld(float scale, const float pos[3]) { return ok(mv_mesh_set_world(m_h, scale, pos)); }
     bool RenderMeshDepth(const float viewProj[16], float shadowVP[16]) { return ok(mv_mesh_render_depth(m_h, viewProj, shadowVP)); }
+    // LightProbe (LightProbe.h): the radiance cube map; RenderEnvironment prepares the colour RT of a frame (the background
+    // given to SetRenderTargets, the environment where the scene depth is 1) — call it before Render, as MultiVolumes.cpp:673-674
+    bool SetEnvironment(const float* cubeRGB, uint32_t size) { return ok(mv_set_environment(m_h, cubeRGB, size)); }
+    bool RenderEnvironment() { return ok(mv_render_environment(m_h)); }
+    // MultiVolumes::SaveImage (MultiVolumes.cpp:744-764): the back buffer as a PNG
+    bool Screenshot(const char* fileName) { return ok(mv_screenshot(m_h, fileName)); }
     // Present with FrameCount = 3 frames in flight: asynchronous read-back of the RGBA8 back buffer into pinned memory
     bool Present(uint8_t* pinnedRGBA8, uint32_t slot) { return ok(mv_present_async(m_h, pinnedRGBA8, slot)); }
     bool WaitPresent(uint32_t slot) { return ok(mv_present_wait(m_h, slot)); }

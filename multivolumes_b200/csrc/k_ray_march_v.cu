@@ -17,6 +17,7 @@
 //     (LibRayMarch.hlsl:39-134: VolumeCull node -> RayMarch node in one DispatchGraph, MultiRayCaster.cpp:1370-1438).
 #include "k_march.cuh"
 #include "k_cull.cuh"
+#include <cstdlib>
 
 namespace mv {
 
@@ -216,6 +217,8 @@ static void launch_view(Caster& c, bool fusedCull, uint32_t phase, int blocksPer
         if (perSM[v] < 1) perSM[v] = 1;
     }
     if (fusedCull) ++c.cullSerial;
+    static const int capEnv = getenv("MV_VIEW_BLOCKS") ? atoi(getenv("MV_VIEW_BLOCKS")) : 0;     // tuning aid: CTAs per SM of the view march
+    if (blocksPerSM <= 0 && capEnv > 0) blocksPerSM = capEnv;
     const int blocks = blocksPerSM > 0 ? min(blocksPerSM, perSM[v]) : perSM[v];
     if (fusedCull) {
         DeviceScene scene = c.scene(); FrameCB cb = c.cb; uint32_t serial = c.cullSerial, ph = phase;
