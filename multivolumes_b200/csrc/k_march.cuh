@@ -105,14 +105,16 @@ MV_D bool ray_misses_box_for_sure(V3 o, V3 d)
 struct MarchCount { uint32_t samples, lightFetches, skipped; };
 
 // Is the brick that holds the sample position known to be empty (Occupancy, mv_internal.h)? `bits` are the bricks of
-// the ray's source volume. The sample's texel coordinate is uvw * G; the texels its trilinear footprint touches lie
-// within half a texel of it, inside the one-texel border the brick's bit accounts for.
-MV_D bool brick_is_empty(const uint32_t* __restrict__ bits, const Occupancy& occ, V3 uvw)
+// the ray's source volume, `pos` the sample position in the volume's local space ([-1, 1]^3). The sample's texel coordinate
+// is (pos / 2 + 1/2) G; the texels its trilinear footprint touches lie within half a texel of it, inside the one-texel
+// border the brick's bit accounts for — which also covers the rounding of this lookup (it is not part of the stated
+// arithmetic: any conservative test gives the same results).
+MV_D bool brick_is_empty(const uint32_t* __restrict__ bits, const Occupancy& occ, V3 pos)
 {
     const int top = (int)occ.bricks - 1;
-    const int bx = min((int)(uvw.x * occ.gridSize) >> occ.shift, top);
-    const int by = min((int)(uvw.y * occ.gridSize) >> occ.shift, top);
-    const int bz = min((int)(uvw.z * occ.gridSize) >> occ.shift, top);
+    const int bx = min((int)fmaf(pos.x, occ.halfBricks, occ.halfBricks), top);
+    const int by = min((int)fmaf(pos.y, occ.halfBricks, occ.halfBricks), top);
+    const int bz = min((int)fmaf(pos.z, occ.halfBricks, occ.halfBricks), top);
     const uint32_t b = ((uint32_t)bz * occ.bricks + (uint32_t)by) * occ.bricks + (uint32_t)bx;
     return (__ldg(bits + (b >> 5)) >> (b & 31)) & 1u;
 }
@@ -140,15 +142,22 @@ MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t 
     // empty run, whose position is known in advance, in the same round trip: no gain. profiles/r01_notes.md)
     bool wasDense = false;
     for (uint32_t i = 0; i < smpCount; ++i) {
-        const V3 pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
+        V3 pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
         if (outside_unit_box(pos)) break;
-        const V3 uvw = local_to_tex3d(pos);
-        if (emptyBits && !wasDense && brick_is_empty(emptyBits, occ, uvw)) {
-            ++mc.samples; ++mc.skipped;
-            t += stepScale;
-            if (t > tMax) break;
-            continue;
+        if (emptyBits && !wasDense) {
+            // consume empty samples while the ray stays in bricks known to be empty: each is one iteration of the reference's
+            // loop (t advances by the base step, the same exits are tested), minus the fetch
+            bool ended = false;
+            while (brick_is_empty(emptyBits, occ, pos)) {
+                ++mc.samples; ++mc.skipped;
+                t += stepScale;
+                if (t > tMax || ++i >= smpCount) { ended = true; break; }
+                pos = {rayOrigin.x + rayDir.x * t, rayOrigin.y + rayDir.y * t, rayOrigin.z + rayDir.z * t};
+                if (outside_unit_box(pos)) { ended = true; break; }
+            }
+            if (ended) break;
         }
+        const V3 uvw = local_to_tex3d(pos);
         const float4 c4 = tex3d_issue(grid, uvw.x, uvw.y, uvw.z);
         float4 l = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (wasDense) l = tex3d_issue(light, uvw.x, uvw.y, uvw.z);

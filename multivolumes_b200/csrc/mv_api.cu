@@ -62,7 +62,7 @@ DeviceScene Caster::scene() const
     s.directStats = ((d.flags & MV_FLAG_COUNT_SAMPLES) && !(shardVolumes && shardWorld > 1)) ? dDirectStats : nullptr;
     s.directCapacity = directCapacity;
     s.volumeTex = dVolumeTex;
-    s.occ.bits = dOcc; s.occ.wordsPerVolume = occWords; s.occ.shift = occShift; s.occ.bricks = occBricks; s.occ.gridSize = (float)d.grid_size;
+    s.occ.bits = dOcc; s.occ.wordsPerVolume = occWords; s.occ.shift = occShift; s.occ.bricks = occBricks; s.occ.gridSize = (float)d.grid_size; s.occ.halfBricks = 0.5f * (float)d.grid_size / (float)(1u << occShift);
     s.lightTex = dLightTex;
     s.lightSurf = dLightSurf;
     s.depth = dDepth;

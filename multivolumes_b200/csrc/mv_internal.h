@@ -131,6 +131,7 @@ struct Occupancy {
     uint32_t shift;                // log2 of the brick edge in texels
     uint32_t bricks;               // bricks per axis
     float gridSize;                // G as float
+    float halfBricks;              // bricks / 2: a local-space coordinate in [-1, 1] times this, plus this, is its brick coordinate
 };
 
 // Everything the kernels need, passed by value.
