@@ -137,7 +137,9 @@ int mv_update_frame(mv_caster* c, const float view_proj[16], const float shadow_
 
 /* Render (:49-50, MultiRayCaster.cpp:355-385) = cull -> light march (one volume, round-robin) ->
  * view march -> OIT resolve into the colour RT; frame index++. The individual passes are exported
- * for the parity tests. */
+ * for the parity tests. `oit_method` is accepted for signature compatibility and ignored: the library has ONE OIT
+ * implementation, the fused per-pixel resolve with the K-buffer semantics of the reference's default branch
+ * (MultiRayCaster.cpp:377-381); its DXR / ray-query variants produce the same layers by other means. */
 int mv_render(mv_caster* c, uint32_t oit_method);
 /* Render with useWorkGraph = true (MultiRayCaster.h:49-50, MultiRayCaster.cpp:358-362, rayMarchWG :1370-1438,
  * LibRayMarch.hlsl:39-134): the light march runs first and takes its volume from the PREVIOUS frame's visible list,

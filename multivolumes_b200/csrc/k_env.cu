@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(256) k_environment(DeviceScene s, FrameCB cb, 
     const size_t pix = (size_t)py * cb.width + px;
     if (!(1.0f <= __ldg(s.depth + pix))) return;                 // DEPTH_READ_LESS_EQUAL against the quad's z = 1
     // PSEnvironment.hlsl:48-56: the pixel centre unprojected at z = 1, ray from the eye through it
-    const float sx = fma1((float)px + 0.5f, 2.0f / cb.viewport[0], -1.0f), sy = fma1((float)py + 0.5f, -(2.0f / cb.viewport[1]), 1.0f);
+    const float sx = fma1((float)px + 0.5f, cb.inv2Viewport[0], -1.0f), sy = fma1((float)py + 0.5f, -cb.inv2Viewport[1], 1.0f);
     const float* M = cb.screenToWorld;
     const float whx = fma1(sx, M[0], fma1(sy, M[4], M[8] + M[12])), why = fma1(sx, M[1], fma1(sy, M[5], M[9] + M[13]));
     const float whz = fma1(sx, M[2], fma1(sy, M[6], M[10] + M[14])), whw = fma1(sx, M[3], fma1(sy, M[7], M[11] + M[15]));
@@ -51,12 +51,17 @@ __global__ void __launch_bounds__(256) k_environment(DeviceScene s, FrameCB cb, 
     const float flx = floorf(fx), fly = floorf(fy);
     const float wx = fx - flx, wy = fy - fly;
     const int i0 = (int)flx, j0 = (int)fly;
-    V4 t[4];
+    V4 t[4];                                                     // (0,0) (1,0) (0,1) (1,1)
+    if (i0 >= 0 && j0 >= 0 && i0 + 1 < S && j0 + 1 < S) {        // the whole footprint on this face (nearly always)
+        const uint2* p = cube + ((uint32_t)face * (uint32_t)S + (uint32_t)j0) * (uint32_t)S + (uint32_t)i0;
+        t[0] = unpack_half4(__ldg(p)); t[1] = unpack_half4(__ldg(p + 1)); t[2] = unpack_half4(__ldg(p + S)); t[3] = unpack_half4(__ldg(p + S + 1));
+    } else {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {                                // (0,0) (1,0) (0,1) (1,1)
-        int f, i, j;
-        cube_resolve_texel(S, face, i0 + (k & 1), j0 + (k >> 1), f, i, j);
-        t[k] = unpack_half4(__ldg(cube + ((size_t)f * S + j) * S + i));
+        for (int k = 0; k < 4; ++k) {
+            int f, i, j;
+            cube_resolve_texel(S, face, i0 + (k & 1), j0 + (k >> 1), f, i, j);
+            t[k] = unpack_half4(__ldg(cube + ((size_t)f * S + j) * S + i));
+        }
     }
     const V4 c = {lerpf(lerpf(t[0].x, t[1].x, wx), lerpf(t[2].x, t[3].x, wx), wy), lerpf(lerpf(t[0].y, t[1].y, wx), lerpf(t[2].y, t[3].y, wx), wy),
                   lerpf(lerpf(t[0].z, t[1].z, wx), lerpf(t[2].z, t[3].z, wx), wy), 0.0f};      // :68 alpha 0

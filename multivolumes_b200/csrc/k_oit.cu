@@ -95,7 +95,7 @@ MV_D V4 cube_cast(const DeviceScene& s, const FrameCB& cb, uint32_t volumeId, ui
 // direction from the eye (not normalised) and the pixel's clip-space x, y.
 MV_D V3 pixel_ray(const FrameCB& cb, int px, int py, float& sx, float& sy)
 {
-    sx = fma1((float)px + 0.5f, 2.0f / cb.viewport[0], -1.0f); sy = fma1((float)py + 0.5f, -(2.0f / cb.viewport[1]), 1.0f);   // uniform divisions: once per launch
+    sx = fma1((float)px + 0.5f, cb.inv2Viewport[0], -1.0f); sy = fma1((float)py + 0.5f, -cb.inv2Viewport[1], 1.0f);
     const float* S = cb.screenToWorld;
     const float whx = fma1(sx, S[0], fma1(sy, S[4], S[12])), why = fma1(sx, S[1], fma1(sy, S[5], S[13]));
     const float whz = fma1(sx, S[2], fma1(sy, S[6], S[14])), whw = fma1(sx, S[3], fma1(sy, S[7], S[15]));

@@ -56,6 +56,8 @@ struct PostArgs {
     uchar4* peerBackBuffer;   // rank 0's back buffer when this rank resolves a band of a multi-GPU frame
     uint2* peerOut[kMaxPeers]; // the peers' copies of `out` (multi-GPU, peers mapped): the next frame's history fetch of ANY rank may land on these rows
     int numPeers;
+    float invW, invH;          // 1 / W, 1 / H (fp32 quotients, computed once on the host)
+    int velocityGiven;         // 0: the velocity field is all zero (none was given): its five taps need not be read
     int peerAllRows;           // 0: only the first and last row of each stripe / band go to the peers (static velocity field: the history fetch stays within one row)
     int W, H, row0, row1;
     int stripeH, rank, world;   // stripeH > 0: interleaved stripes instead of the band
@@ -125,17 +127,20 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
     const int offs[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};   // :46-50
     const float historyMax = 15.0f;                                                                   // :41-43
     const V2 texSize = {(float)W, (float)H};
-    const V2 invSize = {1.0f / texSize.x, 1.0f / texSize.y};
+    const V2 invSize = {a.invW, a.invH};
     const V2 uv = {((float)x + 0.5f) * invSize.x, ((float)y + 0.5f) * invSize.y};
     const float4 own = s_tm[ty + 1][tx + 1];
     // VelocityMax :133-161
-    V2 vmax = load_v(a.velocity, x, y, W, H);
-    float speedSq = fma1(vmax.x, vmax.x, vmax.y * vmax.y);
+    V2 vmax = {0.0f, 0.0f};
+    if (a.velocityGiven) {      // (an all-zero field gives vmax = 0 whichever tap wins)
+        vmax = load_v(a.velocity, x, y, W, H);
+        float speedSq = fma1(vmax.x, vmax.x, vmax.y * vmax.y);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const V2 nb = load_v(a.velocity, x + offs[i + 4][0], y + offs[i + 4][1], W, H);
-        const float sq = fma1(nb.x, nb.x, nb.y * nb.y);
-        if (sq > speedSq) { vmax = nb; speedSq = sq; }
+        for (int i = 0; i < 4; ++i) {
+            const V2 nb = load_v(a.velocity, x + offs[i + 4][0], y + offs[i + 4][1], W, H);
+            const float sq = fma1(nb.x, nb.x, nb.y * nb.y);
+            if (sq > speedSq) { vmax = nb; speedSq = sq; }
+        }
     }
     const V2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
     // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp, fp32 weights
@@ -239,6 +244,8 @@ void launch_postprocess(Caster& c, bool taaOn)
     // that is the pixel itself up to rounding, i.e. within one row, so only the border rows of every stripe need to reach the
     // peers; with a velocity field it can land anywhere, and every row goes out.
     a.peerAllRows = c.velocityGiven ? 1 : 0;
+    a.velocityGiven = c.velocityGiven ? 1 : 0;
+    a.invW = 1.0f / (float)c.d.width; a.invH = 1.0f / (float)c.d.height;
     for (int p = 0; p < kMaxPeers; ++p) a.peerOut[p] = p < a.numPeers ? c.peerHistory[p][c.frameParity] : nullptr;
     a.W = (int)c.d.width; a.H = (int)c.d.height;
     a.row0 = (int)c.row0; a.row1 = (int)c.row1;

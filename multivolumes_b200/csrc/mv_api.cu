@@ -235,6 +235,23 @@ static void wait_upload(Caster& c, cudaStream_t s)
     if (c.lastUpload >= 0) cudaStreamWaitEvent(s, c.uploadDone[c.lastUpload], 0);
 }
 
+// View march and screen-space march of a frame are independent of each other (both read the light maps; one writes the cube
+// maps, the other its result buffer). Sharded over many ranks both are short, latency-bound launches: with directOverlap the
+// screen-space march runs on its own stream beside the view march (uninstrumented frames only).
+static void launch_view_and_direct(Caster& c)
+{
+    if (!c.directOverlap) { launch_ray_march_view(c); launch_ray_cast_direct(c); return; }
+    cudaStream_t mainStream = c.stream;
+    cudaEventRecord(c.directFork, mainStream);
+    cudaStreamWaitEvent(c.directStream, c.directFork, 0);
+    c.stream = c.directStream;
+    launch_ray_cast_direct(c);
+    c.stream = mainStream;
+    cudaEventRecord(c.directJoin, c.directStream);
+    launch_ray_march_view(c);
+    cudaStreamWaitEvent(mainStream, c.directJoin, 0);
+}
+
 static int check_launch(const char* what)
 {
     const cudaError_t e = cudaGetLastError();
@@ -293,6 +310,8 @@ static void destroy_caster(Caster& c)
     for (auto& e : c.presentDone) if (e) cudaEventDestroy(e);
     if (c.frameDone) cudaEventDestroy(c.frameDone);
     if (c.copyStream) { cudaStreamSynchronize(c.copyStream); cudaStreamDestroy(c.copyStream); }
+    if (c.directStream) { cudaStreamSynchronize(c.directStream); cudaStreamDestroy(c.directStream); }
+    for (cudaEvent_t e : {c.directFork, c.directJoin}) if (e) cudaEventDestroy(e);
     if (c.lightStream) { cudaStreamSynchronize(c.lightStream); cudaStreamDestroy(c.lightStream); }
     for (cudaEvent_t e : {c.lightDone, c.commitDone, c.inputsReady, c.cullDone, c.frameEnd[0], c.frameEnd[1]}) if (e) cudaEventDestroy(e);
     c.dPerObject = nullptr; c.dAttribs = nullptr; c.dLists = nullptr;
@@ -370,6 +389,10 @@ static int create_impl(const mv_desc* d, bool shardVolumes, uint32_t shardRank, 
         MV_CUDA_C(cudaEventCreateWithFlags(&c.cullDone, cudaEventDisableTiming));
     }
     MV_CUDA_C(cudaEventCreateWithFlags(&c.frameDone, cudaEventDisableTiming));
+    MV_CUDA_C(cudaStreamCreateWithFlags(&c.directStream, cudaStreamNonBlocking));
+    MV_CUDA_C(cudaEventCreateWithFlags(&c.directFork, cudaEventDisableTiming));
+    MV_CUDA_C(cudaEventCreateWithFlags(&c.directJoin, cudaEventDisableTiming));
+    if (const char* e = getenv("MV_DIRECT_OVERLAP")) c.directOverlap = atoi(e);
     for (auto& e : c.presentDone) MV_CUDA_C(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
 
     // MultiRayCaster.cpp:99-126 — per-source volumes, per-instance light maps and cube maps
@@ -524,6 +547,7 @@ static int create_impl(const mv_desc* d, bool shardVolumes, uint32_t shardRank, 
     c.cb.width = c.d.width; c.cb.height = c.d.height;
     c.cb.maxRaySamples = c.d.max_ray_samples; c.cb.maxLightSamples = c.d.max_light_samples;
     c.cb.viewport[0] = (float)c.d.width; c.cb.viewport[1] = (float)c.d.height;
+    c.cb.inv2Viewport[0] = 2.0f / c.cb.viewport[0]; c.cb.inv2Viewport[1] = 2.0f / c.cb.viewport[1];
     MV_CUDA_C(cudaStreamSynchronize(c.stream));
 #undef MV_TRY
 #undef MV_CUDA_C
@@ -765,6 +789,7 @@ int mv_update_frame(mv_caster* h, const float viewProj[16], const float shadowVP
     FrameCB& cb = c.cb;
     memcpy(cb.eye, eye, 3 * sizeof(float));
     cb.viewport[0] = (float)c.d.width; cb.viewport[1] = (float)c.d.height;
+    cb.inv2Viewport[0] = 2.0f / cb.viewport[0]; cb.inv2Viewport[1] = 2.0f / cb.viewport[1];
     inverse44(viewProj, cb.screenToWorld);
     if (shadowVP) memcpy(cb.shadowViewProj, shadowVP, 16 * sizeof(float));
     else for (int i = 0; i < 16; ++i) cb.shadowViewProj[i] = (i % 5 == 0) ? 1.0f : 0.0f;
@@ -929,10 +954,9 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
         launch_peer_wait(c, kBarrierLight);
         launch_light_commit(c);
-        launch_ray_march_view(c);
+        launch_view_and_direct(c);
         wait_back_buffer_free(c);                   // once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
         launch_peer_barrier(c);                     // every rank's cube-map texels have landed
-        launch_ray_cast_direct(c);
         launch_resolve_oit(c);
     } else if (pipelined(c)) {
         // light stream: cull -> light march into the staging buffer. Waits: the PerObject upload; inputs changed on the main
@@ -956,8 +980,7 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         launch_light_commit(c);
         MV_CUDA(cudaEventRecord(c.commitDone, mainStream));
         c.commitValid = true;
-        launch_ray_march_view(c);
-        launch_ray_cast_direct(c);
+        launch_view_and_direct(c);
         launch_resolve_oit(c);
     } else {
         wait_upload(c, c.stream);

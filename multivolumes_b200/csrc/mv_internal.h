@@ -23,6 +23,7 @@ struct PerObject {
 struct FrameCB {
     float eye[3];
     float viewport[2];
+    float inv2Viewport[2];     // 2 / viewport (the same fp32 quotient the shader's `/ g_viewport * 2` restatement divides out per pixel)
     float screenToWorld[16];
     float shadowViewProj[16];
     float lightPos[4];
@@ -313,6 +314,9 @@ struct Caster {
     int poLastUse[2] = {-1, -1};         // frameEnd slot of the last render that read dPerObject2[q]
     int lastUpload = -1;                 // upload-ring slot of the last PerObject upload
     cudaStream_t copyStream = nullptr;   // mv_present_async: back-buffer read-back overlapping the next frame
+    cudaStream_t directStream = nullptr; // screen-space march beside the view march (directOverlap)
+    cudaEvent_t directFork = nullptr, directJoin = nullptr;
+    int directOverlap = 0;               // MV_DIRECT_OVERLAP: 1 = the two marches of a frame run on two streams (uninstrumented frames)
     cudaEvent_t frameDone = nullptr;     // main stream -> copy stream
     cudaEvent_t presentDone[MV_PRESENT_SLOTS] = {};
     bool presentPending[MV_PRESENT_SLOTS] = {};

@@ -24,11 +24,18 @@ from multivolumes_b200.dist import CudaExchange, ShardedRenderer
 from harness import checker_background, configure
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 mode, out = sys.argv[1], sys.argv[2]
-torch.cuda.set_device(rank)
-dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+# fewer GPUs than ranks: the ranks share devices (CUDA IPC and the device-side barriers work between processes on one GPU,
+# which time-slices them); NCCL refuses that, so the few host-side exchanges of the fused mode go over gloo
+ngpu = torch.cuda.device_count()
+dev = rank %% ngpu
+torch.cuda.set_device(dev)
+if ngpu >= world:
+    dist.init_process_group("nccl", device_id=torch.device("cuda", dev))
+else:
+    dist.init_process_group("gloo")
 kw = dict(grid_size=64, light_grid_size=24, num_volumes=9, num_volume_srcs=3, width=640, height=360)
 # uninstrumented casters take the pipelined paths (frames in flight on two streams); "fused-serial" keeps the counters on
-c = MultiRayCaster(device=rank, count_samples=(os.environ.get("MV_TEST_VARIANT") == "fused-serial"), **kw)
+c = MultiRayCaster(device=dev, count_samples=(os.environ.get("MV_TEST_VARIANT") == "fused-serial"), **kw)
 stream = torch.cuda.Stream()
 c.SetStream(stream.cuda_stream)
 vel = (np.random.RandomState(7).uniform(-1, 1, (360, 640, 2)) * (0.02 if mode != "collective" else 0.0)).astype(np.float16)
@@ -74,8 +81,8 @@ def _single(velocity_scale):
 @pytest.mark.parametrize("mode,world", [("fused", 2), ("fused-overlap", 2), ("fused-serial", 2), ("collective", 2), ("fused", 4), ("fused-serial", 4)])
 def test_multi_gpu_frame_equals_single_gpu(mode, world, tmp_path):
     import torch
-    if torch.cuda.device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
+    if torch.cuda.device_count() < world and (mode == "collective" or world > 2):
+        pytest.skip(f"needs {world} GPUs")        # (the fused modes at world 2 also run with both ranks on ONE GPU)
     script = tmp_path / "worker.py"
     script.write_text(WORKER % dict(root=ROOT, here=HERE))
     out = str(tmp_path / "out.npz")
