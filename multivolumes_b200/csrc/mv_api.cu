@@ -198,9 +198,16 @@ static void record(Caster& c, int i)
 }
 
 // The back buffer may still be read by an mv_present_async copy: order the next writer after it.
-static void wait_back_buffer_free(Caster& c)
+// `beforePeersWrite`: the call sits in front of the barrier after which PEERS may store rows into this rank's back buffer. A copy
+// that reads only this rank's own rows (mv_present_rows_async) cannot be overtaken by those — only by this rank's own next
+// post-process, whose call (beforePeersWrite = false) still waits — so the early wait, which would stall the frame's marches
+// behind the previous frame's read-back, is skipped for it.
+static void wait_back_buffer_free(Caster& c, bool beforePeersWrite = false)
 {
-    if (c.backBufferBusy >= 0) { cudaStreamWaitEvent(c.stream, c.presentDone[c.backBufferBusy], 0); c.backBufferBusy = -1; }
+    if (c.backBufferBusy < 0) return;
+    if (beforePeersWrite && c.backBufferBusyOwnRows) return;
+    cudaStreamWaitEvent(c.stream, c.presentDone[c.backBufferBusy], 0);
+    c.backBufferBusy = -1;
 }
 
 // the per-result counters of the screen-space marches exist only while the sample counters are on
@@ -923,7 +930,7 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         if (!piped) record(c, 3);
         MV_TRY_DIRECT_STATS(c);
         launch_ray_cast_direct(c);
-        wait_back_buffer_free(c);
+        wait_back_buffer_free(c, true);
         launch_peer_barrier(c);                     // every owner's cube-map texels and screen-space march results have landed
         launch_resolve_oit(c);
         if (!piped) { record(c, 4); c.evValid[5] = false; }
@@ -955,7 +962,7 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
         launch_peer_wait(c, kBarrierLight);
         launch_light_commit(c);
         launch_view_and_direct(c);
-        wait_back_buffer_free(c);                   // once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
+        wait_back_buffer_free(c, true);             // once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
         launch_peer_barrier(c);                     // every rank's cube-map texels have landed
         launch_resolve_oit(c);
     } else if (pipelined(c)) {
@@ -1005,13 +1012,13 @@ int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
             c.lightDoneValid = true;
             launch_ray_march_view(c, 1, viewBlocks);
             MV_CUDA(cudaStreamWaitEvent(mainStream, c.lightDone, 0));
-            wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c);
+            wait_back_buffer_free(c, true); launch_peer_barrier(c); launch_light_commit(c);
             launch_ray_march_view(c, 2);
             launch_peer_barrier(c);
         } else {
             launch_ray_march_light(c, -1);
             // sharded: once this rank signals, peers may run ahead into their post-process and store rows into rank 0's back buffer
-            if (c.shardWorld > 1) { wait_back_buffer_free(c); launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
+            if (c.shardWorld > 1) { wait_back_buffer_free(c, true); launch_peer_barrier(c); launch_light_commit(c); }   // slabs of all ranks -> the light volume's array
             record(c, 2);
             launch_ray_march_view(c);
             if (c.shardWorld > 1) launch_peer_barrier(c);                            // every owner's cube maps have landed
@@ -1197,7 +1204,7 @@ int mv_present_async(mv_caster* h, uint8_t* host, uint32_t slot)
     if (host) MV_CUDA(cudaMemcpyAsync(host, c.dBackBuffer, (size_t)c.d.width * c.d.height * 4, cudaMemcpyDeviceToHost, c.copyStream));
     MV_CUDA(cudaEventRecord(c.presentDone[slot], c.copyStream));
     c.presentPending[slot] = true;
-    if (host) c.backBufferBusy = (int)slot;
+    if (host) { c.backBufferBusy = (int)slot; c.backBufferBusyOwnRows = false; }
     return MV_OK;
 }
 

@@ -316,10 +316,11 @@ struct Caster {
     cudaStream_t copyStream = nullptr;   // mv_present_async: back-buffer read-back overlapping the next frame
     cudaStream_t directStream = nullptr; // screen-space march beside the view march (directOverlap)
     cudaEvent_t directFork = nullptr, directJoin = nullptr;
-    int directOverlap = 0;               // MV_DIRECT_OVERLAP: 1 = the two marches of a frame run on two streams (uninstrumented frames)
+    int directOverlap = 1;               // the two marches of a frame run on two streams (uninstrumented frames; MV_DIRECT_OVERLAP=0: one after the other)
     cudaEvent_t frameDone = nullptr;     // main stream -> copy stream
     cudaEvent_t presentDone[MV_PRESENT_SLOTS] = {};
     bool presentPending[MV_PRESENT_SLOTS] = {};
+    bool backBufferBusyOwnRows = false;  // that copy reads only this rank's own rows (mv_present_rows_async)
     int backBufferBusy = -1;             // slot whose copy still reads the back buffer (device-side wait before it is rewritten)
     float* dDepth = nullptr;
     uint16_t* dShadow = nullptr;

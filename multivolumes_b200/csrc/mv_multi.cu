@@ -274,22 +274,20 @@ int mv_present_rows_async(mv_caster* h, uint8_t* host, uint32_t slot)
     const size_t rowBytes = (size_t)c.d.width * 4;
     const unsigned char* src = reinterpret_cast<const unsigned char*>(c.dBackBuffer);
     if (c.shardWorld > 1 && c.stripeH) {
-        // the rank's k-th stripe is rows [(k world + rank) stripeH, ... + stripeH): one strided copy, plus a ragged last stripe
+        // the rank's k-th stripe is rows [(k world + rank) stripeH, ... + stripeH), clipped to the image
         const uint32_t H = c.d.height, sh = c.stripeH, world = c.shardWorld, rank = c.shardRank;
         const uint32_t own = num_own_stripes(H, sh, rank, world);
-        uint32_t full = own;
-        if (own) {
-            const uint32_t lastBegin = ((own - 1) * world + rank) * sh;
-            if (lastBegin + sh > H) --full;
-            const size_t ofs = (size_t)rank * sh * rowBytes, pitch = (size_t)world * sh * rowBytes;
-            if (full) MV_CUDA(cudaMemcpy2DAsync(host + ofs, pitch, src + ofs, pitch, (size_t)sh * rowBytes, full, cudaMemcpyDeviceToHost, c.copyStream));
-            if (full < own) MV_CUDA(cudaMemcpyAsync(host + (size_t)lastBegin * rowBytes, src + (size_t)lastBegin * rowBytes, (size_t)(H - lastBegin) * rowBytes, cudaMemcpyDeviceToHost, c.copyStream));
+        // one plain asynchronous copy per stripe (its rows are contiguous)
+        for (uint32_t k = 0; k < own; ++k) {
+            const uint32_t begin = (k * world + rank) * sh, end = begin + sh < H ? begin + sh : H;
+            MV_CUDA(cudaMemcpyAsync(host + (size_t)begin * rowBytes, src + (size_t)begin * rowBytes, (size_t)(end - begin) * rowBytes, cudaMemcpyDeviceToHost, c.copyStream));
         }
     } else if (c.row1 > c.row0)
         MV_CUDA(cudaMemcpyAsync(host + (size_t)c.row0 * rowBytes, src + (size_t)c.row0 * rowBytes, (size_t)(c.row1 - c.row0) * rowBytes, cudaMemcpyDeviceToHost, c.copyStream));
     MV_CUDA(cudaEventRecord(c.presentDone[slot], c.copyStream));
     c.presentPending[slot] = true;
     c.backBufferBusy = (int)slot;
+    c.backBufferBusyOwnRows = true;
     return MV_OK;
 }
 
