@@ -277,7 +277,9 @@ int mv_present_rows_async(mv_caster* h, uint8_t* host, uint32_t slot)
         // the rank's k-th stripe is rows [(k world + rank) stripeH, ... + stripeH), clipped to the image
         const uint32_t H = c.d.height, sh = c.stripeH, world = c.shardWorld, rank = c.shardRank;
         const uint32_t own = num_own_stripes(H, sh, rank, world);
-        // one plain asynchronous copy per stripe (its rows are contiguous)
+        // one plain asynchronous copy per stripe (its rows are contiguous). Measured on 8 x B200 (profiles/r02_scaling.md): as ONE
+        // pitched cudaMemcpy2DAsync into the registered shared-memory frame the call held the host long enough to cap the
+        // frame loop at 1189 frames/s end to end; as nine 1-D copies it runs at 1585 (the loop without any read-back: 1675)
         for (uint32_t k = 0; k < own; ++k) {
             const uint32_t begin = (k * world + rank) * sh, end = begin + sh < H ? begin + sh : H;
             MV_CUDA(cudaMemcpyAsync(host + (size_t)begin * rowBytes, src + (size_t)begin * rowBytes, (size_t)(end - begin) * rowBytes, cudaMemcpyDeviceToHost, c.copyStream));
