@@ -1,4 +1,6 @@
 #!/bin/bash
+# ncu evidence of a round: (1) per-launch device times of the bench command, (2) one full-metric capture of a cfg4 frame.
+# Run on the GPU box; then tools/ncu_summarise.py gpurun_out/r02_cfg4_frame.ncu-rep cfg4 writes profiles/ncu_summary.json.
 mkdir -p gpurun_out
 # (1) launch list of the bench command (per-launch device time, serialised)
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 400 --csv --log-file gpurun_out/r02_launches_cfg4.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/r2_launch_bench.log 2>&1

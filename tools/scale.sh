@@ -1,6 +1,6 @@
 #!/bin/bash
 # strong-scaling sweep as the driver launches it: N = 1, 2, 4, 8 on one box
-WLS=${WLS:-"cfg2 cfg4"}
+WLS=${WLS:-"cfg4"}
 for wl in $WLS; do
 for n in ${NS:-1 2 4 8}; do
   if [ $n -eq 1 ]; then cmd="python bench.py --gpus 1"; else cmd="python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29520+n)) bench.py --gpus $n"; fi
