@@ -87,6 +87,9 @@ public:
     { return ok(mv_mesh_set(m_h, positions, numVertices, indices, numIndices)); }
     bool SetMeshWorld(float scale, const float pos[3]) { return ok(mv_mesh_set_world(m_h, scale, pos)); }
     bool RenderMeshDepth(const float viewProj[16], float shadowVP[16]) { return ok(mv_mesh_render_depth(m_h, viewProj, shadowVP)); }
+    // ObjectRenderer::UpdateFrame + RenderShadow + Render: shadow pass + shaded base pass (colour, depth, velocity)
+    bool RenderMesh(const float viewProj[16], const float eyePt[3], const float clearRGBA[4], float shadowVP[16])
+    { return ok(mv_mesh_render(m_h, viewProj, eyePt, clearRGBA, shadowVP)); }
     // LightProbe (LightProbe.h): the radiance cube map; RenderEnvironment prepares the colour RT of a frame (the background
     // given to SetRenderTargets, the environment where the scene depth is 1) — call it before Render, as MultiVolumes.cpp:673-674
     bool SetEnvironment(const float* cubeRGB, uint32_t size) { return ok(mv_set_environment(m_h, cubeRGB, size)); }

@@ -168,6 +168,13 @@ int  mv_mesh_set(mv_caster* c, const float* positions_xyz, uint32_t num_vertices
 int  mv_mesh_load_obj(mv_caster* c, const char* path);
 int  mv_mesh_set_world(mv_caster* c, float scale, const float pos[3]);
 int  mv_mesh_render_depth(mv_caster* c, const float view_proj[16], float shadow_vp_out[16]);
+/* ObjectRenderer::Render (ObjectRenderer.cpp:532-553; VSBasePass.hlsl:39-55, PSBasePass.hlsl:94-153): shadow pass + the
+ * shaded base pass. Fills scene depth, the shadow map, the colour target the resolve composites over (clear_rgba where no
+ * triangle covers the pixel; NULL = zeros) and the TAA velocity field from the mesh, with the caster's current light,
+ * ambient and SH coefficients; view_proj and eye are ObjectRenderer::UpdateFrame's arguments (:171). Deviations (mv_mesh.cu header): no sub-pixel
+ * jitter, no radiance cube term, zero velocity on the first frame after mv_mesh_set. */
+int  mv_mesh_render(mv_caster* c, const float view_proj[16], const float eye[3], const float clear_rgba[4], float shadow_vp_out[16]);
+int  mv_read_velocity(mv_caster* c, uint16_t* rg16f);
 int  mv_read_depth(mv_caster* c, float* depth, uint16_t* shadow_d16, uint32_t* shadow_size);
 
 /* ---- the environment under the volumes and the screenshot ----

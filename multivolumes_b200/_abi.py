@@ -73,6 +73,8 @@ _COMMON = {
     "mesh_set": (C.c_int, [_vp, _vp, u32, _vp, u32]),
     "mesh_set_world": (C.c_int, [_vp, f32, P(f32)]),
     "mesh_render_depth": (C.c_int, [_vp, P(f32), P(f32)]),
+    "mesh_render": (C.c_int, [_vp, P(f32), P(f32), P(f32), P(f32)]),
+    "read_velocity": (C.c_int, [_vp, _vp]),
     "read_depth": (C.c_int, [_vp, _vp, _vp, P(u32)]),
     "set_shard": (C.c_int, [_vp, u32, u32]),
     "set_row_band": (C.c_int, [_vp, u32, u32]),
@@ -242,6 +244,21 @@ class CasterBase:
         out = np.zeros(16, np.float32)
         self._ck(self.b.mesh_render_depth(self.h, pa, out.ctypes.data_as(P(f32))), "mesh_render_depth")
         return out.reshape(4, 4)
+
+    def RenderMesh(self, view_proj, eye, clear_rgba=(0.0, 0.0, 0.0, 0.0)):
+        """ObjectRenderer::UpdateFrame(viewProj, eyePt) + RenderShadow + Render: scene depth, shadow map, background colour
+        and TAA velocity all come from the shaded mesh. Returns the light's view-projection (for UpdateFrame)."""
+        a, pa = _fp(np.asarray(view_proj).reshape(16))
+        e, pe = _fp(np.asarray(eye).reshape(3))
+        cl, pcl = _fp(np.asarray(clear_rgba).reshape(4))
+        out = np.zeros(16, np.float32)
+        self._ck(self.b.mesh_render(self.h, pa, pe, pcl, out.ctypes.data_as(P(f32))), "mesh_render")
+        return out.reshape(4, 4)
+
+    def ReadVelocity(self):
+        out = np.empty((self.H, self.W, 2), np.uint16)
+        self._ck(self.b.read_velocity(self.h, out.ctypes.data), "read_velocity")
+        return out
 
     def ReadDepth(self):
         depth = np.empty((self.H, self.W), np.float32)

@@ -307,7 +307,7 @@ static void destroy_caster(Caster& c)
     for (auto& v : c.volumes) kill_volume3d(v);
     for (auto& v : c.lightMaps) kill_volume3d(v);
     void* frees[] = {c.dVolumeTex, c.dLightTex, c.dLightSurf, c.dPerObject2[0], c.dPerObject2[1], c.dVolumeDescs, c.dAttribs2[0], c.dAttribs2[1],
-                     c.dLists2[0], c.dLists2[1], c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dShadowBits, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
+                     c.dLists2[0], c.dLists2[1], c.dStats, c.dMeshPos, c.dMeshIdx, c.dMeshTris, c.dMeshNrm, c.dMeshShade, c.dMeshVis, c.dShadowBits, c.dDirectStats, c.dLightDense, c.dLightRecs, c.dLightItems, c.dLightItemResults, c.dLightSeg, c.dBlock,
                      c.dOcc, c.dDepth, c.dShadow, c.dColor, c.dBackground, c.dVelocity, c.dScratch, c.dPeerFlagPtrs, c.dToneLut, c.dSrcIsProxy, c.dEnvCube};
     for (void* p : frees) if (p) cudaFree(p);
     if (c.hPerObjectPinned) cudaFreeHost(c.hPerObjectPinned);

@@ -259,6 +259,11 @@ struct Caster {
     float* dMeshPos = nullptr;           // V x 3
     uint32_t* dMeshIdx = nullptr;        // 3 T
     void* dMeshTris = nullptr;           // 2 T screen-space records of the pass being rasterised
+    float* dMeshNrm = nullptr;           // V x 3 (recomputed vertex normals)
+    void* dMeshShade = nullptr;          // 2 T records of interpolants for the base pass
+    unsigned long long* dMeshVis = nullptr;   // W x H visibility buffer: depth bits << 32 | record
+    float meshWvpPrev[16] = {};          // last frame's world-view-projection (velocity)
+    bool meshHavePrev = false;
     uint32_t* dShadowBits = nullptr;     // S x S float bit patterns (depth test target of the shadow pass)
     uint32_t meshNumIndices = 0;
     float meshExtent = 1.0f;             // largest AABB extent (ObjectRenderer.cpp:74-76)

@@ -86,6 +86,8 @@ int mvo_sh_project(mvo_caster* c, const float* cube_rgb_f32, uint32_t size, floa
 int mvo_mesh_set(mvo_caster* c, const float* positions_xyz, uint32_t num_vertices, const uint32_t* indices, uint32_t num_indices);
 int mvo_mesh_set_world(mvo_caster* c, float scale, const float pos[3]);
 int mvo_mesh_render_depth(mvo_caster* c, const float view_proj[16], float shadow_vp_out[16]);
+int mvo_mesh_render(mvo_caster* c, const float view_proj[16], const float eye[3], const float clear_rgba[4], float shadow_vp_out[16]);
+int mvo_read_velocity(mvo_caster* c, uint16_t* rg16f);
 int mvo_read_depth(mvo_caster* c, float* depth, uint16_t* shadow_d16, uint32_t* shadow_size);
 
 /* read-backs */

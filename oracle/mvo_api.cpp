@@ -213,6 +213,8 @@ int mvo_mesh_set(mvo_caster* h, const float* pos, uint32_t nv, const uint32_t* i
     Caster& c = h->c;
     c.meshPos.assign(pos, pos + (size_t)nv * 3);
     c.meshIdx.assign(idx, idx + ni);
+    recompute_normals(c.meshPos, c.meshIdx, c.meshNrm);
+    c.meshHavePrev = false;
     c.meshExtent = 1.0f;
     if (ni) {
         float mn[3] = {kFltMax, kFltMax, kFltMax}, mx[3] = {-kFltMax, -kFltMax, -kFltMax};
@@ -254,9 +256,9 @@ void look_at_lh(const double e[3], double M[16])   // XMMatrixLookAtLH(eye, 0, (
     memcpy(M, m, sizeof m);
 }
 }
-int mvo_mesh_render_depth(mvo_caster* h, const float viewProj[16], float shadowVpOut[16])
+static int mesh_render_impl(mvo_caster* h, const float viewProj[16], float shadowVpOut[16], bool basePass, const float* eye, const float* clear)
 {
-    if (!h || !viewProj) return -1;
+    if (!h || !viewProj || (basePass && !eye)) return -1;
     Caster& c = h->c;
     const uint32_t S = 1024;   // m_shadowMapSize
     const double s = c.meshScale;
@@ -265,8 +267,8 @@ int mvo_mesh_render_depth(mvo_caster* h, const float viewProj[16], float shadowV
     for (int i = 0; i < 16; ++i) vp[i] = viewProj[i];
     mul44d(world, vp, wvp);
     const double size = (double)(c.meshExtent * c.meshScale) * 1.5, zn = 1.0, zf = 200.0;
-    const double eye[3] = {c.lightPt.x, c.lightPt.y, c.lightPt.z};
-    look_at_lh(eye, lv);
+    const double lightEye[3] = {c.lightPt.x, c.lightPt.y, c.lightPt.z};
+    look_at_lh(lightEye, lv);
     const double lp[16] = {2.0 / size, 0, 0, 0, 0, 2.0 / size, 0, 0, 0, 0, 1.0 / (zf - zn), 0, 0, 0, -zn / (zf - zn), 1};
     mul44d(lv, lp, lvp);
     mul44d(world, lvp, swvp);
@@ -276,8 +278,31 @@ int mvo_mesh_render_depth(mvo_caster* h, const float viewProj[16], float shadowV
     raster_depth(c.meshPos, c.meshIdx, SW, S, S, sd.data());
     c.shadow.resize((size_t)S * S); c.shadowSize = S;
     for (size_t i = 0; i < sd.size(); ++i) c.shadow[i] = (uint16_t)floorf(sd[i] * 65535.0f + 0.5f);
-    c.depth.resize((size_t)c.d.width * c.d.height);
-    raster_depth(c.meshPos, c.meshIdx, W, c.d.width, c.d.height, c.depth.data());
+    if (!basePass) {
+        c.depth.resize((size_t)c.d.width * c.d.height);
+        raster_depth(c.meshPos, c.meshIdx, W, c.d.width, c.d.height, c.depth.data());
+        return 0;
+    }
+    m43 world43;
+    for (int r = 0; r < 4; ++r) for (int k = 0; k < 3; ++k) world43.m[r][k] = (float)world[r * 4 + k];
+    const m44 prev = c.meshHavePrev ? c.meshWvpPrev : W;
+    c.meshWvpPrev = W; c.meshHavePrev = true;
+    const float zero[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    render_base_pass(c, W, prev, world43, SW, f3{eye[0], eye[1], eye[2]}, clear ? clear : zero);
+    return 0;
+}
+int mvo_mesh_render_depth(mvo_caster* h, const float viewProj[16], float shadowVpOut[16]) { return mesh_render_impl(h, viewProj, shadowVpOut, false, nullptr, nullptr); }
+int mvo_mesh_render(mvo_caster* h, const float viewProj[16], const float eye[3], const float clearRgba[4], float shadowVpOut[16])
+{
+    return mesh_render_impl(h, viewProj, shadowVpOut, true, eye, clearRgba);
+}
+int mvo_read_velocity(mvo_caster* h, uint16_t* out)
+{
+    if (!h || !out) return -1;
+    Caster& c = h->c;
+    const size_t n = (size_t)c.d.width * c.d.height * 2;
+    if (c.velocity.size() != n) memset(out, 0, n * sizeof(uint16_t));
+    else memcpy(out, c.velocity.data(), n * sizeof(uint16_t));
     return 0;
 }
 int mvo_read_depth(mvo_caster* h, float* depth, uint16_t* shadow, uint32_t* shadowSize)

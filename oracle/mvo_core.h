@@ -101,6 +101,8 @@ struct Caster {
     // occluder mesh (mvo_mesh.cpp)
     std::vector<float> meshPos;           // V x 3
     std::vector<uint32_t> meshIdx;        // 3 T
+    std::vector<float> meshNrm;           // V x 3, recomputed
+    m44 meshWvpPrev; bool meshHavePrev = false;
     float meshExtent = 1.0f, meshScale = 1.0f;
     f3 meshPosition = {0.0f, 0.0f, 0.0f};
 };
@@ -118,5 +120,7 @@ void sh_project(const float* cubeRGB, uint32_t size, float out27[27]);
 f4 evaluate_sh_irradiance(const f3 sh[9], f3 norm);
 // mvo_mesh.cpp: depth-only rasterisation of an indexed triangle list under wvp into depth[width * height]
 void raster_depth(const std::vector<float>& pos, const std::vector<uint32_t>& idx, const m44& wvp, uint32_t width, uint32_t height, float* depth);
+void recompute_normals(const std::vector<float>& pos, const std::vector<uint32_t>& idx, std::vector<float>& nrm);
+void render_base_pass(Caster& c, const m44& wvp, const m44& wvpPrev, const m43& world, const m44& shadowWVP, f3 eye, const float clear[4]);
 
 } // namespace mvo

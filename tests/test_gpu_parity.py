@@ -421,6 +421,62 @@ def test_frame_parity_with_rasterised_mesh_occluder():
     _check_image(p.ReadFrame(), o.ReadFrame(), "frame")
 
 
+@pytest.mark.parametrize("mesh,sh", [("sphere", False), ("sphere", True), ("soup", False)])
+def test_mesh_base_pass_bit_exact(mesh, sh):
+    """ObjectRenderer::Render: colour, depth and velocity of the shaded base pass, two frames from two eye points (the second
+    has a non-zero velocity field). The soup has interpenetrating and near-plane-clipped triangles."""
+    from harness import triangle_soup, uv_sphere
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=640, height=360)
+    o, p = _pair(**kw)
+    pos, idx = uv_sphere(radius=5.0, rings=64, sectors=128) if mesh == "sphere" else triangle_soup(2000, seed=11)
+    cams = [scene.default_camera(640, 360), scene.default_camera(640, 360, eye=(9.0, 14.0, -76.0))]
+    for c in (o, p):
+        c.SetLight(scene.LIGHT_PT, scene.LIGHT_COLOR, scene.LIGHT_INTENSITY)
+        c.SetAmbient(scene.AMBIENT_COLOR, scene.AMBIENT_INTENSITY)
+        if sh:
+            c.SetSH(np.random.RandomState(5).uniform(0.0, 0.6, (9, 3)).astype(np.float32))
+        c.SetMesh(pos, idx)
+        c.SetMeshWorld(1.8, (0.0, -9.0, 0.0))
+    for frame, (vp, eye) in enumerate(cams):
+        svps = []
+        for c in (o, p):
+            svps.append(c.RenderMesh(vp, eye, clear_rgba=(0.1, 0.2, 0.3, 0.0)))
+        assert np.array_equal(svps[0], svps[1])
+        (do, so), (dp, sp) = o.ReadDepth(), p.ReadDepth()
+        assert (do < 1.0).sum() > 2000
+        assert np.array_equal(do.view(np.uint32), dp.view(np.uint32)) and np.array_equal(so, sp)
+        fo, fp_ = o.ReadFrame().view(np.uint16), p.ReadFrame().view(np.uint16)
+        assert np.array_equal(fo, fp_), f"frame {frame}: {np.count_nonzero((fo != fp_).any(-1))} pixels differ"
+        vo, vq = o.ReadVelocity(), p.ReadVelocity()
+        assert np.array_equal(vo, vq)
+        assert (vo.view(np.float16) != 0).any() == (frame == 1)
+
+
+def test_frame_parity_over_a_shaded_mesh_with_velocity():
+    """Whole chain with the base pass as the producer of all four inputs (colour, depth, shadow map, velocity): two frames
+    from two eye points, volumes composited over the shaded mesh, TAA reprojecting through the mesh's velocity field."""
+    from harness import uv_sphere
+    kw = dict(grid_size=32, light_grid_size=16, num_volumes=16, num_volume_srcs=4, width=320, height=180)
+    o, p = _pair(**kw)
+    pos, idx = uv_sphere(radius=5.0, rings=32, sectors=64)
+    cams = [scene.default_camera(320, 180), scene.default_camera(320, 180, eye=(6.0, 15.0, -78.0))]
+    for c in (o, p):
+        configure(c, sh=True)
+        c.SetMesh(pos, idx)
+        c.SetMeshWorld(3.6, (0.0, -4.0, 0.0))
+        for vp, eye in cams:
+            svp = c.RenderMesh(vp, eye, clear_rgba=(0.05, 0.05, 0.08, 0.0))
+            c.UpdateFrame(vp, svp, eye)
+            c.Render()
+            c.Postprocess()
+    so, sp = o.GetStats(), p.GetStats()
+    _check_counts(so, sp, ("oit_fragments", "view_samples", "light_samples", "direct_samples"))
+    _check_image(p.ReadFrame(), o.ReadFrame(), "frame")
+    (to, ro), (tp, rp) = o.ReadPost(), p.ReadPost()
+    _check_image(tp, to, "taa")
+    _check_rgba8(rp, ro)
+
+
 # ---------------------------------------------------------------- DDS ingest
 @pytest.mark.parametrize("kind,dx10,res", [("r32f", True, 32), ("r16f", True, 32), ("r8un", False, 32), ("r32f", True, 48), ("r16f", False, 20)])
 def test_dds_volume_ingest(tmp_path, kind, dx10, res):

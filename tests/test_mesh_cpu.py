@@ -160,3 +160,142 @@ def test_raster_order_independence_on_a_soup():
         out.append(o.ReadDepth())
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
     assert (out[0][0] < 1.0).sum() > 1000
+
+
+# ---------------------------------------------------------------- the shaded base pass (ObjectRenderer::Render)
+def _expected_shade(N, ws, eye, light_pt, light_rgbi, ambient_rgbi, sh=None):
+    """PSBasePass.hlsl:94-153 in float64 for unit normal(s) N (..., 3) at world positions ws (..., 3); unshadowed."""
+    N = np.asarray(N, np.float64); ws = np.asarray(ws, np.float64)
+    L = np.asarray(light_pt, np.float64); L = L / np.linalg.norm(L)
+    V = np.asarray(eye, np.float64) - ws; V = V / np.linalg.norm(V, axis=-1, keepdims=True)
+    H = V + L; H = H / np.linalg.norm(H, axis=-1, keepdims=True)
+    sat = lambda x: np.clip(x, 0.0, 1.0)
+    NoL, NoH, NoV = sat((N * L).sum(-1)), sat((N * H).sum(-1)), sat((N * V).sum(-1))
+    brdf = np.array([1.0, 0.6, 0.2]) / np.pi
+    light = np.asarray(light_rgbi[:3], np.float64) * light_rgbi[3]
+    if sh is None:
+        amb = np.asarray(ambient_rgbi[:3], np.float64) * ambient_rgbi[3] * (0.5 + 0.5 * (N[..., 1:2] * 0.5 + 0.5))
+    else:                                                    # SHIrradianceTypeless.hlsli:16-37
+        c1, c2, c3, c4 = 0.429043, 0.511664, 0.247708, 0.886227
+        x, y, z = -N[..., 0:1], -N[..., 1:2], N[..., 2:3]
+        s = np.asarray(sh, np.float64).reshape(9, 3)
+        amb = np.maximum(0.0, c1 * (x * x - y * y) * s[8] + c3 * (3 * z * z - 1) * s[6] + c4 * s[0]
+                         + 2 * c1 * (s[4] * x * y + s[7] * x * z + s[5] * y * z) + 2 * c2 * (s[3] * x + s[1] * y + s[2] * z))
+    fres = (1.0 - NoV) ** 5; fres = fres + (1.0 - fres) * 0.08
+    spec = (NoH ** 64 * fres)[..., None]
+    return (brdf * NoL[..., None] + spec) * light + brdf * amb
+
+
+@pytest.mark.parametrize("facing,use_sh", [(True, False), (False, False), (True, True)])
+def test_base_pass_of_a_clip_space_quad_matches_closed_form(facing, use_sh):
+    """A screen-filling quad given in clip space (identity matrices): constant normal (0, 0, -1 or +1), WSPos = the
+    pixel centre's NDC position, nothing in shadow. Colour against the float64 evaluation of the pixel shader."""
+    W, H = 64, 48
+    o = _oracle(W, H)
+    a, b, c, d = (-1, -1, .25), (1, -1, .25), (1, 1, .25), (-1, 1, .25)
+    tris = [a, c, b, a, d, c] if facing else [a, b, c, a, c, d]          # cross(e1, e2) = -z when facing the eye at z < 0
+    pos = np.asarray(tris, np.float32)
+    eye = (0.3, 0.2, -3.0)
+    light, amb = (0.6, 0.9, -1.0), (0.4, 0.6, 1.0)
+    o.SetLight(light, (1.0, 0.7, 0.3), 2.0)
+    o.SetAmbient(amb, 1.5)
+    sh = None
+    if use_sh:
+        sh = np.random.RandomState(3).uniform(0.0, 0.5, (9, 3)).astype(np.float32); sh[0] += 1.0
+        o.SetSH(sh)
+    o.SetMesh(pos, np.arange(6, dtype=np.uint32))
+    o.SetMeshWorld(1.0, (0, 0, 0))
+    o.RenderMesh(np.eye(4, dtype=np.float32), eye, clear_rgba=(0.1, 0.2, 0.3, 0.0))
+    rgba = o.ReadFrame().astype(np.float64)
+    depth, _ = o.ReadDepth()
+    assert np.all(depth == np.float32(0.25)) and np.all(rgba[..., 3] == 1.0)
+    assert np.all(o.ReadVelocity().view(np.float16) == 0)                # first frame: previous = current (0 * -0.5 = -0)
+    xs = (np.arange(W) + 0.5) / W * 2 - 1; ys = 1 - (np.arange(H) + 0.5) / H * 2
+    ws = np.stack([np.broadcast_to(xs, (H, W)), np.broadcast_to(ys[:, None], (H, W)), np.full((H, W), 0.25)], -1)
+    n = np.array([0.0, 0.0, -1.0 if facing else 1.0])
+    want = _expected_shade(np.broadcast_to(n, ws.shape), ws, eye, light, (1.0, 0.7, 0.3, 2.0), amb + (1.5,), sh)
+    assert np.abs(rgba[..., :3] - want).max() <= 2e-3 * max(1.0, want.max())      # fp16 storage
+    if facing:
+        assert want[..., 0].max() > want[..., 0].min() * 1.01            # the specular / Fresnel terms vary across the quad
+
+
+def test_base_pass_clear_colour_and_uncovered_pixels():
+    W, H = 64, 48
+    o = _oracle(W, H)
+    o.SetMesh(np.asarray([(-1, -1, .5), (0, 1, .5), (1, -1, .5)], np.float32), np.arange(3, dtype=np.uint32))
+    o.RenderMesh(np.eye(4, dtype=np.float32), (0, 0, -3), clear_rgba=(0.25, 0.5, 0.75, 0.0))
+    rgba, (depth, _) = o.ReadFrame(), o.ReadDepth()
+    out = depth == 1.0
+    assert 0 < out.sum() < W * H
+    assert np.all(rgba[out] == np.asarray([0.25, 0.5, 0.75, 0.0], np.float16)) and np.all(rgba[~out][:, 3] == 1.0)
+    d2 = _ndc_mesh(_oracle(W, H), [(-1, -1, .5), (0, 1, .5), (1, -1, .5)], W, H)
+    assert np.array_equal(d2, depth)                                    # same coverage and depth as the depth-only pass
+
+
+def test_base_pass_is_perspective_correct_and_writes_velocity():
+    """One large triangle under the perspective camera, rendered from two eye points in turn. Depth, the view-dependent
+    colour and the velocity (current minus previous clip position of the same surface point) are compared with a float64
+    ray / plane intersection per pixel: a screen-space-linear interpolation would fail all three."""
+    W, H = 160, 90
+    o = _oracle(W, H)
+    tri = np.asarray([(-30, -12, -20), (0, 25, 10), (34, -10, 40)], np.float32)       # strongly slanted in depth
+    nrm = np.cross(tri[1] - tri[0], tri[2] - tri[1]).astype(np.float64); nrm /= np.linalg.norm(nrm)
+    o.SetMesh(tri, np.arange(3, dtype=np.uint32))
+    light, lrgbi, argbi = scene.LIGHT_PT, (1.0, 0.7, 0.3, 2.0), (0.4, 0.6, 1.0, 1.0)
+    o.SetLight(light, lrgbi[:3], lrgbi[3]); o.SetAmbient(argbi[:3], argbi[3])
+    cams = [scene.default_camera(W, H, eye=(4.0, 16.0, -80.0)), scene.default_camera(W, H, eye=(9.0, 14.0, -76.0))]
+    for vp, eye in cams:
+        o.RenderMesh(vp, eye)
+    vp, eye = [np.asarray(x, np.float64) for x in cams[1]]
+    vp0 = np.asarray(cams[0][0], np.float64)
+    rgba, (depth, _), vel = o.ReadFrame().astype(np.float64), o.ReadDepth(), o.ReadVelocity().view(np.float16).astype(np.float64)
+    cov = depth < 1.0
+    assert cov.sum() > 1500
+    inv = np.linalg.inv(vp)
+    xs = (np.arange(W) + 0.5) / W * 2 - 1; ys = 1 - (np.arange(H) + 0.5) / H * 2
+    ndc = np.stack([np.broadcast_to(xs, (H, W)), np.broadcast_to(ys[:, None], (H, W))], -1)
+    def unproject(z):
+        p = np.concatenate([ndc, np.full((H, W, 1), z), np.ones((H, W, 1))], -1) @ inv
+        return p[..., :3] / p[..., 3:]
+    p0, p1 = unproject(0.0), unproject(0.5)
+    dirs = p1 - p0
+    t = ((tri[0].astype(np.float64) - p0) @ nrm) / (dirs @ nrm)
+    ws = p0 + dirs * t[..., None]
+    clip = np.concatenate([ws, np.ones((H, W, 1))], -1) @ vp
+    clip0 = np.concatenate([ws, np.ones((H, W, 1))], -1) @ vp0
+    # interior pixels only (the snapped edges move the boundary by up to 1/256 pixel)
+    inner = cov & np.roll(cov, 1, 0) & np.roll(cov, -1, 0) & np.roll(cov, 1, 1) & np.roll(cov, -1, 1)
+    assert np.abs(depth[inner] - (clip[..., 2] / clip[..., 3])[inner]).max() < 2e-5
+    want_v = (clip[..., :2] / clip[..., 3:] - clip0[..., :2] / clip0[..., 3:]) * np.array([0.5, -0.5])
+    assert np.abs(want_v[inner]).max() > 0.01
+    assert np.abs(vel[inner] - want_v[inner]).max() < 2e-3 * max(1.0, np.abs(want_v[inner]).max()) + 1e-4
+    n = nrm if (nrm @ (eye - ws[inner][0])) != 0 else nrm
+    want = _expected_shade(np.broadcast_to(n, ws.shape), ws, eye, light, lrgbi, argbi)
+    # the triangle may be shadowed by nothing but itself: lit everywhere
+    assert np.abs(rgba[..., :3][inner] - want[inner]).max() <= 3e-3 * max(1.0, want[inner].max())
+
+
+def test_recomputed_normals_of_a_sphere_point_outward_or_inward_consistently():
+    """ObjLoader::recomputeNormals on a UV sphere: the shaded disc is brightest toward the light and the ambient-only
+    limb (NoL = 0) carries the hemisphere term of the normal there."""
+    W, H = 160, 90
+    o = _oracle(W, H)
+    pos, idx = uv_sphere(radius=5.0, rings=48, sectors=96)
+    o.SetMesh(pos, idx)
+    o.SetMeshWorld(2.0, (0.0, 0.0, 0.0))
+    o.SetLight(scene.LIGHT_PT, (1.0, 1.0, 1.0), 1.0); o.SetAmbient((1.0, 1.0, 1.0), 0.0)
+    vp, eye = scene.default_camera(W, H)
+    o.RenderMesh(vp, eye)
+    rgba, (depth, _) = o.ReadFrame().astype(np.float64), o.ReadDepth()
+    cov = depth < 1.0
+    # analytic sphere normal per covered pixel
+    inv = np.linalg.inv(np.asarray(vp, np.float64))
+    xs = (np.arange(W) + 0.5) / W * 2 - 1; ys = 1 - (np.arange(H) + 0.5) / H * 2
+    ndc = np.stack([np.broadcast_to(xs, (H, W)), np.broadcast_to(ys[:, None], (H, W)), depth.astype(np.float64), np.ones((H, W))], -1)
+    p = ndc @ inv; ws = p[..., :3] / p[..., 3:]
+    n = ws / np.maximum(np.linalg.norm(ws, axis=-1, keepdims=True), 1e-9)
+    lit_out = _expected_shade(n, ws, eye, scene.LIGHT_PT, (1, 1, 1, 1.0), (1, 1, 1, 0.0))
+    lit_in = _expected_shade(-n, ws, eye, scene.LIGHT_PT, (1, 1, 1, 1.0), (1, 1, 1, 0.0))
+    inner = cov & np.roll(cov, 2, 0) & np.roll(cov, -2, 0) & np.roll(cov, 2, 1) & np.roll(cov, -2, 1)
+    err_out = np.abs(rgba[..., :3][inner] - lit_out[inner]).mean(); err_in = np.abs(rgba[..., :3][inner] - lit_in[inner]).mean()
+    assert min(err_out, err_in) < 0.02 and max(err_out, err_in) > 5 * min(err_out, err_in)

@@ -3,7 +3,7 @@
 Covers: instrumented (serial) and uninstrumented (frames pipelined on two streams) casters, RGBA16F and density-only
 storage, the plain and the work-graph order, cube-map and direct-scheme volumes, the mesh depth producer, 40 volumes
 (three clusters of the light march's pre-cull); round 2: empty-space bricks forced on (MV_OCC_BRICKS), the environment
-pass, the screenshot, and volume-sharded storage on two virtual ranks of one device (proxies, owner-only marches, peer
+pass, the screenshot, the mesh base pass, and volume-sharded storage on two virtual ranks of one device (proxies, owner-only marches, peer
 stores into the other caster's exchange block, device-side barriers)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,7 +13,7 @@ os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 os.environ["MV_OCC_BRICKS"] = "8"
 import numpy as np
 from multivolumes_b200 import MultiRayCaster, scene
-from harness import checker_background, configure, uv_sphere
+from harness import checker_background, configure, triangle_soup, uv_sphere
 pos, idx = uv_sphere(radius=5.0, rings=16, sectors=32)
 for variant in (dict(count_samples=True), dict(count_samples=False), dict(count_samples=False, density_only=True)):
     c = MultiRayCaster(grid_size=32, light_grid_size=16, num_volumes=40, num_volume_srcs=4, width=320, height=180, **variant)
@@ -24,6 +24,9 @@ for variant in (dict(count_samples=True), dict(count_samples=False), dict(count_
         svp = c.RenderMeshDepth(vp)
         c.SetEnvironment(scene.procedural_sky(16))
         for i in range(4):
+            if i == 3:     # the shaded base pass as producer of colour / depth / shadow map / velocity (soup: clipped triangles)
+                c.SetMesh(*triangle_soup(300, seed=2))
+                svp = c.RenderMesh(vp, e, clear_rgba=(0.1, 0.1, 0.1, 0.0))
             c.UpdateFrame(vp, svp, e); c.RenderEnvironment(); c.Render(use_work_graph=(i == 2)); c.Postprocess(True)
         c.Screenshot("/tmp/mv_sanitize.png")
         print(variant, eye, {k: v for k, v in c.GetStats().items() if k in ("visible_count", "cubemap_count", "light_volume")})
