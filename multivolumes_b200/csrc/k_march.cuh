@@ -129,8 +129,7 @@ MV_D bool brick_is_empty(const uint32_t* __restrict__ bits, const Occupancy& occ
 MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t smpCount, V3 rayOrigin, V3 rayDir,
                   float tMax, bool densityOnly, MarchCount& mc, const uint32_t* __restrict__ emptyBits, const Occupancy& occ)
 {
-    const float maxDist = 2.0f * sqrtf(3.0f);            // g_maxDist, RayMarch.hlsli:17
-    const float stepScale = maxDist / (float)smpCount;
+    const float stepScale = kMaxDist / (float)smpCount;  // g_maxDist, RayMarch.hlsli:17
     V4 scatter = {0.0f, 0.0f, 0.0f, 0.0f};
     float t = 0.0f;
     float prevDensity = 0.0f;
@@ -180,8 +179,7 @@ MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t 
         t += newStep;
         if (t > tMax) break;
     }
-    const float twoPi = 2.0f * kPi;
-    scatter.x /= twoPi; scatter.y /= twoPi; scatter.z /= twoPi;
+    scatter.x *= kInvTwoPi; scatter.y *= kInvTwoPi; scatter.z *= kInvTwoPi;   // CSRayMarch.hlsl:155, as compiled
     return scatter;
 }
 

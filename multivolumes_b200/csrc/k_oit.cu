@@ -372,7 +372,7 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
         const float k1 = 1.0f - result.w;
         result = {fma1(src.x, k1, result.x), fma1(src.y, k1, result.y), fma1(src.z, k1, result.z), fma1(src.w, k1, result.w)};
     }
-    result.w = fminf(result.w, 0.9997f);                                         // PSResolveOIT.hlsl:22
+    result.w = fminf(result.w, kAlphaClamp);                                         // PSResolveOIT.hlsl:22
     if (valid) {
         // premultiplied-alpha blend onto the colour RT (Graphics::PREMULTIPLITED, MultiRayCaster.cpp:931)
         uint2* dst = s.color + (size_t)py * W + px;

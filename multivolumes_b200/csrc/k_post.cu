@@ -29,7 +29,7 @@ MV_D float lerpf(float a, float b, float t) { return fma1(b - a, t, a); }   // l
 // texel, so the whole function is a table over the 65536 half patterns (k_build_tone_lut fills it with exactly this code).
 MV_D unsigned char tone_map_channel(float v)
 {
-    v *= 1.05f / (v + 0.7f);
+    v *= kToneScale / (v + kToneBias);
     v = pow125(fabsf(v));
     float sat = saturate(v);
     if (!(v == v)) sat = 0.0f;
@@ -143,15 +143,15 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
         }
     }
     const V2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
-    // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp, fp32 weights
+    // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp. The texel coordinate is formed the way the texture unit
+    // forms it — fixed point, 8 fractional bits (tex_coord_q8) — so that a fetch at a texel centre returns that texel and
+    // the `historyBlur > 0` test below does not hang on the last ulp of u * W - 0.5; the blend itself is fp32.
     V4 history;
     {
-        const float fx = fma1(uvBack.x, texSize.x, -0.5f), fy = fma1(uvBack.y, texSize.y, -0.5f);
-        const float flx = floorf(fx), fly = floorf(fy);
-        const float wx = fx - flx, wy = fy - fly;
-        const int ix = (int)flx, iy = (int)fly;
-        const int xa = min(max(ix, 0), W - 1), xb = min(max(ix + 1, 0), W - 1);
-        const int ya = min(max(iy, 0), H - 1), yb = min(max(iy + 1, 0), H - 1);
+        const int xq = tex_coord_q8(uvBack.x, W), yq = tex_coord_q8(uvBack.y, H);
+        const float wx = (float)(xq & 255) * 0.00390625f, wy = (float)(yq & 255) * 0.00390625f;
+        const int xa = xq >> 8, xb = min(xa + 1, W - 1);
+        const int ya = yq >> 8, yb = min(ya + 1, H - 1);
         const uint2* rowA = a.history + (size_t)ya * W;
         const uint2* rowB = a.history + (size_t)yb * W;
         const V4 t00 = unpack_half4(__ldg(rowA + xa)), t10 = unpack_half4(__ldg(rowA + xb));
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
         mu = {mu.x + nb.x, mu.y + nb.y, mu.z + nb.z};
         m2 = {fma1(nb.x, nb.x, m2.x), fma1(nb.y, nb.y, m2.y), fma1(nb.z, nb.z, m2.z)};
     }
-    const float ninth = 1.0f / 9.0f;
+    const float ninth = kNinth;
     cur = cur * 0.25f;
     mu = mu * ninth;
     const V3 m2n = m2 * ninth;

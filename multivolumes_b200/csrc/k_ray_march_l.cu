@@ -308,8 +308,7 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_MIN_BLOCKS) k_ray_marc
     const uint32_t count = s.lists->lightDenseCount;
     const cudaTextureObject_t grid0 = s.volumeTex[s.volumeDescs[volumeId] & 0x3fffu];
     const PerObject* po0 = s.perObject + volumeId;
-    const float maxDist = 2.0f * sqrtf(3.0f);
-    const float gStep = maxDist / (float)cb.maxLightSamples;                                        // RayMarch.hlsli:18
+    const float gStep = kMaxDist / (float)cb.maxLightSamples;                                        // RayMarch.hlsli:18
     uint32_t samples = 0;
 
     for (;;) {
@@ -471,8 +470,7 @@ __global__ void __launch_bounds__(kLightThreads) k_light_emit(DeviceScene s, Fra
     const uint32_t count = s.lists->lightDenseCount;
     const bool overflow = s.lists->lightOverflow != 0;
     const PerObject* po0 = s.perObject + volumeId;
-    const float maxDist = 2.0f * sqrtf(3.0f);
-    const float gStep = maxDist / (float)cb.maxLightSamples;
+    const float gStep = kMaxDist / (float)cb.maxLightSamples;
     uint32_t samples = 0;
 
     auto emit = [&](uint32_t recIdx, uint32_t hit, uint32_t resultIdx) {
@@ -545,8 +543,7 @@ __global__ void __launch_bounds__(kLightThreads, MV_LIGHT_AO_MIN_BLOCKS) k_light
     if (light_volume_elsewhere(s, volumeId)) return;
     const uint32_t count = s.lists->lightOverflow ? 0u : s.lists->lightItemCount;   // a multiple of 32
     const PerObject* po0 = s.perObject + volumeId;
-    const float maxDist = 2.0f * sqrtf(3.0f);
-    const float gStep = maxDist / (float)cb.maxLightSamples;
+    const float gStep = kMaxDist / (float)cb.maxLightSamples;
     uint32_t samples = 0;
     for (;;) {
         uint32_t base = 0;

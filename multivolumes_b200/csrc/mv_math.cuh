@@ -28,8 +28,18 @@ constexpr uint32_t kNumCubeMip = 5;
 constexpr uint32_t kNumOitLayers = 8;
 constexpr float kZNear = 1.0f, kZFar = 1000.0f;
 constexpr uint32_t kCubeMapRayMarchBit = 1u << 15;
-constexpr float kAbsorption = 0.8f;
-constexpr float kZeroThreshold = 0.01f;
+// `min16float` literals: the values the reference's SHIPPED shaders hold (Bin/*.cso, DXIL: dxc folds a min16float literal to
+// binary16), not the decimal text of the HLSL. Read off the disassembly (oracle/dxil/container.py) and confirmed by executing
+// those shaders (oracle/dxil/interp.py): with these values the oracle reproduces CSRayMarchV.cso and CSRayMarchL.cso bit for
+// bit; with the source decimals it does not.
+constexpr float kAbsorption = 0.7998046875f;            // ABSORPTION 0.8        -> 0xH3A66
+constexpr float kZeroThreshold = 0.01000213623046875f;  // ZERO_THRESHOLD 0.01   -> 0xH211F
+constexpr float kMaxDist = 3.46484375f;                 // g_maxDist 2 sqrt(3)   -> 0xH42EE
+constexpr float kInvTwoPi = 0.1591796875f;              // "/ (2.0 * PI)"        -> fmul by 0xH3118
+constexpr float kAlphaClamp = 0.99951171875f;           // 0.9997                -> 0xH3BFF (PSResolveOIT.cso)
+constexpr float kNinth = 0.111083984375f;               // "/ 9.0"               -> fmul by 0xH2F1C (CSTemporalAA.cso)
+constexpr float kToneScale = 1.0498046875f;             // 1.05                  -> 0xH3C33 (PSToneMap.cso)
+constexpr float kToneBias = 0.7001953125f;              // 0.7                   -> 0xH399A
 constexpr float kFltMax = 3.402823466e+38f;
 constexpr float kPi = 3.1415926535897f;   // SHIrradiance.hlsli:6
 
@@ -55,6 +65,19 @@ MV_HD float dot(V2 a, V2 b) { return a.x * b.x + a.y * b.y; }
 MV_HD float length(V2 a) { return sqrtf(a.x * a.x + a.y * a.y); }
 // normalize: v * (1 / sqrt(dot(v, v))) with correctly rounded sqrt and divide
 MV_HD V3 normalize(V3 v) { const float inv = 1.0f / sqrtf(dot(v, v)); return v * inv; }
+// Texel coordinate of the normalised coordinate u on an n-texel axis in 1/256 steps, clamp addressing, exactly as the sm_100a
+// texture unit forms it (the unit model probed on the B200, tools/tex_probe.cu: u truncated to 21 fractional bits, rounded to the
+// 1/256 grid).
+MV_HD int tex_coord_q8(float u, int n)
+{
+    float uc = u < -1.0f ? -1.0f : (u > 2.0f ? 2.0f : u);
+    if (!(uc == uc)) uc = 0.0f;
+    const long long uq = (long long)floorf(uc * 2097152.0f);
+    long long xq = ((uq * n + 4096) >> 13) - 128;
+    const long long hi = (long long)(n - 1) * 256;
+    xq = xq < 0 ? 0 : (xq > hi ? hi : xq);
+    return (int)xq;
+}
 MV_HD float saturate(float x) { return fminf(fmaxf(x, 0.0f), 1.0f); }
 MV_HD float lerp(float a, float b, float t) { return a + (b - a) * t; }   // HLSL lerp: x + s(y - x)
 MV_HD float sign(float x) { return (x > 0.0f) ? 1.0f : ((x < 0.0f) ? -1.0f : 0.0f); }

@@ -307,14 +307,14 @@ __global__ void __launch_bounds__(256) k_mesh_shade(const unsigned long long* __
     const float NoH = saturate(dot(N, H)), NoV = saturate(dot(N, V));
     const V3 lightColor = {cb.lightColor[0] * cb.lightColor[3], cb.lightColor[1] * cb.lightColor[3], cb.lightColor[2] * cb.lightColor[3]};
     V3 ambient = {cb.ambient[0] * cb.ambient[3], cb.ambient[1] * cb.ambient[3], cb.ambient[2] * cb.ambient[3]};
-    ambient = ambient * lerp(0.5f, 1.0f, N.y * 0.5f + 0.5f);
+    ambient = ambient * (N.y * 0.25f + 0.75f);                                       // lerp(0.5, 1.0, N.y * 0.5 + 0.5) as PSBasePass.cso folds it
     if (cb.hasSH) ambient = evaluate_sh_irradiance(cb.sh, N);
-    const V3 diffuseBRDF = {1.0f / kPi, 0.6f / kPi, 0.2f / kPi};                      // g_baseColor / PI
+    const V3 diffuseBRDF = {0.318359375f, 0.191040039062f, 0.0636596679688f};          // g_baseColor / PI as the shipped DXIL holds it (0xH3518, 0xH321D, 0xH2C13)
     float p64 = NoH;                                                                 // pow(NoH, 64): six squarings
 #pragma unroll
     for (int k = 0; k < 6; ++k) p64 = p64 * p64;
     const float om = 1.0f - NoV, om2 = om * om, fres5 = (om2 * om2) * om;             // pow(1 - NoV, 5)
-    const float fresnel = lerp(fres5, 1.0f, 0.08f);                                  // Fresnel(NoV, 0.08)
+    const float fresnel = (1.0f - fres5) * 0.0800170898438f + fres5;                  // Fresnel(NoV, 0.08): lerp as compiled, 0.08 -> 0xH2D1F
     const float spec = p64 * fresnel;
     V3 result = {diffuseBRDF.x * NoL + spec, diffuseBRDF.y * NoL + spec, diffuseBRDF.z * NoL + spec};
     result = {result.x * (lightColor.x * shadowT), result.y * (lightColor.y * shadowT), result.z * (lightColor.z * shadowT)};

@@ -111,14 +111,16 @@ int mvo_write_cubemap(mvo_caster* c, uint32_t volume, uint32_t mip, const uint16
 int mvo_write_lightmap_slab(mvo_caster* c, uint32_t volume, uint32_t z0, uint32_t z1, const uint16_t* rgba16f_slab);
 int mvo_write_rows(mvo_caster* c, uint32_t what, uint32_t row0, uint32_t row1, const void* rows);
 
-/* MV_MIN16_CONSTS_AS_HALF: 1 = evaluate with the binary16-rounded `min16float` literals the shipped DXIL
- * holds (g_maxDist 3.4648, ABSORPTION 0.7998, ZERO_THRESHOLD 0.010002, 1/(2 pi) 0.15918, alpha clamp 0.99951, 1/9 0.11108)
- * instead of the fp32 source literals; process-wide. For measuring how far a real D3D12 run may sit from the oracle. */
+/* MV_MIN16_CONSTS_AS_HALF: 1 (the default since the DXIL was disassembled and executed, oracle/dxil) =
+ * the binary16 `min16float` literals the shipped shaders hold (g_maxDist 3.4648, ABSORPTION 0.7998, ZERO_THRESHOLD 0.010002,
+ * 1/(2 pi) 0.15918, alpha clamp 0.99951, 1/9 0.11108, tone map 1.0498 / 0.70020); 0 = the decimal literals of the HLSL text
+ * as fp32. Process-wide. For reporting how far the two readings sit apart (profiles/r02_min16_delta.json). */
 void mvo_set_min16_consts_as_half(int on);
 
 /* stand-alone helpers used by the known-answer tests */
 void  mvo_cube_resolve_texel(int size, int face, int i, int j, int out_face_i_j[3]);   /* seamless Gather addressing of CubeCast */
 void  mvo_sample_volume(mvo_caster* c, uint32_t src, const float uvw[3], float rgba_out[4]);
+void  mvo_sample_lightmap(mvo_caster* c, uint32_t volume, const float uvw[3], float rgba_out[4]);   /* the texture filter of the caster's model */
 float mvo_quantize_r11(float v);
 float mvo_quantize_b10(float v);
 uint16_t mvo_f32_to_f16(float v);

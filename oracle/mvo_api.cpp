@@ -498,14 +498,15 @@ int mvo_render_environment(mvo_caster* h) { if (!h) return -1; render_environmen
 // process-wide: the `min16float` literals as the shipped DXIL holds them (binary16-rounded), SURVEY.md App. B.2
 void mvo_set_min16_consts_as_half(int on)
 {
-    Min16Consts k;
-    if (on) {
-        k.absorption = f16_to_f32(0x3A66);       // 0.7998
-        k.zeroThreshold = f16_to_f32(0x211F);    // 0.010002
-        k.maxDist = f16_to_f32(0x42EE);          // 3.4648
-        k.invTwoPi = f16_to_f32(0x3118);         // 0.15918
-        k.alphaClamp = f16_to_f32(0x3BFF);       // 0.99951
-        k.ninth = f16_to_f32(0x2F1C);            // 0.11108
+    Min16Consts k;                               // on (the default): the shipped DXIL's binary16 literals
+    if (!on) {                                   // off: the decimal literals of the HLSL text, as fp32
+        k.absorption = 0.8f;
+        k.zeroThreshold = 0.01f;
+        k.maxDist = 3.4641016151377544f;         // 2 sqrt(3)
+        k.invTwoPi = 0.0f;                       // divide by 2 pi
+        k.alphaClamp = 0.9997f;
+        k.ninth = 1.0f / 9.0f;
+        k.toneScale = 1.05f; k.toneBias = 0.7f;
     }
     g_min16 = k;
 }
@@ -546,6 +547,11 @@ int mvo_write_rows(mvo_caster* h, uint32_t what, uint32_t row0, uint32_t row1, c
 void mvo_sample_volume(mvo_caster* h, uint32_t src, const float uvw[3], float out[4])
 {
     const f4 r = sample3d(h->c.volumes[src], {uvw[0], uvw[1], uvw[2]}, h->c.filterModel);
+    out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
+}
+void mvo_sample_lightmap(mvo_caster* h, uint32_t volume, const float uvw[3], float out[4])
+{
+    const f4 r = sample3d(h->c.lightMaps[volume], {uvw[0], uvw[1], uvw[2]}, h->c.filterModel);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 float mvo_quantize_r11(float v) { return quantize_ufloat(v, 6); }

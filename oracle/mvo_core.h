@@ -21,12 +21,15 @@ constexpr uint32_t kCubeMapRayMarchBit = 1u << 15;
 // App. B.2), which is what a D3D12 driver would feed its ALUs. mvo_set_min16_consts_as_half(1) switches to those values so
 // that the difference can be measured (tests/test_oracle_kat.py::test_min16_consts_as_half_delta, tools/min16_delta.py).
 struct Min16Consts {
-    float absorption = 0.8f;
-    float zeroThreshold = 0.01f;
-    float maxDist = 3.4641016151377544f;     // 2 sqrt(3), = 2.0f * sqrtf(3.0f) in fp32
-    float invTwoPi = 0.0f;                   // 0 = divide by 2 pi (source form); else the baked reciprocal
-    float alphaClamp = 0.9997f;
-    float ninth = 1.0f / 9.0f;
+    // defaults: the binary16 values the reference's shipped DXIL holds (Bin/*.cso; oracle/dxil). mvo_set_min16_consts_as_half(0)
+    // switches to the decimal literals of the HLSL text, to report how far the two readings sit apart.
+    float absorption = 0.7998046875f;          // 0xH3A66
+    float zeroThreshold = 0.01000213623046875f; // 0xH211F
+    float maxDist = 3.46484375f;               // 0xH42EE
+    float invTwoPi = 0.1591796875f;            // 0xH3118; 0 = divide by 2 pi (source form)
+    float alphaClamp = 0.99951171875f;         // 0xH3BFF
+    float ninth = 0.111083984375f;             // 0xH2F1C
+    float toneScale = 1.0498046875f, toneBias = 0.7001953125f;   // 0xH3C33, 0xH399A (PSToneMap.cso)
 };
 extern Min16Consts g_min16;
 #define kAbsorption (mvo::g_min16.absorption)

@@ -230,13 +230,13 @@ void render_base_pass(Caster& c, const m44& wvp, const m44& wvpPrev, const m43& 
             const float NoH = saturate(dot3(N, H)), NoV = saturate(dot3(N, V));
             const f3 lightColor = {c.lightColor.x * c.lightColor.w, c.lightColor.y * c.lightColor.w, c.lightColor.z * c.lightColor.w};
             f3 ambient = {c.ambient.x * c.ambient.w, c.ambient.y * c.ambient.w, c.ambient.z * c.ambient.w};
-            ambient = ambient * lerp1(0.5f, 1.0f, N.y * 0.5f + 0.5f);
+            ambient = ambient * (N.y * 0.25f + 0.75f);        // lerp(0.5, 1.0, N.y * 0.5 + 0.5) as PSBasePass.cso folds it
             if (c.hasSH) { const f4 irr = evaluate_sh_irradiance(c.sh, N); ambient = {irr.x, irr.y, irr.z}; }
-            const f3 diffuseBRDF = {1.0f / kPi, 0.6f / kPi, 0.2f / kPi};
+            const f3 diffuseBRDF = {0.318359375f, 0.191040039062f, 0.0636596679688f};   // g_baseColor / PI in the shipped DXIL: 0xH3518, 0xH321D, 0xH2C13
             float p64 = NoH;
             for (int k = 0; k < 6; ++k) p64 = p64 * p64;
             const float om = 1.0f - NoV, om2 = om * om, fres5 = (om2 * om2) * om;
-            const float fresnel = lerp1(fres5, 1.0f, 0.08f);
+            const float fresnel = (1.0f - fres5) * 0.0800170898438f + fres5;           // lerp as compiled; 0.08 -> 0xH2D1F
             const float spec = p64 * fresnel;
             f3 result = {diffuseBRDF.x * NoL + spec, diffuseBRDF.y * NoL + spec, diffuseBRDF.z * NoL + spec};
             result = {result.x * (lightColor.x * shadowT), result.y * (lightColor.y * shadowT), result.z * (lightColor.z * shadowT)};

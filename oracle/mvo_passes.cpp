@@ -788,16 +788,16 @@ void temporal_aa(Caster& c, bool taaOn)
                 if (s > speedSq) { vmax = nb; speedSq = s; }
             }
             const f2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
-            // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp, fp32 weights
+            // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp. Texel coordinates in fixed point with 8 fractional
+            // bits, formed as the texture unit forms them (axis_sm100): D3D's contract, and it makes a fetch at a texel centre
+            // return that texel, which the `historyBlur > 0` test below depends on (with fp32 coordinates it hangs on the last
+            // ulp of u * W - 0.5; found by running the reference's CSTemporalAA.cso, oracle/dxil). The blend is fp32.
             f4 history;
             {
-                const float fx = fma1(uvBack.x, texSize.x, -0.5f), fy = fma1(uvBack.y, texSize.y, -0.5f);
-                const float flx = floorf(fx), fly = floorf(fy);
-                const float wx = fx - flx, wy = fy - fly;
-                auto cl = [&](int v, int n) { return std::min(std::max(v, 0), n - 1); };
-                const int ix = (int)flx, iy = (int)fly;
-                const f4 t00 = loadC(hist, cl(ix, W), cl(iy, H)), t10 = loadC(hist, cl(ix + 1, W), cl(iy, H));
-                const f4 t01 = loadC(hist, cl(ix, W), cl(iy + 1, H)), t11 = loadC(hist, cl(ix + 1, W), cl(iy + 1, H));
+                const AxisFix ax = axis_sm100(uvBack.x, W), ay = axis_sm100(uvBack.y, H);
+                const float wx = (float)ax.frac * 0.00390625f, wy = (float)ay.frac * 0.00390625f;
+                const f4 t00 = loadC(hist, ax.i0, ay.i0), t10 = loadC(hist, ax.i1, ay.i0);
+                const f4 t01 = loadC(hist, ax.i0, ay.i1), t11 = loadC(hist, ax.i1, ay.i1);
                 auto L = [&](float a, float b, float cc, float d) { return lerpf(lerpf(a, b, wx), lerpf(cc, d, wx), wy); };
                 history = {L(t00.x, t10.x, t01.x, t11.x), L(t00.y, t10.y, t01.y, t11.y), L(t00.z, t10.z, t01.z, t11.z), L(t00.w, t10.w, t01.w, t11.w)};
             }
@@ -925,7 +925,7 @@ void tone_map(Caster& c)
         float r[3];
         for (int k = 0; k < 3; ++k) {
             float v = f16_to_f32(src[(size_t)i * 4 + k]);
-            v *= 1.05f / (v + 0.7f);                 // PSToneMap.hlsl:23
+            v *= g_min16.toneScale / (v + g_min16.toneBias);   // PSToneMap.hlsl:23
             v = pow125(fabsf(v));                    // :24 pow(abs(result), 1.25)
             // RGBA8_UNORM render-target write: saturate, scale, round to nearest
             float s = saturate(v);

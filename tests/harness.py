@@ -120,3 +120,29 @@ def triangle_soup(count, seed, extent=30.0, size=6.0):
     c[:, 0, 2] = rs.uniform(-110.0, 60.0, count)       # the default camera sits at z = -80
     v = c + rs.uniform(-size, size, (count, 3, 3)) * rs.choice([0.2, 1.0, 6.0], (count, 1, 1))
     return v.reshape(-1, 3).astype(np.float32), np.arange(3 * count, dtype=np.uint32)
+
+
+# ---------------------------------------------------------------- scenes of the DXIL golden vectors (oracle/dxil/make_golden.py)
+DXIL_SCENES = {
+    "a": dict(seed=2, grid=16, light_grid=8, n=3, W=96, H=54, ray=40, light=12),
+    "b": dict(seed=6, grid=16, light_grid=8, n=2, W=96, H=54, ray=40, light=12),
+    "c": dict(seed=11, grid=32, light_grid=12, n=4, W=128, H=72, ray=64, light=16),
+}
+
+
+def dxil_scene(cls, name, light_maps=True, **kw):
+    """A tiny scene (depth map with occluder patches, shadow map, SH lighting, random transforms) set up on a caster of class
+    `cls` up to the cull and, optionally, every light map. Returns (caster, view_proj, eye, depth, shadow)."""
+    cfg = DXIL_SCENES[name]
+    W, H = cfg["W"], cfg["H"]
+    c = cls(grid_size=cfg["grid"], light_grid_size=cfg["light_grid"], num_volumes=cfg["n"], width=W, height=H,
+            max_ray_samples=cfg["ray"], max_light_samples=cfg["light"], **kw)
+    y, x = np.mgrid[0:H, 0:W]
+    depth = np.where((x // 12 + y // 9) % 3 == 0, 0.9985, 1.0).astype(np.float32)
+    shadow = blob_shadow(64)
+    vp, eye = configure(c, sh=True, depth=depth, shadow=shadow, random_transforms=cfg["seed"], eye=(6.0, 18.0, -62.0))
+    c.Cull()
+    if light_maps:
+        for v in range(cfg["n"]):
+            c.RayMarchL(v)
+    return c, vp, eye, depth, shadow

@@ -11,6 +11,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libmv_oracle.so")
 
 _EXTRA = {
     "sample_volume": (None, [_vp, u32, P(f32), P(f32)]),
+    "sample_lightmap": (None, [_vp, u32, P(f32), P(f32)]),
     "quantize_r11": (f32, [f32]),
     "quantize_b10": (f32, [f32]),
     "f32_to_f16": (C.c_uint16, [f32]),

@@ -1,0 +1,158 @@
+"""The oracle — and, on a GPU, the product — against outputs of the reference's OWN compiled shaders.
+
+The reference ships its shaders as DXIL (`/root/reference/Bin/*.cso`). `oracle/dxil/` disassembles them (llvmlite) and executes
+them (a small LLVM-IR / DXIL interpreter with wave intrinsics) on seeded inputs; `python -m oracle.dxil.make_golden` wrote
+the vectors under tests/golden/dxil_*.npz, here, once, and nothing below touches /root/reference. What each vector pins:
+
+  dxil_cull      CSVolumeCull.cso ......... visible / cube-map lists and VolumeInfo (u32 x 4): EXACT, at BASELINE shapes
+  dxil_march_v   CSRayMarchV.cso .......... cube-map texels (RGBA16F) and cube depths: BIT-EXACT
+  dxil_march_l   CSRayMarchL.cso .......... light-map voxels (R11G11B10_FLOAT values): BIT-EXACT
+  dxil_post      CSTemporalAA.cso + PSToneMap.cso ... TAA output within one binary16 step on isolated texels, RGBA8 EXACT
+  dxil_init      CSInitGridData.cso, CSR32FToRGBA16F.cso ... volume texels (RGBA16F): BIT-EXACT
+  dxil_sh        CSSHCubeMap / CSSHSum / CSSHNormalize.cso (no HLSL in the reference) ... 9 x 3 coefficients to 1e-6 relative
+                 (the summation order of a wave reduction is the hardware's)
+
+The texture unit is not shader code: the interpreter's sampler callbacks use the oracle's filter (model 0 = exact fp32
+trilinear, model 1 = the sm_100a unit the product's tex3D runs on); vectors exist for both. `min16float` arithmetic is
+evaluated in fp32 with the binary16 LITERALS the DXIL holds (what a driver without fp16 ALUs executes)."""
+import os
+
+import numpy as np
+import pytest
+
+from harness import DXIL_SCENES, dxil_scene
+from oracle_binding import OracleCaster
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built(oracle_lib):
+    return oracle_lib
+
+
+def _load(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def _product(**kw):
+    from multivolumes_b200 import MultiRayCaster
+    return MultiRayCaster(**kw)
+
+
+def _casters():
+    """(id, factory(filter_model, **kw), filter model of its texture unit or None = any)"""
+    return [pytest.param(lambda model, **kw: OracleCaster(filter_model=model, **kw), None, id="oracle"),
+            pytest.param(lambda model, **kw: _product(**kw), 1, id="product", marks=pytest.mark.gpu)]
+
+
+# ---------------------------------------------------------------------------------------------------------------- cull
+def _cull_cases():
+    g = _load("dxil_cull.npz")
+    return sorted({k.split("/")[0] for k in g.files})
+
+
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("case", _cull_cases())
+def test_cull_equals_the_reference_shader(make, unit, case):
+    g = _load("dxil_cull.npz")
+    G, L, N, W, H = [int(x) for x in g[f"{case}/shape"]]
+    c = make(1, grid_size=G, light_grid_size=L, num_volumes=N, width=W, height=H, max_ray_samples=int(g[f"{case}/max_ray_samples"]))
+    po = g[f"{case}/per_object"]
+    c.SetVolumeWorldMatrices(po[:, 44:56].reshape(N, 4, 3))
+    c.UpdateFrame(g[f"{case}/view_proj"], None, g[f"{case}/eye"])
+    assert np.array_equal(c.ReadPerObject().view(np.uint32), po.view(np.uint32))          # same inputs as the shader saw
+    c.Cull()
+    vis, cub, att = c.ReadVisible(), c.ReadCubeVolumes(), c.ReadAttribs()
+    assert np.array_equal(np.sort(vis), np.sort(g[f"{case}/visible"]))                      # Append order is the hardware's
+    assert np.array_equal(np.sort(cub), np.sort(g[f"{case}/cube_volumes"]))
+    info = g[f"{case}/volume_info"]
+    for v in vis:
+        assert np.array_equal(att[v], info[v].astype(np.uint16)), (v, att[v], info[v])
+
+
+# ---------------------------------------------------------------------------------------------------------------- marches
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("model", [0, 1])
+@pytest.mark.parametrize("name", sorted(DXIL_SCENES))
+def test_view_march_equals_the_reference_shader(make, unit, model, name):
+    if unit is not None and unit != model:
+        pytest.skip("the product's texture unit is the hardware's (model 1)")
+    g = _load("dxil_march_v.npz")
+    c, vp, eye, depth, shadow = dxil_scene(lambda **kw: make(model, **kw), name)
+    c.RayMarchV()
+    cubes = g[f"f{model}/{name}/cubes"]
+    assert np.array_equal(np.sort(c.ReadCubeVolumes()), cubes) and len(cubes) > 0
+    rays = 0
+    for v in cubes:
+        k = f"f{model}/{name}/v{int(v)}"
+        mip = int(g[k + "/mip"])
+        rgba, dep = c.ReadCubeMap(int(v), mip)
+        want_d = g[k + "/depth"]
+        mask = want_d >= 0                                        # texels the shader wrote (visible faces, rays that hit)
+        assert np.array_equal(np.asarray(dep)[mask].view(np.uint32), want_d[mask].view(np.uint32))
+        assert np.array_equal(np.asarray(rgba).view(np.uint16)[mask], g[k + "/rgba"][mask]), (name, int(v))
+        rays += int(mask.sum())
+    assert rays >= 48
+
+
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("model", [0, 1])
+@pytest.mark.parametrize("name", sorted(DXIL_SCENES))
+def test_light_march_equals_the_reference_shader(make, unit, model, name):
+    if unit is not None and unit != model:
+        pytest.skip("the product's texture unit is the hardware's (model 1)")
+    g = _load("dxil_march_l.npz")
+    c, vp, eye, depth, shadow = dxil_scene(lambda **kw: make(model, **kw), name, light_maps=False)
+    checked = 0
+    for v in c.ReadVisible():
+        c.RayMarchL(int(v))
+        got = np.asarray(c.ReadLightMap(int(v))).view(np.float16)[..., :3].astype(np.float32)
+        want = g[f"f{model}/{name}/v{int(v)}"]
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), (name, int(v), int((got != want).sum()))
+        checked += 1
+    assert checked >= 2
+
+
+# ---------------------------------------------------------------------------------------------------------------- TAA + tone map
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_postprocess_against_the_reference_shaders(make, unit, seed):
+    g = _load("dxil_post.npz")
+    cur, hist, vel = [g[f"s{seed}/{k}"].view(np.float16) for k in ("current", "history", "velocity")]
+    H, W = cur.shape[:2]
+    c = make(0, grid_size=32, light_grid_size=16, num_volumes=1, width=W, height=H)
+    c.SetRenderTargets(color=hist); c.Postprocess(False)                      # history := the given image (TAA off copies)
+    c.SetRenderTargets(color=cur, velocity=vel if vel.any() else None); c.Postprocess(True)
+    taa, rgba8 = c.ReadPost()
+    want = g[f"s{seed}/taa_f32"].view(np.float16)
+    got = np.asarray(taa).view(np.float16)
+    ulps = np.abs(got.view(np.int16).astype(np.int32) - want.view(np.int16).astype(np.int32))
+    assert ulps.max() <= 1 and (ulps > 0).mean() < 0.01, (int(ulps.max()), float((ulps > 0).mean()))
+    assert np.array_equal(np.asarray(rgba8), g[f"s{seed}/rgba8_f32"])
+    # evaluated in binary16 instead (a driver WITH fp16 ALUs) the reference itself moves by far more than that
+    f16 = g[f"s{seed}/taa_f16"].view(np.float16).astype(np.float32)
+    assert np.abs(f16 - want.astype(np.float32)).max() > 20 * np.abs(got.astype(np.float32) - want.astype(np.float32)).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------- SH projection
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("name", ["noise8", "sky16"])
+def test_sh_projection_against_the_reference_kernels(make, unit, name):
+    g = _load("dxil_sh.npz")
+    c = make(1, grid_size=32, light_grid_size=16, num_volumes=1, width=64, height=48)
+    got = c.TransformSH(g[name + "/cube"])
+    want = g[name + "/coeffs"]
+    assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------- ingest
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("G", [16, 24])
+def test_volume_init_and_conversion_equal_the_reference_shaders(make, unit, G):
+    g = _load("dxil_init.npz")
+    c = make(1, grid_size=G, light_grid_size=8, num_volumes=1, width=64, height=48)
+    c.InitVolumeData(0, 0, 0)
+    assert np.array_equal(np.asarray(c.ReadVolume(0)).view(np.uint16), g[f"g{G}/rgba"])
+    c.LoadVolumeData(0, g[f"g{G}/density"])
+    assert np.array_equal(np.asarray(c.ReadVolume(0)).view(np.uint16), g[f"g{G}/converted"])

@@ -333,8 +333,11 @@ def test_tone_map_known_answers():
 
 def test_taa_static_image_history_weight_and_identity():
     """CSTemporalAA.hlsl:267-330 on a static constant image with zero velocity: the history weight stored in alpha grows
-    by 1 / historyMax (= 1 / 15) per frame until it saturates at 1 (history.w * 15 + 1, then / 15, :275 / :332), and the
-    colour stays the input colour (neighbourhood box = one point, TM / ITM are inverses up to rounding)."""
+    by 1 / historyMax (= 1 / 15) per frame until it saturates at 1 (history.w * 15 + 1, then / 15, :275 / :332). The colour
+    stays within the neighbourhood box of the input colour: with the shipped shader's 1 / 9 (binary16 0.11108) the box of a
+    constant image is not a point but [0.984 c, 1.016 c] (mu = 0.99976 c, sigma = 0.0156 c), the zero history of the first
+    frame is clamped to its lower end and the sequence creeps up to 0.99 c and stays — CSTemporalAA.cso itself, run by
+    oracle/dxil, gives this very series (0.591, 0.592, 0.5923 ... 0.594 for c = 0.6)."""
     c = _mk(width=32, height=18)
     colour = np.array([0.6, 0.3, 0.1, 1.0], np.float16)
     img = np.empty((18, 32, 4), np.float16); img[...] = colour
@@ -348,7 +351,10 @@ def test_taa_static_image_history_weight_and_identity():
         interior = taa[4:-4, 4:-4].astype(np.float32)
         w = np.float16(min((np.float32(w) * np.float32(15.0) + np.float32(1.0)) / np.float32(15.0), 1.0))
         assert np.abs(interior[..., 3] - np.float32(w)).max() <= 1e-3, (k, interior[0, 0, 3], w)
-        assert np.abs(interior[..., :3] - colour[:3].astype(np.float32)).max() <= 2e-3, k
+        ratio = interior[..., :3] / colour[:3].astype(np.float32)
+        assert ratio.min() >= 0.983 and ratio.max() <= 1.002, (k, ratio.min(), ratio.max())
+        if k == 1: first = interior[..., 0].mean()
+    assert 0.5905 <= first <= 0.5915 and abs(interior[..., 0].mean() - 0.594) < 1e-3
     assert w == np.float16(1.0)
 
 
@@ -460,11 +466,11 @@ def test_cull_lod_and_sample_count_against_independent_evaluation():
 
 
 def test_min16_consts_as_half_delta(oracle_lib):
-    """MV_MIN16_CONSTS_AS_HALF: with the binary16-rounded `min16float` literals of the shipped DXIL the
-    oracle's frame moves — by more than the stated 2e-3 at the pixels where a ray takes one step more or fewer (the sample
-    budget follows g_maxDist) — while lists and attributes (no min16 constant feeds the cull) stay put: the reference's
-    own output is hardware-dependent at that level (numbers for configs[0]: profiles/r02_min16_delta.json). The switch is
-    process-wide and restored here."""
+    """MV_MIN16_CONSTS_AS_HALF: between the binary16 `min16float` literals of the shipped DXIL (the
+    default: with them the oracle reproduces the reference's compiled shaders bit for bit, tests/test_dxil_golden.py) and the
+    decimal literals of the HLSL text the frame moves — by more than the stated 2e-3 at the pixels where a ray takes one
+    step more or fewer (the sample budget follows g_maxDist) — while lists and attributes (no min16 constant feeds the cull)
+    stay put (numbers for configs[0]: profiles/r02_min16_delta.json). The switch is process-wide and restored here."""
     from harness import checker_background, configure, psnr
     from oracle_binding import OracleCaster, oracle_binding
     kw = dict(grid_size=32, light_grid_size=16, num_volumes=4, width=160, height=90)
@@ -479,7 +485,7 @@ def test_min16_consts_as_half_delta(oracle_lib):
             o.Postprocess(True)
             out.append((o.ReadVisible(), o.ReadAttribs(), o.ReadFrame().astype(np.float32), o.GetStats()["view_samples"] + o.GetStats()["direct_samples"]))
     finally:
-        oracle_binding().set_min16_consts_as_half(0)
+        oracle_binding().set_min16_consts_as_half(1)
     (v0, a0, f0, s0), (v1, a1, f1, s1) = out
     assert np.array_equal(v0, v1) and np.array_equal(a0, a1)
     d = np.abs(f0 - f1) / np.maximum(1.0, np.abs(f0))

@@ -1,5 +1,6 @@
 #!/usr/bin/env python
-"""How far a D3D12 run with binary16 `min16float` literals may sit from the oracle's fp32-literal frame:
+"""How far the frame with the HLSL text's decimal `min16float` literals sits from the frame with the binary16 literals the shipped
+DXIL holds (the default of oracle and product):
 renders BASELINE.json configs[0] (4 x 128^3, 1280x720) on the CPU oracle both ways and writes profiles/r02_min16_delta.json.
 Also: the exact-fp32 trilinear sampler against the sm_100 texture-unit model (filter_model 0 vs 1)."""
 import json, os, sys
@@ -21,7 +22,7 @@ def render(half, model):
     bench.build_scene(o, wl, scene, None)
     for i in range(4):
         bench.step_frame(o, wl, scene, 20 * i, lambda vp, svp, eye: (o.UpdateFrame(vp, svp, eye), o.ResetColor(), o.Render(), o.Postprocess(False)))
-    oracle_binding().set_min16_consts_as_half(0)
+    oracle_binding().set_min16_consts_as_half(1)
     return o.ReadFrame().astype(np.float32), o.ReadPost()[1], o.GetStats()
 
 
@@ -31,10 +32,10 @@ def delta(a, b):
             "rgba8_max_diff": int(np.abs(a[1].astype(int) - b[1].astype(int)).max()), "view_samples": [a[2]["view_samples"], b[2]["view_samples"]]}
 
 
-base = render(0, 1)
+base = render(1, 1)
 out = {"workload": "cfg1 (4 x 128^3, 1280x720), 4 frames, TAA off",
-       "min16_consts_as_half_vs_fp32_literals": delta(render(1, 1), base),
-       "exact_fp32_trilinear_vs_sm100_texture_unit_model": delta(render(0, 0), base)}
+       "hlsl_text_fp32_literals_vs_shipped_dxil_binary16_literals": delta(render(0, 1), base),
+       "exact_fp32_trilinear_vs_sm100_texture_unit_model": delta(render(1, 0), base)}
 with open(os.path.join(ROOT, "profiles", "r02_min16_delta.json"), "w") as f:
     json.dump(out, f, indent=1)
 print(json.dumps(out, indent=1))
