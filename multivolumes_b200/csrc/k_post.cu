@@ -127,8 +127,6 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
     const int offs[8][2] = {{-1, 0}, {1, 0}, {0, -1}, {0, 1}, {-1, -1}, {1, -1}, {1, 1}, {-1, 1}};   // :46-50
     const float historyMax = 15.0f;                                                                   // :41-43
     const V2 texSize = {(float)W, (float)H};
-    const V2 invSize = {a.invW, a.invH};
-    const V2 uv = {((float)x + 0.5f) * invSize.x, ((float)y + 0.5f) * invSize.y};
     const float4 own = s_tm[ty + 1][tx + 1];
     // VelocityMax :133-161
     V2 vmax = {0.0f, 0.0f};
@@ -142,12 +140,14 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
             if (sq > speedSq) { vmax = nb; speedSq = sq; }
         }
     }
-    const V2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
     // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp. The texel coordinate is formed the way the texture unit
     // forms it — fixed point, 8 fractional bits (tex_coord_q8) — so that a fetch at a texel centre returns that texel and
     // the `historyBlur > 0` test below does not hang on the last ulp of u * W - 0.5; the blend itself is fp32.
     V4 history;
-    {
+    if (!a.velocityGiven) history = unpack_half4(__ldg(a.history + pix));      // uvBack = the pixel's own centre: weights (1, 0, 0, 0)
+    else {
+        const V2 uv = {((float)x + 0.5f) / texSize.x, ((float)y + 0.5f) / texSize.y};   // :258, a division in the shipped DXIL too
+        const V2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
         const int xq = tex_coord_q8(uvBack.x, W), yq = tex_coord_q8(uvBack.y, H);
         const float wx = (float)(xq & 255) * 0.00390625f, wy = (float)(yq & 255) * 0.00390625f;
         const int xa = xq >> 8, xb = min(xa + 1, W - 1);
@@ -156,8 +156,8 @@ __global__ void __launch_bounds__(kPostW * kPostH) k_postprocess(PostArgs a)
         const uint2* rowB = a.history + (size_t)yb * W;
         const V4 t00 = unpack_half4(__ldg(rowA + xa)), t10 = unpack_half4(__ldg(rowA + xb));
         const V4 t01 = unpack_half4(__ldg(rowB + xa)), t11 = unpack_half4(__ldg(rowB + xb));
-        history = {lerpf(lerpf(t00.x, t10.x, wx), lerpf(t01.x, t11.x, wx), wy), lerpf(lerpf(t00.y, t10.y, wx), lerpf(t01.y, t11.y, wx), wy),
-                   lerpf(lerpf(t00.z, t10.z, wx), lerpf(t01.z, t11.z, wx), wy), lerpf(lerpf(t00.w, t10.w, wx), lerpf(t01.w, t11.w, wx), wy)};
+        history = {lerp_q8(lerp_q8(t00.x, t10.x, wx), lerp_q8(t01.x, t11.x, wx), wy), lerp_q8(lerp_q8(t00.y, t10.y, wx), lerp_q8(t01.y, t11.y, wx), wy),
+                   lerp_q8(lerp_q8(t00.z, t10.z, wx), lerp_q8(t01.z, t11.z, wx), wy), lerp_q8(lerp_q8(t00.w, t10.w, wx), lerp_q8(t01.w, t11.w, wx), wy)};
     }
     // :267-275
     float curHistoryBlur = fma1(fabsf(vmax.x), 4.0f * texSize.x, fabsf(vmax.y) * (4.0f * texSize.y));

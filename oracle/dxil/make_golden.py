@@ -111,19 +111,20 @@ def make_cull():
 # ------------------------------------------------------------------------------------------------ samplers of the harness
 def bilinear_2d(tex, smp, coords, offs, lod, cmp_):
     """SampleLevel(g_smpLinear, uv, 0) on a 2-D texture: clamp addressing, texel coordinates in fixed point with 8 fractional
-    bits as the texture unit forms them (oracle/mvo_sampler.h axis_sm100), fp32 blend."""
+    bits, rounded to nearest (oracle/mvo_sampler.h axis_q8), fp32 blend, zero-weight taps ignored."""
     a = tex.mips[0]
     H, W = a.shape[0], a.shape[1]
     def axis(u, n):
         u = float(np.float32(u)); u = 0.0 if u != u else min(max(u, -1.0), 2.0)
-        xq = ((int(np.floor(np.float32(u) * np.float32(2097152.0))) * n + 4096) >> 13) - 128
+        fx = np.float32(np.float64(np.float32(u)) * n - 0.5)                      # fma(u, n, -0.5)
+        xq = int(np.floor(np.float32(np.float64(fx) * 256.0 + 0.5)))             # fma(fx, 256, 0.5)
         xq = min(max(xq, 0), (n - 1) * 256)
         return xq >> 8, min((xq >> 8) + 1, n - 1), F32((xq & 255) / 256.0)
     x0, x1, wx = axis(coords[0], W); y0, y1, wy = axis(coords[1], H)
     t00, t10 = a[y0, x0].astype(np.float32), a[y0, x1].astype(np.float32)
     t01, t11 = a[y1, x0].astype(np.float32), a[y1, x1].astype(np.float32)
-    top = t00 + (t10 - t00) * wx; bot = t01 + (t11 - t01) * wx
-    r = top + (bot - top) * wy
+    fma = lambda a_, b_, w: a_ if w == 0 else ((b_ - a_).astype(np.float32).astype(np.float64) * np.float64(w) + a_.astype(np.float64)).astype(np.float32)
+    r = fma(fma(t00, t10, wx), fma(t01, t11, wx), wy)
     return [F32(r[k]) if k < r.size else F32(0) for k in range(4)]
 
 

@@ -776,8 +776,7 @@ void temporal_aa(Caster& c, bool taaOn)
     for (int y = (int)c.row0; y < (int)c.row1; ++y)
         for (int x = 0; x < W; ++x) {
             const f2 texSize = {(float)W, (float)H};
-            const f2 invSize = {1.0f / texSize.x, 1.0f / texSize.y};
-            const f2 uv = {((float)x + 0.5f) * invSize.x, ((float)y + 0.5f) * invSize.y};
+            const f2 uv = {((float)x + 0.5f) / texSize.x, ((float)y + 0.5f) / texSize.y};   // :258, a division in the shipped DXIL too
             const f4 current = loadC(c.color, x, y);
             // VelocityMax :133-161
             f2 vmax = loadV(x, y);
@@ -789,16 +788,16 @@ void temporal_aa(Caster& c, bool taaOn)
             }
             const f2 uvBack = {uv.x - vmax.x, uv.y - vmax.y};
             // history.SampleLevel(g_smpLinear, uvBack, 0): bilinear, clamp. Texel coordinates in fixed point with 8 fractional
-            // bits, formed as the texture unit forms them (axis_sm100): D3D's contract, and it makes a fetch at a texel centre
-            // return that texel, which the `historyBlur > 0` test below depends on (with fp32 coordinates it hangs on the last
-            // ulp of u * W - 0.5; found by running the reference's CSTemporalAA.cso, oracle/dxil). The blend is fp32.
+            // bits (axis_q8): D3D's contract, and it makes a fetch at a texel centre return that texel, which the
+            // `historyBlur > 0` test below depends on (with fp32 coordinates it hangs on the last ulp of u * W - 0.5; found by
+            // running the reference's CSTemporalAA.cso, oracle/dxil). The blend is fp32; zero-weight taps do not contribute.
             f4 history;
             {
-                const AxisFix ax = axis_sm100(uvBack.x, W), ay = axis_sm100(uvBack.y, H);
-                const float wx = (float)ax.frac * 0.00390625f, wy = (float)ay.frac * 0.00390625f;
+                const AxisFix ax = axis_q8(uvBack.x, W), ay = axis_q8(uvBack.y, H);
+                const float wx = ax.ffrac, wy = ay.ffrac;
                 const f4 t00 = loadC(hist, ax.i0, ay.i0), t10 = loadC(hist, ax.i1, ay.i0);
                 const f4 t01 = loadC(hist, ax.i0, ay.i1), t11 = loadC(hist, ax.i1, ay.i1);
-                auto L = [&](float a, float b, float cc, float d) { return lerpf(lerpf(a, b, wx), lerpf(cc, d, wx), wy); };
+                auto L = [&](float a, float b, float cc, float d) { return lerp_q8(lerp_q8(a, b, wx), lerp_q8(cc, d, wx), wy); };
                 history = {L(t00.x, t10.x, t01.x, t11.x), L(t00.y, t10.y, t01.y, t11.y), L(t00.z, t10.z, t01.z, t11.z), L(t00.w, t10.w, t01.w, t11.w)};
             }
             // :267-275

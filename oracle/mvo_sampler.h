@@ -53,6 +53,21 @@ inline AxisFix axis_sm100(float u, int n)
     return a;
 }
 
+// 2-D linear fetches of the post-process (TAA history): u * n - 0.5 on the 1/256 grid, rounded to nearest, clamp addressing
+// (D3D11.3 functional spec 7.18.8: fixed-point texel coordinates, at least 8 fractional bits). n <= 16384.
+inline AxisFix axis_q8(float u, int n)
+{
+    float uc = u < -1.0f ? -1.0f : (u > 2.0f ? 2.0f : u);
+    if (!(uc == uc)) uc = 0.0f;
+    int q = (int)floorf(fma1(fma1(uc, (float)n, -0.5f), 256.0f, 0.5f));
+    const int hi = (n - 1) * 256;
+    q = q < 0 ? 0 : (q > hi ? hi : q);
+    AxisFix a;
+    a.i0 = q >> 8; a.frac = q & 255; a.i1 = a.i0 + 1 > n - 1 ? n - 1 : a.i0 + 1; a.ffrac = (float)a.frac * 0.00390625f;
+    return a;
+}
+inline float lerp_q8(float a, float b, float w) { return w == 0.0f ? a : fma1(b - a, w, a); }   // a tap of weight zero does not contribute
+
 inline AxisFix axis_exact(float u, int n)
 {
     const float x = u * (float)n - 0.5f;

@@ -9,6 +9,7 @@ the vectors under tests/golden/dxil_*.npz, here, once, and nothing below touches
   dxil_march_l   CSRayMarchL.cso .......... light-map voxels (R11G11B10_FLOAT values): BIT-EXACT
   dxil_post      CSTemporalAA.cso + PSToneMap.cso ... TAA output within one binary16 step on isolated texels, RGBA8 EXACT
   dxil_init      CSInitGridData.cso, CSR32FToRGBA16F.cso ... volume texels (RGBA16F): BIT-EXACT
+  dxil_base_pass PSBasePass.cso (mesh under the volumes) ... colour (RGBA16F) and velocity: BIT-EXACT on a clip-space quad
   dxil_sh        CSSHCubeMap / CSSHSum / CSSHNormalize.cso (no HLSL in the reference) ... 9 x 3 coefficients to 1e-6 relative
                  (the summation order of a wave reduction is the hardware's)
 
@@ -156,3 +157,20 @@ def test_volume_init_and_conversion_equal_the_reference_shaders(make, unit, G):
     assert np.array_equal(np.asarray(c.ReadVolume(0)).view(np.uint16), g[f"g{G}/rgba"])
     c.LoadVolumeData(0, g[f"g{G}/density"])
     assert np.array_equal(np.asarray(c.ReadVolume(0)).view(np.uint16), g[f"g{G}/converted"])
+
+
+# ---------------------------------------------------------------------------------------------------------------- mesh base pass
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("use_sh", [0, 1])
+def test_base_pass_equals_the_reference_pixel_shader(make, unit, use_sh):
+    from harness import sh_coeffs
+    g = _load("dxil_base_pass.npz")
+    want = g[f"sh{use_sh}/rgba"]
+    H, W = want.shape[:2]
+    c = make(1, grid_size=32, light_grid_size=16, num_volumes=1, width=W, height=H)
+    c.SetLight(g["light"], g["light_rgbi"][:3], float(g["light_rgbi"][3])); c.SetAmbient(g["ambient_rgbi"][:3], float(g["ambient_rgbi"][3]))
+    c.SetSH(sh_coeffs() if use_sh else None)
+    c.SetMesh(g["mesh"], np.arange(6, dtype=np.uint32)); c.SetMeshWorld(1.0, (0, 0, 0))
+    c.RenderMesh(np.eye(4, dtype=np.float32), g["eye"])
+    assert np.array_equal(np.asarray(c.ReadFrame()).view(np.uint16), want)
+    assert np.array_equal(np.asarray(c.ReadVelocity()).view(np.uint16) & 0x7fff, g[f"sh{use_sh}/velocity"] & 0x7fff)   # +-0
