@@ -549,6 +549,23 @@ void mvo_sample_volume(mvo_caster* h, uint32_t src, const float uvw[3], float ou
     const f4 r = sample3d(h->c.volumes[src], {uvw[0], uvw[1], uvw[2]}, h->c.filterModel);
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
+/* oracle/dxil: resolve the frame once more with a per-fragment record (the colour target is restored afterwards) */
+int mvo_debug_oit(mvo_caster* h, uint32_t* count, uint32_t* info, float* data, float* result)
+{
+    if (!h) return -1;
+    Caster& c = h->c;
+    const std::vector<uint16_t> keep = c.color;
+    const mvo_stats st = c.stats;
+    c.debugOIT = true;
+    resolve_oit(c);
+    c.debugOIT = false;
+    c.color = keep; c.stats = st;
+    if (count) std::copy(c.dbgCount.begin(), c.dbgCount.end(), count);
+    if (info) std::copy(c.dbgInfo.begin(), c.dbgInfo.end(), info);
+    if (data) std::copy(c.dbgData.begin(), c.dbgData.end(), data);
+    if (result) std::copy(c.dbgResult.begin(), c.dbgResult.end(), result);
+    return 0;
+}
 void mvo_sample_lightmap(mvo_caster* h, uint32_t volume, const float uvw[3], float out[4])
 {
     const f4 r = sample3d(h->c.lightMaps[volume], {uvw[0], uvw[1], uvw[2]}, h->c.filterModel);

@@ -16,10 +16,11 @@ constexpr float kZNear = 1.0f, kZFar = 1000.0f;
 // Common.hlsli:12, RayMarch.hlsli:11-12,17
 constexpr uint32_t kCubeMapRayMarchBit = 1u << 15;
 // RayMarch.hlsli:11-12, :17; CSRayMarch.hlsl:155; PSResolveOIT.hlsl:22; CSTemporalAA.hlsl (1 / 9). These are `min16float`
-// literals in the HLSL. The reference is compiled WITHOUT -enable-16bit-types, so min-precision is a hint and the oracle's
-// default is fp32 arithmetic with the source literals; the shipped DXIL, however, holds them rounded to binary16 (SURVEY.md
-// App. B.2), which is what a D3D12 driver would feed its ALUs. mvo_set_min16_consts_as_half(1) switches to those values so
-// that the difference can be measured (tests/test_oracle_kat.py::test_min16_consts_as_half_delta, tools/min16_delta.py).
+// literals in the HLSL. The reference is compiled WITHOUT -enable-16bit-types, so min-precision is a hint: arithmetic is fp32
+// here; the LITERALS, however, are folded to binary16 in the shipped DXIL, which is what every D3D12
+// driver feeds its ALUs, and with them — only with them — this oracle reproduces the compiled marches bit for bit
+// (tests/test_dxil_golden.py). mvo_set_min16_consts_as_half(0) switches to the decimal text of the HLSL so that the difference
+// can be measured (tests/test_oracle_kat.py::test_min16_consts_as_half_delta, tools/min16_delta.py).
 struct Min16Consts {
     // defaults: the binary16 values the reference's shipped DXIL holds (Bin/*.cso; oracle/dxil). mvo_set_min16_consts_as_half(0)
     // switches to the decimal literals of the HLSL text, to report how far the two readings sit apart.
@@ -101,6 +102,12 @@ struct Caster {
     // radiance cube map of the environment pass (LightProbe), RGBA16F [face][y][x]
     std::vector<uint16_t> envCube;
     uint32_t envSize = 0;
+    // per-fragment record of the last resolve_oit (mvo_debug_oit; for oracle/dxil: inputs of PSCube / PSResolveOIT per pixel)
+    bool debugOIT = false;
+    std::vector<uint32_t> dbgCount;       // W*H layers per pixel
+    std::vector<uint32_t> dbgInfo;        // W*H*8 x {depth key, volume, cube face (+x -x +y -y +z -z), stored}
+    std::vector<float> dbgData;           // W*H*8 x {lpt xyz, face uv, colour rgba}
+    std::vector<float> dbgResult;         // W*H x rgba: the blended layers before the render-target blend
     // occluder mesh (mvo_mesh.cpp)
     std::vector<float> meshPos;           // V x 3
     std::vector<uint32_t> meshIdx;        // 3 T

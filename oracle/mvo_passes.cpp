@@ -644,6 +644,7 @@ void resolve_oit(Caster& c)
     for (size_t k = 0; k < nvis; ++k) eyeL[k] = mul_p43(c.cb.eyePt, c.perObject[c.visible[k]].WorldI);
     // rows [row0, row1) plus a one-row halo (clipped), read by the TAA of the band's border rows
     const int rowBegin = c.row1 > c.row0 ? std::max((int)c.row0 - 1, 0) : 0, rowEnd = c.row1 > c.row0 ? std::min((int)c.row1 + 1, H) : 0;
+    if (c.debugOIT) { c.dbgCount.assign((size_t)W * H, 0); c.dbgInfo.assign((size_t)W * H * 8 * 4, 0); c.dbgData.assign((size_t)W * H * 8 * 9, 0.0f); c.dbgResult.assign((size_t)W * H * 4, 0.0f); }
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : frags, dRays, dSamples, dLight)
     for (int py = rowBegin; py < rowEnd; ++py)
         for (int px = 0; px < W; ++px) {
@@ -723,10 +724,17 @@ void resolve_oit(Caster& c)
                 f4 src = {0, 0, 0, 0};
                 if (color.w > 0.0f && color.w <= 1.0f)
                     src = {f16_to_f32(f32_to_f16(color.x)), f16_to_f32(f32_to_f16(color.y)), f16_to_f32(f32_to_f16(color.z)), f16_to_f32(f32_to_f16(color.w))};
+                if (c.debugOIT) {
+                    const size_t q = ((size_t)py * W + px) * 8 + l;
+                    float fu, fv; cube_face_uv(fr.lpt, fr.face, fu, fv);
+                    uint32_t* di = &c.dbgInfo[q * 4]; di[0] = fr.key; di[1] = fr.volumeId; di[2] = (uint32_t)fr.face; di[3] = (color.w > 0.0f && color.w <= 1.0f) ? 1u : 0u;
+                    float* dd = &c.dbgData[q * 9]; dd[0] = fr.lpt.x; dd[1] = fr.lpt.y; dd[2] = fr.lpt.z; dd[3] = fu; dd[4] = fv; dd[5] = color.x; dd[6] = color.y; dd[7] = color.z; dd[8] = color.w;
+                }
                 const float k = 1.0f - result.w;
                 result = {fma1(src.x, k, result.x), fma1(src.y, k, result.y), fma1(src.z, k, result.z), fma1(src.w, k, result.w)};
             }
             result.w = fminf(result.w, g_min16.alphaClamp);
+            if (c.debugOIT) { c.dbgCount[(size_t)py * W + px] = (uint32_t)nl; float* dr = &c.dbgResult[((size_t)py * W + px) * 4]; dr[0] = result.x; dr[1] = result.y; dr[2] = result.z; dr[3] = result.w; }
             // premultiplied-alpha blend onto the colour RT (MultiRayCaster.cpp:931)
             uint16_t* dst = &c.color[((size_t)py * W + px) * 4];
             const float ia = 1.0f - result.w;

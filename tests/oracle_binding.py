@@ -12,6 +12,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libmv_oracle.so")
 _EXTRA = {
     "sample_volume": (None, [_vp, u32, P(f32), P(f32)]),
     "sample_lightmap": (None, [_vp, u32, P(f32), P(f32)]),
+    "debug_oit": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "quantize_r11": (f32, [f32]),
     "quantize_b10": (f32, [f32]),
     "f32_to_f16": (C.c_uint16, [f32]),
@@ -44,6 +45,14 @@ class OracleCaster(CasterBase):
     def SetShardVolumes(self, rank, world, proxy_grid):
         """Volume-sharded storage as rank `rank` of `world` sees it (call after the volumes are loaded)."""
         self._ck(self.b.set_shard_volumes(self.h, rank, world, proxy_grid), "set_shard_volumes")
+
+    def DebugOIT(self):
+        """per-pixel fragments of the resolve: (count (H, W), info (H, W, 8, 4) u32 {depth key, volume, face, stored}, data (H, W, 8, 9) f32
+        {lpt xyz, face uv, colour rgba}, result (H, W, 4) f32 before the render-target blend). Leaves the colour target as it was."""
+        cnt = np.zeros((self.H, self.W), np.uint32); info = np.zeros((self.H, self.W, 8, 4), np.uint32)
+        data = np.zeros((self.H, self.W, 8, 9), np.float32); res = np.zeros((self.H, self.W, 4), np.float32)
+        self._ck(self.b.debug_oit(self.h, cnt.ctypes.data, info.ctypes.data, data.ctypes.data, res.ctypes.data), "debug_oit")
+        return cnt, info, data, res
 
     def SampleVolume(self, src, uvw):
         uvw = np.ascontiguousarray(uvw, np.float32).reshape(-1, 3)

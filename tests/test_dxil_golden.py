@@ -7,6 +7,8 @@ the vectors under tests/golden/dxil_*.npz, here, once, and nothing below touches
   dxil_cull      CSVolumeCull.cso ......... visible / cube-map lists and VolumeInfo (u32 x 4): EXACT, at BASELINE shapes
   dxil_march_v   CSRayMarchV.cso .......... cube-map texels (RGBA16F) and cube depths: BIT-EXACT
   dxil_march_l   CSRayMarchL.cso .......... light-map voxels (R11G11B10_FLOAT values): BIT-EXACT
+  dxil_oit       PSCube.cso (CubeCast and RayCast) + PSResolveOIT.cso ... K-buffer colours and the blended pixel: BIT-EXACT
+                 (fragments — depth key, exit point, face uv — from the oracle's analytic rasteriser; every 3rd pixel)
   dxil_post      CSTemporalAA.cso + PSToneMap.cso ... TAA output within one binary16 step on isolated texels, RGBA8 EXACT
   dxil_init      CSInitGridData.cso, CSR32FToRGBA16F.cso ... volume texels (RGBA16F): BIT-EXACT
   dxil_base_pass PSBasePass.cso (mesh under the volumes) ... colour (RGBA16F) and velocity: BIT-EXACT on a clip-space quad
@@ -174,3 +176,36 @@ def test_base_pass_equals_the_reference_pixel_shader(make, unit, use_sh):
     c.RenderMesh(np.eye(4, dtype=np.float32), g["eye"])
     assert np.array_equal(np.asarray(c.ReadFrame()).view(np.uint16), want)
     assert np.array_equal(np.asarray(c.ReadVelocity()).view(np.uint16) & 0x7fff, g[f"sh{use_sh}/velocity"] & 0x7fff)   # +-0
+
+
+# ---------------------------------------------------------------------------------------------------------------- OIT
+@pytest.mark.parametrize("name", sorted(DXIL_SCENES))
+def test_oit_layers_and_blend_equal_the_reference_pixel_shaders(name):
+    """oracle only (the product keeps its K-buffer in registers): per-layer colours as PSCube.cso stores them, the blend as
+    PSResolveOIT.cso returns it"""
+    g = _load("dxil_oit.npz")
+    c, vp, eye, depth, shadow = dxil_scene(OracleCaster, name, filter_model=1)
+    c.RayMarchV()
+    cnt, info, data, result = c.DebugOIT()
+    m = g[f"{name}/done"]
+    assert m.sum() >= 30 and np.array_equal(cnt[m] > 0, np.ones(int(m.sum()), bool))
+    want = g[f"{name}/layers"]
+    got = np.zeros_like(want)
+    for py, px in np.argwhere(m):
+        for l in range(int(cnt[py, px])):
+            if info[py, px, l, 3]:
+                got[py, px, l] = data[py, px, l, 5:9].astype(np.float16).view(np.uint16)
+    assert np.array_equal(got[m], want[m])
+    assert np.array_equal(result[m].view(np.uint32), g[f"{name}/blend"][m].view(np.uint32))
+
+
+@pytest.mark.parametrize("make,unit", _casters())
+@pytest.mark.parametrize("name", sorted(DXIL_SCENES))
+def test_resolved_frame_equals_the_reference_pixel_shaders(make, unit, name):
+    """the frame after the resolve (no background: the render-target blend adds nothing) against PSResolveOIT.cso's output"""
+    g = _load("dxil_oit.npz")
+    c, vp, eye, depth, shadow = dxil_scene(lambda **kw: make(1, **kw), name)
+    c.RayMarchV(); c.ResolveOIT()
+    m = g[f"{name}/done"]
+    frame = np.asarray(c.ReadFrame()).view(np.uint16)
+    assert np.array_equal(frame[m], g[f"{name}/blend"][m].astype(np.float16).view(np.uint16))
