@@ -60,7 +60,8 @@ def _cull_cases():
 def test_cull_equals_the_reference_shader(make, unit, case):
     g = _load("dxil_cull.npz")
     G, L, N, W, H = [int(x) for x in g[f"{case}/shape"]]
-    c = make(1, grid_size=G, light_grid_size=L, num_volumes=N, width=W, height=H, max_ray_samples=int(g[f"{case}/max_ray_samples"]))
+    c = make(1, grid_size=G, light_grid_size=L, num_volumes=N, num_volume_srcs=int(g[f"{case}/srcs"]), width=W, height=H,
+             max_ray_samples=int(g[f"{case}/max_ray_samples"]))
     po = g[f"{case}/per_object"]
     c.SetVolumeWorldMatrices(po[:, 44:56].reshape(N, 4, 3))
     c.UpdateFrame(g[f"{case}/view_proj"], None, g[f"{case}/eye"])
