@@ -79,8 +79,8 @@ def make_cull():
     from oracle_binding import OracleCaster
     cases = {}
     shapes = {"cfg1": dict(grid_size=64, light_grid_size=32, num_volumes=2, width=1280, height=720),
-              "cfg2": dict(grid_size=128, light_grid_size=64, num_volumes=16, width=1920, height=1080),
-              "cfg4": dict(grid_size=256, light_grid_size=128, num_volumes=64, width=3840, height=2160),
+              "cfg2": dict(grid_size=128, light_grid_size=64, num_volumes=16, num_volume_srcs=2, width=1920, height=1080),
+              "cfg4": dict(grid_size=256, light_grid_size=128, num_volumes=64, num_volume_srcs=2, width=3840, height=2160),   # (two sources: the cull does not read the volumes)
               "n512": dict(grid_size=64, light_grid_size=16, num_volumes=512, num_volume_srcs=4, width=2560, height=1440)}
     for name, kw in shapes.items():
         for seed, eye in ((0, (4.0, 16.0, -80.0)), (3, (4.0, 16.0, -80.0)), (5, (10.0, 40.0, -160.0)), (9, (30.0, 8.0, -30.0))):
