@@ -15,7 +15,11 @@
  *   - images are tightly packed, row-major, top row first; RGBA16F = 4 x IEEE binary16;
  *   - volumes are RGBA16F (R16F density with MV_FLAG_DENSITY_ONLY), x fastest then y then z; cube maps are [face][y][x] with the D3D face
  *     order +X,-X,+Y,-Y,+Z,-Z;
- *   - there is NO CPU fallback: mv_create fails with MV_ERR_NO_DEVICE when no sm_100 device exists.
+ *   - there is NO CPU fallback: mv_create fails with MV_ERR_NO_DEVICE when no sm_100 device exists;
+ *   - numerics: the shaders' arithmetic in fp32, in a stated evaluation order, with the `min16float`
+ *     literals the reference's SHIPPED shaders hold (Bin/ *.cso: dxc folds them to binary16 — g_maxDist 3.46484375,
+ *     ABSORPTION 0.7998046875, ZERO_THRESHOLD 0.010002136 ...), not the decimal text of the HLSL: results reproduce those
+ *     compiled shaders (cull, both marches, CubeCast / RayCast, resolve: bit for bit; tests/test_dxil_golden.py).
  */
 #ifndef MV_H
 #define MV_H

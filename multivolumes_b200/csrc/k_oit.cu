@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(256, MV_OIT_MIN_BLOCKS) k_resolve_oit(DeviceSc
         } else color = cube_cast(s, cb, volumeId, a.x, sceneZ, face, lpt, rayDir);
         if (!stored && color.w > 0.0f && color.w <= 1.0f) src = unpack_half4(pack_half4(color));
         const float k1 = 1.0f - result.w;
-        result = {fma1(src.x, k1, result.x), fma1(src.y, k1, result.y), fma1(src.z, k1, result.z), fma1(src.w, k1, result.w)};
+        result = {src.x * k1 + result.x, src.y * k1 + result.y, src.z * k1 + result.z, src.w * k1 + result.w};   // fmul, fadd: as PSResolveOIT.cso has it
     }
     result.w = fminf(result.w, kAlphaClamp);                                         // PSResolveOIT.hlsl:22
     if (valid) {

@@ -716,10 +716,15 @@ class Shader:
             return acc
         if opc == 78:                                            # atomicBinOp(handle, op, c0, c1, c2, value)
             h, bop, v = a[1], a[2], a[6]
-            old = h.load(a[3], a[4] or 0, 1, "i32")[0] if isinstance(h, StructuredBuffer) else int(h.load(a[3])[0])
+            if isinstance(h, Texture):
+                coords = [_sx(c_ or 0, 32) for c_ in a[3:6]]
+                old = int(h.load(0, coords)[0])
+            else:
+                old = h.load(a[3], a[4] or 0, 1, "i32")[0] if isinstance(h, StructuredBuffer) else int(h.load(a[3])[0])
             new = {0: old + v, 1: old & v, 2: old | v, 3: old ^ v, 4: min(_sx(old, 32), _sx(v, 32)), 5: max(_sx(old, 32), _sx(v, 32)),
                    6: min(old, v), 7: max(old, v), 8: v}[bop] & 0xffffffff
-            if isinstance(h, StructuredBuffer): h.store(a[3], a[4] or 0, [new])
+            if isinstance(h, Texture): h.store(coords, [new, 0, 0, 0], 1)
+            elif isinstance(h, StructuredBuffer): h.store(a[3], a[4] or 0, [new])
             else: h.store(a[3], [new, 0, 0, 0], 1)
             return old
         if opc == 130:                                           # legacyF32ToF16

@@ -624,8 +624,15 @@ def make_oit():
     from oracle_binding import OracleCaster
     I.PROMOTE_HALF = True
     flat = {}
-    for name in DXIL_SCENES:
-        o, vp, eye, depth, shadow = dxil_scene(OracleCaster, name, filter_model=1)
+    from harness import nested_scene
+    for name in list(DXIL_SCENES) + ["nested"]:
+        if name == "nested":                                  # 12 concentric volumes: up to 8 blended layers per pixel
+            o, vp, eye = nested_scene(OracleCaster, filter_model=1)
+            depth = np.ones((o.H, o.W), np.float32)
+            o.Cull()
+            for v in range(o.N): o.RayMarchL(v)
+        else:
+            o, vp, eye, depth, shadow = dxil_scene(OracleCaster, name, filter_model=1)
         o.RayMarchV()
         r = oit_case(o, eye, depth)
         m = r["done"]
@@ -645,7 +652,36 @@ def make_oit():
     np.savez_compressed(os.path.join(OUT, "dxil_oit.npz"), **flat)
 
 
-MAKERS = {"oit": make_oit, "base_pass": make_base_pass, "init": make_init, "cull": make_cull, "post": make_post, "march_v": make_march_v, "march_l": make_march_l, "sh": make_sh}
+def make_peel():
+    """PSDepthPeel.cso (the K-buffer insertion: a chain of InterlockedMin over the 8 layers) on pixels where up to 12 nested
+    volumes overlap, fragments fed in draw order; against the layers the oracle keeps."""
+    from harness import nested_scene
+    from oracle_binding import OracleCaster
+    o, vp, eye = nested_scene(OracleCaster, filter_model=1)
+    o.Cull(); o.RayMarchV()
+    cnt, info, data, result = o.DebugOIT()
+    keys = o.all_keys
+    H, W = cnt.shape
+    kd = Texture(np.full((8, H, W, 1), 0xffffffff, np.uint32))
+    ps = shader("PSDepthPeel")
+    res = Resources(uav={0: kd})
+    n_frag = 0
+    for py in range(0, H, 2):
+        for px in range(0, W, 2):
+            for k in keys[py, px]:
+                if k != 0xffffffff:
+                    z = np.array(k, np.uint32).view(np.float32)[()]
+                    ps.run_wave([ps.lane(res, {}, inputs={0: {0: F32(px + 0.5), 1: F32(py + 0.5), 2: z, 3: F32(1)}}, outputs={})])
+                    n_frag += 1
+    m = np.zeros((H, W), bool); m[0::2, 0::2] = True
+    got = kd.a[..., 0].transpose(1, 2, 0)                     # (H, W, 8)
+    want = np.where(np.arange(8)[None, None, :] < cnt[..., None], info[..., 0], 0xffffffff)
+    most = int((keys != 0xffffffff).sum(-1)[m].max())
+    print(f"peel: {n_frag} fragments on {int(m.sum())} pixels, up to {most} per pixel; K-depth layers equal the oracle's: {np.array_equal(got[m], want[m])}")
+    np.savez_compressed(os.path.join(OUT, "dxil_peel.npz"), layers=got, done=m)
+
+
+MAKERS = {"peel": make_peel, "oit": make_oit, "base_pass": make_base_pass, "init": make_init, "cull": make_cull, "post": make_post, "march_v": make_march_v, "march_l": make_march_l, "sh": make_sh}
 
 if __name__ == "__main__":
     for n in (sys.argv[1:] or MAKERS):

@@ -8,7 +8,7 @@
  * load this library; the product (libmv_b200.so) never does.
  *
  * Parity pinning status: PINNED against outputs of the reference itself. The reference ships no
- * golden vectors or CPU path, but it ships its shaders compiled (Bin/*.cso, DXIL); oracle/dxil
+ * golden vectors or CPU path, but it ships its shaders compiled (Bin/ *.cso, DXIL); oracle/dxil
  * disassembles and executes them here, and tests/test_dxil_golden.py holds this library to their
  * outputs (cull exact; light march, view march, CubeCast / RayCast / resolve, volume init, base pass
  * bit-exact; TAA within one binary16 step; SH projection — DXIL-only in the reference — to 4e-7).
@@ -121,7 +121,7 @@ void mvo_set_min16_consts_as_half(int on);
 
 /* stand-alone helpers used by the known-answer tests */
 void  mvo_cube_resolve_texel(int size, int face, int i, int j, int out_face_i_j[3]);   /* seamless Gather addressing of CubeCast */
-int   mvo_debug_oit(mvo_caster* c, uint32_t* count_wh, uint32_t* info_wh8x4, float* data_wh8x9, float* result_wh4);   /* per-fragment record of resolve_oit */
+int   mvo_debug_oit(mvo_caster* c, uint32_t* count_wh, uint32_t* info_wh8x4, float* data_wh8x9, float* result_wh4, uint32_t* all_keys_whn);   /* per-fragment record of resolve_oit */
 void  mvo_sample_volume(mvo_caster* c, uint32_t src, const float uvw[3], float rgba_out[4]);
 void  mvo_sample_lightmap(mvo_caster* c, uint32_t volume, const float uvw[3], float rgba_out[4]);   /* the texture filter of the caster's model */
 float mvo_quantize_r11(float v);

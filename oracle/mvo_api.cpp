@@ -550,7 +550,7 @@ void mvo_sample_volume(mvo_caster* h, uint32_t src, const float uvw[3], float ou
     out[0] = r.x; out[1] = r.y; out[2] = r.z; out[3] = r.w;
 }
 /* oracle/dxil: resolve the frame once more with a per-fragment record (the colour target is restored afterwards) */
-int mvo_debug_oit(mvo_caster* h, uint32_t* count, uint32_t* info, float* data, float* result)
+int mvo_debug_oit(mvo_caster* h, uint32_t* count, uint32_t* info, float* data, float* result, uint32_t* allKeys)
 {
     if (!h) return -1;
     Caster& c = h->c;
@@ -564,6 +564,7 @@ int mvo_debug_oit(mvo_caster* h, uint32_t* count, uint32_t* info, float* data, f
     if (info) std::copy(c.dbgInfo.begin(), c.dbgInfo.end(), info);
     if (data) std::copy(c.dbgData.begin(), c.dbgData.end(), data);
     if (result) std::copy(c.dbgResult.begin(), c.dbgResult.end(), result);
+    if (allKeys) std::copy(c.dbgAllKeys.begin(), c.dbgAllKeys.end(), allKeys);
     return 0;
 }
 void mvo_sample_lightmap(mvo_caster* h, uint32_t volume, const float uvw[3], float out[4])

@@ -108,6 +108,7 @@ struct Caster {
     std::vector<uint32_t> dbgInfo;        // W*H*8 x {depth key, volume, cube face (+x -x +y -y +z -z), stored}
     std::vector<float> dbgData;           // W*H*8 x {lpt xyz, face uv, colour rgba}
     std::vector<float> dbgResult;         // W*H x rgba: the blended layers before the render-target blend
+    std::vector<uint32_t> dbgAllKeys;     // W*H x N: depth key of EVERY fragment of the pixel, in draw (visible-list) order; 0xffffffff = none
     // occluder mesh (mvo_mesh.cpp)
     std::vector<float> meshPos;           // V x 3
     std::vector<uint32_t> meshIdx;        // 3 T

@@ -644,7 +644,7 @@ void resolve_oit(Caster& c)
     for (size_t k = 0; k < nvis; ++k) eyeL[k] = mul_p43(c.cb.eyePt, c.perObject[c.visible[k]].WorldI);
     // rows [row0, row1) plus a one-row halo (clipped), read by the TAA of the band's border rows
     const int rowBegin = c.row1 > c.row0 ? std::max((int)c.row0 - 1, 0) : 0, rowEnd = c.row1 > c.row0 ? std::min((int)c.row1 + 1, H) : 0;
-    if (c.debugOIT) { c.dbgCount.assign((size_t)W * H, 0); c.dbgInfo.assign((size_t)W * H * 8 * 4, 0); c.dbgData.assign((size_t)W * H * 8 * 9, 0.0f); c.dbgResult.assign((size_t)W * H * 4, 0.0f); }
+    if (c.debugOIT) { c.dbgCount.assign((size_t)W * H, 0); c.dbgInfo.assign((size_t)W * H * 8 * 4, 0); c.dbgData.assign((size_t)W * H * 8 * 9, 0.0f); c.dbgResult.assign((size_t)W * H * 4, 0.0f); c.dbgAllKeys.assign((size_t)W * H * c.d.num_volumes, 0xffffffffu); }
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : frags, dRays, dSamples, dLight)
     for (int py = rowBegin; py < rowEnd; ++py)
         for (int px = 0; px < W; ++px) {
@@ -689,6 +689,7 @@ void resolve_oit(Caster& c)
                 if (!(z >= 0.0f && z <= 1.0f)) continue;       // rasteriser depth clip
                 ++frags;
                 Fragment fr = {as_uint(z), volumeId, exitAxis * 2 + (sgn > 0.0f ? 0 : 1), lpt};
+                if (c.debugOIT) c.dbgAllKeys[((size_t)py * W + px) * c.d.num_volumes + k] = fr.key;
                 // keep the kNumOitLayers smallest keys; ties keep list order (stable)
                 int pos = nl;
                 while (pos > 0 && layers[pos - 1].key > fr.key) --pos;
@@ -731,7 +732,7 @@ void resolve_oit(Caster& c)
                     float* dd = &c.dbgData[q * 9]; dd[0] = fr.lpt.x; dd[1] = fr.lpt.y; dd[2] = fr.lpt.z; dd[3] = fu; dd[4] = fv; dd[5] = color.x; dd[6] = color.y; dd[7] = color.z; dd[8] = color.w;
                 }
                 const float k = 1.0f - result.w;
-                result = {fma1(src.x, k, result.x), fma1(src.y, k, result.y), fma1(src.z, k, result.z), fma1(src.w, k, result.w)};
+                result = {src.x * k + result.x, src.y * k + result.y, src.z * k + result.z, src.w * k + result.w};   // fmul, fadd: as PSResolveOIT.cso has it
             }
             result.w = fminf(result.w, g_min16.alphaClamp);
             if (c.debugOIT) { c.dbgCount[(size_t)py * W + px] = (uint32_t)nl; float* dr = &c.dbgResult[((size_t)py * W + px) * 4]; dr[0] = result.x; dr[1] = result.y; dr[2] = result.z; dr[3] = result.w; }

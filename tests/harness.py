@@ -146,3 +146,19 @@ def dxil_scene(cls, name, light_maps=True, **kw):
         for v in range(cfg["n"]):
             c.RayMarchL(v)
     return c, vp, eye, depth, shadow
+
+
+def nested_scene(cls, **kw):
+    """12 concentric volumes of growing size (every pixel through the centre crosses 12 back faces: more than the 8 OIT layers)"""
+    c = cls(grid_size=16, light_grid_size=8, num_volumes=12, num_volume_srcs=2, width=64, height=36, max_ray_samples=24, max_light_samples=8, **kw)
+    for i in range(c.srcs):
+        c.InitVolumeData(i, 1, 77 + i)
+    c.SetLight(scene.LIGHT_PT, scene.LIGHT_COLOR, scene.LIGHT_INTENSITY)
+    c.SetAmbient(scene.AMBIENT_COLOR, scene.AMBIENT_INTENSITY)
+    for i in range(c.N):
+        c.SetVolumeWorld(i, 6.0 + 1.5 * i, (0.3 * i, 0.0, 0.0))
+    c.SetSH(None)
+    c.SetRenderTargets()
+    vp, eye = scene.default_camera(c.W, c.H, eye=(3.0, 9.0, -46.0))
+    c.UpdateFrame(vp, None, eye)
+    return c, vp, eye

@@ -12,7 +12,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libmv_oracle.so")
 _EXTRA = {
     "sample_volume": (None, [_vp, u32, P(f32), P(f32)]),
     "sample_lightmap": (None, [_vp, u32, P(f32), P(f32)]),
-    "debug_oit": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    "debug_oit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "quantize_r11": (f32, [f32]),
     "quantize_b10": (f32, [f32]),
     "f32_to_f16": (C.c_uint16, [f32]),
@@ -51,7 +51,8 @@ class OracleCaster(CasterBase):
         {lpt xyz, face uv, colour rgba}, result (H, W, 4) f32 before the render-target blend). Leaves the colour target as it was."""
         cnt = np.zeros((self.H, self.W), np.uint32); info = np.zeros((self.H, self.W, 8, 4), np.uint32)
         data = np.zeros((self.H, self.W, 8, 9), np.float32); res = np.zeros((self.H, self.W, 4), np.float32)
-        self._ck(self.b.debug_oit(self.h, cnt.ctypes.data, info.ctypes.data, data.ctypes.data, res.ctypes.data), "debug_oit")
+        self.all_keys = np.zeros((self.H, self.W, self.N), np.uint32)      # every fragment's depth key, draw order (0xffffffff = none)
+        self._ck(self.b.debug_oit(self.h, cnt.ctypes.data, info.ctypes.data, data.ctypes.data, res.ctypes.data, self.all_keys.ctypes.data), "debug_oit")
         return cnt, info, data, res
 
     def SampleVolume(self, src, uvw):

@@ -9,6 +9,7 @@ the vectors under tests/golden/dxil_*.npz, here, once, and nothing below touches
   dxil_march_l   CSRayMarchL.cso .......... light-map voxels (R11G11B10_FLOAT values): BIT-EXACT
   dxil_oit       PSCube.cso (CubeCast and RayCast) + PSResolveOIT.cso ... K-buffer colours and the blended pixel: BIT-EXACT
                  (fragments — depth key, exit point, face uv — from the oracle's analytic rasteriser; every 3rd pixel)
+  dxil_peel      PSDepthPeel.cso ... the 8 K-buffer depth layers of pixels crossed by 12 nested volumes: EXACT
   dxil_post      CSTemporalAA.cso + PSToneMap.cso ... TAA output within one binary16 step on isolated texels, RGBA8 EXACT
   dxil_init      CSInitGridData.cso, CSR32FToRGBA16F.cso ... volume texels (RGBA16F): BIT-EXACT
   dxil_base_pass PSBasePass.cso (mesh under the volumes) ... colour (RGBA16F) and velocity: BIT-EXACT on a clip-space quad
@@ -180,14 +181,29 @@ def test_base_pass_equals_the_reference_pixel_shader(make, unit, use_sh):
 
 
 # ---------------------------------------------------------------------------------------------------------------- OIT
-@pytest.mark.parametrize("name", sorted(DXIL_SCENES))
+def _oit_scene(make, name):
+    from harness import nested_scene
+    if name != "nested":
+        return dxil_scene(lambda **kw: make(1, **kw), name)[0]
+    c, vp, eye = nested_scene(lambda **kw: make(1, **kw))
+    c.Cull()
+    for v in range(c.N):
+        c.RayMarchL(v)
+    return c
+
+
+@pytest.mark.parametrize("name", sorted(DXIL_SCENES) + ["nested"])
 def test_oit_layers_and_blend_equal_the_reference_pixel_shaders(name):
     """oracle only (the product keeps its K-buffer in registers): per-layer colours as PSCube.cso stores them, the blend as
     PSResolveOIT.cso returns it"""
     g = _load("dxil_oit.npz")
-    c, vp, eye, depth, shadow = dxil_scene(OracleCaster, name, filter_model=1)
+    c = _oit_scene(lambda model, **kw: OracleCaster(filter_model=model, **kw), name)
     c.RayMarchV()
     cnt, info, data, result = c.DebugOIT()
+    if name == "nested":                                      # PSDepthPeel.cso: the 8 nearest of up to 12 fragments, ascending
+        p = _load("dxil_peel.npz")
+        want_keys = np.where(np.arange(8)[None, None, :] < cnt[..., None], info[..., 0], 0xffffffff)
+        assert np.array_equal(want_keys[p["done"]], p["layers"][p["done"]]) and cnt.max() == 8 and (c.all_keys != 0xffffffff).sum(-1).max() == 12
     m = g[f"{name}/done"]
     assert m.sum() >= 30 and np.array_equal(cnt[m] > 0, np.ones(int(m.sum()), bool))
     want = g[f"{name}/layers"]
@@ -201,11 +217,11 @@ def test_oit_layers_and_blend_equal_the_reference_pixel_shaders(name):
 
 
 @pytest.mark.parametrize("make,unit", _casters())
-@pytest.mark.parametrize("name", sorted(DXIL_SCENES))
+@pytest.mark.parametrize("name", sorted(DXIL_SCENES) + ["nested"])
 def test_resolved_frame_equals_the_reference_pixel_shaders(make, unit, name):
     """the frame after the resolve (no background: the render-target blend adds nothing) against PSResolveOIT.cso's output"""
     g = _load("dxil_oit.npz")
-    c, vp, eye, depth, shadow = dxil_scene(lambda **kw: make(1, **kw), name)
+    c = _oit_scene(make, name)
     c.RayMarchV(); c.ResolveOIT()
     m = g[f"{name}/done"]
     frame = np.asarray(c.ReadFrame()).view(np.uint16)
