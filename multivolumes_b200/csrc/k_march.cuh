@@ -167,12 +167,13 @@ MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t 
             const float dDensity = color.w - prevDensity;
             newStep = get_step(dDensity, transm, color.w, stepScale);
             prevDensity = color.w;
-            color.x *= color.w; color.y *= color.w; color.z *= color.w;   // colours are not pre-multiplied
-            color.x *= l.x; color.y *= l.y; color.z *= l.z;
-            scatter.x += color.x * kAbsorption * transm;
-            scatter.y += color.y * kAbsorption * transm;
-            scatter.z += color.z * kAbsorption * transm;
-            scatter.w += color.w * kAbsorption * transm;
+            // colour (not pre-multiplied) x density x light x ABSORPTION x transmittance, associated as the compiled shaders
+            // have it (CSRayMarchV.cso, PSCube.cso): ((transm * A) * a) once, then * colour * light per channel
+            const float ka = (transm * kAbsorption) * color.w;
+            scatter.x += (ka * color.x) * l.x;
+            scatter.y += (ka * color.y) * l.y;
+            scatter.z += (ka * color.z) * l.z;
+            scatter.w += ka;
             if (transm < kZeroThreshold) break;
         }
         else wasDense = false;

@@ -252,12 +252,13 @@ static f4 march_loop(const Caster& c, uint32_t volumeId, uint32_t volTexId, uint
             const float dDensity = color.w - prevDensity;
             newStep = get_step(dDensity, transm, color.w, stepScale);
             prevDensity = color.w;
-            color.x *= color.w; color.y *= color.w; color.z *= color.w;      // not pre-multiplied
-            color.x *= light.x; color.y *= light.y; color.z *= light.z;
-            scatter.x += color.x * kAbsorption * transm;
-            scatter.y += color.y * kAbsorption * transm;
-            scatter.z += color.z * kAbsorption * transm;
-            scatter.w += color.w * kAbsorption * transm;
+            // colour (not pre-multiplied) x density x light x ABSORPTION x transmittance (:138-141), associated as the compiled
+            // shaders have it (CSRayMarchV.cso %379-%390, PSCube.cso %305-%316): ((transm * A) * a) once, then * colour * light
+            const float ka = (transm * kAbsorption) * color.w;
+            scatter.x += (ka * color.x) * light.x;
+            scatter.y += (ka * color.y) * light.y;
+            scatter.z += (ka * color.z) * light.z;
+            scatter.w += ka;
             if (transm < kZeroThreshold) break;
         }
         t += newStep;

@@ -127,6 +127,7 @@ DXIL_SCENES = {
     "a": dict(seed=2, grid=16, light_grid=8, n=3, W=96, H=54, ray=40, light=12),
     "b": dict(seed=6, grid=16, light_grid=8, n=2, W=96, H=54, ray=40, light=12),
     "c": dict(seed=11, grid=32, light_grid=12, n=4, W=128, H=72, ray=64, light=16),
+    "d": dict(seed=4, grid=16, light_grid=8, n=3, W=96, H=54, ray=48, light=12, inside=True),     # the eye inside volume 0
 }
 
 
@@ -140,7 +141,11 @@ def dxil_scene(cls, name, light_maps=True, **kw):
     y, x = np.mgrid[0:H, 0:W]
     depth = np.where((x // 12 + y // 9) % 3 == 0, 0.9985, 1.0).astype(np.float32)
     shadow = blob_shadow(64)
-    vp, eye = configure(c, sh=True, depth=depth, shadow=shadow, random_transforms=cfg["seed"], eye=(6.0, 18.0, -62.0))
+    vp, eye = configure(c, sh=True, depth=depth, shadow=shadow, random_transforms=cfg["seed"], eye=cfg.get("eye", (6.0, 18.0, -62.0)))
+    if cfg.get("inside"):
+        # a 26-unit box around the eye whose far corner lies straight ahead (so the cull keeps it: it tests corners only)
+        c.SetVolumeWorld(0, 26.0, (eye[0] + 11.14, eye[1] + 7.44, eye[2] + 6.12))
+        c.UpdateFrame(vp, scene.shadow_view_proj(), eye)
     c.Cull()
     if light_maps:
         for v in range(cfg["n"]):
