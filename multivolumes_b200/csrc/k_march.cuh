@@ -69,12 +69,14 @@ MV_D bool compute_ray_origin(V3& rayOrigin, V3 rayDir)
 }
 
 // GetStep, RayMarch.hlsli:182-192
-MV_D float get_step(float dDensity, float transm, float density, float step)
+// factorTh = 1 - transm is handed in: in the view march and RayCast transm is itself 1 - scatter.w, and the compiled shaders
+// use scatter.w there (dxc folds 1 - (1 - x) to x, which is not an identity in fp32); the product is associated as compiled:
+// ((factorTh * 1.5) * factorEv) * factorUi (CSRayMarchV.cso %371-%375, CSRayMarchL.cso %510-%515).
+MV_D float get_step(float dDensity, float factorTh, float density, float step)
 {
     const float factorEv = fminf(1.0f / 256.0f / fabsf(dDensity), 2.0f);
     const float factorUi = fminf(1.0f - density, 1.0f);
-    const float factorTh = 1.0f - transm;
-    return step * fmaxf(1.5f * factorEv * factorUi * factorTh, 1.0f);
+    return fmaxf(((factorTh * 1.5f) * factorEv) * factorUi, 1.0f) * step;
 }
 
 // GetTMax, RayMarch.hlsli:82-92: ray parameter at which the scene depth occludes the ray
@@ -165,7 +167,7 @@ MV_D V4 march_ray(cudaTextureObject_t grid, cudaTextureObject_t light, uint32_t 
             ++mc.lightFetches;
             const float transm = 1.0f - scatter.w;
             const float dDensity = color.w - prevDensity;
-            newStep = get_step(dDensity, transm, color.w, stepScale);
+            newStep = get_step(dDensity, scatter.w, color.w, stepScale);
             prevDensity = color.w;
             // colour (not pre-multiplied) x density x light x ABSORPTION x transmittance, associated as the compiled shaders
             // have it (CSRayMarchV.cso, PSCube.cso): ((transm * A) * a) once, then * colour * light per channel
@@ -199,7 +201,7 @@ MV_D void cast_light_ray(float& transm, cudaTextureObject_t grid, V3 rayOrigin, 
         ++samples;
         const float dDensity = density - prevDensity;
         const float opacity = saturate(density * step);
-        const float newStep = get_step(dDensity, transm, opacity, stepScale);
+        const float newStep = get_step(dDensity, 1.0f - transm, opacity, stepScale);
         prevDensity = density;
         transm *= 1.0f - density * kAbsorption;
         if (transm < kZeroThreshold) break;

@@ -256,12 +256,13 @@ def make_sampler(o, depth=None):
     return sample
 
 
-def march_v_case(o, eye, depth, max_ray_samples):
+def march_v_case(o, eye, depth, max_ray_samples, f32=False):
+    """f32: keep the UAV stores as fp32 (what the shader computed before the RGBA16F conversion)"""
     N, G = o.N, o.G
     po = o.ReadPerObject()
     cubes = o.ReadCubeVolumes()
     att = o.ReadAttribs().astype(np.uint32)
-    cube_maps = [Texture(np.zeros((6, G >> m, G >> m, 4), np.float16)) for v in range(N) for m in range(5)]
+    cube_maps = [Texture(np.zeros((6, G >> m, G >> m, 4), np.float32 if f32 else np.float16)) for v in range(N) for m in range(5)]
     cube_depths = [Texture(np.full((6, G >> m, G >> m, 1), -1.0, np.float32)) for v in range(N) for m in range(5)]
     res = Resources(
         srv={0: ResArray(3, [OracleTex(o, "lightmap", v) for v in range(N)]), 1: ResArray(0, [OracleTex(o, "volume", s) for s in range(o.srcs)]),
@@ -316,7 +317,18 @@ def make_march_v():
                 o, vp, eye, depth, shadow = dxil_scene(OracleCaster, name, filter_model=model)
                 if as_half:
                     dx = march_v_case(o, eye, depth, DXIL_SCENES[name]["ray"])
+                    dx32 = march_v_case(o, eye, depth, DXIL_SCENES[name]["ray"], f32=True)
+                    o.DebugF32(True)
                 o.RayMarchV()
+                if as_half:
+                    cube32, _ = o.DebugF32(True)
+                    bad = tot = 0
+                    for v, (mip, rgba32, dep) in dx32.items():
+                        s_ = o.G >> mip
+                        m_ = dep >= 0
+                        bad += int((cube32[v, :, :s_, :s_].view(np.uint32)[m_] != rgba32.view(np.uint32)[m_]).sum()); tot += int(m_.sum()) * 4
+                        flat[f"f{model}/{name}/v{v}/rgba_f32"] = rgba32
+                    print(f"march_v filter {model} scene {name}: fp32 scatter before the RGBA16F store: {bad}/{tot} values differ")
                 for v, (mip, rgba, dep) in dx.items():
                     orgba, odep = o.ReadCubeMap(v, mip)
                     mask = dep >= 0                                      # texels the shader wrote
@@ -566,7 +578,7 @@ def make_cube_callbacks(o, frag):
     return sample, gather
 
 
-def oit_case(o, eye, depth, stride=3):
+def oit_case(o, eye, depth, stride=3, f32=False):
     """PSCube.cso per fragment and PSResolveOIT.cso per pixel, on every stride-th pixel, from the fragments the oracle's
     analytic rasteriser produced (depth key, exit point on the cube, face uv); returns per-layer colours and the blend."""
     N, G, W, H = o.N, o.G, o.W, o.H
@@ -583,14 +595,14 @@ def oit_case(o, eye, depth, stride=3):
                 cubes_c.append(None); cubes_d.append(None)
     frag = {}
     sample, gather = make_cube_callbacks(o, frag)
-    kcolors = Texture(np.zeros((8, H, W, 4), np.float16), quantise=lambda k, v: np.float16(v))
+    kcolors = Texture(np.zeros((8, H, W, 4), np.float32)) if f32 else Texture(np.zeros((8, H, W, 4), np.float16), quantise=lambda k, v: np.float16(v))
     kdepths = Texture(np.full((8, H, W, 1), 0xffffffff, np.uint32))
     res = Resources(
         srv={0: ResArray(3, [OracleTex(o, "lightmap", v) for v in range(N)]), 1: ResArray(0, [OracleTex(o, "volume", s) for s in range(o.srcs)]),
              2: Texture(depth[..., None]), 3: StructuredBuffer(per_object_bytes(po), 224), 4: ResArray(0, cubes_c), 5: ResArray(0, cubes_d), 6: kdepths},
         uav={0: kcolors}, cbv={0: CBuffer(per_frame_bytes(eye, (W, H)))}, sampler={0: "linear"}, sample=sample, gather=gather)
     ps, rs = shader("PSCube"), shader("PSResolveOIT")
-    layers = np.zeros((H, W, 8, 4), np.float16); stored = np.zeros((H, W, 8), np.uint8); blend = np.zeros((H, W, 4), np.float32); done = np.zeros((H, W), bool)
+    layers = np.zeros((H, W, 8, 4), np.float32 if f32 else np.float16); stored = np.zeros((H, W, 8), np.uint8); blend = np.zeros((H, W, 4), np.float32); done = np.zeros((H, W), bool)
     for py in range(0, H, stride):
         for px in range(0, W, stride):
             n = int(cnt[py, px])
@@ -635,7 +647,14 @@ def make_oit():
             o, vp, eye, depth, shadow = dxil_scene(OracleCaster, name, filter_model=1)
         o.RayMarchV()
         r = oit_case(o, eye, depth)
+        r32 = oit_case(o, eye, depth, f32=True)
         m = r["done"]
+        w32 = np.zeros_like(r32["layers"])
+        for py, px in np.argwhere(m):
+            for l in range(int(r["count"][py, px])):
+                if r["info"][py, px, l, 3]:
+                    w32[py, px, l] = r["data"][py, px, l, 5:9]
+        print(f"oit scene {name}: fp32 fragment colours before the RGBA16F store: {int((w32.view(np.uint32)[m] != r32['layers'].view(np.uint32)[m]).sum())}/{int(m.sum()) * 32} values differ")
         # per-layer colours: the oracle's, rounded to the K-colour format
         want = np.zeros_like(r["layers"])
         cnt, info, data = r["count"], r["info"], r["data"]

@@ -567,6 +567,18 @@ int mvo_debug_oit(mvo_caster* h, uint32_t* count, uint32_t* info, float* data, f
     if (allKeys) std::copy(c.dbgAllKeys.begin(), c.dbgAllKeys.end(), allKeys);
     return 0;
 }
+/* oracle/dxil: keep fp32 copies of what the marches computed (what = 0 off, 1 on); read them back with out != NULL */
+int mvo_debug_f32(mvo_caster* h, int on, float* cubeOut, float* lightOut)
+{
+    if (!h) return -1;
+    Caster& c = h->c;
+    const size_t G = c.d.grid_size, L = c.d.light_grid_size;
+    if (on && !c.debugF32) { c.dbgCubeF32.assign((size_t)c.d.num_volumes * 6 * G * G * 4, 0.0f); c.dbgLightF32.assign(L * L * L * 3, 0.0f); }
+    c.debugF32 = on != 0;
+    if (cubeOut && !c.dbgCubeF32.empty()) std::copy(c.dbgCubeF32.begin(), c.dbgCubeF32.end(), cubeOut);
+    if (lightOut && !c.dbgLightF32.empty()) std::copy(c.dbgLightF32.begin(), c.dbgLightF32.end(), lightOut);
+    return 0;
+}
 void mvo_sample_lightmap(mvo_caster* h, uint32_t volume, const float uvw[3], float out[4])
 {
     const f4 r = sample3d(h->c.lightMaps[volume], {uvw[0], uvw[1], uvw[2]}, h->c.filterModel);

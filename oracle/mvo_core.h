@@ -108,6 +108,9 @@ struct Caster {
     std::vector<uint32_t> dbgInfo;        // W*H*8 x {depth key, volume, cube face (+x -x +y -y +z -z), stored}
     std::vector<float> dbgData;           // W*H*8 x {lpt xyz, face uv, colour rgba}
     std::vector<float> dbgResult;         // W*H x rgba: the blended layers before the render-target blend
+    bool debugF32 = false;                // keep the last marches' outputs before their format conversion (mvo_debug_f32)
+    std::vector<float> dbgCubeF32;        // N x 6 x G x G x 4: scatter of the view march at the volume's mip (top-left corner of the slab)
+    std::vector<float> dbgLightF32;       // L^3 x 3: the light march's value before the R11G11B10 store
     std::vector<uint32_t> dbgAllKeys;     // W*H x N: depth key of EVERY fragment of the pixel, in draw (visible-list) order; 0xffffffff = none
     // occluder mesh (mvo_mesh.cpp)
     std::vector<float> meshPos;           // V x 3

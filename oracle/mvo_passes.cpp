@@ -202,12 +202,14 @@ static bool compute_ray_origin(f3& rayOrigin, f3 rayDir)   // :128-155
     return isHit;
 }
 
-static inline float get_step(float dDensity, float transm, float density, float step)   // :182-192
+// :182-192. factorTh = 1 - transm is handed in: in the view march and RayCast transm is itself 1 - scatter.w and the compiled
+// shaders use scatter.w there (dxc folds 1 - (1 - x) to x, not an identity in fp32); the product is associated as compiled:
+// ((factorTh * 1.5) * factorEv) * factorUi (CSRayMarchV.cso %371-%375, CSRayMarchL.cso %510-%515).
+static inline float get_step(float dDensity, float factorTh, float density, float step)
 {
     const float factorEv = fminf(1.0f / 256.0f / fabsf(dDensity), 2.0f);
     const float factorUi = fminf(1.0f - density, 1.0f);
-    const float factorTh = 1.0f - transm;
-    return step * fmaxf(1.5f * factorEv * factorUi * factorTh, 1.0f);
+    return fmaxf(((factorTh * 1.5f) * factorEv) * factorUi, 1.0f) * step;
 }
 
 static float get_tmax(f3 pos, f3 rayOrigin, f3 rayDir, const m44& wvpi)   // :82-92
@@ -250,7 +252,7 @@ static f4 march_loop(const Caster& c, uint32_t volumeId, uint32_t volTexId, uint
             ++mc.lightFetches;
             const float transm = 1.0f - scatter.w;
             const float dDensity = color.w - prevDensity;
-            newStep = get_step(dDensity, transm, color.w, stepScale);
+            newStep = get_step(dDensity, scatter.w, color.w, stepScale);
             prevDensity = color.w;
             // colour (not pre-multiplied) x density x light x ABSORPTION x transmittance (:138-141), associated as the compiled
             // shaders have it (CSRayMarchV.cso %379-%390, PSCube.cso %305-%316): ((transm * A) * a) once, then * colour * light
@@ -336,6 +338,11 @@ void ray_march_view(Caster& c)
                     const f4 scatter = march_loop(c, volumeId, volTexId, smpCount, rayOrigin, rayDir, tMax, mc);
                     uint16_t* o = &cm.color[mip][idx * 4];
                     o[0] = f32_to_f16(scatter.x); o[1] = f32_to_f16(scatter.y); o[2] = f32_to_f16(scatter.z); o[3] = f32_to_f16(scatter.w);
+                    if (c.debugF32) {
+                        const size_t G = c.d.grid_size;
+                        float* q = &c.dbgCubeF32[((((size_t)volumeId * 6 + face) * G + y) * G + x) * 4];
+                        q[0] = scatter.x; q[1] = scatter.y; q[2] = scatter.z; q[3] = scatter.w;
+                    }
                     ++rays; samples += mc.samples; lightFetches += mc.lightFetches;
                 }
         }
@@ -406,7 +413,7 @@ static void cast_light_ray(const Caster& c, float& transm, uint32_t volTexId, f3
         ++samples;
         const float dDensity = density - prevDensity;
         const float opacity = saturate(density * step);
-        const float newStep = get_step(dDensity, transm, opacity, stepScale);
+        const float newStep = get_step(dDensity, 1.0f - transm, opacity, stepScale);
         prevDensity = density;
         transm *= 1.0f - density * kAbsorption;
         if (transm < kZeroThreshold) break;
@@ -497,6 +504,7 @@ void ray_march_light(Caster& c, int volumeOverride)
                 f3 ambient = {c.cb.ambient.x * c.cb.ambient.w, c.cb.ambient.y * c.cb.ambient.w, c.cb.ambient.z * c.cb.ambient.w};
                 if (c.hasSH) ambient = {ao * irradiance.x, ao * irradiance.y, ao * irradiance.z};   // :117
                 const f3 out = {shadow * lightColor.x + ambient.x, shadow * lightColor.y + ambient.y, shadow * lightColor.z + ambient.z};
+                if (c.debugF32) { float* q = &c.dbgLightF32[(((size_t)z * L + y) * L + x) * 3]; q[0] = out.x; q[1] = out.y; q[2] = out.z; }
                 uint16_t* o = &lm.texels[(((size_t)z * L + y) * L + x) * 4];
                 // R11G11B10_FLOAT store, kept in an RGBA16F texel (exactly representable)
                 o[0] = f32_to_f16(quantize_ufloat(out.x, 6));

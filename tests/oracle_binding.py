@@ -12,6 +12,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libmv_oracle.so")
 _EXTRA = {
     "sample_volume": (None, [_vp, u32, P(f32), P(f32)]),
     "sample_lightmap": (None, [_vp, u32, P(f32), P(f32)]),
+    "debug_f32": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "debug_oit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "quantize_r11": (f32, [f32]),
     "quantize_b10": (f32, [f32]),
@@ -45,6 +46,12 @@ class OracleCaster(CasterBase):
     def SetShardVolumes(self, rank, world, proxy_grid):
         """Volume-sharded storage as rank `rank` of `world` sees it (call after the volumes are loaded)."""
         self._ck(self.b.set_shard_volumes(self.h, rank, world, proxy_grid), "set_shard_volumes")
+
+    def DebugF32(self, on=True):
+        """keep (on) / read back the marches' fp32 outputs before the RGBA16F / R11G11B10F stores: (cube (N, 6, G, G, 4), light (L, L, L, 3))"""
+        cube = np.zeros((self.N, 6, self.G, self.G, 4), np.float32); light = np.zeros((self.L,) * 3 + (3,), np.float32)
+        self._ck(self.b.debug_f32(self.h, 1 if on else 0, cube.ctypes.data, light.ctypes.data), "debug_f32")
+        return cube, light
 
     def DebugOIT(self):
         """per-pixel fragments of the resolve: (count (H, W), info (H, W, 8, 4) u32 {depth key, volume, face, stored}, data (H, W, 8, 9) f32

@@ -5,7 +5,7 @@ them (a small LLVM-IR / DXIL interpreter with wave intrinsics) on seeded inputs;
 the vectors under tests/golden/dxil_*.npz, here, once, and nothing below touches /root/reference. What each vector pins:
 
   dxil_cull      CSVolumeCull.cso ......... visible / cube-map lists and VolumeInfo (u32 x 4): EXACT, at BASELINE shapes
-  dxil_march_v   CSRayMarchV.cso .......... cube-map texels (RGBA16F) and cube depths: BIT-EXACT
+  dxil_march_v   CSRayMarchV.cso .......... cube-map texels (RGBA16F) and cube depths: BIT-EXACT (the oracle: also the fp32 values before the store)
   dxil_march_l   CSRayMarchL.cso .......... light-map voxels (R11G11B10_FLOAT values): BIT-EXACT
   dxil_oit       PSCube.cso (CubeCast and RayCast) + PSResolveOIT.cso ... K-buffer colours and the blended pixel: BIT-EXACT
                  (fragments — depth key, exit point, face uv — from the oracle's analytic rasteriser; every 3rd pixel)
@@ -85,6 +85,8 @@ def test_view_march_equals_the_reference_shader(make, unit, model, name):
         pytest.skip("the product's texture unit is the hardware's (model 1)")
     g = _load("dxil_march_v.npz")
     c, vp, eye, depth, shadow = dxil_scene(lambda **kw: make(model, **kw), name)
+    if unit is None:
+        c.DebugF32(True)
     c.RayMarchV()
     cubes = g[f"f{model}/{name}/cubes"]
     assert np.array_equal(np.sort(c.ReadCubeVolumes()), cubes) and len(cubes) > 0
@@ -97,6 +99,9 @@ def test_view_march_equals_the_reference_shader(make, unit, model, name):
         mask = want_d >= 0                                        # texels the shader wrote (visible faces, rays that hit)
         assert np.array_equal(np.asarray(dep)[mask].view(np.uint32), want_d[mask].view(np.uint32))
         assert np.array_equal(np.asarray(rgba).view(np.uint16)[mask], g[k + "/rgba"][mask]), (name, int(v))
+        if unit is None:                                          # the oracle also keeps the fp32 scatter: equal before the RGBA16F store too
+            s = c.G >> mip
+            assert np.array_equal(c.DebugF32(True)[0][int(v), :, :s, :s].view(np.uint32)[mask], g[k + "/rgba_f32"].view(np.uint32)[mask])
         rays += int(mask.sum())
     assert rays >= 48
 
