@@ -700,7 +700,65 @@ def make_peel():
     np.savez_compressed(os.path.join(OUT, "dxil_peel.npz"), layers=got, done=m)
 
 
-MAKERS = {"peel": make_peel, "oit": make_oit, "base_pass": make_base_pass, "init": make_init, "cull": make_cull, "post": make_post, "march_v": make_march_v, "march_l": make_march_l, "sh": make_sh}
+# ------------------------------------------------------------------------------------------------ PSEnvironment
+def make_env():
+    """PSEnvironment.cso per pixel (the view ray through screenToWorld, one cube fetch). The cube fetch is the texture unit's:
+    face selection, seamless bilinear footprint and fp32 blend as the oracle's environment pass has them."""
+    import ctypes as C
+    import oracle.dxil.interp as I
+    from multivolumes_b200 import scene
+    from oracle_binding import OracleCaster
+    I.PROMOTE_HALF = True
+    W, H, S = 64, 36, 16
+    o = OracleCaster(filter_model=1, grid_size=16, light_grid_size=8, num_volumes=1, width=W, height=H)
+    sky = scene.procedural_sky(S).astype(np.float32)
+    o.SetEnvironment(sky)
+    o.SetRenderTargets()
+    vp, eye = scene.default_camera(W, H, eye=(14.0, 9.0, -30.0))
+    o.UpdateFrame(vp, None, eye)
+    o.RenderEnvironment()
+    got = o.ReadFrame()
+    cube = sky.astype(np.float16).astype(np.float32)             # the pass reads an RGBA16F cube
+    out3 = (C.c_int * 3)()
+
+    def sample(tex, smp, coords, offs, lod, cmp_):
+        d = [F32(coords[0]), F32(coords[1]), F32(coords[2])]
+        ax, ay, az = abs(d[0]), abs(d[1]), abs(d[2])
+        if ax >= ay and ax >= az: face, ma = (0 if d[0] > 0 else 1), ax
+        elif ay >= az: face, ma = (2 if d[1] > 0 else 3), ay
+        else: face, ma = (4 if d[2] > 0 else 5), az
+        im = F32(1) / ma
+        p = [F32(d[k] * im) for k in range(3)]
+        h = F32(0.5)
+        u, v = {0: (F32(F32(-p[2] * h) + h), F32(F32(-p[1] * h) + h)), 1: (F32(F32(p[2] * h) + h), F32(F32(-p[1] * h) + h)),
+                2: (F32(F32(p[0] * h) + h), F32(F32(p[2] * h) + h)), 3: (F32(F32(p[0] * h) + h), F32(F32(-p[2] * h) + h)),
+                4: (F32(F32(p[0] * h) + h), F32(F32(-p[1] * h) + h)), 5: (F32(F32(-p[0] * h) + h), F32(F32(-p[1] * h) + h))}[face]
+        fx, fy = _fma(u, S, -0.5), _fma(v, S, -0.5)
+        i0, j0 = int(np.floor(fx)), int(np.floor(fy))
+        wx, wy = F32(fx - np.floor(fx)), F32(fy - np.floor(fy))
+        t = []
+        for k in range(4):
+            o.b.cube_resolve_texel(S, face, i0 + (k & 1), j0 + (k >> 1), out3)
+            t.append(cube[out3[0], out3[2], out3[1]])
+        lerp = lambda a, b, w: _fma(F32(b - a), w, a)
+        return [lerp(lerp(t[0][c], t[1][c], wx), lerp(t[2][c], t[3][c], wx), wy) for c in range(3)] + [F32(0)]
+
+    # cbPerFrame of PSEnvironment: g_eyePt (row 0), g_screenToWorld (rows 1-4, column-major)
+    cb = np.zeros(20, np.float32); cb[0:3] = eye; cb[4:20] = o.ReadPerFrame()["screen_to_world"].T.reshape(16)
+    res = Resources(srv={0: cube}, cbv={0: CBuffer(cb.tobytes())}, sampler={0: "linear"}, sample=sample)
+    ps = shader("PSEnvironment")
+    out = np.zeros((H, W, 4), np.float16)
+    for y in range(H):
+        for x in range(W):
+            o_ = {}
+            ps.run_wave([ps.lane(res, {}, inputs={0: {0: F32(x + 0.5), 1: F32(y + 0.5)}, 1: {0: F32((x + 0.5) / W), 1: F32((y + 0.5) / H)}}, outputs=o_)])
+            out[y, x] = [np.float16(o_[0][k]) for k in range(4)]
+    ulps = np.abs(got.view(np.int16).astype(np.int32) - out.view(np.int16).astype(np.int32))
+    print(f"environment {W}x{H}: oracle vs PSEnvironment.cso: max {int(ulps.max())} binary16 steps, {float((ulps > 0).mean()) * 100:.2f} % of halves differ")
+    np.savez_compressed(os.path.join(OUT, "dxil_env.npz"), rgba=out.view(np.uint16), sky=sky, view_proj=vp, eye=np.asarray(eye, np.float32))
+
+
+MAKERS = {"env": make_env, "peel": make_peel, "oit": make_oit, "base_pass": make_base_pass, "init": make_init, "cull": make_cull, "post": make_post, "march_v": make_march_v, "march_l": make_march_l, "sh": make_sh}
 
 if __name__ == "__main__":
     for n in (sys.argv[1:] or MAKERS):

@@ -123,6 +123,7 @@ void mvo_set_min16_consts_as_half(int on);
 void  mvo_cube_resolve_texel(int size, int face, int i, int j, int out_face_i_j[3]);   /* seamless Gather addressing of CubeCast */
 int   mvo_debug_oit(mvo_caster* c, uint32_t* count_wh, uint32_t* info_wh8x4, float* data_wh8x9, float* result_wh4, uint32_t* all_keys_whn);   /* per-fragment record of resolve_oit */
 int   mvo_debug_f32(mvo_caster* c, int on, float* cube_n6ggx4, float* light_lllx3);   /* fp32 outputs of the marches before their format conversion */
+void  mvo_read_per_frame(mvo_caster* c, float* out37);   /* eye 3, viewport 2, screenToWorld 16, shadowViewProj 16 */
 void  mvo_sample_volume(mvo_caster* c, uint32_t src, const float uvw[3], float rgba_out[4]);
 void  mvo_sample_lightmap(mvo_caster* c, uint32_t volume, const float uvw[3], float rgba_out[4]);   /* the texture filter of the caster's model */
 float mvo_quantize_r11(float v);

@@ -579,6 +579,13 @@ int mvo_debug_f32(mvo_caster* h, int on, float* cubeOut, float* lightOut)
     if (lightOut && !c.dbgLightF32.empty()) std::copy(c.dbgLightF32.begin(), c.dbgLightF32.end(), lightOut);
     return 0;
 }
+/* oracle/dxil: cbPerFrame as the shaders see it (row-vector matrices, un-transposed): eye 3, viewport 2, screenToWorld 16, shadowViewProj 16 */
+void mvo_read_per_frame(mvo_caster* h, float* out37)
+{
+    const PerFrame& f = h->c.cb;
+    out37[0] = f.eyePt.x; out37[1] = f.eyePt.y; out37[2] = f.eyePt.z; out37[3] = f.viewport.x; out37[4] = f.viewport.y;
+    memcpy(out37 + 5, f.screenToWorld.m, 64); memcpy(out37 + 21, f.shadowViewProj.m, 64);
+}
 void mvo_sample_lightmap(mvo_caster* h, uint32_t volume, const float uvw[3], float out[4])
 {
     const f4 r = sample3d(h->c.lightMaps[volume], {uvw[0], uvw[1], uvw[2]}, h->c.filterModel);

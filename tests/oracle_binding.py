@@ -12,6 +12,7 @@ ORACLE_SO = os.path.join(ROOT, "oracle", "_build", "libmv_oracle.so")
 _EXTRA = {
     "sample_volume": (None, [_vp, u32, P(f32), P(f32)]),
     "sample_lightmap": (None, [_vp, u32, P(f32), P(f32)]),
+    "read_per_frame": (None, [_vp, P(f32)]),
     "debug_f32": (C.c_int, [_vp, C.c_int, _vp, _vp]),
     "debug_oit": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "quantize_r11": (f32, [f32]),
@@ -46,6 +47,11 @@ class OracleCaster(CasterBase):
     def SetShardVolumes(self, rank, world, proxy_grid):
         """Volume-sharded storage as rank `rank` of `world` sees it (call after the volumes are loaded)."""
         self._ck(self.b.set_shard_volumes(self.h, rank, world, proxy_grid), "set_shard_volumes")
+
+    def ReadPerFrame(self):
+        out = np.zeros(37, np.float32)
+        self.b.read_per_frame(self.h, out.ctypes.data_as(P(f32)))
+        return dict(eye=out[0:3], viewport=out[3:5], screen_to_world=out[5:21].reshape(4, 4), shadow_view_proj=out[21:37].reshape(4, 4))
 
     def DebugF32(self, on=True):
         """keep (on) / read back the marches' fp32 outputs before the RGBA16F / R11G11B10F stores: (cube (N, 6, G, G, 4), light (L, L, L, 3))"""

@@ -12,6 +12,7 @@ the vectors under tests/golden/dxil_*.npz, here, once, and nothing below touches
   dxil_peel      PSDepthPeel.cso ... the 8 K-buffer depth layers of pixels crossed by 12 nested volumes: EXACT
   dxil_post      CSTemporalAA.cso + PSToneMap.cso ... TAA output within one binary16 step on isolated texels, RGBA8 EXACT
   dxil_init      CSInitGridData.cso, CSR32FToRGBA16F.cso ... volume texels (RGBA16F): BIT-EXACT
+  dxil_env       PSEnvironment.cso ... the sky behind the volumes (RGBA16F): BIT-EXACT
   dxil_base_pass PSBasePass.cso (mesh under the volumes) ... colour (RGBA16F) and velocity: BIT-EXACT on a clip-space quad
   dxil_sh        CSSHCubeMap / CSSHSum / CSSHNormalize.cso (no HLSL in the reference) ... 9 x 3 coefficients to 1e-6 relative
                  (the summation order of a wave reduction is the hardware's)
@@ -231,3 +232,18 @@ def test_resolved_frame_equals_the_reference_pixel_shaders(make, unit, name):
     m = g[f"{name}/done"]
     frame = np.asarray(c.ReadFrame()).view(np.uint16)
     assert np.array_equal(frame[m], g[f"{name}/blend"][m].astype(np.float16).view(np.uint16))
+
+
+# ---------------------------------------------------------------------------------------------------------------- environment
+@pytest.mark.parametrize("make,unit", _casters())
+def test_environment_equals_the_reference_pixel_shader(make, unit):
+    g = _load("dxil_env.npz")
+    want = g["rgba"]
+    H, W = want.shape[:2]
+    c = make(1, grid_size=16, light_grid_size=8, num_volumes=1, width=W, height=H)
+    c.SetEnvironment(g["sky"])
+    c.SetRenderTargets()
+    c.UpdateFrame(g["view_proj"], None, g["eye"])
+    c.RenderEnvironment()
+    got = np.asarray(c.ReadFrame()).view(np.uint16)
+    assert (want[..., :3] != 0).mean() > 0.9 and np.array_equal(got, want)
