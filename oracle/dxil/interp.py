@@ -35,6 +35,10 @@ _err = np.seterr(all="ignore")
 # them in binary32 (what a driver without native fp16 ALUs does, e.g. NVIDIA's D3D12 driver; the half CONSTANTS stay the
 # binary16 values dxc wrote); False evaluates them in binary16 as written.
 PROMOTE_HALF = True
+# FMad (dx.op.tertiary 46) may be fused or not at the implementation's discretion. False (default): a * b rounded, then + c
+# rounded. True: one rounding (evaluated in binary64, where the product of two binary32 numbers is exact) — for measuring how far
+# the two legal readings of the same shader sit apart (profiles/r02_notes.md section 8).
+FUSE_FMAD = False
 
 
 # ----------------------------------------------------------------------------------------------- parsing
@@ -689,8 +693,11 @@ class Shader:
             x, y = _sx(a[1], 32), _sx(a[2], 32); return (max(x, y) if opc == 37 else min(x, y)) & 0xffffffff
         if opc in (39, 40):
             return max(a[1], a[2]) if opc == 39 else min(a[1], a[2])
-        if opc == 46:                                            # FMad: unfused
-            T = type(a[1]); return T(T(a[1] * a[2]) + a[3])
+        if opc == 46:                                            # FMad: unfused unless FUSE_FMAD
+            T = type(a[1])
+            if FUSE_FMAD and T is F32:
+                return F32(np.float64(a[1]) * np.float64(a[2]) + np.float64(a[3]))
+            return T(T(a[1] * a[2]) + a[3])
         if opc == 47:
             return F32(np.float64(a[1]) * np.float64(a[2]) + np.float64(a[3]))
         if opc in (48, 49):
