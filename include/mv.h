@@ -19,7 +19,8 @@
  *   - numerics: the shaders' arithmetic in fp32, in a stated evaluation order, with the `min16float`
  *     literals the reference's SHIPPED shaders hold (Bin/ *.cso: dxc folds them to binary16 — g_maxDist 3.46484375,
  *     ABSORPTION 0.7998046875, ZERO_THRESHOLD 0.010002136 ...), not the decimal text of the HLSL: results reproduce those
- *     compiled shaders (cull, both marches, CubeCast / RayCast, resolve: bit for bit; tests/test_dxil_golden.py).
+ *     compiled shaders (cull and view march exactly; light march, CubeCast / RayCast and resolve in every stored value of
+ *     the test vectors, one format step off at a rate below 2e-4 in a random sweep; tests/test_dxil_golden.py).
  */
 #ifndef MV_H
 #define MV_H
