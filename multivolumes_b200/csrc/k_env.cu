@@ -23,13 +23,15 @@ namespace {
 MV_D float lerpf(float a, float b, float t) { return fma1(b - a, t, a); }
 
 // one thread per pixel of the rows this rank resolves (+ the halo rows its TAA reads)
-__global__ void __launch_bounds__(256) k_environment(DeviceScene s, FrameCB cb, const uint2* __restrict__ cube, int S)
+__global__ void __launch_bounds__(256) k_environment(DeviceScene s, FrameCB cb, const uint2* __restrict__ cube, int S, const uint2* __restrict__ background)
 {
     const int px = (int)(blockIdx.x * 32 + (threadIdx.x & 31)), py = (int)(blockIdx.y * 8 + (threadIdx.x >> 5));
     if (px >= (int)cb.width || py >= (int)cb.height) return;
     if (s.shardWorld > 1 && !row_is_resolved_here(s, cb, py)) return;
     const size_t pix = (size_t)py * cb.width + px;
-    if (!(1.0f <= __ldg(s.depth + pix))) return;                 // DEPTH_READ_LESS_EQUAL against the quad's z = 1
+    // DEPTH_READ_LESS_EQUAL against the quad's z = 1. `background` (may be null): the copy of the mesh pass's colour into the
+    // colour target folded into this pass — an occluded pixel takes it, a sky pixel is overwritten anyway
+    if (!(1.0f <= __ldg(s.depth + pix))) { if (background) s.color[pix] = __ldg(background + pix); return; }
     // PSEnvironment.hlsl:48-56: the pixel centre unprojected at z = 1, ray from the eye through it
     const float sx = fma1((float)px + 0.5f, cb.inv2Viewport[0], -1.0f), sy = fma1((float)py + 0.5f, -cb.inv2Viewport[1], 1.0f);
     const float* M = cb.screenToWorld;
@@ -92,10 +94,10 @@ void chunk(std::vector<unsigned char>& out, const char* type, const std::vector<
 
 } // namespace
 
-void launch_environment(Caster& c)
+void launch_environment(Caster& c, bool copyBackground)
 {
     dim3 grid((c.d.width + 31) / 32, (c.d.height + 7) / 8);
-    k_environment<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb, c.dEnvCube, (int)c.envSize);
+    k_environment<<<grid, 256, 0, c.stream>>>(c.scene(), c.cb, c.dEnvCube, (int)c.envSize, copyBackground ? c.dBackground : nullptr);
 }
 
 } // namespace mv
@@ -135,8 +137,10 @@ int mv_render_environment(mv_caster* h)
 {
     MV_ENTER(h);
     const size_t px = (size_t)c.d.width * c.d.height;
-    MV_CUDA(cudaMemcpyAsync(c.dColor, c.dBackground, px * 8, cudaMemcpyDeviceToDevice, c.stream));     // what the mesh pass left (mv_reset_color)
-    if (c.dEnvCube) launch_environment(c);
+    // what the mesh pass left (mv_reset_color): a copy of its own, or — one GPU, whole frame — done by the environment kernel
+    const bool fold = c.dEnvCube && c.shardWorld == 1 && c.row0 == 0 && c.row1 == c.d.height;
+    if (!fold) MV_CUDA(cudaMemcpyAsync(c.dColor, c.dBackground, px * 8, cudaMemcpyDeviceToDevice, c.stream));
+    if (c.dEnvCube) launch_environment(c, fold);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) MV_FAIL(MV_ERR_CUDA, "k_environment launch failed: %s", cudaGetErrorString(e));
     return MV_OK;

@@ -216,7 +216,7 @@ void launch_ray_cast_direct(Caster& c);
 void launch_resolve_oit(Caster& c);
 void launch_postprocess(Caster& c, bool taaOn);
 void build_tone_lut(Caster& c);
-void launch_environment(Caster& c);
+void launch_environment(Caster& c, bool copyBackground);
 
 struct Volume3D {
     bool proxy = false;                  // volume-sharded storage: an R16F density proxy of another rank's source
