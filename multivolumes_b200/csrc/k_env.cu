@@ -94,6 +94,13 @@ void chunk(std::vector<unsigned char>& out, const char* type, const std::vector<
 
 } // namespace
 
+void flush_deferred(Caster& c)
+{
+    if (!c.envDeferred) return;
+    c.envDeferred = false;
+    launch_environment(c, true);          // deferral implies the fold conditions (mv_render_environment)
+}
+
 void launch_environment(Caster& c, bool copyBackground)
 {
     dim3 grid((c.d.width + 31) / 32, (c.d.height + 7) / 8);
@@ -112,7 +119,8 @@ void launch_environment(Caster& c, bool copyBackground)
 #define MV_ENTER(h)            \
     MV_REQUIRE(h != nullptr);  \
     Caster& c = h->c;          \
-    MV_CUDA(cudaSetDevice(c.device))
+    MV_CUDA(cudaSetDevice(c.device)); \
+    flush_deferred(c)
 
 extern "C" {
 
@@ -139,6 +147,9 @@ int mv_render_environment(mv_caster* h)
     const size_t px = (size_t)c.d.width * c.d.height;
     // what the mesh pass left (mv_reset_color): a copy of its own, or — one GPU, whole frame — done by the environment kernel
     const bool fold = c.dEnvCube && c.shardWorld == 1 && c.row0 == 0 && c.row1 == c.d.height;
+    // one GPU, frames pipelined: the pass is owed to the next mv_render, which runs it on the screen-space march's stream beside the
+    // view march; any other call on the handle runs it first (flush_deferred in MV_ENTER)
+    if (fold && frame_is_pipelined_on_one_gpu(c)) { c.envDeferred = true; return MV_OK; }
     if (!fold) MV_CUDA(cudaMemcpyAsync(c.dColor, c.dBackground, px * 8, cudaMemcpyDeviceToDevice, c.stream));
     if (c.dEnvCube) launch_environment(c, fold);
     const cudaError_t e = cudaGetLastError();

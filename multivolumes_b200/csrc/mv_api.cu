@@ -223,10 +223,13 @@ static bool pipelined_sharded(const Caster& c)
 {
     return c.overlapLight && c.shardPipeline && c.shardWorld > 1 && !c.shardVolumes && c.peersMapped && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES));
 }
+bool frame_is_pipelined_on_one_gpu(const Caster& c);
 static bool pipelined(const Caster& c)
 {
     return (c.overlapLight && (c.shardWorld == 1 || c.shardVolumes) && !(c.d.flags & (MV_FLAG_COUNT_SAMPLES | MV_FLAG_TIME_PASSES))) || pipelined_sharded(c);
 }
+
+bool frame_is_pipelined_on_one_gpu(const Caster& c) { return c.shardWorld == 1 && !c.shardVolumes && c.directOverlap && pipelined(c); }
 
 // A new frame's lists and attributes go into the other buffer (the previous frame's resolve may still read its own)
 static void flip_frame_lists(Caster& c)
@@ -247,11 +250,14 @@ static void wait_upload(Caster& c, cudaStream_t s)
 // screen-space march runs on its own stream beside the view march (uninstrumented frames only).
 static void launch_view_and_direct(Caster& c)
 {
-    if (!c.directOverlap) { launch_ray_march_view(c); launch_ray_cast_direct(c); return; }
+    if (!c.directOverlap) { flush_deferred(c); launch_ray_march_view(c); launch_ray_cast_direct(c); return; }
     cudaStream_t mainStream = c.stream;
     cudaEventRecord(c.directFork, mainStream);
     cudaStreamWaitEvent(c.directStream, c.directFork, 0);
     c.stream = c.directStream;
+    // an owed environment pass (ALU-bound, writes the colour target the resolve reads after the join) runs here, beside the
+    // texture-bound view march
+    if (c.envDeferred) { c.envDeferred = false; launch_environment(c, true); }
     launch_ray_cast_direct(c);
     c.stream = mainStream;
     cudaEventRecord(c.directJoin, c.directStream);
@@ -582,6 +588,11 @@ void mv_destroy(mv_caster* h)
 #define MV_ENTER(h)                                  \
     MV_REQUIRE(h != nullptr);                        \
     Caster& c = h->c;                                \
+    MV_CUDA(cudaSetDevice(c.device));                \
+    flush_deferred(c)
+#define MV_ENTER_KEEP(h)                             \
+    MV_REQUIRE(h != nullptr);                        \
+    Caster& c = h->c;                                \
     MV_CUDA(cudaSetDevice(c.device))
 
 int mv_volume_init_procedural(mv_caster* h, uint32_t src, uint32_t mode, uint32_t seed)
@@ -881,7 +892,8 @@ int mv_resolve_oit(mv_caster* h)
 
 int mv_render(mv_caster* h, uint32_t oit)   // MultiRayCaster.cpp:355-385
 {
-    MV_ENTER(h);
+    MV_ENTER_KEEP(h);
+    if (c.envDeferred && !frame_is_pipelined_on_one_gpu(c)) flush_deferred(c);
     (void)oit;   // one OIT implementation: the K-buffer semantics of the default branch (:377-381)
     if (c.shardWorld > 1 && !c.peersMapped) {
         set_error(c.shardVolumes ? "volume-sharded caster without mapped peers (mv_ipc_import / mv_set_peer_block)"

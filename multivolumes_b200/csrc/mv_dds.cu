@@ -54,7 +54,8 @@ uint32_t rd32(const unsigned char* p) { return (uint32_t)p[0] | ((uint32_t)p[1] 
 #define MV_ENTER(h)            \
     MV_REQUIRE(h != nullptr);  \
     Caster& c = h->c;          \
-    MV_CUDA(cudaSetDevice(c.device))
+    MV_CUDA(cudaSetDevice(c.device)); \
+    flush_deferred(c)
 
 extern "C" {
 

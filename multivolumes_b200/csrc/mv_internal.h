@@ -217,6 +217,10 @@ void launch_resolve_oit(Caster& c);
 void launch_postprocess(Caster& c, bool taaOn);
 void build_tone_lut(Caster& c);
 void launch_environment(Caster& c, bool copyBackground);
+// mv_render_environment may leave its pass to the next mv_render (Caster::envDeferred), which runs it beside the view march;
+// every other entry point runs it first (MV_ENTER)
+void flush_deferred(Caster& c);
+bool frame_is_pipelined_on_one_gpu(const Caster& c);
 
 struct Volume3D {
     bool proxy = false;                  // volume-sharded storage: an R16F density proxy of another rank's source
@@ -259,6 +263,7 @@ struct Caster {
     float* dMeshPos = nullptr;           // V x 3
     uint32_t* dMeshIdx = nullptr;        // 3 T
     void* dMeshTris = nullptr;           // 2 T screen-space records of the pass being rasterised
+    bool envDeferred = false;            // an environment pass is owed to the colour target (see flush_deferred)
     float* dMeshNrm = nullptr;           // V x 3 (recomputed vertex normals)
     void* dMeshShade = nullptr;          // 2 T records of interpolants for the base pass
     unsigned long long* dMeshVis = nullptr;   // W x H visibility buffer: depth bits << 32 | record

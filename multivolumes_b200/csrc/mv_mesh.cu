@@ -396,7 +396,8 @@ int raster_pass(Caster& c, const float wvp[16], uint32_t width, uint32_t height,
 #define MV_ENTER(h)            \
     MV_REQUIRE(h != nullptr);  \
     Caster& c = h->c;          \
-    MV_CUDA(cudaSetDevice(c.device))
+    MV_CUDA(cudaSetDevice(c.device)); \
+    flush_deferred(c)
 
 extern "C" {
 

@@ -102,7 +102,8 @@ int check_peer_timeout(Caster& c)
 #define MV_ENTER(h)            \
     MV_REQUIRE(h != nullptr);  \
     Caster& c = h->c;          \
-    MV_CUDA(cudaSetDevice(c.device))
+    MV_CUDA(cudaSetDevice(c.device)); \
+    flush_deferred(c)
 
 static int refresh_peers(Caster& c)
 {
