@@ -23,11 +23,12 @@ namespace mv {
 
 namespace {
 
-// 5 CTAs x 256 threads / SM = 40 resident warps (<= 51 registers): the loop is latency-bound on a
-// dependent texture round trip per step, measured T = 0.088 ms + 5.55 ms / warps-per-SM on cfg 2 up to
-// 32 warps, flattening beyond 40; 6 CTAs (40 registers) spills and is no faster (profiles/r01_notes.md)
+// 6 CTAs x 256 threads / SM = 48 resident warps (<= 40 registers): the loop is latency-bound on a dependent texture round
+// trip per step, so resident warps are what buys throughput. Round 1 measured no gain beyond 40 warps on cfg 2 with the
+// kernel of that time; on the round-2 kernel (empty-space bricks, light fetch issued with the density fetch) and cfg 4:
+// 4 / 5 / 6 / 7 / 8 CTAs = 0.947 / 0.837 / 0.780 / 0.863 / 0.863 ms (same-box A/B, profiles/r02_notes.md section 9).
 #ifndef MV_MARCH_MIN_BLOCKS
-#define MV_MARCH_MIN_BLOCKS 5
+#define MV_MARCH_MIN_BLOCKS 6
 #endif
 constexpr int kMarchThreads = 256;
 constexpr int kMarchWarps = kMarchThreads / 32;
